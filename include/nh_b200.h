@@ -1,0 +1,205 @@
+/*
+ * nh_b200.h -- C ABI of libnh_b200.so, the sm_100a kernel library behind
+ * nano-hevc's block-coding hot path.
+ *
+ * The reference (Luodian/nano-hevc) is pure Python + numpy and has no FFI of
+ * its own: its "operator API" is the flat set of module-level functions
+ * re-exported by nano_hevc/__init__.py:5-48.  Every entry point below names the
+ * reference function (file:line, relative to the reference checkout) it
+ * replaces; INTEGRATION.md shows the ctypes stub a maintainer of the reference
+ * would add to route that function here.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types.
+ *   - unless a function says "host", every data pointer is a DEVICE pointer
+ *     owned by the caller; the library allocates nothing persistent.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *     the call returns without synchronising.
+ *   - return 0 on success, a negative NH_E_* code on failure (never throws);
+ *     nh_last_error() returns a thread-local description of the last failure.
+ *   - blocks are "block-major": block b of an (B, N, N) tensor occupies N*N
+ *     consecutive elements, rows first.  Pixels / predictions / residuals /
+ *     reconstructions are int16, coefficients / levels are int32 (the
+ *     reference's dtype contract).
+ *   - size is 4, 8, 16 or 32; any other value -> NH_E_SIZE (the reference
+ *     raises ValueError("Unsupported transform size"), transform.py:151).
+ *   - qp is clamped to [0, 51] exactly like quant.py:35.
+ *   - intra modes: 0 = planar, 1 = DC, 2..34 = angular (intra.py:1-17).
+ */
+#ifndef NH_B200_H
+#define NH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NH_OK 0
+#define NH_E_SIZE (-1)   /* unsupported block size            */
+#define NH_E_ARG (-2)    /* bad argument (null, negative, mode out of range, misaligned) */
+#define NH_E_CUDA (-3)   /* CUDA runtime error; see nh_last_error() */
+#define NH_E_NOMEM (-4)  /* caller-provided scratch too small  */
+
+#define NH_COST_SAD 0
+#define NH_COST_SATD 1
+
+/* ------------------------------------------------------------------ meta */
+int nh_version(void);
+const char* nh_last_error(void);
+/* 1 when a CUDA device of compute capability 10.x is usable by this process. */
+int nh_device_ok(void);
+
+/* Tables, computed on the host (no device needed).
+ * nano_hevc/transform.py:20-135 (DST4, DCT4/8/16/32) -> out[size*size] */
+int nh_get_transform_matrix(int size, int use_dst, int32_t* out_host);
+/* nano_hevc/intra.py:24-29 INTRA_PRED_ANGLE[mode-2]; mode 2..34 */
+int nh_get_intra_pred_angle(int mode, int* angle_out);
+/* nano_hevc/quant.py:25-38 get_qp_params */
+int nh_get_qp_params(int qp, int* per_out, int* rem_out);
+/* nano_hevc/quant.py:21-22 QUANT_SCALE[rem], DEQUANT_SCALE[rem]; rem 0..5 */
+int nh_get_quant_scales(int rem, int* quant_scale_out, int* dequant_scale_out);
+
+/* ------------------------------------------- K4: transforms (batched) */
+/* nano_hevc/transform.py:154-196 forward_transform(residual, use_dst).
+ * residual: (B,N,N) int16 when residual_is_i32 == 0, int32 otherwise. */
+int nh_forward_transform(const void* residual, int residual_is_i32, int32_t* coeff,
+                         int64_t n_blocks, int size, int use_dst, void* stream);
+/* nano_hevc/transform.py:199-238 inverse_transform(coeff, use_dst). */
+int nh_inverse_transform(const int32_t* coeff, int32_t* residual, int64_t n_blocks, int size,
+                         int use_dst, void* stream);
+
+/* ---------------------------------------------- K5: quant (batched) */
+/* nano_hevc/quant.py:41-79 quantize(coeff, qp, size, is_intra) / :126-137 quantize_block */
+int nh_quantize(const int32_t* coeff, int32_t* level, int64_t n_elems, int qp, int size,
+                int is_intra, void* stream);
+/* nano_hevc/quant.py:82-123 dequantize(level, qp, size) / :140-150 dequantize_block
+ * (`size` is accepted and ignored, as in the reference). */
+int nh_dequantize(const int32_t* level, int32_t* coeff, int64_t n_elems, int qp, int size,
+                  void* stream);
+
+/* ------------------------------------------ K2: predictors (batched) */
+/* nano_hevc/intra.py:46-62 intra_dc_predict(top, left, size); top,left (B,N) */
+int nh_intra_dc_predict(const int16_t* top, const int16_t* left, int16_t* pred, int64_t n_blocks,
+                        int size, void* stream);
+/* nano_hevc/intra.py:81-113 intra_planar_predict(top, left, top_right, bottom_left, size);
+ * top,left (B,N); top_right, bottom_left (B,) */
+int nh_intra_planar_predict(const int16_t* top, const int16_t* left, const int16_t* top_right,
+                            const int16_t* bottom_left, int16_t* pred, int64_t n_blocks, int size,
+                            void* stream);
+/* nano_hevc/intra.py:116-207 intra_angular_predict(top, left, top_left, mode, size).
+ * top, left: (B, 2N+1) with index 0 = the array's corner slot; top_left (B,).
+ * modes: (B,) uint8 per-block modes, or NULL to use `mode` for every block.
+ * With allow_dc_planar != 0, mode 1 / 0 select DC / planar computed from
+ * top[1..N], left[1..N], TR = top[N+1], BL = left[N+1]. */
+int nh_intra_predict_modes(const int16_t* top, const int16_t* left, const int16_t* top_left,
+                           const uint8_t* modes, int mode, int allow_dc_planar, int16_t* pred,
+                           int64_t n_blocks, int size, void* stream);
+
+/* --------------------------------- K3: residual / reconstruct / clip */
+/* nano_hevc/intra.py:65-67 residual_block */
+int nh_residual_block(const int16_t* orig, const int16_t* pred, int16_t* residual, int64_t n_elems,
+                      void* stream);
+/* nano_hevc/intra.py:70-72 reconstruct_block (residual int32 is truncated to int16 first) */
+int nh_reconstruct_block(const int16_t* pred, const int32_t* residual, int16_t* out,
+                         int64_t n_elems, void* stream);
+/* nano_hevc/intra.py:75-78 clip_to_pixel_range */
+int nh_clip_to_pixel_range(const int16_t* in, int16_t* out, int64_t n_elems, int bit_depth,
+                           void* stream);
+
+/* ------------------------------------------------ K6: fused pipeline */
+/* predict -> residual -> forward -> quantize -> dequantize -> inverse ->
+ * reconstruct -> clip in one kernel (composition of README.md:55-71 /
+ * docs/frames_and_panes.md:319-338).  Any of the four outputs may be NULL.
+ *
+ * DC / planar from given N-sample references (config 2):
+ *   orig (B,N,N); top,left (B,N); top_right,bottom_left (B,);
+ *   modes (B,) uint8 with values 0/1, or NULL -> `mode` for all blocks. */
+int nh_fused_pipeline_dcplanar(const int16_t* orig, const int16_t* top, const int16_t* left,
+                               const int16_t* top_right, const int16_t* bottom_left,
+                               const uint8_t* modes, int mode, int64_t n_blocks, int size, int qp,
+                               int is_intra, int use_dst, int bit_depth, int16_t* pred,
+                               int32_t* coeff, int32_t* levels, int16_t* recon, void* stream);
+/* Any of the 35 modes from padded (B, 2N+1) references (K1 convention). */
+int nh_fused_pipeline_modes(const int16_t* orig, const int16_t* top, const int16_t* left,
+                            const int16_t* top_left, const uint8_t* modes, int mode,
+                            int64_t n_blocks, int size, int qp, int is_intra, int use_dst,
+                            int bit_depth, int16_t* pred, int32_t* coeff, int32_t* levels,
+                            int16_t* recon, void* stream);
+
+/* ---------------------------------------------- K1: reference gather */
+/* nano_hevc/block.py:38-55 BlockView.get_top_neighbors / get_left_neighbors /
+ * get_top_left_neighbor for every full block of a plane in iterate_blocks
+ * order (block.py:68-74), with the 128 substitution at frame edges and
+ * replicate-last padding to 2N+1 entries (intra.py:174-178).
+ * plane (H, pitch) int16; n_top / n_left = samples requested per side
+ * (2N/2N for source neighbours, 2N/N for reconstructed neighbours).
+ * top,left (B, 2N+1) [index 0 = corner]; corner (B,). */
+int nh_gather_refs(const int16_t* plane, int height, int width, int pitch, int size, int n_top,
+                   int n_left, int16_t* top, int16_t* left, int16_t* corner, void* stream);
+/* (H,W) plane <-> (B,N,N) block-major, iterate_blocks order, partial blocks skipped. */
+int nh_plane_to_blocks(const int16_t* plane, int height, int width, int pitch, int size,
+                       int16_t* blocks, void* stream);
+int nh_blocks_to_plane(const int16_t* blocks, int height, int width, int pitch, int size,
+                       int16_t* plane, void* stream);
+
+/* ---------------------------------- K7 / K8: frame coders with search */
+/* Exhaustive 35-mode search (candidate order 1,0,2..34; first strict minimum,
+ * i.e. DC beats planar on ties -- __main__.py:96 -- then the lowest angular
+ * mode) with SAD (metrics.py:24-26) or SATD (sum of satd_4x4, metrics.py:29-43)
+ * cost, then the winner through the K6 chain with use_dst = (size == 4).
+ *
+ * recon_neighbours == 0 (config 3): references come from the SOURCE plane,
+ *   n_top = n_left = 2N; every block independent.
+ * recon_neighbours == 1 (config 5): references come from the RECON plane
+ *   (zero-initialised by this call), n_top = 2N, n_left = N; blocks are coded
+ *   in an anti-diagonal wavefront that honours the raster-order dependencies.
+ *
+ * src (H, pitch) int16.  Outputs, block-major in raster block order (any may be
+ * NULL except recon_plane when recon_neighbours == 1):
+ *   modes (B,) u8; costs (B,) i32; pred (B,N,N) i16; coeff, levels (B,N,N) i32;
+ *   recon_plane (H, pitch) i16 -- uncovered rows/columns are set to 0.
+ * progress: device scratch of nh_encode_frame_scratch_bytes(height, size) bytes
+ *   (only used when recon_neighbours == 1; may be NULL otherwise). */
+int64_t nh_encode_frame_scratch_bytes(int height, int size);
+int nh_encode_frame(const int16_t* src, int height, int width, int pitch, int size, int cost_kind,
+                    int qp, int recon_neighbours, int bit_depth, uint8_t* modes, int32_t* costs,
+                    int16_t* pred, int32_t* coeff, int32_t* levels, int16_t* recon_plane,
+                    void* scratch, int64_t scratch_bytes, void* stream);
+
+/* -------------------------------------------------- K9: reductions */
+/* Integer numerators of nano_hevc/metrics.py: out[0] = sum (a-b)^2  (mse/psnr, :7-21),
+ * out[1] = sum |a-b| (sad, :24-26).  a, b int16, n_elems elements; out: 2 x int64 on the
+ * device, zeroed by this call.  PSNR is finished on the host in float64. */
+int nh_reduce_sse_sad(const int16_t* a, const int16_t* b, int64_t n_elems, int64_t* out,
+                      void* stream);
+/* Same over a (height, width) window of two pitched planes. */
+int nh_reduce_sse_sad_2d(const int16_t* a, int pitch_a, const int16_t* b, int pitch_b, int height,
+                         int width, int64_t* out, void* stream);
+/* Per-block costs of (B,N,N) pairs: sad (B,) i32 and satd (B,) i32 (sum of satd_4x4 over the
+ * 4x4 sub-blocks, metrics.py:29-43), energy (B,) i64 = sum (a-b)^2 (residual_energy, :46-48).
+ * Any output may be NULL. */
+int nh_block_costs(const int16_t* a, const int16_t* b, int64_t n_blocks, int size, int32_t* sad,
+                   int32_t* satd, int64_t* energy, void* stream);
+/* Level statistics: out[0] = number of non-zero levels (quant.py:171-173 count_nonzero). */
+int nh_count_nonzero(const int32_t* levels, int64_t n_elems, int64_t* out, void* stream);
+
+/* ------------------------------------- host-buffer entry point (e2e) */
+/* Same computation as nh_fused_pipeline_dcplanar but every pointer is a HOST
+ * pointer (pinned memory recommended).  The library copies the inputs to the
+ * current device in chunks, runs the kernel and copies the requested outputs
+ * back, overlapping H2D, compute and D2H on internal streams, and returns
+ * after the last byte has landed.  device_scratch is a caller-provided device
+ * buffer of at least nh_host_pipeline_scratch_bytes(size, chunk_blocks) bytes. */
+int64_t nh_host_pipeline_scratch_bytes(int size, int64_t chunk_blocks);
+int nh_host_pipeline_dcplanar(const int16_t* orig, const int16_t* top, const int16_t* left,
+                              const int16_t* top_right, const int16_t* bottom_left,
+                              const uint8_t* modes, int mode, int64_t n_blocks, int size, int qp,
+                              int is_intra, int use_dst, int bit_depth, int16_t* pred,
+                              int32_t* coeff, int32_t* levels, int16_t* recon,
+                              void* device_scratch, int64_t scratch_bytes, int64_t chunk_blocks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NH_B200_H */

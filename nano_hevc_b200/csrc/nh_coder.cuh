@@ -1,0 +1,240 @@
+// nh_coder.cuh -- the group-cooperative block coder shared by
+//   * nh_fused_pipeline_modes  (any of the 35 modes from given padded references),
+//   * nh_encode_frame, source neighbours        (K7: 35-mode search + winner pipeline),
+//   * nh_encode_frame, reconstructed neighbours (K8: anti-diagonal wavefront).
+//
+// G lanes cooperate on one N x N block (G = N: several blocks per warp, throughput mode;
+// G = 32: one block per warp, latency mode for the wavefront).  Shared memory per group:
+//   refs   top[0..2N], left[0..2N]      (index 0 = corner slot)
+//   O      N x N int16                  (original pixels, later the reconstruction)
+//   M      RowsTile<N> int32            (working matrix of the separable transforms)
+#pragma once
+#include "nh_block.cuh"
+
+namespace nh {
+
+template <int N, int G>
+struct CoderCfg {
+    static constexpr int SB = N * N / 16;               // 4x4 sub-blocks per block
+    static constexpr int SPL = SB >= G ? SB / G : 1;    // sub-blocks per lane
+    static constexpr int MS = SB >= G ? 1 : G / SB;     // mode splits (lanes sharing a sub-block)
+    static constexpr int SBL = SB >= G ? G : SB;        // lanes that sum one mode's cost
+    static constexpr int REF_W = 2 * N + 2;             // padded to an even count
+    static constexpr int O_PITCH = N + 2;               // int16 elements; odd word pitch spreads banks
+    static constexpr int REFS_BYTES = 2 * REF_W * 2;
+    static constexpr int O_BYTES = ((N * O_PITCH * 2 + 15) / 16) * 16;
+    static constexpr int M_BYTES = RowsTile<N>::WORDS * 4;
+    static constexpr int GROUP_BYTES = ((REFS_BYTES + 15) / 16) * 16 + O_BYTES + M_BYTES;
+};
+
+struct SmemRef {  // accessor for nh::ref_at / angular_sample over shared-memory references
+    const int16_t* p;
+    const int16_t* s;
+    int c;
+    __device__ __forceinline__ int pri(int k) const { return (int)p[k]; }
+    __device__ __forceinline__ int sec(int k) const { return (int)s[k]; }
+    __device__ __forceinline__ int corner() const { return c; }
+};
+
+// One predicted sample of `mode` at (x, y) from padded shared-memory references.
+template <int N>
+__device__ __forceinline__ int predict_px(int mode, int x, int y, const int16_t* top,
+                                          const int16_t* left, int corner, int dc) {
+    if (mode == 1) return dc;
+    if (mode == 0) return planar_px<N>(x, y, left[1 + y], top[1 + x], top[N + 1], left[N + 1]);
+    const AngleInfo ai = angle_info(mode);
+    SmemRef r;
+    r.c = corner;
+    if (ai.vertical) { r.p = top; r.s = left; return angular_sample(r, ai, x, y); }
+    r.p = left; r.s = top;
+    return angular_sample(r, ai, y, x);
+}
+
+// Cost of one 4x4 sub-block at (sx, sy): SAD (metrics.py:24-26) or satd_4x4 (metrics.py:29-43).
+template <int N>
+__device__ __forceinline__ int subblock_cost(int mode, int sx, int sy, const int (&o)[16],
+                                             const int16_t* top, const int16_t* left, int corner,
+                                             int dc, int cost_kind) {
+    int d[16];
+    if (mode >= 2) {
+        // Angular: (int_part, frac) depend on the scan line only, hoist them.
+        const AngleInfo ai = angle_info(mode);
+        SmemRef r;
+        r.c = corner;
+        if (ai.vertical) { r.p = top; r.s = left; } else { r.p = left; r.s = top; }
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const int scan = (ai.vertical ? sy : sx) + s;
+            const int p = (scan + 1) * ai.angle;
+            const int ip = p >> 5, f = p & 31;
+            const int b0 = (ai.vertical ? sx : sy) + 1 + ip;
+            int v[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) v[k] = (k < 4 || f != 0) ? ref_at(r, b0 + k, ai.inv) : 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int pv = angular_px(v[k], v[k + 1], f);
+                const int e = ai.vertical ? (s * 4 + k) : (k * 4 + s);  // (y, x) of this sample
+                d[e] = o[e] - pv;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+            d[e] = o[e] - predict_px<N>(mode, sx + (e & 3), sy + (e >> 2), top, left, corner, dc);
+    }
+    int c = 0;
+    if (cost_kind == NH_COST_SAD) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) c += abs(d[e]);
+    } else {
+        // H . d . H^T with the 4x4 +-1 Hadamard of metrics.py:36-41 (row order irrelevant
+        // for the sum of absolute values).
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // columns
+            int a0 = d[j] + d[4 + j], a1 = d[j] - d[4 + j];
+            int a2 = d[8 + j] + d[12 + j], a3 = d[8 + j] - d[12 + j];
+            d[j] = a0 + a2; d[4 + j] = a1 + a3; d[8 + j] = a0 - a2; d[12 + j] = a1 - a3;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // rows
+            int a0 = d[4 * i] + d[4 * i + 1], a1 = d[4 * i] - d[4 * i + 1];
+            int a2 = d[4 * i + 2] + d[4 * i + 3], a3 = d[4 * i + 2] - d[4 * i + 3];
+            c += abs(a0 + a2) + abs(a1 + a3) + abs(a0 - a2) + abs(a1 - a3);
+        }
+    }
+    return c;
+}
+
+// Exhaustive 35-mode search.  Candidate order 1, 0, 2, 3, ..., 34; the first strict
+// minimum wins (DC beats planar on ties -- __main__.py:96 -- then the lowest angular mode).
+// `gl` = lane within the group.  Returns key = (cost << 6) | order position, identical on
+// every lane of the group.
+template <int N, int G>
+__device__ __forceinline__ int search_modes(int gl, const int16_t* O, const int16_t* top,
+                                            const int16_t* left, int corner, int dc, int cost_kind) {
+    using Cfg = CoderCfg<N, G>;
+    constexpr int SBW = N / 4;
+    int o[Cfg::SPL][16];
+    int sx[Cfg::SPL], sy[Cfg::SPL];
+#pragma unroll
+    for (int i = 0; i < Cfg::SPL; ++i) {
+        const int sb = (Cfg::MS == 1) ? gl + i * G : gl % Cfg::SB;
+        sx[i] = (sb % SBW) * 4;
+        sy[i] = (sb / SBW) * 4;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) o[i][e] = (int)O[(sy[i] + (e >> 2)) * Cfg::O_PITCH + sx[i] + (e & 3)];
+    }
+    const int ms = (Cfg::MS == 1) ? 0 : gl / Cfg::SB;
+    int best = 0x7fffffff;
+    constexpr int ITERS = (35 + Cfg::MS - 1) / Cfg::MS;
+    for (int it = 0; it < ITERS; ++it) {
+        const int pos = it * Cfg::MS + ms;          // position in the candidate order
+        const bool active = pos < 35;
+        const int mode = !active ? 1 : (pos == 0 ? 1 : (pos == 1 ? 0 : pos));
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < Cfg::SPL; ++i)
+            c += subblock_cost<N>(mode, sx[i], sy[i], o[i], top, left, corner, dc, cost_kind);
+#pragma unroll
+        for (int off = Cfg::SBL / 2; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+        const int key = active ? ((c << 6) | pos) : 0x7fffffff;
+        best = key < best ? key : best;
+    }
+    // warp-level argmin across the mode splits
+#pragma unroll
+    for (int off = G / 2; off >= Cfg::SBL; off >>= 1) {
+        int other = __shfl_xor_sync(0xffffffffu, best, off);
+        best = other < best ? other : best;
+    }
+    return best;
+}
+
+__device__ __forceinline__ int mode_of_key(int key) {
+    const int pos = key & 63;
+    return pos == 0 ? 1 : (pos == 1 ? 0 : pos);
+}
+
+struct CoderOut {
+    uint8_t* modes;     // (B,)
+    int32_t* costs;     // (B,)
+    int16_t* pred;      // (B,N,N)
+    int32_t* coeff;     // (B,N,N)
+    int32_t* levels;    // (B,N,N)
+    int16_t* recon;     // (B,N,N) block-major, or NULL
+    int16_t* recon_plane;  // (H, pitch) or NULL
+    int pitch;
+};
+
+// Winner pipeline for one block: row owner r (< N) predicts row r, then the K6 chain through
+// the shared working matrix.  All lanes of the warp must call this (it contains __syncwarp).
+// The reconstruction is left in O (pitch O_PITCH) for the caller to copy out.
+template <int N, int G>
+__device__ __forceinline__ void code_block(int gl, bool valid, int64_t b, int mode, int16_t* O,
+                                           int* M, const int16_t* top, const int16_t* left,
+                                           int corner, int dc, const QuantParams& qp, int maxv,
+                                           bool use_dst, const CoderOut& out) {
+    using Cfg = CoderCfg<N, G>;
+    constexpr int NN = N * N;
+    const int r = gl;
+    const bool rowlane = r < N;
+    uint32_t pw[N / 2];
+    if (rowlane) {
+        int p[N], res[N];
+#pragma unroll
+        for (int x = 0; x < N; ++x) p[x] = predict_px<N>(mode, x, r, top, left, corner, dc);
+        pack_row<N>(p, pw);
+        if (valid && out.pred) store_row16<N>(out.pred + b * NN + r * N, pw);
+#pragma unroll
+        for (int x = 0; x < N; ++x) res[x] = sext16((int)O[r * Cfg::O_PITCH + x] - sext16(p[x]));
+        store_row_smem<N>(M, r, res);
+    }
+    __syncwarp();
+    if (rowlane) {
+        if (N == 4 && use_dst) col_pass<N, N == 4, false>(M, r);
+        else col_pass<N, false, false>(M, r);
+    }
+    __syncwarp();
+    if (rowlane) {
+        int c[N], lv[N], dq[N];
+        if (N == 4 && use_dst) row_pass<N, N == 4, false>(M, r, c);
+        else row_pass<N, false, false>(M, r, c);
+        if (valid && out.coeff) store_row32<N>(out.coeff + b * NN + r * N, c);
+        quant_dequant_row<N>(c, qp, lv, dq);
+        if (valid && out.levels) store_row32<N>(out.levels + b * NN + r * N, lv);
+        store_row_smem<N>(M, r, dq);
+    }
+    __syncwarp();
+    if (rowlane) {
+        if (N == 4 && use_dst) col_pass<N, N == 4, true>(M, r);
+        else col_pass<N, false, true>(M, r);
+    }
+    __syncwarp();
+    if (rowlane) {
+        int res[N];
+        if (N == 4 && use_dst) row_pass<N, N == 4, true>(M, r, res);
+        else row_pass<N, false, true>(M, r, res);
+        uint32_t ow[N / 2];
+#pragma unroll
+        for (int k = 0; k < N / 2; ++k) {
+            const int a = recon_px(lo16(pw[k]), res[2 * k], maxv);
+            const int c2 = recon_px(hi16(pw[k]), res[2 * k + 1], maxv);
+            ow[k] = pack16(a, c2);
+            O[r * Cfg::O_PITCH + 2 * k] = (int16_t)a;
+            O[r * Cfg::O_PITCH + 2 * k + 1] = (int16_t)c2;
+        }
+        if (valid && out.recon) store_row16<N>(out.recon + b * NN + r * N, ow);
+    }
+    __syncwarp();
+}
+
+// DC value from padded shared-memory references (top[1..N], left[1..N]).
+template <int N>
+__device__ __forceinline__ int dc_from_refs(const int16_t* top, const int16_t* left) {
+    int s = 0;
+#pragma unroll
+    for (int k = 1; k <= N; ++k) s += (int)top[k] + (int)left[k];
+    return dc_value<N>(s);
+}
+
+}  // namespace nh

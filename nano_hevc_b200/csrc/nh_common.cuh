@@ -1,0 +1,112 @@
+// nh_common.cuh -- error plumbing, launch geometry and the warp-level staging
+// helpers shared by every translation unit of libnh_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/nh_b200.h"
+#include "nh_math.cuh"
+
+#define NH_API extern "C" __attribute__((visibility("default")))
+
+namespace nh {
+
+// Thread-local description of the last failure (nh_last_error()).
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+inline int log2_size(int size) {
+    switch (size) {
+        case 4: return 2;
+        case 8: return 3;
+        case 16: return 4;
+        case 32: return 5;
+        default: return -1;
+    }
+}
+
+// Persistent-style grid: `ctas_per_sm` CTAs on every SM of the current device,
+// never more CTAs than there are work items of `items_per_cta`.
+int sm_count();
+inline int grid_for(int64_t items, int64_t items_per_cta, int ctas_per_sm) {
+    int64_t need = (items + items_per_cta - 1) / items_per_cta;
+    int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+#define NH_CHECK_LAUNCH(what)                                  \
+    do {                                                       \
+        cudaError_t e__ = cudaGetLastError();                  \
+        if (e__ != cudaSuccess) return nh::cuda_fail(e__, what); \
+    } while (0)
+
+#if defined(__CUDACC__)
+// ----------------------------------------------------------- device helpers
+__device__ __forceinline__ int lo16(uint32_t w) { return (int)(short)(w & 0xffffu); }
+__device__ __forceinline__ int hi16(uint32_t w) { return (int)w >> 16; }
+__device__ __forceinline__ uint32_t pack16(int lo, int hi) {
+    return __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410);
+}
+
+// Streaming (evict-first) 128-bit global accesses: every tensor of the
+// pipeline is touched exactly once, so nothing should linger in L2.
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+    return __ldcs(reinterpret_cast<const uint4*>(p));
+}
+__device__ __forceinline__ void stg_stream(void* p, uint4 v) {
+    __stcs(reinterpret_cast<uint4*>(p), v);
+}
+
+// Warp tile staging.  A warp tile is 32 "units" of UNIT_BYTES contiguous
+// bytes in global memory (one unit per lane).  In shared memory unit u lives
+// at u * (UNIT_BYTES + 16): the 16-byte pad makes the per-lane 128-bit
+// accesses (lane l touching its own unit) conflict-free, while the cooperative
+// copy below (8 or 16 consecutive lanes sweep one unit) stays conflict-free too.
+template <int UNIT_BYTES>
+struct WarpTile {
+    static constexpr int kPitch = UNIT_BYTES + 16;
+    static constexpr int kBytes = 32 * kPitch;
+    static constexpr int kChunksPerUnit = UNIT_BYTES / 16;
+    static constexpr int kIters = kChunksPerUnit;  // 32 lanes x 16 B per iteration
+
+    // global (linear) -> shared (padded); chunks_valid = number of valid 16-byte chunks
+    // (< 32 * kChunksPerUnit only on the ragged last tile).
+    static __device__ __forceinline__ void load(unsigned char* smem, const unsigned char* gmem,
+                                                int lane, int chunks_valid) {
+        uint4 v[kIters];  // all loads in flight before the first shared-memory store
+#pragma unroll
+        for (int it = 0; it < kIters; ++it) {
+            int c = it * 32 + lane;
+            v[it] = (c < chunks_valid) ? ldg_stream(gmem + (size_t)c * 16) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int it = 0; it < kIters; ++it) {
+            int c = it * 32 + lane;
+            int u = c / kChunksPerUnit, k = c % kChunksPerUnit;
+            *reinterpret_cast<uint4*>(smem + u * kPitch + k * 16) = v[it];
+        }
+    }
+    // shared (padded) -> global (linear)
+    static __device__ __forceinline__ void store(const unsigned char* smem, unsigned char* gmem,
+                                                 int lane, int chunks_valid) {
+        uint4 v[kIters];
+#pragma unroll
+        for (int it = 0; it < kIters; ++it) {
+            int c = it * 32 + lane;
+            int u = c / kChunksPerUnit, k = c % kChunksPerUnit;
+            v[it] = *reinterpret_cast<const uint4*>(smem + u * kPitch + k * 16);
+        }
+#pragma unroll
+        for (int it = 0; it < kIters; ++it) {
+            int c = it * 32 + lane;
+            if (c < chunks_valid) stg_stream(gmem + (size_t)c * 16, v[it]);
+        }
+    }
+    static __device__ __forceinline__ uint4* unit(unsigned char* smem, int lane) {
+        return reinterpret_cast<uint4*>(smem + lane * kPitch);
+    }
+};
+#endif  // __CUDACC__
+
+}  // namespace nh

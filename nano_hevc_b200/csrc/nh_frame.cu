@@ -1,0 +1,396 @@
+// nh_frame.cu -- frame-level entry points:
+//   K1  nh_gather_refs / nh_plane_to_blocks / nh_blocks_to_plane   (block.py:38-74)
+//   K6' nh_fused_pipeline_modes   (any of the 35 modes from given padded references)
+//   K7  nh_encode_frame, recon_neighbours = 0   (35-mode search + winner pipeline)
+//   K8  nh_encode_frame, recon_neighbours = 1   (anti-diagonal wavefront on the recon plane)
+#include "nh_coder.cuh"
+
+namespace nh {
+
+// Neighbour fetch with the reference's substitution rules (block.py:38-55) and
+// replicate-last padding (intra.py:174-178) folded into an index clamp.
+// COHERENT: read through L2 (ld.cg) because another SM may just have written the sample.
+template <bool COHERENT>
+__device__ __forceinline__ int plane_px(const int16_t* plane, int64_t idx) {
+    if constexpr (COHERENT) return (int)__ldcg(plane + idx);
+    else return (int)__ldg(plane + idx);
+}
+
+template <bool COHERENT>
+__device__ __forceinline__ int top_ref(const int16_t* plane, int H, int W, int pitch, int x, int y,
+                                       int n_top, int k) {  // k = 0 .. 2N
+    if (k == 0) return (x == 0 || y == 0) ? 128 : plane_px<COHERENT>(plane, (int64_t)(y - 1) * pitch + x - 1);
+    if (y == 0) return 128;
+    int last = x + n_top - 1;
+    if (last > W - 1) last = W - 1;
+    int col = x + k - 1;
+    if (col > last) col = last;
+    return plane_px<COHERENT>(plane, (int64_t)(y - 1) * pitch + col);
+}
+
+template <bool COHERENT>
+__device__ __forceinline__ int left_ref(const int16_t* plane, int H, int W, int pitch, int x, int y,
+                                        int n_left, int k) {
+    if (k == 0) return (x == 0 || y == 0) ? 128 : plane_px<COHERENT>(plane, (int64_t)(y - 1) * pitch + x - 1);
+    if (x == 0) return 128;
+    int last = y + n_left - 1;
+    if (last > H - 1) last = H - 1;
+    int row = y + k - 1;
+    if (row > last) row = last;
+    return plane_px<COHERENT>(plane, (int64_t)row * pitch + x - 1);
+}
+
+// ------------------------------------------------------------------------ K1
+__global__ void __launch_bounds__(256)
+    gather_refs_kernel(const int16_t* __restrict__ plane, int H, int W, int pitch, int N, int n_top,
+                       int n_left, int16_t* __restrict__ top, int16_t* __restrict__ left,
+                       int16_t* __restrict__ corner) {
+    const int bw = W / N, bh = H / N, RW = 2 * N + 1;
+    const int64_t total = (int64_t)bw * bh * RW;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = t / RW;
+        const int k = (int)(t % RW);
+        const int x = (int)(b % bw) * N, y = (int)(b / bw) * N;
+        const int tv = top_ref<false>(plane, H, W, pitch, x, y, n_top, k);
+        const int lv = left_ref<false>(plane, H, W, pitch, x, y, n_left, k);
+        top[t] = (int16_t)tv;
+        left[t] = (int16_t)lv;
+        if (k == 0) corner[b] = (int16_t)tv;
+    }
+}
+
+template <bool TO_BLOCKS>
+__global__ void __launch_bounds__(256)
+    reblock_kernel(const int16_t* __restrict__ in, int H, int W, int pitch, int N,
+                   int16_t* __restrict__ out) {
+    const int bw = W / N, bh = H / N;
+    const int64_t total = (int64_t)bw * bh * N * N;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        // t enumerates plane samples of the covered region row by row (coalesced on the plane side)
+        const int cw = bw * N;
+        const int py = (int)(t / cw), px = (int)(t % cw);
+        const int64_t b = (int64_t)(py / N) * bw + px / N;
+        const int64_t bi = b * N * N + (py % N) * N + (px % N);
+        const int64_t pi = (int64_t)py * pitch + px;
+        if (TO_BLOCKS) out[bi] = in[pi];
+        else out[pi] = in[bi];
+    }
+}
+
+// --------------------------------------------------------------- coder kernel
+enum { SRC_ARRAYS = 0, SRC_PLANE = 1, SRC_WAVEFRONT = 2 };
+
+struct CoderArgs {
+    // SRC_ARRAYS
+    const int16_t* orig;   // (B,N,N)
+    const int16_t* top;    // (B,2N+1)
+    const int16_t* left;   // (B,2N+1)
+    const int16_t* top_left;  // (B,)
+    const uint8_t* modes_in;  // (B,) or NULL
+    int mode;
+    // SRC_PLANE / SRC_WAVEFRONT
+    const int16_t* src;    // (H, pitch)
+    int H, W, pitch;
+    int cost_kind;
+    int* progress;         // [bh] blocks finished per block row, then [bh] = row ticket counter
+    // common
+    int64_t n_blocks;
+    QuantParams qp;
+    int maxv;
+    int use_dst;
+    CoderOut out;
+};
+
+template <int N, int G, int SRC>
+__global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(const CoderArgs a) {
+    using Cfg = CoderCfg<N, G>;
+    constexpr int GPW = 32 / G;  // groups (blocks) per warp
+    constexpr int WARPS = SRC == SRC_WAVEFRONT ? 1 : 4;
+    __shared__ __align__(16) unsigned char smem[WARPS * GPW * Cfg::GROUP_BYTES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane / G, gl = lane % G;
+    unsigned char* base = smem + (warp * GPW + g) * Cfg::GROUP_BYTES;
+    int16_t* top = reinterpret_cast<int16_t*>(base);
+    int16_t* left = top + Cfg::REF_W;
+    int16_t* O = reinterpret_cast<int16_t*>(base + ((Cfg::REFS_BYTES + 15) / 16) * 16);
+    int* M = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(O) + Cfg::O_BYTES);
+
+    const int bw = SRC == SRC_ARRAYS ? 1 : a.W / N;
+    const int bh = SRC == SRC_ARRAYS ? 1 : a.H / N;
+
+    if constexpr (SRC == SRC_WAVEFRONT) {
+        // One warp per block row, rows handed out in order by a ticket counter so that a
+        // waiting warp only ever waits on a row that a resident warp already owns.
+        int* ticket = a.progress + bh;
+        for (;;) {
+            int by = 0;
+            if (lane == 0) by = atomicAdd(ticket, 1);
+            by = __shfl_sync(0xffffffffu, by, 0);
+            if (by >= bh) break;
+            for (int bx = 0; bx < bw; ++bx) {
+                if (by > 0) {  // above-right block (or the whole row above) must be reconstructed
+                    const int need = bx + 2 < bw ? bx + 2 : bw;
+                    if (lane == 0) {
+                        const volatile int* p = a.progress + (by - 1);
+                        while (*p < need) __nanosleep(64);
+                        __threadfence();
+                    }
+                    __syncwarp();
+                }
+                const int x = bx * N, y = by * N;
+                const int64_t b = (int64_t)by * bw + bx;
+                const int16_t* rp = a.out.recon_plane;
+                for (int k = gl; k <= 2 * N; k += G) {
+                    top[k] = (int16_t)top_ref<true>(rp, a.H, a.W, a.pitch, x, y, 2 * N, k);
+                    left[k] = (int16_t)left_ref<true>(rp, a.H, a.W, a.pitch, x, y, N, k);
+                }
+                for (int e = gl; e < N * N; e += G)
+                    O[(e / N) * Cfg::O_PITCH + (e % N)] = __ldg(a.src + (int64_t)(y + e / N) * a.pitch + x + e % N);
+                __syncwarp();
+                const int corner = (int)top[0];
+                const int dc = dc_from_refs<N>(top, left);
+                const int key = search_modes<N, G>(gl, O, top, left, corner, dc, a.cost_kind);
+                const int mode = mode_of_key(key);
+                if (gl == 0) {
+                    if (a.out.modes) a.out.modes[b] = (uint8_t)mode;
+                    if (a.out.costs) a.out.costs[b] = key >> 6;
+                }
+                code_block<N, G>(gl, true, b, mode, O, M, top, left, corner, dc, a.qp, a.maxv,
+                                 a.use_dst != 0, a.out);
+                for (int e = gl; e < N * N; e += G)
+                    a.out.recon_plane[(int64_t)(y + e / N) * a.pitch + x + e % N] = O[(e / N) * Cfg::O_PITCH + (e % N)];
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) {
+                    volatile int* p = a.progress + by;
+                    *p = bx + 1;
+                }
+            }
+        }
+        return;
+    } else {
+        const int64_t n_tiles = (a.n_blocks + GPW - 1) / GPW;
+        for (int64_t tile = (int64_t)blockIdx.x * WARPS + warp; tile < n_tiles;
+             tile += (int64_t)gridDim.x * WARPS) {
+            const int64_t b = tile * GPW + g;
+            const bool valid = b < a.n_blocks;
+            int corner = 0, x = 0, y = 0;
+            if constexpr (SRC == SRC_ARRAYS) {
+                if (valid) {
+                    for (int k = gl; k <= 2 * N; k += G) {
+                        top[k] = a.top[b * (2 * N + 1) + k];
+                        left[k] = a.left[b * (2 * N + 1) + k];
+                    }
+                    for (int e = gl; e < N * N; e += G)
+                        O[(e / N) * Cfg::O_PITCH + (e % N)] = __ldg(a.orig + b * N * N + e);
+                    corner = (int)a.top_left[b];
+                }
+            } else {
+                if (valid) {
+                    x = (int)(b % bw) * N;
+                    y = (int)(b / bw) * N;
+                    for (int k = gl; k <= 2 * N; k += G) {
+                        top[k] = (int16_t)top_ref<false>(a.src, a.H, a.W, a.pitch, x, y, 2 * N, k);
+                        left[k] = (int16_t)left_ref<false>(a.src, a.H, a.W, a.pitch, x, y, 2 * N, k);
+                    }
+                    for (int e = gl; e < N * N; e += G)
+                        O[(e / N) * Cfg::O_PITCH + (e % N)] = __ldg(a.src + (int64_t)(y + e / N) * a.pitch + x + e % N);
+                }
+            }
+            if (!valid) {  // keep shared memory defined for the idle groups of a ragged tile
+                for (int k = gl; k <= 2 * N; k += G) top[k] = left[k] = 0;
+                for (int e = gl; e < N * N; e += G) O[(e / N) * Cfg::O_PITCH + (e % N)] = 0;
+            }
+            __syncwarp();
+            if constexpr (SRC == SRC_PLANE) corner = (int)top[0];
+            const int dc = dc_from_refs<N>(top, left);
+            int mode;
+            if constexpr (SRC == SRC_ARRAYS) {
+                mode = (valid && a.modes_in) ? (int)a.modes_in[b] : a.mode;
+                if (mode > 34) mode = 34;  // launcher validates the scalar; clamp per-block garbage
+            } else {
+                const int key = search_modes<N, G>(gl, O, top, left, corner, dc, a.cost_kind);
+                mode = mode_of_key(key);
+                if (valid && gl == 0) {
+                    if (a.out.modes) a.out.modes[b] = (uint8_t)mode;
+                    if (a.out.costs) a.out.costs[b] = key >> 6;
+                }
+            }
+            code_block<N, G>(gl, valid, b, mode, O, M, top, left, corner, dc, a.qp, a.maxv,
+                             a.use_dst != 0, a.out);
+            if constexpr (SRC == SRC_PLANE) {
+                if (valid && a.out.recon_plane)
+                    for (int e = gl; e < N * N; e += G)
+                        a.out.recon_plane[(int64_t)(y + e / N) * a.pitch + x + e % N] =
+                            O[(e / N) * Cfg::O_PITCH + (e % N)];
+            }
+            __syncwarp();
+        }
+    }
+}
+
+template <int N, int G, int SRC>
+static int launch_coder(const CoderArgs& a, int grid, cudaStream_t st) {
+    coder_kernel<N, G, SRC><<<grid, SRC == SRC_WAVEFRONT ? 32 : 128, 0, st>>>(a);
+    NH_CHECK_LAUNCH("coder_kernel");
+    return NH_OK;
+}
+
+template <int SRC>
+static int dispatch_coder(const CoderArgs& a, int size, cudaStream_t st) {
+    if (SRC == SRC_WAVEFRONT) {
+        int bh = a.H / size;
+        int grid = bh < sm_count() * 16 ? bh : sm_count() * 16;
+        if (grid < 1) grid = 1;
+        switch (size) {
+            case 4: return launch_coder<4, 32, SRC_WAVEFRONT>(a, grid, st);
+            case 8: return launch_coder<8, 32, SRC_WAVEFRONT>(a, grid, st);
+            case 16: return launch_coder<16, 32, SRC_WAVEFRONT>(a, grid, st);
+            default: return launch_coder<32, 32, SRC_WAVEFRONT>(a, grid, st);
+        }
+    }
+    int grid = grid_for(a.n_blocks, 4 * (32 / size), 8);
+    switch (size) {
+        case 4: return launch_coder<4, 4, SRC == SRC_WAVEFRONT ? SRC_PLANE : SRC>(a, grid, st);
+        case 8: return launch_coder<8, 8, SRC == SRC_WAVEFRONT ? SRC_PLANE : SRC>(a, grid, st);
+        case 16: return launch_coder<16, 16, SRC == SRC_WAVEFRONT ? SRC_PLANE : SRC>(a, grid, st);
+        default: return launch_coder<32, 32, SRC == SRC_WAVEFRONT ? SRC_PLANE : SRC>(a, grid, st);
+    }
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace nh
+
+using namespace nh;
+
+NH_API int nh_gather_refs(const int16_t* plane, int height, int width, int pitch, int size, int n_top,
+                          int n_left, int16_t* top, int16_t* left, int16_t* corner, void* stream) {
+    if (log2_size(size) < 0) { set_error("Unsupported transform size: %d", size); return NH_E_SIZE; }
+    if (!plane || !top || !left || !corner || height < 0 || width < 0 || pitch < width ||
+        n_top < 1 || n_top > 2 * size || n_left < 1 || n_left > 2 * size) {
+        set_error("nh_gather_refs: bad argument (null pointer, pitch < width, or n_top/n_left outside 1..2N)");
+        return NH_E_ARG;
+    }
+    int64_t B = (int64_t)(height / size) * (width / size);
+    if (B == 0) return NH_OK;
+    int grid = grid_for(B * (2 * size + 1), 256, 8);
+    gather_refs_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        plane, height, width, pitch, size, n_top, n_left, top, left, corner);
+    NH_CHECK_LAUNCH("gather_refs_kernel");
+    return NH_OK;
+}
+
+static int reblock(const int16_t* in, int height, int width, int pitch, int size, int16_t* out,
+                   bool to_blocks, void* stream) {
+    if (log2_size(size) < 0) { set_error("Unsupported transform size: %d", size); return NH_E_SIZE; }
+    if (!in || !out || height < 0 || width < 0 || pitch < width) {
+        set_error("plane/block conversion: bad argument");
+        return NH_E_ARG;
+    }
+    int64_t n = (int64_t)(height / size) * (width / size) * size * size;
+    if (n == 0) return NH_OK;
+    int grid = grid_for(n, 256, 8);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (to_blocks) reblock_kernel<true><<<grid, 256, 0, st>>>(in, height, width, pitch, size, out);
+    else reblock_kernel<false><<<grid, 256, 0, st>>>(in, height, width, pitch, size, out);
+    NH_CHECK_LAUNCH("reblock_kernel");
+    return NH_OK;
+}
+
+NH_API int nh_plane_to_blocks(const int16_t* plane, int height, int width, int pitch, int size,
+                              int16_t* blocks, void* stream) {
+    return reblock(plane, height, width, pitch, size, blocks, true, stream);
+}
+
+NH_API int nh_blocks_to_plane(const int16_t* blocks, int height, int width, int pitch, int size,
+                              int16_t* plane, void* stream) {
+    return reblock(blocks, height, width, pitch, size, plane, false, stream);
+}
+
+NH_API int nh_fused_pipeline_modes(const int16_t* orig, const int16_t* top, const int16_t* left,
+                                   const int16_t* top_left, const uint8_t* modes, int mode,
+                                   int64_t n_blocks, int size, int qp, int is_intra, int use_dst,
+                                   int bit_depth, int16_t* pred, int32_t* coeff, int32_t* levels,
+                                   int16_t* recon, void* stream) {
+    int l2 = log2_size(size);
+    if (l2 < 0) { set_error("Unsupported transform size: %d", size); return NH_E_SIZE; }
+    if (!orig || !top || !left || !top_left || n_blocks < 0) {
+        set_error("nh_fused_pipeline_modes: null input or negative block count");
+        return NH_E_ARG;
+    }
+    if (!modes && (mode < 0 || mode > 34)) {
+        set_error("nh_fused_pipeline_modes: mode %d out of range 0..34", mode);
+        return NH_E_ARG;
+    }
+    if (bit_depth < 1 || bit_depth > 15) {
+        set_error("nh_fused_pipeline_modes: bit_depth %d out of range", bit_depth);
+        return NH_E_ARG;
+    }
+    if (!aligned16(pred) || !aligned16(coeff) || !aligned16(levels) || !aligned16(recon)) {
+        set_error("nh_fused_pipeline_modes: output tensors must be 16-byte aligned");
+        return NH_E_ARG;
+    }
+    if (n_blocks == 0) return NH_OK;
+    CoderArgs a{};
+    a.orig = orig; a.top = top; a.left = left; a.top_left = top_left; a.modes_in = modes; a.mode = mode;
+    a.n_blocks = n_blocks;
+    a.qp = make_quant_params(qp, l2, is_intra);
+    a.maxv = (1 << bit_depth) - 1;
+    a.use_dst = use_dst;
+    a.out = CoderOut{nullptr, nullptr, pred, coeff, levels, recon, nullptr, 0};
+    return dispatch_coder<SRC_ARRAYS>(a, size, reinterpret_cast<cudaStream_t>(stream));
+}
+
+NH_API int64_t nh_encode_frame_scratch_bytes(int height, int size) {
+    if (log2_size(size) < 0 || height < 0) return 0;
+    return ((int64_t)(height / size) + 2) * 4;
+}
+
+NH_API int nh_encode_frame(const int16_t* src, int height, int width, int pitch, int size,
+                           int cost_kind, int qp, int recon_neighbours, int bit_depth, uint8_t* modes,
+                           int32_t* costs, int16_t* pred, int32_t* coeff, int32_t* levels,
+                           int16_t* recon_plane, void* scratch, int64_t scratch_bytes, void* stream) {
+    int l2 = log2_size(size);
+    if (l2 < 0) { set_error("Unsupported transform size: %d", size); return NH_E_SIZE; }
+    if (!src || height < 0 || width < 0 || pitch < width ||
+        (cost_kind != NH_COST_SAD && cost_kind != NH_COST_SATD) || bit_depth < 1 || bit_depth > 15) {
+        set_error("nh_encode_frame: bad argument");
+        return NH_E_ARG;
+    }
+    if (recon_neighbours && !recon_plane) {
+        set_error("nh_encode_frame: recon_plane is required when recon_neighbours != 0");
+        return NH_E_ARG;
+    }
+    if (!aligned16(pred) || !aligned16(coeff) || !aligned16(levels)) {
+        set_error("nh_encode_frame: output tensors must be 16-byte aligned");
+        return NH_E_ARG;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (recon_plane) {  // Plane.zeros semantics (frame.py:41-43): uncovered samples stay 0
+        cudaError_t e = cudaMemsetAsync(recon_plane, 0, (size_t)height * pitch * sizeof(int16_t), st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(recon_plane)");
+    }
+    const int bw = width / size, bh = height / size;
+    if (bw == 0 || bh == 0) return NH_OK;
+    CoderArgs a{};
+    a.src = src; a.H = height; a.W = width; a.pitch = pitch; a.cost_kind = cost_kind;
+    a.n_blocks = (int64_t)bw * bh;
+    a.qp = make_quant_params(qp, l2, 1);
+    a.maxv = (1 << bit_depth) - 1;
+    a.use_dst = size == 4;  // docs/frames_and_panes.md:328-329
+    a.out = CoderOut{modes, costs, pred, coeff, levels, nullptr, recon_plane, pitch};
+    if (!recon_neighbours) return dispatch_coder<SRC_PLANE>(a, size, st);
+    const int64_t need = nh_encode_frame_scratch_bytes(height, size);
+    if (!scratch || scratch_bytes < need) {
+        set_error("nh_encode_frame: scratch of %lld bytes required, got %lld", (long long)need,
+                  (long long)scratch_bytes);
+        return NH_E_NOMEM;
+    }
+    cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)need, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(scratch)");
+    a.progress = reinterpret_cast<int*>(scratch);
+    return dispatch_coder<SRC_WAVEFRONT>(a, size, st);
+}

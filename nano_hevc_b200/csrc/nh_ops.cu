@@ -1,0 +1,442 @@
+// nh_ops.cu -- the batched single-stage operators behind the reference's
+// per-block functions: K2 predictors, K3 residual / reconstruct / clip,
+// K4 forward / inverse transforms, K5 quantize / dequantize.
+#include "nh_block.cuh"
+
+namespace nh {
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// =================================================================== K4
+// N = 4, 8: one lane owns 64 coefficients (one 8x8 block / four 4x4 blocks),
+// staged through padded shared memory for fully coalesced 128-bit traffic.
+constexpr int kXfWarps = 8;
+
+template <int N, bool DST, bool INV, bool IN32>
+__global__ void __launch_bounds__(kXfWarps * 32, 2)
+    transform_unit_kernel(const void* __restrict__ in, int32_t* __restrict__ out, int64_t n_blocks) {
+    constexpr int NN = N * N;
+    constexpr int BPU = 64 / NN;
+    using TIn = WarpTile<IN32 ? 256 : 128>;
+    using TOut = WarpTile<256>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* s = smem_raw + warp * TOut::kBytes;  // one buffer, reused for input and output
+
+    const int64_t n_units = (n_blocks + BPU - 1) / BPU;
+    const int64_t n_tiles = (n_units + 31) / 32;
+    for (int64_t tile = (int64_t)blockIdx.x * kXfWarps + warp; tile < n_tiles;
+         tile += (int64_t)gridDim.x * kXfWarps) {
+        const int64_t blk0 = tile * 32 * BPU;
+        int64_t rem = n_blocks - blk0;
+        const int blocks_valid = (int)(rem < 32 * BPU ? rem : 32 * BPU);
+        constexpr int kInElem = IN32 ? 4 : 2;
+        TIn::load(s, reinterpret_cast<const unsigned char*>(in) + blk0 * NN * kInElem, lane,
+                  blocks_valid * (NN * kInElem / 16));
+        __syncwarp();
+        int v[BPU][N][N];
+        int* flat = &v[0][0][0];
+        const uint4* ui = TIn::unit(s, lane);
+        if constexpr (IN32) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                uint4 t = ui[e];
+                flat[4 * e] = (int)t.x; flat[4 * e + 1] = (int)t.y;
+                flat[4 * e + 2] = (int)t.z; flat[4 * e + 3] = (int)t.w;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                uint4 t = ui[e];
+                flat[8 * e] = lo16(t.x); flat[8 * e + 1] = hi16(t.x);
+                flat[8 * e + 2] = lo16(t.y); flat[8 * e + 3] = hi16(t.y);
+                flat[8 * e + 4] = lo16(t.z); flat[8 * e + 5] = hi16(t.z);
+                flat[8 * e + 6] = lo16(t.w); flat[8 * e + 7] = hi16(t.w);
+            }
+        }
+        __syncwarp();  // everyone has consumed the input tile before it is overwritten
+#pragma unroll
+        for (int q = 0; q < BPU; ++q) transform2d<N, DST, INV>(v[q]);
+        uint4* uo = TOut::unit(s, lane);
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+            uo[e] = make_uint4(flat[4 * e], flat[4 * e + 1], flat[4 * e + 2], flat[4 * e + 3]);
+        __syncwarp();
+        TOut::store(s, reinterpret_cast<unsigned char*>(out + blk0 * NN), lane,
+                    blocks_valid * (NN * 4 / 16));
+        __syncwarp();
+    }
+}
+
+// N = 16, 32: N lanes per block through the shared-memory working matrix.
+constexpr int kRowsWarps = 4;
+
+template <int N, bool INV, bool IN32>
+__global__ void __launch_bounds__(kRowsWarps * 32)
+    transform_rows_kernel(const void* __restrict__ in, int32_t* __restrict__ out, int64_t n_blocks) {
+    constexpr int NN = N * N;
+    constexpr int BPW = 32 / N;
+    __shared__ __align__(16) int smem[kRowsWarps][BPW * RowsTile<N>::WORDS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane / N, r = lane % N;
+    int* M = smem[warp] + g * RowsTile<N>::WORDS;
+    const int64_t n_tiles = (n_blocks + BPW - 1) / BPW;
+    for (int64_t tile = (int64_t)blockIdx.x * kRowsWarps + warp; tile < n_tiles;
+         tile += (int64_t)gridDim.x * kRowsWarps) {
+        const int64_t b = tile * BPW + g;
+        const bool valid = b < n_blocks;
+        int x[N];
+        if (valid) {
+            if constexpr (IN32) {
+                load_row32<N>(reinterpret_cast<const int32_t*>(in) + b * NN + r * N, x);
+            } else {
+                uint32_t w[N / 2];
+                load_row16<N>(reinterpret_cast<const int16_t*>(in) + b * NN + r * N, w);
+                unpack_row<N>(w, x);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < N; ++k) x[k] = 0;
+        }
+        store_row_smem<N>(M, r, x);
+        __syncwarp();
+        col_pass<N, false, INV>(M, r);
+        __syncwarp();
+        int y[N];
+        row_pass<N, false, INV>(M, r, y);
+        if (valid) store_row32<N>(out + b * NN + r * N, y);
+        __syncwarp();
+    }
+}
+
+template <int N, bool DST, bool INV, bool IN32>
+static int launch_transform_unit(const void* in, int32_t* out, int64_t n_blocks, cudaStream_t st) {
+    constexpr int kSmem = kXfWarps * WarpTile<256>::kBytes;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(transform_unit_kernel<N, DST, INV, IN32>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(transform_unit_kernel)");
+        configured = true;
+    }
+    constexpr int BPU = 64 / (N * N);
+    int grid = grid_for((n_blocks + BPU - 1) / BPU, kXfWarps * 32, 2);
+    transform_unit_kernel<N, DST, INV, IN32><<<grid, kXfWarps * 32, kSmem, st>>>(in, out, n_blocks);
+    NH_CHECK_LAUNCH("transform_unit_kernel");
+    return NH_OK;
+}
+
+template <int N, bool INV, bool IN32>
+static int launch_transform_rows(const void* in, int32_t* out, int64_t n_blocks, cudaStream_t st) {
+    int grid = grid_for(n_blocks, kRowsWarps * (32 / N), 4);
+    transform_rows_kernel<N, INV, IN32><<<grid, kRowsWarps * 32, 0, st>>>(in, out, n_blocks);
+    NH_CHECK_LAUNCH("transform_rows_kernel");
+    return NH_OK;
+}
+
+template <bool INV, bool IN32>
+static int dispatch_transform(const void* in, int32_t* out, int64_t n_blocks, int size, int use_dst,
+                              cudaStream_t st) {
+    switch (size) {
+        case 4:
+            return use_dst ? launch_transform_unit<4, true, INV, IN32>(in, out, n_blocks, st)
+                           : launch_transform_unit<4, false, INV, IN32>(in, out, n_blocks, st);
+        case 8: return launch_transform_unit<8, false, INV, IN32>(in, out, n_blocks, st);
+        case 16: return launch_transform_rows<16, INV, IN32>(in, out, n_blocks, st);
+        case 32: return launch_transform_rows<32, INV, IN32>(in, out, n_blocks, st);
+    }
+    return NH_E_SIZE;
+}
+
+// =================================================================== K5 / K3
+// Pure element-wise streams: 128-bit vector body plus a scalar tail.
+template <class F>
+__global__ void __launch_bounds__(256) map_i32_kernel(const int32_t* __restrict__ in,
+                                                      int32_t* __restrict__ out, int64_t n, F f) {
+    const int64_t n4 = n / 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        uint4 v = ldg_stream(in + 4 * i);
+        stg_stream(out + 4 * i, make_uint4((uint32_t)f((int)v.x), (uint32_t)f((int)v.y),
+                                           (uint32_t)f((int)v.z), (uint32_t)f((int)v.w)));
+    }
+    for (int64_t i = 4 * n4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = f(in[i]);
+}
+
+struct QuantF {
+    QuantParams p;
+    __device__ int operator()(int c) const { return quantize_one(c, p); }
+};
+struct DequantF {
+    QuantParams p;
+    __device__ int operator()(int l) const { return dequantize_one(l, p); }
+};
+
+// kind 0: residual = orig - pred (intra.py:65-67); 1: clip (intra.py:75-78, b unused)
+template <int KIND>
+__global__ void __launch_bounds__(256) map_i16_kernel(const int16_t* __restrict__ a,
+                                                      const int16_t* __restrict__ b,
+                                                      int16_t* __restrict__ out, int64_t n, int maxv) {
+    auto f = [&](int x, int y) -> int {
+        if constexpr (KIND == 0) return sext16(x - y);
+        else return clip_pixel(x, maxv);
+    };
+    const int64_t n8 = n / 8;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        uint4 va = ldg_stream(a + 8 * i);
+        uint4 vb = KIND == 0 ? ldg_stream(b + 8 * i) : make_uint4(0, 0, 0, 0);
+        uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w}, wo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            wo[k] = pack16(f(lo16(wa[k]), lo16(wb[k])), f(hi16(wa[k]), hi16(wb[k])));
+        stg_stream(out + 8 * i, make_uint4(wo[0], wo[1], wo[2], wo[3]));
+    }
+    for (int64_t i = 8 * n8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = (int16_t)f((int)a[i], KIND == 0 ? (int)b[i] : 0);
+}
+
+// intra.py:70-72: pred (int16) + residual (int32 truncated to int16), int16 wrap-around.
+__global__ void __launch_bounds__(256) reconstruct_kernel(const int16_t* __restrict__ pred,
+                                                          const int32_t* __restrict__ res,
+                                                          int16_t* __restrict__ out, int64_t n) {
+    const int64_t n8 = n / 8;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        uint4 p = ldg_stream(pred + 8 * i);
+        uint4 r0 = ldg_stream(res + 8 * i), r1 = ldg_stream(res + 8 * i + 4);
+        uint32_t pw[4] = {p.x, p.y, p.z, p.w};
+        int r[8] = {(int)r0.x, (int)r0.y, (int)r0.z, (int)r0.w, (int)r1.x, (int)r1.y, (int)r1.z, (int)r1.w};
+        uint32_t wo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            wo[k] = pack16(sext16(lo16(pw[k]) + sext16(r[2 * k])), sext16(hi16(pw[k]) + sext16(r[2 * k + 1])));
+        stg_stream(out + 8 * i, make_uint4(wo[0], wo[1], wo[2], wo[3]));
+    }
+    for (int64_t i = 8 * n8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = (int16_t)sext16((int)pred[i] + sext16(res[i]));
+}
+
+static int grid_elems(int64_t n, int per_thread) {
+    return grid_for((n + per_thread - 1) / per_thread, 256, 8);
+}
+
+// =================================================================== K2
+// One lane = one row of one block; N lanes per block.  Reference arrays are read
+// straight from global memory (they are tiny next to the prediction written).
+struct GlobalRef {  // accessor for nh::ref_at / angular_sample
+    const int16_t* p;   // primary array (2N+1 entries)
+    const int16_t* s;   // secondary array
+    int c;              // top_left argument
+    __device__ int pri(int k) const { return (int)__ldg(p + k); }
+    __device__ int sec(int k) const { return (int)__ldg(s + k); }
+    __device__ int corner() const { return c; }
+};
+
+// kind 0: DC from (B,N) refs; 1: planar from (B,N) refs + tr/bl; 2: modes from padded refs
+template <int N, int KIND>
+__global__ void __launch_bounds__(256)
+    predict_rows_kernel(const int16_t* __restrict__ top, const int16_t* __restrict__ left,
+                        const int16_t* __restrict__ aux0, const int16_t* __restrict__ aux1,
+                        const uint8_t* __restrict__ modes, int mode, int allow_dc_planar,
+                        int16_t* __restrict__ pred, int64_t n_blocks) {
+    const int64_t total = n_blocks * N;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int64_t b = t / N;
+        const int r = (int)(t % N);
+        int p[N];
+        if constexpr (KIND == 0 || KIND == 1) {
+            const int16_t* tp = top + b * N;
+            const int16_t* lp = left + b * N;
+            if constexpr (KIND == 0) {
+                int s = 0;
+#pragma unroll
+                for (int k = 0; k < N; ++k) s += (int)__ldg(tp + k) + (int)__ldg(lp + k);
+                int dc = dc_value<N>(s);
+#pragma unroll
+                for (int x = 0; x < N; ++x) p[x] = dc;
+            } else {
+                int tv[N];
+#pragma unroll
+                for (int k = 0; k < N; ++k) tv[k] = (int)__ldg(tp + k);
+                planar_row<N>(r, (int)__ldg(lp + r), tv, (int)__ldg(aux0 + b), (int)__ldg(aux1 + b), p);
+            }
+        } else {
+            const int16_t* tp = top + b * (2 * N + 1);
+            const int16_t* lp = left + b * (2 * N + 1);
+            const int m = modes ? (int)modes[b] : mode;
+            if (m == 1 && allow_dc_planar) {
+                int s = 0;
+#pragma unroll
+                for (int k = 1; k <= N; ++k) s += (int)__ldg(tp + k) + (int)__ldg(lp + k);
+                int dc = dc_value<N>(s);
+#pragma unroll
+                for (int x = 0; x < N; ++x) p[x] = dc;
+            } else if (m == 0 && allow_dc_planar) {
+                int tv[N];
+#pragma unroll
+                for (int k = 0; k < N; ++k) tv[k] = (int)__ldg(tp + 1 + k);
+                planar_row<N>(r, (int)__ldg(lp + 1 + r), tv, (int)__ldg(tp + N + 1),
+                              (int)__ldg(lp + N + 1), p);
+            } else {
+                const AngleInfo ai = angle_info(m < 2 ? 2 : (m > 34 ? 34 : m));  // launcher validates
+                GlobalRef ref;
+                ref.c = (int)__ldg(aux0 + b);
+                if (ai.vertical) { ref.p = tp; ref.s = lp; } else { ref.p = lp; ref.s = tp; }
+#pragma unroll
+                for (int x = 0; x < N; ++x)
+                    p[x] = ai.vertical ? angular_sample(ref, ai, x, r) : angular_sample(ref, ai, r, x);
+            }
+        }
+        int16_t* out = pred + b * (N * N) + r * N;
+        uint32_t w[N / 2];
+        pack_row<N>(p, w);
+        store_row16<N>(out, w);
+    }
+}
+
+template <int KIND>
+static int launch_predict(const int16_t* top, const int16_t* left, const int16_t* aux0,
+                          const int16_t* aux1, const uint8_t* modes, int mode, int allow,
+                          int16_t* pred, int64_t n_blocks, int size, cudaStream_t st) {
+    if (n_blocks == 0) return NH_OK;
+    int grid = grid_for(n_blocks * size, 256, 8);
+    switch (size) {
+        case 4: predict_rows_kernel<4, KIND><<<grid, 256, 0, st>>>(top, left, aux0, aux1, modes, mode, allow, pred, n_blocks); break;
+        case 8: predict_rows_kernel<8, KIND><<<grid, 256, 0, st>>>(top, left, aux0, aux1, modes, mode, allow, pred, n_blocks); break;
+        case 16: predict_rows_kernel<16, KIND><<<grid, 256, 0, st>>>(top, left, aux0, aux1, modes, mode, allow, pred, n_blocks); break;
+        case 32: predict_rows_kernel<32, KIND><<<grid, 256, 0, st>>>(top, left, aux0, aux1, modes, mode, allow, pred, n_blocks); break;
+        default: set_error("Unsupported transform size: %d", size); return NH_E_SIZE;
+    }
+    NH_CHECK_LAUNCH("predict_rows_kernel");
+    return NH_OK;
+}
+
+}  // namespace nh
+
+using namespace nh;
+
+#define NH_REQUIRE_SIZE(size)                                      \
+    if (log2_size(size) < 0) {                                     \
+        set_error("Unsupported transform size: %d", (int)(size)); \
+        return NH_E_SIZE;                                          \
+    }
+#define NH_REQUIRE(cond, msg)  \
+    if (!(cond)) {             \
+        set_error("%s", msg);  \
+        return NH_E_ARG;       \
+    }
+
+NH_API int nh_forward_transform(const void* residual, int residual_is_i32, int32_t* coeff,
+                                int64_t n_blocks, int size, int use_dst, void* stream) {
+    NH_REQUIRE_SIZE(size);
+    NH_REQUIRE(residual && coeff && n_blocks >= 0, "nh_forward_transform: null pointer or negative count");
+    NH_REQUIRE(aligned16(residual) && aligned16(coeff), "nh_forward_transform: tensors must be 16-byte aligned");
+    if (n_blocks == 0) return NH_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return residual_is_i32 ? dispatch_transform<false, true>(residual, coeff, n_blocks, size, use_dst, st)
+                           : dispatch_transform<false, false>(residual, coeff, n_blocks, size, use_dst, st);
+}
+
+NH_API int nh_inverse_transform(const int32_t* coeff, int32_t* residual, int64_t n_blocks, int size,
+                                int use_dst, void* stream) {
+    NH_REQUIRE_SIZE(size);
+    NH_REQUIRE(residual && coeff && n_blocks >= 0, "nh_inverse_transform: null pointer or negative count");
+    NH_REQUIRE(aligned16(residual) && aligned16(coeff), "nh_inverse_transform: tensors must be 16-byte aligned");
+    if (n_blocks == 0) return NH_OK;
+    return dispatch_transform<true, true>(coeff, residual, n_blocks, size, use_dst,
+                                          reinterpret_cast<cudaStream_t>(stream));
+}
+
+NH_API int nh_quantize(const int32_t* coeff, int32_t* level, int64_t n, int qp, int size, int is_intra,
+                       void* stream) {
+    NH_REQUIRE_SIZE(size);
+    NH_REQUIRE(coeff && level && n >= 0, "nh_quantize: null pointer or negative count");
+    NH_REQUIRE(aligned16(coeff) && aligned16(level), "nh_quantize: tensors must be 16-byte aligned");
+    if (n == 0) return NH_OK;
+    QuantF f{make_quant_params(qp, log2_size(size), is_intra)};
+    map_i32_kernel<<<grid_elems(n, 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(coeff, level, n, f);
+    NH_CHECK_LAUNCH("nh_quantize");
+    return NH_OK;
+}
+
+NH_API int nh_dequantize(const int32_t* level, int32_t* coeff, int64_t n, int qp, int size, void* stream) {
+    (void)size;  // quant.py:82-123 ignores it
+    NH_REQUIRE(coeff && level && n >= 0, "nh_dequantize: null pointer or negative count");
+    NH_REQUIRE(aligned16(coeff) && aligned16(level), "nh_dequantize: tensors must be 16-byte aligned");
+    if (n == 0) return NH_OK;
+    DequantF f{make_quant_params(qp, 2, 1)};
+    map_i32_kernel<<<grid_elems(n, 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(level, coeff, n, f);
+    NH_CHECK_LAUNCH("nh_dequantize");
+    return NH_OK;
+}
+
+NH_API int nh_residual_block(const int16_t* orig, const int16_t* pred, int16_t* residual, int64_t n,
+                             void* stream) {
+    NH_REQUIRE(orig && pred && residual && n >= 0, "nh_residual_block: null pointer or negative count");
+    NH_REQUIRE(aligned16(orig) && aligned16(pred) && aligned16(residual), "nh_residual_block: tensors must be 16-byte aligned");
+    if (n == 0) return NH_OK;
+    map_i16_kernel<0><<<grid_elems(n, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(orig, pred, residual, n, 0);
+    NH_CHECK_LAUNCH("nh_residual_block");
+    return NH_OK;
+}
+
+NH_API int nh_clip_to_pixel_range(const int16_t* in, int16_t* out, int64_t n, int bit_depth, void* stream) {
+    NH_REQUIRE(in && out && n >= 0, "nh_clip_to_pixel_range: null pointer or negative count");
+    NH_REQUIRE(bit_depth >= 1 && bit_depth <= 15, "nh_clip_to_pixel_range: bit_depth out of range 1..15");
+    NH_REQUIRE(aligned16(in) && aligned16(out), "nh_clip_to_pixel_range: tensors must be 16-byte aligned");
+    if (n == 0) return NH_OK;
+    map_i16_kernel<1><<<grid_elems(n, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, in, out, n, (1 << bit_depth) - 1);
+    NH_CHECK_LAUNCH("nh_clip_to_pixel_range");
+    return NH_OK;
+}
+
+NH_API int nh_reconstruct_block(const int16_t* pred, const int32_t* residual, int16_t* out, int64_t n,
+                                void* stream) {
+    NH_REQUIRE(pred && residual && out && n >= 0, "nh_reconstruct_block: null pointer or negative count");
+    NH_REQUIRE(aligned16(pred) && aligned16(residual) && aligned16(out), "nh_reconstruct_block: tensors must be 16-byte aligned");
+    if (n == 0) return NH_OK;
+    reconstruct_kernel<<<grid_elems(n, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pred, residual, out, n);
+    NH_CHECK_LAUNCH("nh_reconstruct_block");
+    return NH_OK;
+}
+
+NH_API int nh_intra_dc_predict(const int16_t* top, const int16_t* left, int16_t* pred, int64_t n_blocks,
+                               int size, void* stream) {
+    NH_REQUIRE_SIZE(size);
+    NH_REQUIRE(top && left && pred && n_blocks >= 0, "nh_intra_dc_predict: null pointer or negative count");
+    NH_REQUIRE(aligned16(pred), "nh_intra_dc_predict: pred must be 16-byte aligned");
+    return launch_predict<0>(top, left, nullptr, nullptr, nullptr, 1, 0, pred, n_blocks, size,
+                             reinterpret_cast<cudaStream_t>(stream));
+}
+
+NH_API int nh_intra_planar_predict(const int16_t* top, const int16_t* left, const int16_t* top_right,
+                                   const int16_t* bottom_left, int16_t* pred, int64_t n_blocks,
+                                   int size, void* stream) {
+    NH_REQUIRE_SIZE(size);
+    NH_REQUIRE(top && left && top_right && bottom_left && pred && n_blocks >= 0,
+               "nh_intra_planar_predict: null pointer or negative count");
+    NH_REQUIRE(aligned16(pred), "nh_intra_planar_predict: pred must be 16-byte aligned");
+    return launch_predict<1>(top, left, top_right, bottom_left, nullptr, 0, 0, pred, n_blocks, size,
+                             reinterpret_cast<cudaStream_t>(stream));
+}
+
+NH_API int nh_intra_predict_modes(const int16_t* top, const int16_t* left, const int16_t* top_left,
+                                  const uint8_t* modes, int mode, int allow_dc_planar, int16_t* pred,
+                                  int64_t n_blocks, int size, void* stream) {
+    NH_REQUIRE_SIZE(size);
+    NH_REQUIRE(top && left && top_left && pred && n_blocks >= 0,
+               "nh_intra_predict_modes: null pointer or negative count");
+    NH_REQUIRE(aligned16(pred), "nh_intra_predict_modes: pred must be 16-byte aligned");
+    if (!modes) {
+        int lo = allow_dc_planar ? 0 : 2;
+        if (mode < lo || mode > 34) {
+            set_error("nh_intra_predict_modes: mode %d out of range %d..34", mode, lo);
+            return NH_E_ARG;
+        }
+    }
+    return launch_predict<2>(top, left, top_left, nullptr, modes, mode, allow_dc_planar, pred, n_blocks,
+                             size, reinterpret_cast<cudaStream_t>(stream));
+}

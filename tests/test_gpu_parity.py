@@ -1,0 +1,462 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libnh_b200.so) against
+  * the golden vectors generated from the unmodified reference (tests/golden/*.npz),
+  * the CPU oracle (oracle/, test infrastructure) on seeded inputs,
+  * size-independent properties at BASELINE.json's full sizes.
+Integer outputs must be bit-exact; PSNR must match to 1e-9 relative."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from conftest import golden
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+SIZES = (4, 8, 16, 32)
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def P():
+    import nano_hevc_b200 as pkg
+    assert pkg._lib.lib().nh_device_ok() == 1, pkg._lib.last_error()
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def Bt():
+    from nano_hevc_b200 import batched
+    return batched
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV)
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+def eq(a, b, what=""):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if not np.array_equal(a, b):
+        bad = np.argwhere(a != b)
+        raise AssertionError(f"{what}: {len(bad)} mismatches, first at {bad[0]}: got {a[tuple(bad[0])]} want {b[tuple(bad[0])]}")
+
+
+# ------------------------------------------------------------------ config 1
+def test_readme_quickstart_per_block_api(P):
+    """BASELINE config 1 / SURVEY golden vector G1 through the reference's own per-block API."""
+    g = golden("readme.npz")
+    pred = P.intra_dc_predict(g["top"], g["left"], 4)
+    assert pred.dtype == np.int16
+    eq(pred, g["pred"], "pred")
+    eq(P.intra_dc_predict_4x4(g["top"], g["left"]), g["pred"], "pred4x4")
+    res = P.residual_block(g["orig"], pred)
+    assert res.dtype == np.int16
+    eq(res, g["res"], "res")
+    for t, dst in (("dst", True), ("dct", False)):
+        co = P.forward_transform(res, use_dst=dst)
+        assert co.dtype == np.int32
+        eq(co, g[f"coeff_{t}"], "coeff")
+        lv = P.quantize_block(co, 22)
+        eq(lv, g[f"levels_{t}"], "levels")
+        dq = P.dequantize_block(lv, 22)
+        eq(dq, g[f"dq_{t}"], "dq")
+        rr = P.inverse_transform(dq, use_dst=dst)
+        eq(rr, g[f"rres_{t}"], "rres")
+        rec = P.clip_to_pixel_range(P.reconstruct_block(pred, rr))
+        assert rec.dtype == np.int16
+        eq(rec, g[f"recon_{t}"], "recon")
+    assert P.psnr(g["orig"], g["recon_dst"]) == pytest.approx(float(g["psnr"]), rel=1e-12)
+    assert P.sad(g["orig"], pred) == int(g["sad"])
+    assert P.satd_4x4(g["orig"], pred) == int(g["satd"])
+    assert P.count_nonzero(g["levels_dst"]) == 0 and P.is_all_zero(g["levels_dst"])
+
+
+def test_reference_known_answers(P):
+    # tests/test_intra_angular.py:69-85 (non-standard negative-angle projection, Q3)
+    top = np.array([0, 10, 20, 30, 40, 50, 60, 70, 80], np.int16)
+    left = np.array([0, 5, 5, 5, 5, 5, 5, 5, 5], np.int16)
+    exp = np.array([[0, 10, 20, 30], [0, 0, 10, 20], [5, 0, 0, 10], [5, 5, 0, 0]], np.int16)
+    eq(P.intra_angular_predict(top, left, 0, 18, 4), exp)
+    # tests/test_intra_angular.py:25-43: 9-entry arrays at size 8 (replicate-last padding)
+    top = np.array([99, 100, 110, 120, 130, 0, 0, 0, 0], np.int16)
+    left = np.array([99, 50, 50, 50, 50, 0, 0, 0, 0], np.int16)
+    for n in (4, 8):
+        p = P.intra_angular_predict(top, left, 99, 26, n)
+        assert [int(v) for v in p[0, :4]] == [100, 110, 120, 130] and np.all(p[:, 0] == 100)
+    # tests/test_intra_planar.py:56-76
+    p = P.intra_planar_predict(np.array([64, 128, 192, 255], np.int16), np.array([64, 128, 192, 255], np.int16), 255, 255, 4)
+    eq(p, O.intra_planar_predict([64, 128, 192, 255], [64, 128, 192, 255], 255, 255, 4))
+    # tests/test_quant.py:70-77
+    assert int(P.quantize(np.array([[5]], np.int32), 40, 4)[0, 0]) == 0
+    # dequant asymmetry
+    for qp, lv, want in ((0, 1, 3), (0, -1, -2), (0, 3, 8), (0, -3, -7), (5, 1, 5), (5, -1, -4),
+                         (22, 1, 32), (22, -1, -32), (51, 1, 912), (51, -1, -912)):
+        assert int(P.dequantize(np.array([[lv]], np.int32), qp, 4)[0, 0]) == want
+    # DST4 of a constant 255 block (G2)
+    want = np.array([[911, 279, 136, 60], [278, 85, 41, 18], [136, 42, 20, 9], [61, 19, 9, 4]])
+    eq(P.forward_transform(np.full((4, 4), 255, np.int16), use_dst=True), want)
+    with pytest.raises(ValueError, match="Unsupported transform size"):
+        P.forward_transform(np.zeros((5, 5), np.int16))
+    with pytest.raises(IndexError):
+        P.intra_angular_predict(top, left, 0, 35, 4)
+
+
+# --------------------------------------------------------------- predictors
+@pytest.mark.parametrize("n", SIZES)
+def test_predictors_golden(P, Bt, n):
+    g = golden("predictors.npz")
+    top, left = g[f"dc_top_{n}"], g[f"dc_left_{n}"]
+    eq(host(Bt.intra_dc_predict_batched(dev(top), dev(left), n)), g[f"dc_pred_{n}"], "dc batched")
+    eq(host(Bt.intra_planar_predict_batched(dev(top), dev(left), dev(g[f"pl_tr_{n}"]), dev(g[f"pl_bl_{n}"]), n)),
+       g[f"pl_pred_{n}"], "planar batched")
+    eq(P.intra_dc_predict(top[0], left[0], n), g[f"dc_pred_{n}"][0])
+    eq(P.intra_planar_predict(top[1], left[1], int(g[f"pl_tr_{n}"][1]), int(g[f"pl_bl_{n}"][1]), n),
+       g[f"pl_pred_{n}"][1])
+    at, al, ac = g[f"ang_top_{n}"], g[f"ang_left_{n}"], g[f"ang_corner_{n}"]
+    A = at.shape[0]
+    # all 33 modes x A cases in one batch with a per-block mode tensor
+    modes = np.repeat(np.arange(2, 35, dtype=np.uint8), A)
+    tt, ll, cc = np.tile(at, (33, 1)), np.tile(al, (33, 1)), np.tile(ac, 33)
+    got = host(Bt.intra_angular_predict_batched(dev(tt), dev(ll), dev(cc), dev(modes), n))
+    want = g[f"ang_pred_{n}"].transpose(1, 0, 2, 3).reshape(-1, n, n)
+    eq(got, want, "angular batched")
+    for m in (2, 10, 11, 18, 25, 26, 34):
+        eq(host(Bt.intra_angular_predict_batched(dev(at), dev(al), dev(ac), m, n)), g[f"ang_pred_{n}"][:, m - 2], f"mode {m}")
+        eq(P.intra_angular_predict(at[0], al[0], int(ac[0]), m, n), g[f"ang_pred_{n}"][0, m - 2])
+    st, sl = g[f"short_top_{n}"], g[f"short_left_{n}"]
+    for m in range(2, 35):
+        eq(P.intra_angular_predict(st, sl, int(st[0]), m, n), g[f"short_pred_{n}"][m - 2], f"short mode {m}")
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_predict_modes_vs_oracle(Bt, n):
+    rng = np.random.default_rng(100 + n)
+    B = 70
+    top = rng.integers(0, 1024, (B, 2 * n + 1)).astype(np.int16)
+    left = rng.integers(0, 1024, (B, 2 * n + 1)).astype(np.int16)
+    corner = rng.integers(0, 1024, B).astype(np.int16)
+    modes = (np.arange(B) % 35).astype(np.uint8)
+    got = host(Bt.intra_predict_modes_batched(dev(top), dev(left), dev(corner), dev(modes), n))
+    for b in range(B):
+        eq(got[b], O.predict_mode(top[b], left[b], corner[b], int(modes[b]), n), f"block {b} mode {modes[b]}")
+
+
+# --------------------------------------------------------------- transforms
+@pytest.mark.parametrize("tag", ["4", "4dst", "8", "16", "32"])
+def test_transforms_golden(P, Bt, tag):
+    g = golden("transforms.npz")
+    n, dst = int(tag.replace("dst", "")), tag.endswith("dst")
+    x, fw, cin, inv = g[f"x_{tag}"], g[f"fwd_{tag}"], g[f"cin_{tag}"], g[f"inv_{tag}"]
+    eq(host(Bt.forward_transform_batched(dev(x), dst)), fw, "forward int16 in")
+    eq(host(Bt.forward_transform_batched(dev(x.astype(np.int32)), dst)), fw, "forward int32 in")
+    eq(host(Bt.inverse_transform_batched(dev(cin), dst)), inv, "inverse")
+    eq(P.forward_transform(x[0], use_dst=dst), fw[0])
+    eq(P.inverse_transform(cin[0], use_dst=dst), inv[0])
+    named = {4: (P.forward_transform_4x4, P.inverse_transform_4x4), 8: (P.forward_transform_8x8, P.inverse_transform_8x8),
+             16: (P.forward_transform_16x16, P.inverse_transform_16x16), 32: (P.forward_transform_32x32, P.inverse_transform_32x32)}[n]
+    if not dst:
+        eq(named[0](x[1]), fw[1])
+        eq(named[1](cin[1]), inv[1])
+
+
+@pytest.mark.parametrize("tag", ["4", "4dst", "8", "16", "32"])
+@pytest.mark.parametrize("B", [1, 3, 31, 129, 1000])
+def test_transforms_vs_oracle_ragged(Bt, tag, B):
+    n, dst = int(tag.replace("dst", "")), tag.endswith("dst")
+    rng = np.random.default_rng(B * 7 + n)
+    x = rng.integers(-255, 256, (B, n, n)).astype(np.int16)
+    x[0] = rng.integers(-32768, 32768, (n, n))
+    want = O.forward_transform_batch(x.astype(np.int32), dst)
+    got = host(Bt.forward_transform_batched(dev(x), dst))
+    eq(got, want, "forward")
+    eq(host(Bt.inverse_transform_batched(dev(want), dst)), O.inverse_transform_batch(want, dst), "inverse")
+    wide = rng.integers(-2**31, 2**31, (min(B, 8), n, n)).astype(np.int32)  # wrap-around accumulators
+    eq(host(Bt.forward_transform_batched(dev(wide), dst)), O.forward_transform_batch(wide, dst), "forward wide")
+    eq(host(Bt.inverse_transform_batched(dev(wide), dst)), O.inverse_transform_batch(wide, dst), "inverse wide")
+
+
+# -------------------------------------------------------------------- quant
+@pytest.mark.parametrize("n", SIZES)
+def test_quant_golden_qp_sweep(P, Bt, n):
+    g = golden("quant.npz")
+    c, lv, big = dev(g[f"c_{n}"]), dev(g[f"lv_{n}"]), dev(g[f"big_{n}"])
+    for i, qp in enumerate(range(-2, 54)):
+        eq(host(Bt.quantize_batched(c, qp, n, True)), g[f"q_intra_{n}"][i], f"q intra {qp}")
+        eq(host(Bt.quantize_batched(c, qp, n, False)), g[f"q_inter_{n}"][i], f"q inter {qp}")
+        eq(host(Bt.dequantize_batched(lv, qp)), g[f"dq_{n}"][i], f"dq {qp}")
+    for i, qp in enumerate((0, 22, 51)):
+        eq(host(Bt.quantize_batched(big, qp, n)), g[f"qbig_{n}"][i], f"qbig {qp}")
+        eq(host(Bt.dequantize_batched(big, qp)), g[f"dqbig_{n}"][i], f"dqbig {qp}")
+    eq(P.quantize_block(g[f"c_{n}"], 27), g[f"q_intra_{n}"][29])
+    eq(P.dequantize_block(g[f"lv_{n}"], 27), g[f"dq_{n}"][29])
+    # odd element counts exercise the scalar tail
+    flat = dev(g[f"c_{n}"].reshape(-1)[:13])
+    eq(host(Bt.quantize_batched(flat, 30, n)), O.quantize(g[f"c_{n}"].reshape(-1)[:13], 30, n))
+
+
+def test_elementwise_ops(P, Bt):
+    rng = np.random.default_rng(3)
+    for cnt in (1, 7, 8, 1000, 4099):
+        a = rng.integers(-32768, 32768, cnt).astype(np.int16)
+        b = rng.integers(-32768, 32768, cnt).astype(np.int16)
+        r32 = rng.integers(-2**31, 2**31, cnt).astype(np.int32)
+        eq(host(Bt.residual_block_batched(dev(a), dev(b))), O.residual_block(a, b), "residual")
+        eq(host(Bt.reconstruct_block_batched(dev(a), dev(r32))), O.reconstruct_block(a, r32), "reconstruct")
+        for bd in (8, 10):
+            eq(host(Bt.clip_to_pixel_range_batched(dev(a), bd)), O.clip_to_pixel_range(a, bd), "clip")
+    # tests/test_intra_dc.py:163-177
+    eq(P.clip_to_pixel_range(np.array([[-10, 0, 128, 255, 300]], np.int16)), [[0, 0, 128, 255, 255]])
+    eq(P.clip_to_pixel_range(np.array([[-10, 0, 512, 1023, 2000]], np.int16), bit_depth=10), [[0, 0, 512, 1023, 1023]])
+
+
+# ------------------------------------------------------------ fused pipeline
+def _dcplanar_inputs(rng, B, n, hi=256):
+    orig = rng.integers(0, hi, (B, n, n)).astype(np.int16)
+    top = rng.integers(0, hi, (B, n)).astype(np.int16)
+    left = rng.integers(0, hi, (B, n)).astype(np.int16)
+    tr = rng.integers(0, hi, B).astype(np.int16)
+    bl = rng.integers(0, hi, B).astype(np.int16)
+    return orig, top, left, tr, bl
+
+
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("B", [1, 5, 127, 128, 1031])
+def test_fused_dcplanar_vs_oracle(Bt, n, B):
+    rng = np.random.default_rng(1000 * n + B)
+    orig, top, left, tr, bl = _dcplanar_inputs(rng, B, n)
+    d = [dev(v) for v in (orig, top, left, tr, bl)]
+    mixed = (rng.integers(0, 2, B)).astype(np.uint8)
+    for mode, qp, dst in ((1, 22, False), (0, 27, False), (mixed, 32, n == 4), (mixed, 37, False), (0, 0, n == 4), (1, 51, False)):
+        m = dev(mode) if isinstance(mode, np.ndarray) else mode
+        got = Bt.fused_block_pipeline(*d, m, qp, use_dst=dst)
+        want = O.pipeline_dcplanar_batch(orig, top, left, tr, bl, mode, qp, use_dst=dst)
+        for name, w in zip(("pred", "coeff", "levels", "recon"), want):
+            eq(host(getattr(got, name)), w, f"{name} n={n} B={B} qp={qp}")
+    # optional outputs: only levels + recon requested
+    got = Bt.fused_block_pipeline(*d, 1, 27, outputs=("levels", "recon"))
+    want = O.pipeline_dcplanar_batch(orig, top, left, tr, bl, 1, 27)
+    assert got.pred is None and got.coeff is None
+    eq(host(got.levels), want[2]); eq(host(got.recon), want[3])
+    # inter dead zone and 10-bit pixels
+    o10 = _dcplanar_inputs(rng, B, n, 1024)
+    got = Bt.fused_block_pipeline(*[dev(v) for v in o10], 0, 30, is_intra=False, bit_depth=10)
+    want = O.pipeline_dcplanar_batch(*o10, 0, 30, is_intra=False, bit_depth=10)
+    for name, w in zip(("pred", "coeff", "levels", "recon"), want):
+        eq(host(getattr(got, name)), w, f"10-bit {name}")
+
+
+def test_fused_dcplanar_empty_and_errors(Bt):
+    z = lambda *s: torch.zeros(s, dtype=torch.int16, device=DEV)
+    got = Bt.fused_block_pipeline(z(0, 8, 8), z(0, 8), z(0, 8), z(0), z(0), 1, 27)
+    assert got.recon.shape == (0, 8, 8)
+    with pytest.raises(ValueError, match="Unsupported transform size"):
+        Bt.fused_block_pipeline(z(2, 12, 12), z(2, 12), z(2, 12), z(2), z(2), 1, 27)
+    with pytest.raises(ValueError):
+        Bt.fused_block_pipeline(z(2, 8, 8), z(2, 8), z(2, 8), z(2), z(2), 5, 27)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Bt.fused_block_pipeline(torch.zeros((2, 8, 8), dtype=torch.int16), z(2, 8), z(2, 8), z(2), z(2), 1, 27)
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_fused_modes_vs_oracle(Bt, n):
+    rng = np.random.default_rng(50 + n)
+    B = 35 * 3 + 2
+    orig = rng.integers(0, 256, (B, n, n)).astype(np.int16)
+    top = rng.integers(0, 256, (B, 2 * n + 1)).astype(np.int16)
+    left = rng.integers(0, 256, (B, 2 * n + 1)).astype(np.int16)
+    corner = rng.integers(0, 256, B).astype(np.int16)
+    modes = (np.arange(B) % 35).astype(np.uint8)
+    for qp in (22, 37):
+        got = Bt.fused_block_pipeline_modes(dev(orig), dev(top), dev(left), dev(corner), dev(modes), qp, use_dst=(n == 4))
+        want = O.pipeline_modes_batch(orig, top, left, corner, modes, qp, use_dst=(n == 4))
+        for name, w in zip(("pred", "coeff", "levels", "recon"), want):
+            eq(host(getattr(got, name)), w, f"{name} n={n} qp={qp}")
+    got = Bt.fused_block_pipeline_modes(dev(orig), dev(top), dev(left), dev(corner), 26, 27)
+    want = O.pipeline_modes_batch(orig, top, left, corner, 26, 27)
+    eq(host(got.recon), want[3], "uniform mode 26")
+
+
+# ------------------------------------------------------------------ config 2
+def _cfg2_refs(plane, n):
+    """Given references with the CLI convention: N samples per side, 128 substitution,
+    top_right = top[-1], bottom_left = left[-1] (__main__.py:126-127)."""
+    top, left, _ = O.gather_refs_frame(plane, n, n, n)
+    return top[:, 1:n + 1].copy(), left[:, 1:n + 1].copy(), top[:, n].copy(), left[:, n].copy()
+
+
+@pytest.mark.timeout(600)
+def test_config2_1080p_frame(Bt):
+    """1080p synthetic luma, 8x8 blocks, DC and planar from given refs, QP 22/27/32/37: every
+    output tensor bit-exact against the oracle on the whole frame."""
+    rng = np.random.default_rng(1234)
+    H, W, n = 1080, 1920, 8
+    yy, xx = np.mgrid[0:H, 0:W]
+    plane = np.clip(40 + (150 * xx) // (W - 1) + (60 * yy) // (H - 1) + rng.integers(-12, 13, (H, W)), 0, 255).astype(np.int16)
+    blocks = O.blocks_from_plane(plane, n)
+    assert blocks.shape[0] == 32400
+    eq(host(Bt.plane_to_blocks(dev(plane), n)), blocks, "plane_to_blocks")
+    top, left, tr, bl = _cfg2_refs(plane, n)
+    d = [dev(v) for v in (blocks, top, left, tr, bl)]
+    thr = O.n_host_threads()
+    for mode in (1, 0):
+        for qp in (22, 27, 32, 37):
+            got = Bt.fused_block_pipeline(*d, mode, qp)
+            want = O.pipeline_dcplanar_batch(blocks, top, left, tr, bl, mode, qp, threads=thr)
+            for name, w in zip(("pred", "coeff", "levels", "recon"), want):
+                eq(host(getattr(got, name)), w, f"{name} mode={mode} qp={qp}")
+            # PSNR of the reconstructed frame: integer SSE on the GPU, float64 finish on the host
+            rec_plane = Bt.blocks_to_plane(got.recon, H, W)
+            sse = int(Bt.sse_sad(dev(plane), rec_plane)[0].item())
+            ref_psnr = O.psnr(plane, host(rec_plane))
+            assert Bt.psnr_from_sse(sse, H * W) == pytest.approx(ref_psnr, rel=1e-9)
+
+
+# --------------------------------------------------------------- K1 gather
+@pytest.mark.parametrize("n", SIZES)
+def test_gather_refs_golden_and_oracle(Bt, n):
+    g = golden("frames.npz")
+    src = g[f"src_{n}"]
+    for rn, (T, L) in ((0, (2 * n, 2 * n)), (1, (2 * n, n))):
+        if rn == 1:
+            continue  # recon-neighbour refs come from the recon plane: covered by the wavefront test
+        top, left, corner = Bt.gather_refs(dev(src), n, T, L)
+        eq(host(top), g[f"top_{n}_sad_0"], "top"); eq(host(left), g[f"left_{n}_sad_0"], "left")
+        eq(host(corner), g[f"corner_{n}_sad_0"], "corner")
+    rng = np.random.default_rng(n)
+    plane = rng.integers(0, 256, (3 * n + 5, 5 * n + 3)).astype(np.int16)
+    for T, L in ((2 * n, 2 * n), (2 * n, n), (n, n)):
+        top, left, corner = Bt.gather_refs(dev(plane), n, T, L)
+        wt, wl, wc = O.gather_refs_frame(plane, n, T, L)
+        eq(host(top), wt, f"top T={T}"); eq(host(left), wl, f"left L={L}"); eq(host(corner), wc, "corner")
+    eq(host(Bt.blocks_to_plane(Bt.plane_to_blocks(dev(plane), n), *plane.shape))[: 3 * n, : 5 * n], plane[: 3 * n, : 5 * n])
+
+
+# ------------------------------------------------------- K7 / K8 frame coders
+FRAME_CASES = [(n, cost, rn) for n in SIZES for cost in ("sad", "satd") for rn in (0, 1)
+               if not (n == 32 and cost == "satd" and rn == 0)]
+
+
+@pytest.mark.parametrize("n,cost,rn", FRAME_CASES)
+def test_encode_frame_golden(Bt, n, cost, rn):
+    """Odd-shaped frames (partial blocks, truncated neighbour slices) against literal loops over
+    the reference's own functions (tests/golden/make_golden.py: ref_encode_frame)."""
+    g = golden("frames.npz")
+    src = g[f"src_{n}"]
+    qp = 27 if cost == "sad" else 22
+    r = Bt.encode_frame(dev(src), n, cost=cost, qp=qp, recon_neighbours=bool(rn))
+    tag = f"{n}_{cost}_{rn}"
+    eq(host(r.modes), g[f"modes_{tag}"], "modes"); eq(host(r.costs), g[f"costs_{tag}"], "costs")
+    eq(host(r.pred), g[f"pred_{tag}"], "pred"); eq(host(r.coeff), g[f"coeff_{tag}"], "coeff")
+    eq(host(r.levels), g[f"levels_{tag}"], "levels")
+    eq(host(r.recon_plane), g[f"recon_plane_{tag}"], "recon_plane")
+    sse = int(Bt.sse_sad(dev(src), r.recon_plane)[0].item())
+    assert Bt.psnr_from_sse(sse, src.size) == pytest.approx(float(g[f"psnr_{tag}"]), rel=1e-9)
+
+
+@pytest.mark.parametrize("n", (4, 8))
+@pytest.mark.parametrize("rn", (0, 1))
+def test_encode_frame_noise_golden(Bt, n, rn):
+    g = golden("frames.npz")
+    r = Bt.encode_frame(dev(g["noise"]), n, cost="sad", qp=22, recon_neighbours=bool(rn))
+    tag = f"{n}_{rn}"
+    eq(host(r.modes), g[f"noise_modes_{tag}"], "modes"); eq(host(r.levels), g[f"noise_levels_{tag}"], "levels")
+    eq(host(r.recon_plane), g[f"noise_recon_plane_{tag}"], "recon_plane")
+
+
+def _smooth(H, W, seed):
+    rng = np.random.default_rng(4321 + seed)
+    yy, xx = np.mgrid[0:H, 0:W]
+    base = 40 + (150 * xx) // max(W - 1, 1) + (60 * yy) // max(H - 1, 1)
+    return np.clip(base + rng.integers(-12, 13, (H, W)), 0, 255).astype(np.int16)
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("n,cost", [(4, "sad"), (8, "satd"), (16, "sad"), (32, "satd"), (32, "sad")])
+@pytest.mark.parametrize("rn", (0, 1))
+def test_encode_frame_vs_oracle_medium(Bt, n, cost, rn):
+    """A 360x640 frame (180x320 for the wavefront), all outputs bit-exact against the C oracle."""
+    H, W = (184, 328) if rn else (360, 648)
+    src = _smooth(H, W, n + rn)
+    src[: H // 2] = np.random.default_rng(n).integers(0, 256, (H // 2, W))  # noise half: non-zero levels
+    r = Bt.encode_frame(dev(src), n, cost=cost, qp=24, recon_neighbours=bool(rn))
+    w = O.encode_frame(src, n, cost=cost, qp=24, recon_neighbours=bool(rn), threads=O.n_host_threads())
+    for name in ("modes", "costs", "pred", "coeff", "levels", "recon_plane"):
+        eq(host(getattr(r, name)), w[name], f"{name} n={n} {cost} rn={rn}")
+
+
+# ------------------------------------------------------------------ metrics
+def test_metrics_golden(P, Bt):
+    g = golden("metrics.npz")
+    sad, satd, en = Bt.block_costs(dev(g["a4"]), dev(g["b4"]))
+    eq(host(sad), g["sad4"]); eq(host(satd), g["satd4"]); eq(host(en), g["energy4"])
+    for i in range(3):
+        assert P.sad(g["a4"][i], g["b4"][i]) == int(g["sad4"][i])
+        assert P.satd_4x4(g["a4"][i], g["b4"][i]) == int(g["satd4"][i])
+        assert P.residual_energy(g["a4"][i] - g["b4"][i]) == int(g["energy4"][i])
+    A, B = g["A"], g["B"]
+    assert P.sad(A, B) == int(g["sad_AB"])
+    assert P.mse(A, B) == pytest.approx(float(g["mse_AB"]), rel=1e-12)
+    assert P.psnr(A, B) == pytest.approx(float(g["psnr_AB"]), rel=1e-12)
+    assert P.psnr(A, A) == float("inf")
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_block_costs_vs_oracle(Bt, n):
+    rng = np.random.default_rng(n)
+    B = 77
+    a = rng.integers(0, 256, (B, n, n)).astype(np.int16)
+    b = rng.integers(0, 256, (B, n, n)).astype(np.int16)
+    sad, satd, en = Bt.block_costs(dev(a), dev(b))
+    eq(host(sad), [O.sad(a[i], b[i]) for i in range(B)], "sad")
+    eq(host(satd), [O.satd_block(a[i], b[i]) for i in range(B)], "satd")
+    eq(host(en), [O.sse(a[i], b[i]) for i in range(B)], "energy")
+    lv = rng.integers(-1, 2, (B, n, n)).astype(np.int32)
+    assert int(Bt.count_nonzero_batched(dev(lv)).item()) == int(np.count_nonzero(lv))
+
+
+# ---------------------------------------------- full-size properties (config 4)
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("tag", ["4", "4dst", "8", "16", "32"])
+def test_config4_one_million_blocks_properties(Bt, tag):
+    """2^20 blocks per size (BASELINE config 4).  The oracle cannot cover this in seconds, so:
+    (a) a strided subsample is compared bit-exactly, (b) the batch result must equal the result of
+    the same blocks in a shuffled order (position independence), (c) fused == composition of the
+    single-stage kernels, (d) linearity of the first pass: T(x) + T(-x) rounding identity bounds."""
+    n, dst = int(tag.replace("dst", "")), tag.endswith("dst")
+    B = 1 << 20
+    gen = torch.Generator(device=DEV).manual_seed(99 + n)
+    x = torch.randint(-255, 256, (B, n, n), generator=gen, device=DEV, dtype=torch.int16)
+    fw = Bt.forward_transform_batched(x, dst)
+    idx = torch.arange(0, B, 4099, device=DEV)
+    xs = host(x[idx])
+    eq(host(fw[idx]), O.forward_transform_batch(xs.astype(np.int32), dst, threads=O.n_host_threads()), "subsample forward")
+    perm = torch.randperm(B, generator=gen, device=DEV)
+    assert torch.equal(Bt.forward_transform_batched(x[perm], dst), fw[perm])
+    for qp in (0, 22, 37, 51):
+        lv = Bt.quantize_batched(fw, qp, n)
+        dq = Bt.dequantize_batched(lv, qp)
+        inv = Bt.inverse_transform_batched(dq, dst)
+        eq(host(inv[idx]), O.inverse_transform_batch(host(dq[idx]), dst), f"subsample inverse qp={qp}")
+        eq(host(lv[idx]), O.quantize(host(fw[idx]), qp, n), f"subsample quant qp={qp}")
+        # sign symmetry of quantisation (quant.py:76-79): q(-c) == -q(c)
+        assert torch.equal(Bt.quantize_batched(-fw, qp, n), -lv)
+    del fw, lv, dq, inv
+    # fused kernel == composition of single-stage kernels on the same blocks (zero prediction refs)
+    z = torch.zeros((B, n), dtype=torch.int16, device=DEV)
+    zb = torch.zeros((B,), dtype=torch.int16, device=DEV)
+    pix = (x.abs() % 256).to(torch.int16)
+    got = Bt.fused_block_pipeline(pix, z, z, zb, zb, 1, 30, use_dst=dst)
+    assert int(got.pred.abs().max().item()) == 0
+    co = Bt.forward_transform_batched(pix, dst)
+    assert torch.equal(got.coeff, co)
+    lv = Bt.quantize_batched(co, 30, n)
+    assert torch.equal(got.levels, lv)
+    rec = Bt.clip_to_pixel_range_batched(Bt.reconstruct_block_batched(got.pred, Bt.inverse_transform_batched(Bt.dequantize_batched(lv, 30), dst)))
+    assert torch.equal(got.recon, rec)

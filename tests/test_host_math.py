@@ -1,0 +1,94 @@
+"""The integer code the kernels use (nano_hevc_b200/csrc/nh_math.cuh), compiled for the HOST by
+tests/shim/host_shim.cpp, against the golden vectors of the reference and the C oracle.  This runs
+without a GPU and catches arithmetic mistakes before any GPU time is spent."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import ROOT, golden
+
+SIZES = (4, 8, 16, 32)
+
+
+@pytest.fixture(scope="module")
+def shim(tmp_path_factory):
+    out = tmp_path_factory.mktemp("shim") / "libhost_shim.so"
+    src = os.path.join(ROOT, "tests", "shim", "host_shim.cpp")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fwrapv", "-o", str(out), src])
+    return C.CDLL(str(out))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _xf(shim, x, n, dst, inv):
+    x = np.ascontiguousarray(x, np.int32)
+    out = np.empty_like(x)
+    assert shim.shim_transform2d(n, int(dst), int(inv), _p(x), _p(out)) == 0
+    return out
+
+
+def test_tables(shim):
+    g = golden("tables.npz")
+    for n in SIZES:
+        m = np.array([[shim.shim_matrix(n, i, j) for j in range(n)] for i in range(n)])
+        assert np.array_equal(m, g[f"DCT{n}"])
+    assert [shim.shim_angle(m) for m in range(2, 35)] == list(g["INTRA_PRED_ANGLE"])
+    for a, inv in ((-2, -4096), (-5, -1638), (-9, -910), (-13, -630), (-17, -482), (-21, -390),
+                   (-26, -315), (-32, -256), (0, 0), (5, 0)):
+        assert shim.shim_inv_angle(a) == inv
+
+
+@pytest.mark.parametrize("tag", ["4", "4dst", "8", "16", "32"])
+def test_butterfly_transforms_match_reference(shim, tag):
+    g = golden("transforms.npz")
+    n, dst = int(tag.replace("dst", "")), tag.endswith("dst")
+    for x, want in zip(g[f"x_{tag}"], g[f"fwd_{tag}"]):
+        assert np.array_equal(_xf(shim, x, n, dst, False), want)
+    for c, want in zip(g[f"cin_{tag}"], g[f"inv_{tag}"]):
+        assert np.array_equal(_xf(shim, c, n, dst, True), want)
+    # full-range int32 inputs: wrap-around accumulators must agree with the oracle's loop form
+    rng = np.random.default_rng(5)
+    for _ in range(4):
+        x = rng.integers(-2**31, 2**31, (n, n)).astype(np.int32)
+        assert np.array_equal(_xf(shim, x, n, dst, False), O.forward_transform(x, dst))
+        assert np.array_equal(_xf(shim, x, n, dst, True), O.inverse_transform(x, dst))
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_quant_dequant(shim, n):
+    g = golden("quant.npz")
+    l2 = {4: 2, 8: 3, 16: 4, 32: 5}[n]
+    c, lv, big = g[f"c_{n}"], g[f"lv_{n}"], g[f"big_{n}"]
+    out = np.empty_like(c)
+    for i, qp in enumerate(range(-2, 54)):
+        shim.shim_quant(_p(c), _p(out), C.c_int64(c.size), qp, l2, 1)
+        assert np.array_equal(out, g[f"q_intra_{n}"][i]), qp
+        shim.shim_quant(_p(c), _p(out), C.c_int64(c.size), qp, l2, 0)
+        assert np.array_equal(out, g[f"q_inter_{n}"][i]), qp
+        shim.shim_dequant(_p(lv), _p(out), C.c_int64(lv.size), qp)
+        assert np.array_equal(out, g[f"dq_{n}"][i]), qp
+    for i, qp in enumerate((0, 22, 51)):
+        shim.shim_quant(_p(big), _p(out), C.c_int64(big.size), qp, l2, 1)
+        assert np.array_equal(out, g[f"qbig_{n}"][i]), qp
+        shim.shim_dequant(_p(big), _p(out), C.c_int64(big.size), qp)
+        assert np.array_equal(out, g[f"dqbig_{n}"][i]), qp
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_predictors(shim, n):
+    g = golden("predictors.npz")
+    at, al, ac = g[f"ang_top_{n}"], g[f"ang_left_{n}"], g[f"ang_corner_{n}"]
+    out = np.empty((n, n), np.int16)
+    for a in range(at.shape[0]):
+        for m in range(2, 35):
+            shim.shim_predict_mode(n, _p(at[a]), _p(al[a]), int(ac[a]), m, _p(out))
+            assert np.array_equal(out, g[f"ang_pred_{n}"][a, m - 2]), (n, a, m)
+        for m in (0, 1):
+            shim.shim_predict_mode(n, _p(at[a]), _p(al[a]), int(ac[a]), m, _p(out))
+            assert np.array_equal(out, O.predict_mode(at[a], al[a], ac[a], m, n))
