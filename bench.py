@@ -150,7 +150,7 @@ def run_reference(args, rank, world):
         return
     import oracle as O
     threads = O.n_host_threads()
-    sample_frames = max(1, min(64, threads // 2))
+    sample_frames = max(2, min(128, 2 * threads))
     for _ in range(args.warmup):
         cpu_port_rate(1, threads)
     t_total, px_total = 0.0, 0
@@ -298,7 +298,7 @@ def run_ours(args, rank, world, local_rank):
         if world == 1 and not args.no_cpu:
             import oracle as O
             thr = O.n_host_threads()
-            frames_cpu = max(1, min(32, thr // 2))
+            frames_cpu = max(2, min(128, 4 * thr))  # ~15-30 core-seconds of CPU work
             rate, dt = cpu_port_rate(frames_cpu, thr)
             cpu = {"value": rate, "unit": UNIT, "cores": thr, "kind": "port",
                    "sample": f"{frames_cpu} frames x {PASSES} passes of the same workload, {dt:.1f} s wall"}

@@ -317,6 +317,7 @@ NH_API int nh_fused_pipeline_modes(const int16_t* orig, const int16_t* top, cons
                                    int16_t* recon, void* stream) {
     int l2 = log2_size(size);
     if (l2 < 0) { set_error("Unsupported transform size: %d", size); return NH_E_SIZE; }
+    if (n_blocks == 0) return NH_OK;
     if (!orig || !top || !left || !top_left || n_blocks < 0) {
         set_error("nh_fused_pipeline_modes: null input or negative block count");
         return NH_E_ARG;

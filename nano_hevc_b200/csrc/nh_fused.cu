@@ -304,6 +304,7 @@ NH_API int nh_fused_pipeline_dcplanar(const int16_t* orig, const int16_t* top, c
     using namespace nh;
     int l2 = log2_size(size);
     if (l2 < 0) { set_error("Unsupported transform size: %d", size); return NH_E_SIZE; }
+    if (n_blocks == 0) return NH_OK;
     if (n_blocks < 0 || !orig || !top || !left || !top_right || !bottom_left) {
         set_error("nh_fused_pipeline_dcplanar: null input or negative block count");
         return NH_E_ARG;
