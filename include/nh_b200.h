@@ -120,6 +120,10 @@ int nh_fused_pipeline_dcplanar(const int16_t* orig, const int16_t* top, const in
                                const uint8_t* modes, int mode, int64_t n_blocks, int size, int qp,
                                int is_intra, int use_dst, int bit_depth, int16_t* pred,
                                int32_t* coeff, int32_t* levels, int16_t* recon, void* stream);
+/* Selects the kernel generation behind nh_fused_pipeline_dcplanar for size 4 / 8:
+ * 2 (default: cp.async prefetch + TMA bulk stores + 32-bit pixel-domain quant with an exact
+ * fallback) or 1 (first generation, kept for A/B profiling).  Results are identical. */
+int nh_set_fused_impl(int generation);
 /* Any of the 35 modes from padded (B, 2N+1) references (K1 convention). */
 int nh_fused_pipeline_modes(const int16_t* orig, const int16_t* top, const int16_t* left,
                             const int16_t* top_left, const uint8_t* modes, int mode,

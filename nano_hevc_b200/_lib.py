@@ -42,6 +42,7 @@ PROTOTYPES = {
     "nh_clip_to_pixel_range": (_i, [_p, _p, _i64, _i, _p]),
     "nh_fused_pipeline_dcplanar": (_i, [_p, _p, _p, _p, _p, _p, _i, _i64, _i, _i, _i, _i, _i,
                                         _p, _p, _p, _p, _p]),
+    "nh_set_fused_impl": (_i, [_i]),
     "nh_fused_pipeline_modes": (_i, [_p, _p, _p, _p, _p, _i, _i64, _i, _i, _i, _i, _i,
                                      _p, _p, _p, _p, _p]),
     "nh_gather_refs": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),

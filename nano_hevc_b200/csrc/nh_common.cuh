@@ -58,6 +58,37 @@ __device__ __forceinline__ void stg_stream(void* p, uint4 v) {
     __stcs(reinterpret_cast<uint4*>(p), v);
 }
 
+
+// ---- asynchronous copies -------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+// LDGSTS: 16 bytes global -> shared without a register round trip (L2 only, no L1 allocation).
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+}
+// TMA 1-D bulk store shared -> global (SASS: UBLKCP), tracked by per-thread bulk groups.
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// Wait until at most PENDING of this thread's bulk groups still have to READ their source.
+template <int PENDING>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
+}
+// Make generic-proxy shared-memory writes visible to the async proxy (TMA) before a bulk store.
+__device__ __forceinline__ void fence_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 // Warp tile staging.  A warp tile is 32 "units" of UNIT_BYTES contiguous
 // bytes in global memory (one unit per lane).  In shared memory unit u lives
 // at u * (UNIT_BYTES + 16): the 16-byte pad makes the per-lane 128-bit

@@ -14,6 +14,8 @@
 //   * N = 16, 32 ("rows" kernels): N lanes own one block; lane = row for global
 //     I/O and the second pass, lane = column for the first pass, with the
 //     transposition going through an N x (N+4) int32 shared-memory matrix.
+#include <cstdlib>
+
 #include "nh_block.cuh"
 
 namespace nh {
@@ -182,6 +184,291 @@ __global__ void __launch_bounds__(kUnitWarps * 32, 2) fused_unit_kernel(const Fu
     }
 }
 
+// ------------------------------------------------------- unit kernels, v2
+// Same lane mapping as above, restructured around asynchronous copies:
+//   * the next tile's pixels are prefetched with cp.async (LDGSTS) into the second int16 tile
+//     while the current tile is being coded (hides the long-scoreboard stall of v1);
+//   * every output leaves through per-lane TMA 1-D bulk stores (cp.async.bulk, 128 B = one full
+//     cache line each) straight from the lane's own shared-memory unit, so the LDS + STG staging
+//     sweeps and their __syncwarp()s disappear;
+//   * quant / dequant run in 32 bits when the lane's inputs lie in the pixel domain [0, 4095]
+//     (checked on the packed words as they stream in); a lane that sees anything else recodes
+//     its unit with the exact int64 reference arithmetic in a cold, loop-based routine.
+constexpr int kV2Warps = 4;  // 128 threads per CTA, 3 CTAs per SM
+
+template <int N>
+__device__ __noinline__ void slow_transform(int* blk, bool dst, bool inv) {
+    constexpr int shift = Log2<N>::v + 5;
+    constexpr int rnd = 1 << (shift - 1);
+    int tmp[N * N];
+    auto T = [&](int i, int k) -> int {
+        return (dst && N == 4) ? dst4(i & 3, k & 3) : cosv((i * (32 / N)) * (2 * k + 1));
+    };
+#pragma unroll 1
+    for (int i = 0; i < N; ++i)
+#pragma unroll 1
+        for (int j = 0; j < N; ++j) {
+            unsigned acc = 0;
+#pragma unroll 1
+            for (int k = 0; k < N; ++k) acc += (unsigned)(inv ? T(k, i) : T(i, k)) * (unsigned)blk[k * N + j];
+            tmp[i * N + j] = (int)(acc + (unsigned)rnd) >> shift;
+        }
+#pragma unroll 1
+    for (int i = 0; i < N; ++i)
+#pragma unroll 1
+        for (int j = 0; j < N; ++j) {
+            unsigned acc = 0;
+#pragma unroll 1
+            for (int k = 0; k < N; ++k) acc += (unsigned)tmp[i * N + k] * (unsigned)(inv ? T(k, j) : T(j, k));
+            blk[i * N + j] = (int)(acc + (unsigned)rnd) >> shift;
+        }
+}
+
+// Exact (any int16 input) coding of one block straight from / to global memory.  Cold path.
+template <int N>
+__device__ __noinline__ void slow_block(const FusedArgs& a, int64_t b, bool dst) {
+    constexpr int NN = N * N;
+    int blk[NN];
+    int16_t pr[NN];
+    const int mode = a.modes ? (int)a.modes[b] : a.mode;
+    int s = 0;
+#pragma unroll 1
+    for (int k = 0; k < N; ++k) s += (int)a.top[b * N + k] + (int)a.left[b * N + k];
+    const int dc = dc_value<N>(s);
+    const int tr = a.top_right[b], bl = a.bottom_left[b];
+#pragma unroll 1
+    for (int e = 0; e < NN; ++e) {
+        const int y = e / N, x = e % N;
+        const int p = mode == 1 ? dc : planar_px<N>(x, y, (int)a.left[b * N + y], (int)a.top[b * N + x], tr, bl);
+        pr[e] = (int16_t)p;
+        blk[e] = sext16((int)a.orig[b * NN + e] - sext16(p));
+        if (a.pred) a.pred[b * NN + e] = (int16_t)p;
+    }
+    slow_transform<N>(blk, dst, false);
+#pragma unroll 1
+    for (int e = 0; e < NN; ++e) {
+        if (a.coeff) a.coeff[b * NN + e] = blk[e];
+        const int lv = quantize_one(blk[e], a.qp);
+        if (a.levels) a.levels[b * NN + e] = lv;
+        blk[e] = dequantize_one(lv, a.qp);
+    }
+    slow_transform<N>(blk, dst, true);
+    if (a.recon) {
+#pragma unroll 1
+        for (int e = 0; e < NN; ++e) a.recon[b * NN + e] = (int16_t)recon_px((int)pr[e], blk[e], a.maxv);
+    }
+}
+
+template <int N, bool DST>
+__global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit_kernel_v2(const FusedArgs a, const FastQuant fq) {
+    constexpr int NN = N * N;
+    constexpr int BPU = 64 / NN;
+    using T16 = WarpTile<128>;
+    constexpr int kWarpBytes = 3 * T16::kBytes + T16::kBytes;  // 2 pixel tiles + 2 int32 half tiles
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* wbase = smem_raw + warp * kWarpBytes;
+    unsigned char* s16[2] = {wbase, wbase + T16::kBytes};
+    // int32 outputs go out in two 128-byte halves per lane (rows 0-3 / 4-7 of an 8x8 block, blocks
+    // 0-1 / 2-3 of a 4x4 unit) so that one half can be rewritten while the other is still being read
+    unsigned char* s32h[2] = {wbase + 2 * T16::kBytes, wbase + 3 * T16::kBytes};
+
+    const int64_t n_units = (a.n_blocks + BPU - 1) / BPU;
+    const int64_t n_tiles = (n_units + 31) / 32;
+    const int64_t warp_stride = (int64_t)gridDim.x * kV2Warps;
+    int64_t tile = (int64_t)blockIdx.x * kV2Warps + warp;
+
+    auto prefetch = [&](int64_t t, unsigned char* dst) {
+        const int64_t blk0 = t * 32 * BPU;
+        const int64_t rem = a.n_blocks - blk0;
+        const int chunks = (int)(rem < 32 * BPU ? rem : 32 * BPU) * (NN * 2 / 16);
+        const unsigned char* g = reinterpret_cast<const unsigned char*>(a.orig + blk0 * NN);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int c = it * 32 + lane;
+            if (c < chunks) cp_async16(smem_u32(dst + (c >> 3) * T16::kPitch + (c & 7) * 16), g + (size_t)c * 16);
+        }
+    };
+
+    if (tile < n_tiles) prefetch(tile, s16[0]);
+    cp_async_commit();
+    int cur = 0;
+    for (; tile < n_tiles; tile += warp_stride, cur ^= 1) {
+        const int64_t blk0 = tile * 32 * BPU;
+        const int64_t ub = blk0 + (int64_t)lane * BPU;  // first block of this lane's unit
+        int64_t urem = a.n_blocks - ub;
+        const int ublocks = urem >= BPU ? BPU : (urem > 0 ? (int)urem : 0);  // valid blocks in the unit
+
+        // -- references of this lane's blocks: loads in flight while the pixel tile lands
+        uint32_t tw[BPU][N / 2], lw[BPU][N / 2];
+        int tr[BPU], bl[BPU], mode[BPU];
+#pragma unroll
+        for (int q = 0; q < BPU; ++q) {
+            mode[q] = a.mode;
+            if (q < ublocks) {
+                load_row16<N>(a.top + (ub + q) * N, tw[q]);
+                load_row16<N>(a.left + (ub + q) * N, lw[q]);
+                tr[q] = a.top_right[ub + q];
+                bl[q] = a.bottom_left[ub + q];
+                if (a.modes) mode[q] = a.modes[ub + q];
+            } else {
+#pragma unroll
+                for (int k = 0; k < N / 2; ++k) tw[q][k] = lw[q][k] = 0;
+                tr[q] = bl[q] = 0;
+            }
+        }
+        // bulk groups of the previous tile: all but its reconstruction (the newest) have been read
+        bulk_wait_read<1>();
+        cp_async_wait<0>();
+        __syncwarp();
+
+        int res[BPU][N][N];
+        uint4* u16 = T16::unit(s16[cur], lane);
+        uint32_t ood = 0;  // out-of-domain bits: any sample outside [0, 4095]
+#pragma unroll
+        for (int q = 0; q < BPU; ++q) {
+            int top[N], left[N];
+            unpack_row<N>(tw[q], top);
+            unpack_row<N>(lw[q], left);
+#pragma unroll
+            for (int k = 0; k < N / 2; ++k) ood |= (tw[q][k] | lw[q][k]) & 0xF000F000u;
+            ood |= (uint32_t)(tr[q] | bl[q]) & 0xFFFFF000u;
+            int* rq = &res[q][0][0];
+            if (mode[q] == 1) {
+                int s = 0;
+#pragma unroll
+                for (int k = 0; k < N; ++k) s += top[k] + left[k];
+                const int dc = dc_value<N>(s);
+                const uint32_t dcw = pack16(dc, dc);
+#pragma unroll
+                for (int c = 0; c < NN / 8; ++c) {
+                    uint4 v = u16[q * (NN / 8) + c];
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        ood |= w[k] & 0xF000F000u;
+                        rq[8 * c + 2 * k] = lo16(w[k]) - dc;
+                        rq[8 * c + 2 * k + 1] = hi16(w[k]) - dc;
+                    }
+                    u16[q * (NN / 8) + c] = make_uint4(dcw, dcw, dcw, dcw);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < NN / 8; ++c) {
+                    uint4 v = u16[q * (NN / 8) + c];
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                    int p[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int e = 8 * c + k, y = e / N, x = e % N;
+                        p[k] = planar_px<N>(x, y, left[y], top[x], tr[q], bl[q]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        ood |= w[k] & 0xF000F000u;
+                        rq[8 * c + 2 * k] = lo16(w[k]) - p[2 * k];
+                        rq[8 * c + 2 * k + 1] = hi16(w[k]) - p[2 * k + 1];
+                    }
+                    u16[q * (NN / 8) + c] = make_uint4(pack16(p[0], p[1]), pack16(p[2], p[3]),
+                                                       pack16(p[4], p[5]), pack16(p[6], p[7]));
+                }
+            }
+        }
+        const bool fast = ood == 0;              // in the pixel domain: 32-bit arithmetic is exact
+        const bool emit = fast && ublocks > 0;   // this lane issues bulk stores
+        const uint32_t nb16 = (uint32_t)ublocks * NN * 2, nb32 = (uint32_t)ublocks * NN * 4;
+        // int32 halves: bytes of this lane's unit that fall into half 0 / half 1
+        const uint32_t h0 = nb32 < 128 ? nb32 : 128, h1 = nb32 > 128 ? nb32 - 128 : 0;
+
+        // G1: prediction
+        if (a.pred && emit) {
+            fence_async_smem();
+            bulk_store(a.pred + ub * NN, smem_u32(u16), nb16);
+        }
+        bulk_commit();
+
+        // -- forward transform (in-thread, both passes)
+#pragma unroll
+        for (int q = 0; q < BPU; ++q) transform2d<N, DST, false>(res[q]);
+        int* flat = &res[0][0][0];
+        uint4* uh[2] = {T16::unit(s32h[0], lane), T16::unit(s32h[1], lane)};
+        // G2, G3: coefficients
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (a.coeff) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    uh[h][e] = make_uint4(flat[32 * h + 4 * e], flat[32 * h + 4 * e + 1],
+                                          flat[32 * h + 4 * e + 2], flat[32 * h + 4 * e + 3]);
+                const uint32_t nb = h ? h1 : h0;
+                if (emit && nb) {
+                    fence_async_smem();
+                    bulk_store(reinterpret_cast<unsigned char*>(a.coeff + ub * NN) + 128 * h, smem_u32(uh[h]), nb);
+                }
+            }
+            bulk_commit();
+        }
+        // the previous tile's reconstruction has been read by now: its tile can take the prefetch
+        bulk_wait_read<3>();
+        __syncwarp();
+        if (tile + warp_stride < n_tiles) prefetch(tile + warp_stride, s16[cur ^ 1]);
+        cp_async_commit();
+
+        // -- quantise (levels out) and dequantise in place; G4, G5: levels
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            bulk_wait_read<1>();  // the coefficient half that used this buffer has been read
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                int* r = flat + 32 * h + 4 * e;
+                int l[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    l[k] = quantize_fast(r[k], fq);
+                    r[k] = dequantize_fast(l[k], fq);
+                }
+                if (a.levels) uh[h][e] = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+            const uint32_t nb = h ? h1 : h0;
+            if (a.levels && emit && nb) {
+                fence_async_smem();
+                bulk_store(reinterpret_cast<unsigned char*>(a.levels + ub * NN) + 128 * h, smem_u32(uh[h]), nb);
+            }
+            bulk_commit();
+        }
+        // -- inverse transform, reconstruct against the prediction still in the pixel tile
+#pragma unroll
+        for (int q = 0; q < BPU; ++q) transform2d<N, DST, true>(res[q]);
+        // G6: reconstruction (G1 read the prediction long ago; wait for it before overwriting)
+        bulk_wait_read<4>();
+        if (a.recon) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint4 pv = u16[c];
+                const int* r = flat + 8 * c;
+                uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w}, ow[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    ow[k] = pack16(recon_px(lo16(pw[k]), r[2 * k], a.maxv),
+                                   recon_px(hi16(pw[k]), r[2 * k + 1], a.maxv));
+                u16[c] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+            if (emit) {
+                fence_async_smem();
+                bulk_store(a.recon + ub * NN, smem_u32(u16), nb16);
+            }
+        }
+        bulk_commit();
+        // -- a lane whose inputs left the pixel domain recodes its unit exactly (cold path)
+        if (!fast) {
+            for (int q = 0; q < ublocks; ++q) slow_block<N>(a, ub + q, DST);
+        }
+        __syncwarp();
+    }
+    cp_async_wait<0>();
+    bulk_wait_read<0>();
+}
+
 // ------------------------------------------------------------ rows kernels
 constexpr int kRowsWarps = 4;  // 128 threads per CTA
 
@@ -265,7 +552,7 @@ __global__ void __launch_bounds__(kRowsWarps * 32) fused_rows_kernel(const Fused
 }
 
 template <int N, bool DST>
-static int launch_unit(const FusedArgs& a, cudaStream_t st) {
+static int launch_unit_v1(const FusedArgs& a, cudaStream_t st) {
     constexpr int BPU = 64 / (N * N);
     constexpr int kSmem = kUnitWarps * (WarpTile<128>::kBytes + WarpTile<256>::kBytes);
     static bool configured = false;
@@ -282,6 +569,40 @@ static int launch_unit(const FusedArgs& a, cudaStream_t st) {
     return NH_OK;
 }
 
+template <int N, bool DST>
+static int launch_unit_v2(const FusedArgs& a, cudaStream_t st) {
+    constexpr int BPU = 64 / (N * N);
+    constexpr int kSmem = kV2Warps * 4 * WarpTile<128>::kBytes;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(fused_unit_kernel_v2<N, DST>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fused_unit_kernel_v2)");
+        configured = true;
+    }
+    int64_t units = (a.n_blocks + BPU - 1) / BPU;
+    int grid = grid_for(units, (int64_t)kV2Warps * 32, 3);
+    fused_unit_kernel_v2<N, DST><<<grid, kV2Warps * 32, kSmem, st>>>(a, make_fast_quant(a.qp));
+    NH_CHECK_LAUNCH("fused_unit_kernel_v2");
+    return NH_OK;
+}
+
+// Kernel generation used for N = 4, 8: 2 (default) or 1 (first generation, kept for A/B
+// profiling).  Set by nh_set_fused_impl() or the NH_FUSED_IMPL=v1 environment variable.
+static int g_fused_impl = 0;
+static bool use_v1() {
+    if (g_fused_impl == 0) {
+        const char* e = getenv("NH_FUSED_IMPL");
+        g_fused_impl = (e && e[0] == 'v' && e[1] == '1') ? 1 : 2;
+    }
+    return g_fused_impl == 1;
+}
+
+template <int N, bool DST>
+static int launch_unit(const FusedArgs& a, cudaStream_t st) {
+    return use_v1() ? launch_unit_v1<N, DST>(a, st) : launch_unit_v2<N, DST>(a, st);
+}
+
 template <int N>
 static int launch_rows(const FusedArgs& a, cudaStream_t st) {
     constexpr int BPW = 32 / N;
@@ -294,6 +615,15 @@ static int launch_rows(const FusedArgs& a, cudaStream_t st) {
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace nh
+
+NH_API int nh_set_fused_impl(int generation) {
+    if (generation != 1 && generation != 2) {
+        nh::set_error("nh_set_fused_impl: generation must be 1 or 2, got %d", generation);
+        return NH_E_ARG;
+    }
+    nh::g_fused_impl = generation;
+    return NH_OK;
+}
 
 NH_API int nh_fused_pipeline_dcplanar(const int16_t* orig, const int16_t* top, const int16_t* left,
                                       const int16_t* top_right, const int16_t* bottom_left,

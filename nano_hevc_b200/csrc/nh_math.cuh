@@ -224,6 +224,40 @@ NH_HD int dequantize_one(int level, const QuantParams& p) {
     return (int)(unsigned)(unsigned long long)c;
 }
 
+
+// 32-bit quant / dequant for the PIXEL DOMAIN: exact whenever |coeff| * 26214 + offset < 2^31,
+// which holds for every coefficient the forward transform can produce from residuals in
+// [-4095, 4095] (|coeff| <= 32394).  Kernels check the domain of their inputs and
+// fall back to the int64 form above otherwise.
+struct FastQuant {
+    int mf, q_shift, off_pos, off_neg;  // level = (c*mf + (c < 0 ? off_neg : off_pos)) >> q_shift
+    int dq_mult, dq_rnd, dq_shift;      // coeff = (level*dq_mult + dq_rnd) >> dq_shift
+};
+NH_HD FastQuant make_fast_quant(const QuantParams& p) {
+    FastQuant f;
+    f.mf = p.mf;
+    f.q_shift = p.q_shift;
+    f.off_pos = (int)p.q_offset;
+    // -floor((|c|*mf + off) / 2^s) == floor((c*mf + 2^s - 1 - off) / 2^s) for c < 0
+    f.off_neg = (int)((1LL << p.q_shift) - 1 - p.q_offset);
+    if (p.per < 4) {
+        f.dq_mult = p.scale;
+        f.dq_shift = 4 - p.per;
+        f.dq_rnd = 1 << (f.dq_shift - 1);
+    } else {
+        f.dq_mult = p.scale << (p.per - 4);
+        f.dq_shift = 0;
+        f.dq_rnd = 0;
+    }
+    return f;
+}
+NH_HD int quantize_fast(int c, const FastQuant& f) {
+    return (c * f.mf + (c < 0 ? f.off_neg : f.off_pos)) >> f.q_shift;
+}
+NH_HD int dequantize_fast(int level, const FastQuant& f) {
+    return (level * f.dq_mult + f.dq_rnd) >> f.dq_shift;
+}
+
 // ------------------------------------------------------------ small helpers
 NH_HD int clip_pixel(int v, int maxv) { return v < 0 ? 0 : (v > maxv ? maxv : v); }
 NH_HD int sext16(int v) { return (int)(short)v; }

@@ -37,6 +37,14 @@ void shim_dequant(const int32_t* l, int32_t* out, int64_t n, int qp) {
     QuantParams p = make_quant_params(qp, 2, 1);
     for (int64_t i = 0; i < n; ++i) out[i] = dequantize_one(l[i], p);
 }
+void shim_quant_fast(const int32_t* c, int32_t* out, int64_t n, int qp, int log2n, int intra) {
+    FastQuant f = make_fast_quant(make_quant_params(qp, log2n, intra));
+    for (int64_t i = 0; i < n; ++i) out[i] = quantize_fast(c[i], f);
+}
+void shim_dequant_fast(const int32_t* l, int32_t* out, int64_t n, int qp) {
+    FastQuant f = make_fast_quant(make_quant_params(qp, 2, 1));
+    for (int64_t i = 0; i < n; ++i) out[i] = dequantize_fast(l[i], f);
+}
 int shim_matrix(int n, int i, int j) {
     switch (n) { case 4: return dct<4>(i, j); case 8: return dct<8>(i, j);
                  case 16: return dct<16>(i, j); case 32: return dct<32>(i, j); }

@@ -252,6 +252,38 @@ def test_fused_dcplanar_vs_oracle(Bt, n, B):
         eq(host(getattr(got, name)), w, f"10-bit {name}")
 
 
+@pytest.mark.parametrize("n", (4, 8))
+@pytest.mark.parametrize("gen", (1, 2))
+def test_fused_unit_generations_and_out_of_domain(Bt, n, gen):
+    """Both kernel generations; blocks whose samples leave the pixel domain [0, 4095] (where the
+    32-bit fast path of generation 2 is not exact) must still match the int64 reference arithmetic."""
+    from nano_hevc_b200 import _lib
+    rng = np.random.default_rng(77 + n)
+    B = 999
+    orig, top, left, tr, bl = _dcplanar_inputs(rng, B, n)
+    wild = rng.random(B) < 0.2
+    orig[wild] = rng.integers(-32768, 32768, (int(wild.sum()), n, n))
+    w2 = rng.random(B) < 0.1
+    top[w2] = rng.integers(-32768, 32768, (int(w2.sum()), n))
+    w3 = rng.random(B) < 0.1
+    tr[w3] = rng.integers(4096, 32768, int(w3.sum()))
+    orig[5] = 4095; orig[6] = 4096; left[7] = -1
+    modes = rng.integers(0, 2, B).astype(np.uint8)
+    _lib.check(_lib.lib().nh_set_fused_impl(gen))
+    try:
+        for qp, intra in ((0, True), (27, True), (51, False)):
+            got = Bt.fused_block_pipeline(*[dev(v) for v in (orig, top, left, tr, bl)], dev(modes), qp,
+                                          is_intra=intra, use_dst=(n == 4))
+            want = O.pipeline_dcplanar_batch(orig, top, left, tr, bl, modes, qp, is_intra=intra, use_dst=(n == 4))
+            for name, w in zip(("pred", "coeff", "levels", "recon"), want):
+                eq(host(getattr(got, name)), w, f"{name} gen={gen} n={n} qp={qp}")
+        got = Bt.fused_block_pipeline(*[dev(v) for v in (orig, top, left, tr, bl)], 1, 30, outputs=("coeff", "recon"))
+        want = O.pipeline_dcplanar_batch(orig, top, left, tr, bl, 1, 30)
+        eq(host(got.coeff), want[1]); eq(host(got.recon), want[3])
+    finally:
+        _lib.check(_lib.lib().nh_set_fused_impl(2))
+
+
 def test_fused_dcplanar_empty_and_errors(Bt):
     z = lambda *s: torch.zeros(s, dtype=torch.int16, device=DEV)
     got = Bt.fused_block_pipeline(z(0, 8, 8), z(0, 8), z(0, 8), z(0), z(0), 1, 27)

@@ -92,3 +92,22 @@ def test_predictors(shim, n):
         for m in (0, 1):
             shim.shim_predict_mode(n, _p(at[a]), _p(al[a]), int(ac[a]), m, _p(out))
             assert np.array_equal(out, O.predict_mode(at[a], al[a], ac[a], m, n))
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_fast_quant_is_exact_in_the_pixel_domain(shim, n):
+    """32-bit quant / dequant (kernel fast path) == the int64 oracle for every coefficient the
+    forward transform can produce from residuals in [-4095, 4095] and every QP."""
+    l2 = {4: 2, 8: 3, 16: 4, 32: 5}[n]
+    rng = np.random.default_rng(n)
+    c = np.concatenate([np.arange(-32394, 32395, 7), rng.integers(-32394, 32395, 4000),
+                        [-32394, 32394, -1, 0, 1]]).astype(np.int32)
+    out = np.empty_like(c)
+    for qp in range(0, 52):
+        for intra in (1, 0):
+            shim.shim_quant_fast(_p(c), _p(out), C.c_int64(c.size), qp, l2, intra)
+            want = O.quantize(c, qp, n, bool(intra))
+            assert np.array_equal(out, want), (qp, intra)
+        lv = O.quantize(c, qp, n, True)
+        shim.shim_dequant_fast(_p(lv), _p(out), C.c_int64(lv.size), qp)
+        assert np.array_equal(out, O.dequantize(lv, qp)), qp
