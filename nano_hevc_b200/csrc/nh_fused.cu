@@ -188,9 +188,9 @@ __global__ void __launch_bounds__(kUnitWarps * 32, 2) fused_unit_kernel(const Fu
 // Same lane mapping as above, restructured around asynchronous copies:
 //   * the next tile's pixels are prefetched with cp.async (LDGSTS) into the second int16 tile
 //     while the current tile is being coded (hides the long-scoreboard stall of v1);
-//   * every output leaves through per-lane TMA 1-D bulk stores (cp.async.bulk, 128 B = one full
-//     cache line each) straight from the lane's own shared-memory unit, so the LDS + STG staging
-//     sweeps and their __syncwarp()s disappear;
+//   * (measured and rejected, profiles/r1_notes.md: per-lane TMA 1-D bulk stores -- UBLKCP takes
+//     uniform-register operands, so a per-lane bulk store compiles to a 32-iteration waterfall
+//     loop; outputs therefore keep the cooperative, fully coalesced LDS.128 + STG.128 sweep);
 //   * quant / dequant run in 32 bits when the lane's inputs lie in the pixel domain [0, 4095]
 //     (checked on the packed words as they stream in); a lane that sees anything else recodes
 //     its unit with the exact int64 reference arithmetic in a cold, loop-based routine.
@@ -264,14 +264,13 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit_kernel_v2(const F
     constexpr int NN = N * N;
     constexpr int BPU = 64 / NN;
     using T16 = WarpTile<128>;
-    constexpr int kWarpBytes = 3 * T16::kBytes + T16::kBytes;  // 2 pixel tiles + 2 int32 half tiles
+    using T32 = WarpTile<256>;
+    constexpr int kWarpBytes = 2 * T16::kBytes + T32::kBytes;  // 2 pixel tiles (double buffer) + 1 int32 tile
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* wbase = smem_raw + warp * kWarpBytes;
     unsigned char* s16[2] = {wbase, wbase + T16::kBytes};
-    // int32 outputs go out in two 128-byte halves per lane (rows 0-3 / 4-7 of an 8x8 block, blocks
-    // 0-1 / 2-3 of a 4x4 unit) so that one half can be rewritten while the other is still being read
-    unsigned char* s32h[2] = {wbase + 2 * T16::kBytes, wbase + 3 * T16::kBytes};
+    unsigned char* s32 = wbase + 2 * T16::kBytes;
 
     const int64_t n_units = (a.n_blocks + BPU - 1) / BPU;
     const int64_t n_tiles = (n_units + 31) / 32;
@@ -296,7 +295,10 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit_kernel_v2(const F
     for (; tile < n_tiles; tile += warp_stride, cur ^= 1) {
         const int64_t blk0 = tile * 32 * BPU;
         const int64_t ub = blk0 + (int64_t)lane * BPU;  // first block of this lane's unit
-        int64_t urem = a.n_blocks - ub;
+        const int64_t trem = a.n_blocks - blk0;
+        const int blocks_valid = (int)(trem < 32 * BPU ? trem : 32 * BPU);
+        const int chunks16 = blocks_valid * (NN * 2 / 16), chunks32 = blocks_valid * (NN * 4 / 16);
+        const int64_t urem = a.n_blocks - ub;
         const int ublocks = urem >= BPU ? BPU : (urem > 0 ? (int)urem : 0);  // valid blocks in the unit
 
         // -- references of this lane's blocks: loads in flight while the pixel tile lands
@@ -317,9 +319,11 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit_kernel_v2(const F
                 tr[q] = bl[q] = 0;
             }
         }
-        // bulk groups of the previous tile: all but its reconstruction (the newest) have been read
-        bulk_wait_read<1>();
-        cp_async_wait<0>();
+        // the other pixel tile is free (its reconstruction left at the end of the previous
+        // iteration): start fetching the next tile into it, then wait for the current one
+        if (tile + warp_stride < n_tiles) prefetch(tile + warp_stride, s16[cur ^ 1]);
+        cp_async_commit();
+        cp_async_wait<1>();
         __syncwarp();
 
         int res[BPU][N][N];
@@ -374,73 +378,43 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit_kernel_v2(const F
                 }
             }
         }
-        const bool fast = ood == 0;              // in the pixel domain: 32-bit arithmetic is exact
-        const bool emit = fast && ublocks > 0;   // this lane issues bulk stores
-        const uint32_t nb16 = (uint32_t)ublocks * NN * 2, nb32 = (uint32_t)ublocks * NN * 4;
-        // int32 halves: bytes of this lane's unit that fall into half 0 / half 1
-        const uint32_t h0 = nb32 < 128 ? nb32 : 128, h1 = nb32 > 128 ? nb32 - 128 : 0;
-
-        // G1: prediction
-        if (a.pred && emit) {
-            fence_async_smem();
-            bulk_store(a.pred + ub * NN, smem_u32(u16), nb16);
-        }
-        bulk_commit();
+        const bool fast = ood == 0;  // in the pixel domain: 32-bit arithmetic is exact
+        __syncwarp();
+        if (a.pred) T16::store(s16[cur], reinterpret_cast<unsigned char*>(a.pred + blk0 * NN), lane, chunks16);
+        __syncwarp();  // the tile keeps the prediction until the reconstruction rewrites it
 
         // -- forward transform (in-thread, both passes)
 #pragma unroll
         for (int q = 0; q < BPU; ++q) transform2d<N, DST, false>(res[q]);
         int* flat = &res[0][0][0];
-        uint4* uh[2] = {T16::unit(s32h[0], lane), T16::unit(s32h[1], lane)};
-        // G2, G3: coefficients
+        uint4* u32 = T32::unit(s32, lane);
+        if (a.coeff) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            if (a.coeff) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                    uh[h][e] = make_uint4(flat[32 * h + 4 * e], flat[32 * h + 4 * e + 1],
-                                          flat[32 * h + 4 * e + 2], flat[32 * h + 4 * e + 3]);
-                const uint32_t nb = h ? h1 : h0;
-                if (emit && nb) {
-                    fence_async_smem();
-                    bulk_store(reinterpret_cast<unsigned char*>(a.coeff + ub * NN) + 128 * h, smem_u32(uh[h]), nb);
-                }
-            }
-            bulk_commit();
+            for (int e = 0; e < 16; ++e)
+                u32[e] = make_uint4(flat[4 * e], flat[4 * e + 1], flat[4 * e + 2], flat[4 * e + 3]);
+            __syncwarp();
+            T32::store(s32, reinterpret_cast<unsigned char*>(a.coeff + blk0 * NN), lane, chunks32);
+            __syncwarp();
         }
-        // the previous tile's reconstruction has been read by now: its tile can take the prefetch
-        bulk_wait_read<3>();
-        __syncwarp();
-        if (tile + warp_stride < n_tiles) prefetch(tile + warp_stride, s16[cur ^ 1]);
-        cp_async_commit();
-
-        // -- quantise (levels out) and dequantise in place; G4, G5: levels
+        // -- quantise (levels out) and dequantise in place, 32-bit pixel-domain arithmetic
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            bulk_wait_read<1>();  // the coefficient half that used this buffer has been read
+        for (int e = 0; e < 16; ++e) {
+            int* r = flat + 4 * e;
+            int l[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                int* r = flat + 32 * h + 4 * e;
-                int l[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    l[k] = quantize_fast(r[k], fq);
-                    r[k] = dequantize_fast(l[k], fq);
-                }
-                if (a.levels) uh[h][e] = make_uint4(l[0], l[1], l[2], l[3]);
+            for (int k = 0; k < 4; ++k) {
+                l[k] = quantize_fast(r[k], fq);
+                r[k] = dequantize_fast(l[k], fq);
             }
-            const uint32_t nb = h ? h1 : h0;
-            if (a.levels && emit && nb) {
-                fence_async_smem();
-                bulk_store(reinterpret_cast<unsigned char*>(a.levels + ub * NN) + 128 * h, smem_u32(uh[h]), nb);
-            }
-            bulk_commit();
+            if (a.levels) u32[e] = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+        if (a.levels) {
+            __syncwarp();
+            T32::store(s32, reinterpret_cast<unsigned char*>(a.levels + blk0 * NN), lane, chunks32);
         }
         // -- inverse transform, reconstruct against the prediction still in the pixel tile
 #pragma unroll
         for (int q = 0; q < BPU; ++q) transform2d<N, DST, true>(res[q]);
-        // G6: reconstruction (G1 read the prediction long ago; wait for it before overwriting)
-        bulk_wait_read<4>();
         if (a.recon) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -453,20 +427,18 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit_kernel_v2(const F
                                    recon_px(hi16(pw[k]), r[2 * k + 1], a.maxv));
                 u16[c] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             }
-            if (emit) {
-                fence_async_smem();
-                bulk_store(a.recon + ub * NN, smem_u32(u16), nb16);
-            }
+            __syncwarp();
+            T16::store(s16[cur], reinterpret_cast<unsigned char*>(a.recon + blk0 * NN), lane, chunks16);
         }
-        bulk_commit();
-        // -- a lane whose inputs left the pixel domain recodes its unit exactly (cold path)
+        __syncwarp();
+        // -- a lane whose inputs left the pixel domain recodes its unit exactly (cold path); the
+        //    __syncwarp above orders the cooperative stores of its unit before these stores
         if (!fast) {
             for (int q = 0; q < ublocks; ++q) slow_block<N>(a, ub + q, DST);
         }
         __syncwarp();
     }
     cp_async_wait<0>();
-    bulk_wait_read<0>();
 }
 
 // ------------------------------------------------------------ rows kernels
@@ -572,7 +544,7 @@ static int launch_unit_v1(const FusedArgs& a, cudaStream_t st) {
 template <int N, bool DST>
 static int launch_unit_v2(const FusedArgs& a, cudaStream_t st) {
     constexpr int BPU = 64 / (N * N);
-    constexpr int kSmem = kV2Warps * 4 * WarpTile<128>::kBytes;
+    constexpr int kSmem = kV2Warps * (2 * WarpTile<128>::kBytes + WarpTile<256>::kBytes);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(fused_unit_kernel_v2<N, DST>,
