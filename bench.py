@@ -186,6 +186,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     assert _lib.lib().nh_device_ok() == 1, _lib.last_error()
     _lib.check(_lib.lib().nh_set_fused_impl(args.fused_impl))
