@@ -19,12 +19,16 @@ struct CoderCfg {
     static constexpr int SPL = SB >= G ? SB / G : 1;    // sub-blocks per lane
     static constexpr int MS = SB >= G ? 1 : G / SB;     // mode splits (lanes sharing a sub-block)
     static constexpr int SBL = SB >= G ? G : SB;        // lanes that sum one mode's cost
-    static constexpr int REF_W = 2 * N + 2;             // padded to an even count
+    static constexpr int REF_W = 2 * N + 4;             // 2N+1 entries + padding read by the packed loads
+    static constexpr int NEG_W = N + 4;                 // projected extension (N) + ref[0..3]
+    static constexpr int NEG_MODES = 15;                // modes 11..25 have a negative angle
     static constexpr int O_PITCH = N + 2;               // int16 elements; odd word pitch spreads banks
     static constexpr int REFS_BYTES = 2 * REF_W * 2;
+    static constexpr int NEG_BYTES = ((NEG_MODES * NEG_W * 2 + 15) / 16) * 16;
     static constexpr int O_BYTES = ((N * O_PITCH * 2 + 15) / 16) * 16;
     static constexpr int M_BYTES = RowsTile<N>::WORDS * 4;
-    static constexpr int GROUP_BYTES = ((REFS_BYTES + 15) / 16) * 16 + O_BYTES + M_BYTES;
+    static constexpr int REFS_PAD = ((REFS_BYTES + 15) / 16) * 16;
+    static constexpr int GROUP_BYTES = REFS_PAD + NEG_BYTES + O_BYTES + M_BYTES;
 };
 
 struct SmemRef {  // accessor for nh::ref_at / angular_sample over shared-memory references
@@ -142,6 +146,171 @@ __device__ __forceinline__ int search_modes(int gl, const int16_t* O, const int1
         best = key < best ? key : best;
     }
     // warp-level argmin across the mode splits
+#pragma unroll
+    for (int off = G / 2; off >= Cfg::SBL; off >>= 1) {
+        int other = __shfl_xor_sync(0xffffffffu, best, off);
+        best = other < best ? other : best;
+    }
+    return best;
+}
+
+// ------------------------------------------------------------------ 8-bit fast search
+// When every reference and every original sample of the tile lies in [0, 255] the search runs on
+// packed data: four predicted samples per register (bytes), interpolation on 16-bit pairs
+//   ((32-f)*(R[k],R[k+1]) + f*(R[k+1],R[k+2]) + (16,16)) >> 5        -- two pixels per IMAD pair,
+// SAD with VABSDIFF4.U8.ACC (four pixels per instruction).  Values <= 8176 never carry between the
+// 16-bit lanes and never wrap int16, so the result equals intra.py:191-207 exactly.
+//
+// Horizontal modes (mode < 18) are evaluated on the TRANSPOSED sub-block: pred[y][x] for scan
+// line x and base y is the "vertical" formula applied to the left references, and both SAD and
+// sum|H d H^T| are invariant under transposition of d.
+//
+// Negative angles read ref[k < 0] = secondary[((k+1)*inv + 128) >> 8].  build_neg_arrays() lays
+// that projection out contiguously per mode: neg[m][j] = ref_m[j - N] for j = 0 .. N+3, so a
+// 5-sample window that starts below zero is a plain contiguous read.
+template <int N, int G>
+__device__ __forceinline__ void build_neg_arrays(int gl, const int16_t* top, const int16_t* left,
+                                                 int16_t* neg) {
+    using Cfg = CoderCfg<N, G>;
+    for (int t = gl; t < Cfg::NEG_MODES * N; t += G) {
+        const int mi = t / N, j = t % N;         // mode 11 + mi, element k = j - N
+        const int mode = 11 + mi;
+        const int k = j - N;
+        const int16_t* sec = mode >= 18 ? left : top;
+        const int proj = ((k + 1) * inv_angle_of_mode(mode) + 128) >> 8;
+        // entries below (N*angle)>>5 are never read; clamp the index so the load stays in bounds
+        neg[mi * Cfg::NEG_W + j] = sec[proj > 2 * N ? 2 * N : proj];
+    }
+    for (int t = gl; t < Cfg::NEG_MODES * 4; t += G) {
+        const int mi = t >> 2, j = t & 3;
+        const int16_t* pri = (11 + mi) >= 18 ? top : left;
+        neg[mi * Cfg::NEG_W + N + j] = pri[j];   // pri[0] is the corner in the plane coders
+    }
+}
+
+// Four predicted samples (bytes) of one scan line: R = halfword array (4-byte aligned), h = index of
+// the first sample's ref[k], f = fraction.
+__device__ __forceinline__ void pred_row4_pairs(const int16_t* R, int h, int f, uint32_t& lo, uint32_t& hi) {
+    const uint32_t* W = reinterpret_cast<const uint32_t*>(R) + (h >> 1);
+    const uint32_t w0 = W[0], w1 = W[1], w2 = W[2];
+    const uint32_t selA = (h & 1) ? 0x5432u : 0x3210u, selB = selA + 0x2222u;
+    const uint32_t a01 = __byte_perm(w0, w1, selA), a12 = __byte_perm(w0, w1, selB);
+    const uint32_t a23 = __byte_perm(w1, w2, selA), a34 = __byte_perm(w1, w2, selB);
+    const uint32_t g = 32u - (uint32_t)f;
+    lo = (g * a01 + (uint32_t)f * a12 + 0x00100010u) >> 5;   // bytes 0 and 2 hold samples 0, 1
+    hi = (g * a23 + (uint32_t)f * a34 + 0x00100010u) >> 5;   // bytes 0 and 2 hold samples 2, 3
+}
+
+template <int N, int G>
+__device__ __forceinline__ int subblock_cost_u8(int mode, int sx, int sy, const uint32_t (&ow)[4],
+                                                const uint32_t (&owT)[4], const int16_t* top,
+                                                const int16_t* left, const int16_t* neg, int dc,
+                                                int cost_kind) {
+    using Cfg = CoderCfg<N, G>;
+    uint32_t pr[4];        // predicted rows in scan order, 4 bytes each
+    bool transposed = false;
+    if (mode >= 2) {
+        const int angle = intra_angle(mode);
+        const bool vertical = mode >= 18;
+        transposed = !vertical;
+        const int16_t* pos = vertical ? top : left;
+        const int16_t* ng = neg + (mode - 11) * Cfg::NEG_W + N;   // only dereferenced for modes 11..25
+        const int b0 = vertical ? sx : sy, s0 = vertical ? sy : sx;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int p = (s0 + j + 1) * angle;
+            const int ip = p >> 5, f = p & 31;
+            const int k = b0 + 1 + ip;
+            const int16_t* R = k < 0 ? ng : pos;
+            uint32_t lo, hi;
+            pred_row4_pairs(R, k, f, lo, hi);   // every array starts 4-byte aligned
+            pr[j] = __byte_perm(lo, hi, 0x6420);
+        }
+    } else if (mode == 1) {
+        const uint32_t d4 = (uint32_t)dc * 0x01010101u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pr[j] = d4;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                v[i] = planar_px<N>(sx + i, sy + j, left[1 + sy + j], top[1 + sx + i], top[N + 1], left[N + 1]);
+            pr[j] = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+        }
+    }
+    int c = 0;
+    if (cost_kind == NH_COST_SAD) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c = (int)(__vsadu4(pr[j], transposed ? owT[j] : ow[j]) + (uint32_t)c);
+    } else {
+        int d[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t o4 = transposed ? owT[j] : ow[j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                d[4 * j + i] = (int)((o4 >> (8 * i)) & 0xff) - (int)((pr[j] >> (8 * i)) & 0xff);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int a0 = d[j] + d[4 + j], a1 = d[j] - d[4 + j];
+            int a2 = d[8 + j] + d[12 + j], a3 = d[8 + j] - d[12 + j];
+            d[j] = a0 + a2; d[4 + j] = a1 + a3; d[8 + j] = a0 - a2; d[12 + j] = a1 - a3;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int a0 = d[4 * i] + d[4 * i + 1], a1 = d[4 * i] - d[4 * i + 1];
+            int a2 = d[4 * i + 2] + d[4 * i + 3], a3 = d[4 * i + 2] - d[4 * i + 3];
+            c += abs(a0 + a2) + abs(a1 + a3) + abs(a0 - a2) + abs(a1 - a3);
+        }
+    }
+    return c;
+}
+
+// Same contract as search_modes(); requires all samples of the block in [0, 255] and
+// build_neg_arrays() done (and a __syncwarp() since).
+template <int N, int G>
+__device__ __forceinline__ int search_modes_u8(int gl, const int16_t* O, const int16_t* top,
+                                               const int16_t* left, const int16_t* neg, int dc,
+                                               int cost_kind) {
+    using Cfg = CoderCfg<N, G>;
+    constexpr int SBW = N / 4;
+    uint32_t ow[Cfg::SPL][4], owT[Cfg::SPL][4];
+    int sx[Cfg::SPL], sy[Cfg::SPL];
+#pragma unroll
+    for (int i = 0; i < Cfg::SPL; ++i) {
+        const int sb = (Cfg::MS == 1) ? gl + i * G : gl % Cfg::SB;
+        sx[i] = (sb % SBW) * 4;
+        sy[i] = (sb / SBW) * 4;
+        uint32_t v[4][4];
+#pragma unroll
+        for (int y = 0; y < 4; ++y)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) v[y][x] = (uint32_t)(uint16_t)O[(sy[i] + y) * Cfg::O_PITCH + sx[i] + x];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            ow[i][r] = v[r][0] | (v[r][1] << 8) | (v[r][2] << 16) | (v[r][3] << 24);
+            owT[i][r] = v[0][r] | (v[1][r] << 8) | (v[2][r] << 16) | (v[3][r] << 24);
+        }
+    }
+    const int ms = (Cfg::MS == 1) ? 0 : gl / Cfg::SB;
+    int best = 0x7fffffff;
+    constexpr int ITERS = (35 + Cfg::MS - 1) / Cfg::MS;
+    for (int it = 0; it < ITERS; ++it) {
+        const int pos = it * Cfg::MS + ms;
+        const bool active = pos < 35;
+        const int mode = !active ? 1 : (pos == 0 ? 1 : (pos == 1 ? 0 : pos));
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < Cfg::SPL; ++i)
+            c += subblock_cost_u8<N, G>(mode, sx[i], sy[i], ow[i], owT[i], top, left, neg, dc, cost_kind);
+#pragma unroll
+        for (int off = Cfg::SBL / 2; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+        const int key = active ? ((c << 6) | pos) : 0x7fffffff;
+        best = key < best ? key : best;
+    }
 #pragma unroll
     for (int off = G / 2; off >= Cfg::SBL; off >>= 1) {
         int other = __shfl_xor_sync(0xffffffffu, best, off);

@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
     unsigned char* base = smem + (warp * GPW + g) * Cfg::GROUP_BYTES;
     int16_t* top = reinterpret_cast<int16_t*>(base);
     int16_t* left = top + Cfg::REF_W;
-    int16_t* O = reinterpret_cast<int16_t*>(base + ((Cfg::REFS_BYTES + 15) / 16) * 16);
+    int16_t* neg = reinterpret_cast<int16_t*>(base + Cfg::REFS_PAD);
+    int16_t* O = reinterpret_cast<int16_t*>(base + Cfg::REFS_PAD + Cfg::NEG_BYTES);
     int* M = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(O) + Cfg::O_BYTES);
 
     const int bw = SRC == SRC_ARRAYS ? 1 : a.W / N;
@@ -142,16 +143,32 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                 const int x = bx * N, y = by * N;
                 const int64_t b = (int64_t)by * bw + bx;
                 const int16_t* rp = a.out.recon_plane;
-                for (int k = gl; k <= 2 * N; k += G) {
-                    top[k] = (int16_t)top_ref<true>(rp, a.H, a.W, a.pitch, x, y, 2 * N, k);
-                    left[k] = (int16_t)left_ref<true>(rp, a.H, a.W, a.pitch, x, y, N, k);
+                int ood = 0;  // any sample outside [0, 255] disables the packed 8-bit search
+                for (int k = gl; k < Cfg::REF_W; k += G) {
+                    const int kk = k <= 2 * N ? k : 2 * N;
+                    const int tv = top_ref<true>(rp, a.H, a.W, a.pitch, x, y, 2 * N, kk);
+                    const int lv = left_ref<true>(rp, a.H, a.W, a.pitch, x, y, N, kk);
+                    top[k] = (int16_t)tv;
+                    left[k] = (int16_t)lv;
+                    ood |= tv | lv;
                 }
-                for (int e = gl; e < N * N; e += G)
-                    O[(e / N) * Cfg::O_PITCH + (e % N)] = __ldg(a.src + (int64_t)(y + e / N) * a.pitch + x + e % N);
+                for (int e = gl; e < N * N; e += G) {
+                    const int v = __ldg(a.src + (int64_t)(y + e / N) * a.pitch + x + e % N);
+                    O[(e / N) * Cfg::O_PITCH + (e % N)] = (int16_t)v;
+                    ood |= v;
+                }
+                const bool fast8 = !__any_sync(0xffffffffu, (ood & ~0xff) != 0);
                 __syncwarp();
                 const int corner = (int)top[0];
                 const int dc = dc_from_refs<N>(top, left);
-                const int key = search_modes<N, G>(gl, O, top, left, corner, dc, a.cost_kind);
+                int key;
+                if (fast8) {
+                    build_neg_arrays<N, G>(gl, top, left, neg);
+                    __syncwarp();
+                    key = search_modes_u8<N, G>(gl, O, top, left, neg, dc, a.cost_kind);
+                } else {
+                    key = search_modes<N, G>(gl, O, top, left, corner, dc, a.cost_kind);
+                }
                 const int mode = mode_of_key(key);
                 if (gl == 0) {
                     if (a.out.modes) a.out.modes[b] = (uint8_t)mode;
@@ -176,7 +193,7 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
              tile += (int64_t)gridDim.x * WARPS) {
             const int64_t b = tile * GPW + g;
             const bool valid = b < a.n_blocks;
-            int corner = 0, x = 0, y = 0;
+            int corner = 0, x = 0, y = 0, ood = 0;
             if constexpr (SRC == SRC_ARRAYS) {
                 if (valid) {
                     for (int k = gl; k <= 2 * N; k += G) {
@@ -191,18 +208,26 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                 if (valid) {
                     x = (int)(b % bw) * N;
                     y = (int)(b / bw) * N;
-                    for (int k = gl; k <= 2 * N; k += G) {
-                        top[k] = (int16_t)top_ref<false>(a.src, a.H, a.W, a.pitch, x, y, 2 * N, k);
-                        left[k] = (int16_t)left_ref<false>(a.src, a.H, a.W, a.pitch, x, y, 2 * N, k);
+                    for (int k = gl; k < Cfg::REF_W; k += G) {
+                        const int kk = k <= 2 * N ? k : 2 * N;
+                        const int tv = top_ref<false>(a.src, a.H, a.W, a.pitch, x, y, 2 * N, kk);
+                        const int lv = left_ref<false>(a.src, a.H, a.W, a.pitch, x, y, 2 * N, kk);
+                        top[k] = (int16_t)tv;
+                        left[k] = (int16_t)lv;
+                        ood |= tv | lv;
                     }
-                    for (int e = gl; e < N * N; e += G)
-                        O[(e / N) * Cfg::O_PITCH + (e % N)] = __ldg(a.src + (int64_t)(y + e / N) * a.pitch + x + e % N);
+                    for (int e = gl; e < N * N; e += G) {
+                        const int v = __ldg(a.src + (int64_t)(y + e / N) * a.pitch + x + e % N);
+                        O[(e / N) * Cfg::O_PITCH + (e % N)] = (int16_t)v;
+                        ood |= v;
+                    }
                 }
             }
             if (!valid) {  // keep shared memory defined for the idle groups of a ragged tile
-                for (int k = gl; k <= 2 * N; k += G) top[k] = left[k] = 0;
+                for (int k = gl; k < Cfg::REF_W; k += G) top[k] = left[k] = 0;
                 for (int e = gl; e < N * N; e += G) O[(e / N) * Cfg::O_PITCH + (e % N)] = 0;
             }
+            const bool fast8 = !__any_sync(0xffffffffu, (ood & ~0xff) != 0);
             __syncwarp();
             if constexpr (SRC == SRC_PLANE) corner = (int)top[0];
             const int dc = dc_from_refs<N>(top, left);
@@ -211,7 +236,14 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                 mode = (valid && a.modes_in) ? (int)a.modes_in[b] : a.mode;
                 if (mode > 34) mode = 34;  // launcher validates the scalar; clamp per-block garbage
             } else {
-                const int key = search_modes<N, G>(gl, O, top, left, corner, dc, a.cost_kind);
+                int key;
+                if (fast8) {  // warp-uniform: the shuffles inside both searches span the warp
+                    build_neg_arrays<N, G>(gl, top, left, neg);
+                    __syncwarp();
+                    key = search_modes_u8<N, G>(gl, O, top, left, neg, dc, a.cost_kind);
+                } else {
+                    key = search_modes<N, G>(gl, O, top, left, corner, dc, a.cost_kind);
+                }
                 mode = mode_of_key(key);
                 if (valid && gl == 0) {
                     if (a.out.modes) a.out.modes[b] = (uint8_t)mode;

@@ -423,6 +423,21 @@ def test_encode_frame_vs_oracle_medium(Bt, n, cost, rn):
         eq(host(getattr(r, name)), w[name], f"{name} n={n} {cost} rn={rn}")
 
 
+@pytest.mark.parametrize("n,cost", [(4, "satd"), (8, "sad"), (16, "satd"), (32, "sad")])
+@pytest.mark.parametrize("rn", (0, 1))
+def test_encode_frame_10bit_uses_generic_search(Bt, n, cost, rn):
+    """10-bit content disables the packed 8-bit search: the generic int16 path must match too
+    (and a frame mixing 8-bit and wider samples exercises the per-tile switch)."""
+    rng = np.random.default_rng(900 + n + rn)
+    H, W = 3 * n + 2, 6 * n + 5
+    src = np.clip(_smooth(H, W, n) * 4 + rng.integers(-30, 31, (H, W)), 0, 1023).astype(np.int16)
+    src[:, : W // 2] = src[:, : W // 2] // 4  # left half stays 8-bit
+    r = Bt.encode_frame(dev(src), n, cost=cost, qp=30, recon_neighbours=bool(rn), bit_depth=10)
+    w = O.encode_frame(src, n, cost=cost, qp=30, recon_neighbours=bool(rn), bit_depth=10)
+    for name in ("modes", "costs", "pred", "coeff", "levels", "recon_plane"):
+        eq(host(getattr(r, name)), w[name], f"{name} n={n} {cost} rn={rn}")
+
+
 # ------------------------------------------------------------------ metrics
 def test_metrics_golden(P, Bt):
     g = golden("metrics.npz")
