@@ -335,14 +335,62 @@ struct CoderOut {
     int pitch;
 };
 
+// Row r of the winning mode for the 8-bit fast path: references come from the contiguous per-mode
+// arrays of build_neg_arrays() (k < 0) or the plain reference arrays (k >= 0); no int16 wrap can
+// occur for 8-bit samples, so the interpolation is the plain formula of intra.py:206-207.
+template <int N, int G>
+__device__ __forceinline__ void predict_row_u8(int mode, int r, const int16_t* top, const int16_t* left,
+                                               const int16_t* neg, int dc, int (&p)[N]) {
+    using Cfg = CoderCfg<N, G>;
+    if (mode == 1) {
+#pragma unroll
+        for (int x = 0; x < N; ++x) p[x] = dc;
+        return;
+    }
+    if (mode == 0) {
+        int tv[N];
+#pragma unroll
+        for (int x = 0; x < N; ++x) tv[x] = top[1 + x];
+        planar_row<N>(r, (int)left[1 + r], tv, (int)top[N + 1], (int)left[N + 1], p);
+        return;
+    }
+    const int angle = intra_angle(mode);
+    const bool vertical = mode >= 18;
+    const int16_t* pos = vertical ? top : left;
+    const int16_t* ng = neg + (mode - 11) * Cfg::NEG_W + N;  // only dereferenced when k < 0
+    auto ref = [&](int k) -> int { return (int)(k < 0 ? ng : pos)[k]; };
+    if (vertical) {
+        const int pr = (r + 1) * angle;
+        const int ip = pr >> 5, f = pr & 31;
+        int v[N + 1];
+#pragma unroll
+        for (int x = 0; x <= N; ++x) v[x] = (x < N || f != 0) ? ref(x + 1 + ip) : 0;
+#pragma unroll
+        for (int x = 0; x < N; ++x) p[x] = ((32 - f) * v[x] + f * v[x + 1] + 16) >> 5;
+    } else {
+#pragma unroll
+        for (int x = 0; x < N; ++x) {
+            const int pr = (x + 1) * angle;
+            const int ip = pr >> 5, f = pr & 31;
+            const int k = r + 1 + ip;
+            const int a = ref(k);
+            const int b2 = f != 0 ? ref(k + 1) : 0;
+            p[x] = ((32 - f) * a + f * b2 + 16) >> 5;
+        }
+    }
+}
+
 // Winner pipeline for one block: row owner r (< N) predicts row r, then the K6 chain through
 // the shared working matrix.  All lanes of the warp must call this (it contains __syncwarp).
 // The reconstruction is left in O (pitch O_PITCH) for the caller to copy out.
+// fast8 (warp-uniform): every sample of the block is 8-bit and `neg` is built -> packed-domain
+// prediction and exact 32-bit quant (FastQuant); otherwise the generic int16 / int64 arithmetic.
 template <int N, int G>
 __device__ __forceinline__ void code_block(int gl, bool valid, int64_t b, int mode, int16_t* O,
                                            int* M, const int16_t* top, const int16_t* left,
-                                           int corner, int dc, const QuantParams& qp, int maxv,
-                                           bool use_dst, const CoderOut& out) {
+                                           int corner, int dc, const QuantParams& qp,
+                                           const FastQuant& fq, bool fast8, const int16_t* neg,
+                                           int maxv, bool use_dst, const CoderOut& out) {
     using Cfg = CoderCfg<N, G>;
     constexpr int NN = N * N;
     const int r = gl;
@@ -350,8 +398,12 @@ __device__ __forceinline__ void code_block(int gl, bool valid, int64_t b, int mo
     uint32_t pw[N / 2];
     if (rowlane) {
         int p[N], res[N];
+        if (fast8) {
+            predict_row_u8<N, G>(mode, r, top, left, neg, dc, p);
+        } else {
 #pragma unroll
-        for (int x = 0; x < N; ++x) p[x] = predict_px<N>(mode, x, r, top, left, corner, dc);
+            for (int x = 0; x < N; ++x) p[x] = predict_px<N>(mode, x, r, top, left, corner, dc);
+        }
         pack_row<N>(p, pw);
         if (valid && out.pred) store_row16<N>(out.pred + b * NN + r * N, pw);
 #pragma unroll
@@ -369,7 +421,15 @@ __device__ __forceinline__ void code_block(int gl, bool valid, int64_t b, int mo
         if (N == 4 && use_dst) row_pass<N, N == 4, false>(M, r, c);
         else row_pass<N, false, false>(M, r, c);
         if (valid && out.coeff) store_row32<N>(out.coeff + b * NN + r * N, c);
-        quant_dequant_row<N>(c, qp, lv, dq);
+        if (fast8) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                lv[k] = quantize_fast(c[k], fq);
+                dq[k] = dequantize_fast(lv[k], fq);
+            }
+        } else {
+            quant_dequant_row<N>(c, qp, lv, dq);
+        }
         if (valid && out.levels) store_row32<N>(out.levels + b * NN + r * N, lv);
         store_row_smem<N>(M, r, dq);
     }
@@ -389,8 +449,7 @@ __device__ __forceinline__ void code_block(int gl, bool valid, int64_t b, int mo
             const int a = recon_px(lo16(pw[k]), res[2 * k], maxv);
             const int c2 = recon_px(hi16(pw[k]), res[2 * k + 1], maxv);
             ow[k] = pack16(a, c2);
-            O[r * Cfg::O_PITCH + 2 * k] = (int16_t)a;
-            O[r * Cfg::O_PITCH + 2 * k + 1] = (int16_t)c2;
+            *reinterpret_cast<uint32_t*>(O + r * Cfg::O_PITCH + 2 * k) = ow[k];
         }
         if (valid && out.recon) store_row16<N>(out.recon + b * NN + r * N, ow);
     }

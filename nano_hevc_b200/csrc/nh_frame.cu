@@ -98,6 +98,7 @@ struct CoderArgs {
     // common
     int64_t n_blocks;
     QuantParams qp;
+    FastQuant fq;
     int maxv;
     int use_dst;
     CoderOut out;
@@ -131,31 +132,48 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
             by = __shfl_sync(0xffffffffu, by, 0);
             if (by >= bh) break;
             for (int bx = 0; bx < bw; ++bx) {
+                const int x = bx * N, y = by * N;
+                const int64_t b = (int64_t)by * bw + bx;
+                // original pixels do not depend on any neighbour: fetch them before the wait
+                constexpr int OPL = (N * N + G - 1) / G;  // orig samples per lane
+                int ov[OPL];
+#pragma unroll
+                for (int i = 0; i < OPL; ++i) {
+                    const int e = gl + i * G;
+                    ov[i] = e < N * N ? (int)__ldg(a.src + (int64_t)(y + e / N) * a.pitch + x + e % N) : 0;
+                }
+                int ood = 0;  // any sample outside [0, 255] disables the packed 8-bit search
+                // left references = right-most column of the block this warp has just reconstructed
+                // (still in O); bottom-left is not reconstructed yet -> replicate (n_left = N)
+                for (int k = gl + 1; k < Cfg::REF_W; k += G) {
+                    const int kk = k <= N ? k : N;
+                    const int lv = bx == 0 ? 128 : (int)O[(kk - 1) * Cfg::O_PITCH + (N - 1)];
+                    left[k] = (int16_t)lv;
+                    ood |= lv;
+                }
+                __syncwarp();  // O is about to be overwritten with the next block's pixels
                 if (by > 0) {  // above-right block (or the whole row above) must be reconstructed
                     const int need = bx + 2 < bw ? bx + 2 : bw;
                     if (lane == 0) {
                         const volatile int* p = a.progress + (by - 1);
-                        while (*p < need) __nanosleep(64);
+                        while (*p < need) __nanosleep(20);
                         __threadfence();
                     }
                     __syncwarp();
                 }
-                const int x = bx * N, y = by * N;
-                const int64_t b = (int64_t)by * bw + bx;
                 const int16_t* rp = a.out.recon_plane;
-                int ood = 0;  // any sample outside [0, 255] disables the packed 8-bit search
                 for (int k = gl; k < Cfg::REF_W; k += G) {
                     const int kk = k <= 2 * N ? k : 2 * N;
                     const int tv = top_ref<true>(rp, a.H, a.W, a.pitch, x, y, 2 * N, kk);
-                    const int lv = left_ref<true>(rp, a.H, a.W, a.pitch, x, y, N, kk);
                     top[k] = (int16_t)tv;
-                    left[k] = (int16_t)lv;
-                    ood |= tv | lv;
+                    ood |= tv;
+                    if (k == 0) left[0] = (int16_t)tv;
                 }
-                for (int e = gl; e < N * N; e += G) {
-                    const int v = __ldg(a.src + (int64_t)(y + e / N) * a.pitch + x + e % N);
-                    O[(e / N) * Cfg::O_PITCH + (e % N)] = (int16_t)v;
-                    ood |= v;
+#pragma unroll
+                for (int i = 0; i < OPL; ++i) {
+                    const int e = gl + i * G;
+                    if (e < N * N) O[(e / N) * Cfg::O_PITCH + (e % N)] = (int16_t)ov[i];
+                    ood |= ov[i];
                 }
                 const bool fast8 = !__any_sync(0xffffffffu, (ood & ~0xff) != 0);
                 __syncwarp();
@@ -174,8 +192,8 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                     if (a.out.modes) a.out.modes[b] = (uint8_t)mode;
                     if (a.out.costs) a.out.costs[b] = key >> 6;
                 }
-                code_block<N, G>(gl, true, b, mode, O, M, top, left, corner, dc, a.qp, a.maxv,
-                                 a.use_dst != 0, a.out);
+                code_block<N, G>(gl, true, b, mode, O, M, top, left, corner, dc, a.qp, a.fq, fast8, neg,
+                                 a.maxv, a.use_dst != 0, a.out);
                 for (int e = gl; e < N * N; e += G)
                     a.out.recon_plane[(int64_t)(y + e / N) * a.pitch + x + e % N] = O[(e / N) * Cfg::O_PITCH + (e % N)];
                 __threadfence();
@@ -250,8 +268,8 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                     if (a.out.costs) a.out.costs[b] = key >> 6;
                 }
             }
-            code_block<N, G>(gl, valid, b, mode, O, M, top, left, corner, dc, a.qp, a.maxv,
-                             a.use_dst != 0, a.out);
+            code_block<N, G>(gl, valid, b, mode, O, M, top, left, corner, dc, a.qp, a.fq,
+                             SRC != SRC_ARRAYS && fast8, neg, a.maxv, a.use_dst != 0, a.out);
             if constexpr (SRC == SRC_PLANE) {
                 if (valid && a.out.recon_plane)
                     for (int e = gl; e < N * N; e += G)
@@ -371,6 +389,7 @@ NH_API int nh_fused_pipeline_modes(const int16_t* orig, const int16_t* top, cons
     a.orig = orig; a.top = top; a.left = left; a.top_left = top_left; a.modes_in = modes; a.mode = mode;
     a.n_blocks = n_blocks;
     a.qp = make_quant_params(qp, l2, is_intra);
+    a.fq = make_fast_quant(a.qp);
     a.maxv = (1 << bit_depth) - 1;
     a.use_dst = use_dst;
     a.out = CoderOut{nullptr, nullptr, pred, coeff, levels, recon, nullptr, 0};
@@ -412,6 +431,7 @@ NH_API int nh_encode_frame(const int16_t* src, int height, int width, int pitch,
     a.src = src; a.H = height; a.W = width; a.pitch = pitch; a.cost_kind = cost_kind;
     a.n_blocks = (int64_t)bw * bh;
     a.qp = make_quant_params(qp, l2, 1);
+    a.fq = make_fast_quant(a.qp);
     a.maxv = (1 << bit_depth) - 1;
     a.use_dst = size == 4;  // docs/frames_and_panes.md:328-329
     a.out = CoderOut{modes, costs, pred, coeff, levels, nullptr, recon_plane, pitch};
