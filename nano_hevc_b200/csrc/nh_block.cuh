@@ -63,6 +63,33 @@ __device__ __forceinline__ void store_row_smem(int* M, int i, const int (&v)[N])
             make_int4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
+// Both separable passes of a 2-D transform with ONE inlined copy of the butterfly: every pass
+// reads a column (lane = column index), transforms it and -- after the first pass -- writes the
+// result back as a ROW, i.e. transposed, so that the second pass is again "read column lane".
+//   forward: pass 0  temp[i][j] = sum_k T[i][k] X[k][j]      (lane j; stored as Mt[j][i])
+//            pass 1  coeff[i][j] = sum_k temp[i][k] T[j][k]  (lane i reads Mt[k][i] = temp[i][k])
+//   inverse: same with T^T (transform.py:222-236).
+// Sharing the code between the passes halves the instruction footprint of the 16- and 32-point
+// kernels (70 KB -> 38 KB at N = 32; profiles/r1_notes.md).  On return `out` is row `lane` of the result.
+template <int N, bool DST, bool INV, bool DP = false>
+__device__ __forceinline__ void two_pass_transform(int* M, int lane, bool active, int (&out)[N]) {
+    constexpr int P = RowsTile<N>::PITCH;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        if (active) {
+            int x[N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) x[k] = M[k * P + lane];
+            pass1d<N, DST, INV, DP>(x, out);
+        }
+        if (pass == 0) {
+            __syncwarp();  // every lane has read its column
+            if (active) store_row_smem<N>(M, lane, out);
+            __syncwarp();
+        }
+    }
+}
+
 // ---- packed rows: N int16 as N/2 32-bit words --------------------------------
 template <int N>
 __device__ __forceinline__ void load_row16(const int16_t* p, uint32_t (&w)[N / 2]) {

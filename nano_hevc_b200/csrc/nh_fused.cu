@@ -289,7 +289,36 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit_kernel_v2(const F
         }
     };
 
-    if (tile < n_tiles) prefetch(tile, s16[0]);
+    // References of one lane's unit, software-pipelined one tile ahead like the pixels.
+    struct Refs {
+        uint32_t tw[BPU][N / 2], lw[BPU][N / 2];
+        int tr[BPU], bl[BPU], mode[BPU];
+    };
+    auto load_refs = [&](int64_t t, Refs& r) {
+        const int64_t ub = (t * 32 + lane) * BPU;
+        const int64_t urem = a.n_blocks - ub;
+#pragma unroll
+        for (int q = 0; q < BPU; ++q) {
+            r.mode[q] = a.mode;
+            if (q < urem) {
+                load_row16<N>(a.top + (ub + q) * N, r.tw[q]);
+                load_row16<N>(a.left + (ub + q) * N, r.lw[q]);
+                r.tr[q] = a.top_right[ub + q];
+                r.bl[q] = a.bottom_left[ub + q];
+                if (a.modes) r.mode[q] = a.modes[ub + q];
+            } else {
+#pragma unroll
+                for (int k = 0; k < N / 2; ++k) r.tw[q][k] = r.lw[q][k] = 0;
+                r.tr[q] = r.bl[q] = 0;
+            }
+        }
+    };
+
+    Refs nxt;
+    if (tile < n_tiles) {
+        prefetch(tile, s16[0]);
+        load_refs(tile, nxt);
+    }
     cp_async_commit();
     int cur = 0;
     for (; tile < n_tiles; tile += warp_stride, cur ^= 1) {
@@ -301,24 +330,16 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit_kernel_v2(const F
         const int64_t urem = a.n_blocks - ub;
         const int ublocks = urem >= BPU ? BPU : (urem > 0 ? (int)urem : 0);  // valid blocks in the unit
 
-        // -- references of this lane's blocks: loads in flight while the pixel tile lands
+        // this tile's references were fetched one iteration ago
         uint32_t tw[BPU][N / 2], lw[BPU][N / 2];
         int tr[BPU], bl[BPU], mode[BPU];
 #pragma unroll
         for (int q = 0; q < BPU; ++q) {
-            mode[q] = a.mode;
-            if (q < ublocks) {
-                load_row16<N>(a.top + (ub + q) * N, tw[q]);
-                load_row16<N>(a.left + (ub + q) * N, lw[q]);
-                tr[q] = a.top_right[ub + q];
-                bl[q] = a.bottom_left[ub + q];
-                if (a.modes) mode[q] = a.modes[ub + q];
-            } else {
 #pragma unroll
-                for (int k = 0; k < N / 2; ++k) tw[q][k] = lw[q][k] = 0;
-                tr[q] = bl[q] = 0;
-            }
+            for (int k = 0; k < N / 2; ++k) { tw[q][k] = nxt.tw[q][k]; lw[q][k] = nxt.lw[q][k]; }
+            tr[q] = nxt.tr[q]; bl[q] = nxt.bl[q]; mode[q] = nxt.mode[q];
         }
+        if (tile + warp_stride < n_tiles) load_refs(tile + warp_stride, nxt);
         // the other pixel tile is free (its reconstruction left at the end of the previous
         // iteration): start fetching the next tile into it, then wait for the current one
         if (tile + warp_stride < n_tiles) prefetch(tile + warp_stride, s16[cur ^ 1]);
@@ -444,8 +465,36 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit_kernel_v2(const F
 // ------------------------------------------------------------ rows kernels
 constexpr int kRowsWarps = 4;  // 128 threads per CTA
 
+// Cold path of the rows kernels: the tile from the residual rows in M onwards with the plain int32
+// butterflies and the int64 quant of the reference -- exact for any int16 input.
 template <int N>
-__global__ void __launch_bounds__(kRowsWarps * 32) fused_rows_kernel(const FusedArgs a) {
+__device__ __noinline__ void rows_tile_exact(const FusedArgs& a, int* M, int r, bool valid, int64_t b,
+                                             const uint32_t (&pw)[N / 2]) {
+    constexpr int NN = N * N;
+    {
+        int c[N], lv[N], dq[N];
+        two_pass_transform<N, false, false, false>(M, r, true, c);
+        if (valid && a.coeff) store_row32<N>(a.coeff + b * NN + r * N, c);
+        quant_dequant_row<N>(c, a.qp, lv, dq);
+        if (valid && a.levels) store_row32<N>(a.levels + b * NN + r * N, lv);
+        __syncwarp();
+        store_row_smem<N>(M, r, dq);
+    }
+    __syncwarp();
+    int res[N];
+    two_pass_transform<N, false, true, false>(M, r, true, res);
+    if (valid && a.recon) {
+        uint32_t ow[N / 2];
+#pragma unroll
+        for (int k = 0; k < N / 2; ++k)
+            ow[k] = pack16(recon_px(lo16(pw[k]), res[2 * k], a.maxv),
+                           recon_px(hi16(pw[k]), res[2 * k + 1], a.maxv));
+        store_row16<N>(a.recon + b * NN + r * N, ow);
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(kRowsWarps * 32, 4) fused_rows_kernel(const FusedArgs a, const FastQuant fq) {
     constexpr int NN = N * N;
     constexpr int BPW = 32 / N;  // blocks per warp
     __shared__ __align__(16) int smem[kRowsWarps][BPW * RowsTile<N>::WORDS];
@@ -454,37 +503,54 @@ __global__ void __launch_bounds__(kRowsWarps * 32) fused_rows_kernel(const Fused
     int* M = smem[warp] + g * RowsTile<N>::WORDS;
 
     const int64_t n_tiles = (a.n_blocks + BPW - 1) / BPW;
-    const int64_t warp_global = (int64_t)blockIdx.x * kRowsWarps + warp;
     const int64_t warp_stride = (int64_t)gridDim.x * kRowsWarps;
+    int64_t tile = (int64_t)blockIdx.x * kRowsWarps + warp;
 
-    for (int64_t tile = warp_global; tile < n_tiles; tile += warp_stride) {
+    // this lane's row of original pixels, software-pipelined one tile ahead
+    uint32_t nxt_ow[N / 2];
+    auto load_orig = [&](int64_t t) {
+        const int64_t b = t * BPW + g;
+        if (b < a.n_blocks) {
+            load_row16<N>(a.orig + b * NN + r * N, nxt_ow);
+        } else {
+#pragma unroll
+            for (int k = 0; k < N / 2; ++k) nxt_ow[k] = 0;
+        }
+    };
+    if (tile < n_tiles) load_orig(tile);
+
+    for (; tile < n_tiles; tile += warp_stride) {
         const int64_t b = tile * BPW + g;
         const bool valid = b < a.n_blocks;
         uint32_t pw[N / 2];  // prediction row, kept packed for the reconstruction
+        uint32_t ood = 0;    // out-of-domain bits: any sample outside [0, 4095]
         {
             int o[N], p[N];
+            unpack_row<N>(nxt_ow, o);
+#pragma unroll
+            for (int k = 0; k < N / 2; ++k) ood |= nxt_ow[k] & 0xF000F000u;
+            if (tile + warp_stride < n_tiles) load_orig(tile + warp_stride);
             if (valid) {
-                uint32_t ow[N / 2];
-                load_row16<N>(a.orig + b * NN + r * N, ow);
-                unpack_row<N>(ow, o);
-                int mode = a.modes ? (int)a.modes[b] : a.mode;
-                uint32_t tw[N / 2];
+                const int mode = a.modes ? (int)a.modes[b] : a.mode;
+                uint32_t tw[N / 2], lw[N / 2];
                 load_row16<N>(a.top + b * N, tw);
+                load_row16<N>(a.left + b * N, lw);
+                const int tr = a.top_right[b], bl = a.bottom_left[b];
+#pragma unroll
+                for (int k = 0; k < N / 2; ++k) ood |= (tw[k] | lw[k]) & 0xF000F000u;
+                ood |= (uint32_t)(tr | bl) & 0xFFFFF000u;
                 if (mode == 1) {
-                    uint32_t lw[N / 2];
-                    load_row16<N>(a.left + b * N, lw);
-                    int dc = dc_value<N>(sum_row<N>(tw) + sum_row<N>(lw));
+                    const int dc = dc_value<N>(sum_row<N>(tw) + sum_row<N>(lw));
 #pragma unroll
                     for (int x = 0; x < N; ++x) p[x] = dc;
                 } else {
                     int top[N];
                     unpack_row<N>(tw, top);
-                    planar_row<N>(r, (int)a.left[b * N + r], top, (int)a.top_right[b],
-                                  (int)a.bottom_left[b], p);
+                    planar_row<N>(r, (int)a.left[b * N + r], top, tr, bl, p);
                 }
             } else {
 #pragma unroll
-                for (int x = 0; x < N; ++x) o[x] = p[x] = 0;
+                for (int x = 0; x < N; ++x) p[x] = 0;
             }
             pack_row<N>(p, pw);
             if (valid && a.pred) store_row16<N>(a.pred + b * NN + r * N, pw);
@@ -493,23 +559,27 @@ __global__ void __launch_bounds__(kRowsWarps * 32) fused_rows_kernel(const Fused
             for (int x = 0; x < N; ++x) res[x] = sext16(o[x] - sext16(p[x]));
             store_row_smem<N>(M, r, res);
         }
+        // Pixel domain [0, 4095] for every sample this warp touched => 32-bit quant and the IDP.2A
+        // butterflies are exact (bounds in DESIGN.md section 3); anything else takes the cold path.
+        const bool fast = !__any_sync(0xffffffffu, ood != 0);
         __syncwarp();
-        col_pass<N, false, false>(M, r);
-        __syncwarp();
-        {
-            int c[N], lv[N], dq[N];
-            row_pass<N, false, false>(M, r, c);
-            if (valid && a.coeff) store_row32<N>(a.coeff + b * NN + r * N, c);
-            quant_dequant_row<N>(c, a.qp, lv, dq);
-            if (valid && a.levels) store_row32<N>(a.levels + b * NN + r * N, lv);
-            store_row_smem<N>(M, r, dq);  // lane r read row r and is the only writer of row r
-        }
-        __syncwarp();
-        col_pass<N, false, true>(M, r);
-        __syncwarp();
-        {
+        if (fast) {
+            {
+                int c[N], lv[N], dq[N];
+                two_pass_transform<N, false, false, true>(M, r, true, c);
+                if (valid && a.coeff) store_row32<N>(a.coeff + b * NN + r * N, c);
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    lv[k] = quantize_fast(c[k], fq);
+                    dq[k] = dequantize_fast(lv[k], fq);
+                }
+                if (valid && a.levels) store_row32<N>(a.levels + b * NN + r * N, lv);
+                __syncwarp();  // every lane has read its column of the second forward pass
+                store_row_smem<N>(M, r, dq);
+            }
+            __syncwarp();
             int res[N];
-            row_pass<N, false, true>(M, r, res);
+            two_pass_transform<N, false, true, true>(M, r, true, res);
             if (valid && a.recon) {
                 uint32_t ow[N / 2];
 #pragma unroll
@@ -518,6 +588,8 @@ __global__ void __launch_bounds__(kRowsWarps * 32) fused_rows_kernel(const Fused
                                    recon_px(hi16(pw[k]), res[2 * k + 1], a.maxv));
                 store_row16<N>(a.recon + b * NN + r * N, ow);
             }
+        } else {
+            rows_tile_exact<N>(a, M, r, valid, b, pw);
         }
         __syncwarp();
     }
@@ -579,7 +651,7 @@ template <int N>
 static int launch_rows(const FusedArgs& a, cudaStream_t st) {
     constexpr int BPW = 32 / N;
     int grid = grid_for(a.n_blocks, (int64_t)kRowsWarps * BPW, 4);
-    fused_rows_kernel<N><<<grid, kRowsWarps * 32, 0, st>>>(a);
+    fused_rows_kernel<N><<<grid, kRowsWarps * 32, 0, st>>>(a, make_fast_quant(a.qp));
     NH_CHECK_LAUNCH("fused_rows_kernel");
     return NH_OK;
 }

@@ -133,9 +133,76 @@ NH_HD void inv_core(const int* c, int* out) {
     }
 }
 
+// ---- 2-way int16 x int8 dot products (IDP.2A) for the widest odd part ----------------------
+// B200 issues IDP.2A at the IMAD rate (tools/ubench_int.cu), so packing two 16-bit operands per
+// register halves the multiply instructions of the (N/2)^2-term odd part, which is 3/4 of all
+// multiplies of a butterfly.  Exact as long as every packed operand fits int16; the kernels that
+// use it prove that from the pixel domain of their inputs and fall back to
+// the plain int32 cores otherwise.  The host build emulates the instruction INCLUDING the int16
+// truncation of its lanes, so an out-of-range operand shows up as a mismatch in the CPU tests.
+NH_HD int pack_s16(int lo, int hi) {
+#if defined(__CUDA_ARCH__)
+    return (int)__byte_perm((unsigned)lo, (unsigned)hi, 0x5410);
+#else
+    return (int)(((unsigned)lo & 0xffffu) | ((unsigned)hi << 16));
+#endif
+}
+NH_HD int dp2a_s16s8(int a, int b, int c) {
+#if defined(__CUDA_ARCH__)
+    return __dp2a_lo(a, b, c);
+#else
+    return (int)(short)(a & 0xffff) * (int)(signed char)(b & 0xff) +
+           (int)(short)((unsigned)a >> 16) * (int)(signed char)((b >> 8) & 0xff) + c;
+#endif
+}
+NH_HD constexpr int coef_pair(int c0, int c1) { return (c0 & 0xff) | ((c1 & 0xff) << 8); }
+
+template <int N, int S>
+NH_HD void fwd_core_dp(const int* x, int* y) {
+    int e[N / 2], o[N / 2], pk[N / 4];
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k) {
+        e[k] = x[k] + x[N - 1 - k];
+        o[k] = x[k] - x[N - 1 - k];
+    }
+    fwd_core<N / 2, 2 * S>(e, y);
+#pragma unroll
+    for (int t = 0; t < N / 4; ++t) pk[t] = pack_s16(o[2 * t], o[2 * t + 1]);
+#pragma unroll
+    for (int m = 0; m < N / 2; ++m) {
+        int acc = 0;
+#pragma unroll
+        for (int t = 0; t < N / 4; ++t)
+            acc = dp2a_s16s8(pk[t], coef_pair(dct<N>(2 * m + 1, 2 * t), dct<N>(2 * m + 1, 2 * t + 1)), acc);
+        y[(2 * m + 1) * S] = acc;
+    }
+}
+
+template <int N, int S>
+NH_HD void inv_core_dp(const int* c, int* out) {
+    int e[N / 2], o[N / 2], pk[N / 4];
+    inv_core<N / 2, 2 * S>(c, e);
+#pragma unroll
+    for (int t = 0; t < N / 4; ++t) pk[t] = pack_s16(c[(4 * t + 1) * S], c[(4 * t + 3) * S]);
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k) {
+        int acc = 0;
+#pragma unroll
+        for (int t = 0; t < N / 4; ++t)
+            acc = dp2a_s16s8(pk[t], coef_pair(dct<N>(4 * t + 1, k), dct<N>(4 * t + 3, k)), acc);
+        o[k] = acc;
+    }
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k) {
+        out[k] = e[k] + o[k];
+        out[N - 1 - k] = e[k] - o[k];
+    }
+}
+
 // One rounded 1-D pass.  FWD: out[i] = (sum_k T[i][k] in[k] + rnd) >> shift
 //                        INV: out[i] = (sum_k T[k][i] in[k] + rnd) >> shift
-template <int N, bool DST, bool INV>
+// DP = true selects the IDP.2A form of the widest odd part (operands must fit int16).
+template <int N, bool DST, bool INV, bool DP = false>
 NH_HD void pass1d(const int (&in)[N], int (&out)[N]) {
     constexpr int shift = Log2<N>::v + 5;
     constexpr int rnd = 1 << (shift - 1);
@@ -148,6 +215,9 @@ NH_HD void pass1d(const int (&in)[N], int (&out)[N]) {
             for (int k = 0; k < 4; ++k) a += (INV ? dst4(k, i) : dst4(i, k)) * in[k];
             acc[i] = a;
         }
+    } else if constexpr (DP && N >= 8) {
+        if constexpr (INV) inv_core_dp<N, 1>(in, acc);
+        else fwd_core_dp<N, 1>(in, acc);
     } else if constexpr (INV) {
         inv_core<N, 1>(in, acc);
     } else {

@@ -16,7 +16,35 @@ static void run2d(const int32_t* in, int32_t* out) {
         for (int j = 0; j < N; ++j) out[i * N + j] = b[i][j];
 }
 
+// Same data flow as two_pass_transform (nh_block.cuh) with the IDP.2A butterflies.
+template <int N, bool INV>
+static void run2d_dp(const int32_t* in, int32_t* out) {
+    static int m[N][N], t[N][N];
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) m[i][j] = in[i * N + j];
+    for (int j = 0; j < N; ++j) {  // pass 0: column j -> row j of the transposed intermediate
+        int x[N], y[N];
+        for (int k = 0; k < N; ++k) x[k] = m[k][j];
+        pass1d<N, false, INV, true>(x, y);
+        for (int i = 0; i < N; ++i) t[j][i] = y[i];
+    }
+    for (int i = 0; i < N; ++i) {  // pass 1: column i of the transposed intermediate -> row i
+        int x[N], y[N];
+        for (int k = 0; k < N; ++k) x[k] = t[k][i];
+        pass1d<N, false, INV, true>(x, y);
+        for (int j = 0; j < N; ++j) out[i * N + j] = y[j];
+    }
+}
+
 extern "C" {
+int shim_transform2d_dp(int n, int inv, const int32_t* in, int32_t* out) {
+    switch (n) {
+        case 8: inv ? run2d_dp<8, true>(in, out) : run2d_dp<8, false>(in, out); return 0;
+        case 16: inv ? run2d_dp<16, true>(in, out) : run2d_dp<16, false>(in, out); return 0;
+        case 32: inv ? run2d_dp<32, true>(in, out) : run2d_dp<32, false>(in, out); return 0;
+    }
+    return -1;
+}
 int shim_transform2d(int n, int dst, int inv, const int32_t* in, int32_t* out) {
     switch (n) {
         case 4:

@@ -252,15 +252,15 @@ def test_fused_dcplanar_vs_oracle(Bt, n, B):
         eq(host(getattr(got, name)), w, f"10-bit {name}")
 
 
-@pytest.mark.parametrize("n", (4, 8))
+@pytest.mark.parametrize("n", SIZES)
 @pytest.mark.parametrize("gen", (1, 2))
 def test_fused_unit_generations_and_out_of_domain(Bt, n, gen):
     """Both kernel generations; blocks whose samples leave the pixel domain [0, 4095] (where the
     32-bit fast path of generation 2 is not exact) must still match the int64 reference arithmetic."""
     from nano_hevc_b200 import _lib
     rng = np.random.default_rng(77 + n)
-    B = 999
-    orig, top, left, tr, bl = _dcplanar_inputs(rng, B, n)
+    B = 999 if n <= 8 else 211
+    orig, top, left, tr, bl = _dcplanar_inputs(rng, B, n, 4096 if gen == 2 else 256)
     wild = rng.random(B) < 0.2
     orig[wild] = rng.integers(-32768, 32768, (int(wild.sum()), n, n))
     w2 = rng.random(B) < 0.1

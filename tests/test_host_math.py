@@ -111,3 +111,37 @@ def test_fast_quant_is_exact_in_the_pixel_domain(shim, n):
         lv = O.quantize(c, qp, n, True)
         shim.shim_dequant_fast(_p(lv), _p(out), C.c_int64(lv.size), qp)
         assert np.array_equal(out, O.dequantize(lv, qp)), qp
+
+
+def _xf_dp(shim, x, n, inv):
+    x = np.ascontiguousarray(x, np.int32)
+    out = np.empty_like(x)
+    assert shim.shim_transform2d_dp(n, int(inv), _p(x), _p(out)) == 0
+    return out
+
+
+@pytest.mark.parametrize("n", (16, 32))
+def test_dp2a_butterflies_exact_in_the_pixel_domain(shim, n):
+    """The IDP.2A butterflies (int16-lane operands, emulated WITH lane truncation on the host) must
+    equal the reference through the whole fused chain for residuals in [-4095, 4095]: worst-case
+    sign patterns of every basis function pair, random blocks, and every QP."""
+    rng = np.random.default_rng(n)
+    T = O.get_matrix(n)
+    cases = [rng.integers(-4095, 4096, (n, n)) for _ in range(6)]
+    for i in (0, 1, 2, 3, n // 2, n - 3, n - 2, n - 1):
+        for j in (0, 1, n // 2 - 1, n - 2, n - 1):
+            cases.append(4095 * np.sign(np.outer(T[i], T[j]) + 0.5).astype(np.int64))   # max |coeff[i][j]|
+            cases.append(-4095 * np.sign(np.outer(T[i], T[j]) + 0.5).astype(np.int64))
+    cases.append(4095 * ((np.indices((n, n)).sum(0) % 2) * 2 - 1))
+    for res in cases:
+        res = res.astype(np.int32)
+        want = O.forward_transform(res)
+        assert np.array_equal(_xf_dp(shim, res, n, False), want)
+        assert np.abs(want).max() <= 32394
+        for qp in (0, 5, 17, 23, 24, 30, 37, 45, 51):
+            dq = O.dequantize(O.quantize(want, qp, n), qp)
+            assert np.array_equal(_xf_dp(shim, dq, n, True), O.inverse_transform(dq)), qp
+    # the emulation really truncates: an operand beyond int16 must break the equality
+    big = np.zeros((n, n), np.int32)
+    big[0, 0], big[n - 1, 0] = 30000, -30000
+    assert not np.array_equal(_xf_dp(shim, big, n, False), O.forward_transform(big))
