@@ -188,6 +188,12 @@ int nh_block_costs(const int16_t* a, const int16_t* b, int64_t n_blocks, int siz
 /* Level statistics: out[0] = number of non-zero levels (quant.py:171-173 count_nonzero). */
 int nh_count_nonzero(const int32_t* levels, int64_t n_elems, int64_t* out, void* stream);
 
+/* nano_hevc/quant.py:153-168 estimate_bits: *nnz_out = number of non-zero levels, *sum_log2_out =
+ * sum over the levels of log2(|level| + 1) in float64 (device scalars, zeroed by this call).  The
+ * estimate is int(sum_log2 + 2 * nnz), finished on the host. */
+int nh_level_stats(const int32_t* levels, int64_t n_elems, int64_t* nnz_out, double* sum_log2_out,
+                   void* stream);
+
 /* ------------------------------------- host-buffer entry point (e2e) */
 /* Same computation as nh_fused_pipeline_dcplanar but every pointer is a HOST
  * pointer (pinned memory recommended).  The library copies the inputs to the

@@ -171,6 +171,12 @@ def count_nonzero(levels: np.ndarray) -> int:
     return int(batched.count_nonzero_batched(_dev(levels, np.int32)).item())
 
 
+def estimate_bits(level: np.ndarray) -> int:
+    """quant.py:153-168."""
+    from . import batched
+    return batched.estimate_bits_batched(_dev(level, np.int32))
+
+
 def is_all_zero(levels: np.ndarray) -> bool:
     """quant.py:176-178."""
     return count_nonzero(levels) == 0
@@ -321,6 +327,6 @@ __all__ = [
     "forward_transform_8x8", "inverse_transform_8x8", "forward_transform_16x16",
     "inverse_transform_16x16", "forward_transform_32x32", "inverse_transform_32x32",
     "DCT4", "DCT8", "DCT16", "DCT32", "DST4", "quantize", "dequantize", "quantize_block",
-    "dequantize_block", "get_qp_params", "count_nonzero", "is_all_zero", "QUANT_SCALE",
+    "dequantize_block", "get_qp_params", "count_nonzero", "is_all_zero", "estimate_bits", "QUANT_SCALE",
     "DEQUANT_SCALE", "psnr", "mse", "sad", "satd_4x4", "residual_energy",
 ]

@@ -402,6 +402,17 @@ def count_nonzero_batched(levels):
     return out[0]
 
 
+def estimate_bits_batched(levels) -> int:
+    """quant.py:153-168 over a whole tensor: int(sum(log2(|l| + 1) + 2 * (l != 0)))."""
+    dev = _require_cuda(levels)
+    lv = _c(levels, torch.int32)
+    nnz = torch.empty((1,), dtype=torch.int64, device=dev)
+    s = torch.empty((1,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().nh_level_stats(_ptr(lv), lv.numel(), _ptr(nnz), _ptr(s), _stream()))
+    return int(float(s.item()) + 2.0 * int(nnz.item()))
+
+
 def psnr_from_sse(sse: int, count: int, peak: int = 255) -> float:
     """metrics.py:13-21 finished on the host in float64 from the exact integer SSE."""
     import numpy as np

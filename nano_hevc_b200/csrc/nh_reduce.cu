@@ -85,6 +85,32 @@ __global__ void __launch_bounds__(256)
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(reinterpret_cast<unsigned long long*>(out), (unsigned long long)c);
 }
 
+// quant.py:153-168 estimate_bits: sum(log2(|l| + 1)) in float64 plus the non-zero count (the host adds
+// 2 bits per non-zero level and truncates, like int(np.sum(...))).
+__global__ void __launch_bounds__(256)
+    level_stats_kernel(const int32_t* __restrict__ lv, int64_t n, int64_t* nnz_out, double* sum_out) {
+    long long c = 0;
+    double s = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int v = lv[i];
+        if (v != 0) {
+            ++c;
+            const unsigned a = (unsigned)(v < 0 ? -(long long)v : (long long)v);
+            s += log2((double)a + 1.0);
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        c += __shfl_xor_sync(0xffffffffu, c, off);
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+    }
+    if ((threadIdx.x & 31) == 0 && c) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(nnz_out), (unsigned long long)c);
+        atomicAdd(sum_out, s);
+    }
+}
+
 // Per-block costs: one lane per 4x4 sub-block, N*N/16 lanes per block.
 template <int N>
 __global__ void __launch_bounds__(256)
@@ -218,5 +244,21 @@ NH_API int nh_count_nonzero(const int32_t* levels, int64_t n, int64_t* out, void
     if (n == 0) return NH_OK;
     count_nonzero_kernel<<<grid_for(n / 4 + 1, 256, 4), 256, 0, st>>>(levels, n, out);
     NH_CHECK_LAUNCH("count_nonzero_kernel");
+    return NH_OK;
+}
+
+NH_API int nh_level_stats(const int32_t* levels, int64_t n, int64_t* nnz_out, double* sum_log2_out,
+                          void* stream) {
+    if (!levels || !nnz_out || !sum_log2_out || n < 0) {
+        set_error("nh_level_stats: null pointer or negative count");
+        return NH_E_ARG;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(nnz_out, 0, sizeof(int64_t), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(sum_log2_out, 0, sizeof(double), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(level stats)");
+    if (n == 0) return NH_OK;
+    level_stats_kernel<<<grid_for(n, 256 * 8, 4), 256, 0, st>>>(levels, n, nnz_out, sum_log2_out);
+    NH_CHECK_LAUNCH("level_stats_kernel");
     return NH_OK;
 }

@@ -140,6 +140,17 @@ def dequantize_block(level, qp):
     return dequantize(level, qp)
 
 
+def estimate_bits(level):
+    """quant.py:153-168 (numpy restatement: float64 sum, truncated)."""
+    a = np.abs(np.asarray(level))
+    return int(np.sum(np.log2(a + 1) + (a > 0) * 2))
+
+
+def count_nonzero(level):
+    """quant.py:171-173."""
+    return int(np.count_nonzero(level))
+
+
 def intra_dc_predict(top, left, size):
     out = np.empty((size, size), np.int16)
     lib().nho_intra_dc_predict(_p(_i16(top)), _p(_i16(left)), size, _p(out))

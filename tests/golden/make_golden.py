@@ -291,6 +291,24 @@ def g_frames():
     save("frames.npz", **out)
 
 
+def g_stats():
+    """Level statistics (quant.py:153-178): estimate_bits / count_nonzero / is_all_zero."""
+    from nano_hevc.quant import estimate_bits, count_nonzero, is_all_zero
+    rng = np.random.default_rng(31)
+    out = {}
+    cases = [rng.integers(-300, 301, (8, 8)), rng.integers(-3, 4, (32, 32)), np.zeros((4, 4), np.int64),
+             rng.integers(-13600, 13601, (16, 16)), (2 ** rng.integers(0, 12, (8, 8))) - 1,
+             rng.integers(-1, 2, (1000, 64))]
+    for i, c in enumerate(cases):
+        c = c.astype(np.int32)
+        out[f"lv_{i}"] = c
+        out[f"bits_{i}"] = np.array(estimate_bits(c), np.int64)
+        out[f"nnz_{i}"] = np.array(count_nonzero(c), np.int64)
+        out[f"zero_{i}"] = np.array(bool(is_all_zero(c)))
+    out["n_cases"] = np.array(len(cases), np.int64)
+    save("stats.npz", **out)
+
+
 def g_cli():
     """Whole-program goldens: encode_frame_intra (__main__.py:142-189) on create_test_frame."""
     out = {}
@@ -314,4 +332,5 @@ if __name__ == "__main__":
     g_metrics()
     g_readme()
     g_cli()
+    g_stats()
     g_frames()

@@ -438,6 +438,34 @@ def test_encode_frame_10bit_uses_generic_search(Bt, n, cost, rn):
         eq(host(getattr(r, name)), w[name], f"{name} n={n} {cost} rn={rn}")
 
 
+# ------------------------------------------- level statistics
+def test_level_statistics_golden(P, Bt):
+    g = golden("stats.npz")
+    for i in range(int(g["n_cases"])):
+        lv = g[f"lv_{i}"]
+        assert P.estimate_bits(lv) == int(g[f"bits_{i}"]), i
+        assert P.count_nonzero(lv) == int(g[f"nnz_{i}"]), i
+        assert P.is_all_zero(lv) == bool(g[f"zero_{i}"]), i
+        assert Bt.estimate_bits_batched(dev(lv)) == int(g[f"bits_{i}"])
+
+
+# ------------------------------------------- CLI-faithful frame encode
+@pytest.mark.parametrize("tag,bs", [("64x64_8", 8), ("96x128_16", 16)])
+def test_cli_encode_frame_intra_golden(tag, bs):
+    """Whole-program golden of the reference CLI (encode_frame_intra on create_test_frame):
+    reconstructed luma plane, DC / planar / block counts over Y+U+V, Y-PSNR."""
+    from nano_hevc_b200 import frame_encode
+    g = golden("cli.npz")
+    y = g[f"y_{tag}"]
+    H, W = y.shape
+    u = np.full((H // 2, W // 2), 128, np.int16)  # create_test_frame chroma (__main__.py:46-47)
+    (ry, ru, rv), stats = frame_encode.encode_frame_intra(dev(y), dev(u), dev(u.copy()), bs)
+    eq(host(ry), g[f"recon_y_{tag}"], "recon_y")
+    assert [stats["dc"], stats["planar"], stats["blocks"]] == [int(v) for v in g[f"stats_{tag}"]]
+    assert frame_encode.y_psnr(dev(y), ry) == pytest.approx(float(g[f"psnr_y_{tag}"]), rel=1e-9)
+    assert int(host(ru).min()) == 128 and int(host(rv).max()) == 128
+
+
 # ------------------------------------------------------------------ metrics
 def test_metrics_golden(P, Bt):
     g = golden("metrics.npz")

@@ -210,3 +210,12 @@ def test_batched_matches_per_block():
             cb, lb, rb = O.block_pipeline(orig[b], pb, 22)
             assert np.array_equal(p[b], pb) and np.array_equal(c[b], cb)
             assert np.array_equal(l[b], lb) and np.array_equal(r[b], rb)
+
+
+def test_level_statistics():
+    g = golden("stats.npz")
+    for i in range(int(g["n_cases"])):
+        lv = g[f"lv_{i}"]
+        assert O.estimate_bits(lv) == int(g[f"bits_{i}"])
+        assert O.count_nonzero(lv) == int(g[f"nnz_{i}"])
+        assert (O.count_nonzero(lv) == 0) == bool(g[f"zero_{i}"])
