@@ -89,6 +89,48 @@ __device__ __forceinline__ void fence_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ---- TMA tensor-map copies + mbarrier (warp-uniform: issued by ONE elected lane) ------------------
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(mbar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// 2-D tile global -> shared (SASS: UTMALDG); completion is signalled on `mbar` as transaction bytes.
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap, int c0, int c1, uint32_t mbar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"(mbar)
+        : "memory");
+}
+// 2-D tile shared -> global (SASS: UTMASTG), tracked by the issuing thread's bulk groups.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, int c0, int c1, uint32_t smem_src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap),
+                 "r"(c0), "r"(c1), "r"(smem_src)
+                 : "memory");
+}
+template <int PENDING>
+__device__ __forceinline__ void bulk_wait_all() {  // full completion (global writes performed)
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(PENDING) : "memory");
+}
+
 // Warp tile staging.  A warp tile is 32 "units" of UNIT_BYTES contiguous
 // bytes in global memory (one unit per lane).  In shared memory unit u lives
 // at u * (UNIT_BYTES + 16): the 16-byte pad makes the per-lane 128-bit

@@ -14,6 +14,8 @@
 //   * N = 16, 32 ("rows" kernels): N lanes own one block; lane = row for global
 //     I/O and the second pass, lane = column for the first pass, with the
 //     transposition going through an N x (N+4) int32 shared-memory matrix.
+#include <cuda.h>
+
 #include <cstdlib>
 
 #include "nh_block.cuh"
@@ -462,6 +464,263 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit_kernel_v2(const F
     cp_async_wait<0>();
 }
 
+// ------------------------------------------------------- unit kernels, v3 (TMA)
+// Generation 2 with the staging sweeps replaced by tensor-map TMA copies issued by ONE elected lane:
+//   * the next pixel tile arrives through cp.async.bulk.tensor (UTMALDG) into a 128B-swizzled shared
+//     tile and is awaited on an mbarrier;
+//   * pred / coeff / levels / recon leave through cp.async.bulk.tensor stores (UTMASTG) straight from
+//     the swizzled tiles the lanes wrote, tracked by the elected lane's bulk groups.
+// Tensors are viewed as [units][64 elements]; a box is 32 units x 128 bytes (int32 tensors: two boxes
+// per tile, elements 0-31 and 32-63 of every unit).  With SWIZZLE_128B the 16-byte chunk k of row t
+// sits at t*128 + ((k ^ (t & 7)) << 4): a lane's 128-bit accesses to its own row are conflict-free
+// and the tile in shared memory is contiguous, so one instruction moves it.
+struct TmaMaps {
+    CUtensorMap orig, pred, coeff, levels, recon;
+};
+
+template <int N, bool DST>
+__global__ void __launch_bounds__(kV2Warps * 32, 3)
+    fused_unit_kernel_v3(const FusedArgs a, const FastQuant fq, const __grid_constant__ TmaMaps maps,
+                         const int64_t n_units) {
+    constexpr int NN = N * N;
+    constexpr int BPU = 64 / NN;
+    constexpr int kTile = 4096;                         // 32 rows x 128 bytes
+    constexpr int kWarpBytes = 4 * kTile;               // 2 pixel tiles + 2 int32 half tiles
+    extern __shared__ unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // 1024-byte alignment is required by the 128B swizzle pattern
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t wbase = base + warp * kWarpBytes;
+    const uint32_t s16[2] = {wbase, wbase + kTile};
+    const uint32_t s32h[2] = {wbase + 2 * kTile, wbase + 3 * kTile};
+    const uint32_t mbar[2] = {base + kV2Warps * kWarpBytes + warp * 16, base + kV2Warps * kWarpBytes + warp * 16 + 8};
+    // this lane's row in a tile, and its swizzled chunk addresses
+    const uint32_t row = lane * 128;
+    const uint32_t sw = lane & 7;
+    auto chunk = [&](uint32_t tile, int k) -> uint32_t { return tile + row + (((uint32_t)k ^ sw) << 4); };
+    auto lds128 = [](uint32_t addr) -> uint4 {
+        uint4 v;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+        return v;
+    };
+    auto sts128 = [](uint32_t addr, uint4 v) {
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    };
+
+    if (lane == 0) {
+        mbar_init(mbar[0], 1);
+        mbar_init(mbar[1], 1);
+        fence_mbar_init();
+    }
+    fence_async_smem();
+    __syncwarp();
+
+    const int64_t n_tiles = (n_units + 31) / 32;
+    const int64_t warp_stride = (int64_t)gridDim.x * kV2Warps;
+    int64_t tile = (int64_t)blockIdx.x * kV2Warps + warp;
+
+    struct Refs {
+        uint32_t tw[BPU][N / 2], lw[BPU][N / 2];
+        int tr[BPU], bl[BPU], mode[BPU];
+    };
+    auto load_refs = [&](int64_t t, Refs& r) {
+        const int64_t unit = t * 32 + lane;
+        const int64_t ub = unit * BPU;
+#pragma unroll
+        for (int q = 0; q < BPU; ++q) {
+            r.mode[q] = a.mode;
+            if (unit < n_units) {
+                load_row16<N>(a.top + (ub + q) * N, r.tw[q]);
+                load_row16<N>(a.left + (ub + q) * N, r.lw[q]);
+                r.tr[q] = a.top_right[ub + q];
+                r.bl[q] = a.bottom_left[ub + q];
+                if (a.modes) r.mode[q] = a.modes[ub + q];
+            } else {
+#pragma unroll
+                for (int k = 0; k < N / 2; ++k) r.tw[q][k] = r.lw[q][k] = 0;
+                r.tr[q] = r.bl[q] = 0;
+            }
+        }
+    };
+    auto issue_load = [&](int64_t t, int buf) {  // elected lane only
+        mbar_arrive_expect_tx(mbar[buf], kTile);
+        tma_load_2d(s16[buf], &maps.orig, 0, (int)(t * 32), mbar[buf]);
+    };
+
+    Refs nxt;
+    if (tile < n_tiles) {
+        if (lane == 0) issue_load(tile, 0);
+        load_refs(tile, nxt);
+    }
+    int cur = 0;
+    uint32_t it = 0;  // iteration counter: buffer `cur` is on its (it >> 1)-th use
+    for (; tile < n_tiles; tile += warp_stride, cur ^= 1, ++it) {
+        const int unit0 = (int)(tile * 32);
+        const int64_t unit = tile * 32 + lane;
+        const int64_t ub = unit * BPU;
+        const bool uvalid = unit < n_units;
+
+        uint32_t tw[BPU][N / 2], lw[BPU][N / 2];
+        int tr[BPU], bl[BPU], mode[BPU];
+#pragma unroll
+        for (int q = 0; q < BPU; ++q) {
+#pragma unroll
+            for (int k = 0; k < N / 2; ++k) { tw[q][k] = nxt.tw[q][k]; lw[q][k] = nxt.lw[q][k]; }
+            tr[q] = nxt.tr[q]; bl[q] = nxt.bl[q]; mode[q] = nxt.mode[q];
+        }
+        if (tile + warp_stride < n_tiles) load_refs(tile + warp_stride, nxt);
+
+        // bulk groups of the previous iteration: everything but its reconstruction has been read
+        if (lane == 0) bulk_wait_read<1>();
+        mbar_wait(mbar[cur], (it >> 1) & 1);   // this tile's pixels have landed
+        __syncwarp();
+
+        int res[BPU][N][N];
+        uint32_t ood = 0;
+#pragma unroll
+        for (int q = 0; q < BPU; ++q) {
+            int top[N], left[N];
+            unpack_row<N>(tw[q], top);
+            unpack_row<N>(lw[q], left);
+#pragma unroll
+            for (int k = 0; k < N / 2; ++k) ood |= (tw[q][k] | lw[q][k]) & 0xF000F000u;
+            ood |= (uint32_t)(tr[q] | bl[q]) & 0xFFFFF000u;
+            int* rq = &res[q][0][0];
+            int dc = 0;
+            if (mode[q] == 1) {
+                int s = 0;
+#pragma unroll
+                for (int k = 0; k < N; ++k) s += top[k] + left[k];
+                dc = dc_value<N>(s);
+            }
+#pragma unroll
+            for (int c = 0; c < NN / 8; ++c) {
+                const uint32_t addr = chunk(s16[cur], q * (NN / 8) + c);
+                const uint4 v = lds128(addr);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                int p[8];
+                if (mode[q] == 1) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) p[k] = dc;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int e = 8 * c + k, y = e / N, x = e % N;
+                        p[k] = planar_px<N>(x, y, left[y], top[x], tr[q], bl[q]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    ood |= w[k] & 0xF000F000u;
+                    rq[8 * c + 2 * k] = lo16(w[k]) - p[2 * k];
+                    rq[8 * c + 2 * k + 1] = hi16(w[k]) - p[2 * k + 1];
+                }
+                sts128(addr, make_uint4(pack16(p[0], p[1]), pack16(p[2], p[3]), pack16(p[4], p[5]), pack16(p[6], p[7])));
+            }
+        }
+        const bool fast = ood == 0 || !uvalid;
+        // G1: prediction
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            if (a.pred) tma_store_2d(&maps.pred, 0, unit0, s16[cur]);
+            bulk_commit();
+        }
+
+        // -- forward transform (in-thread, both passes)
+#pragma unroll
+        for (int q = 0; q < BPU; ++q) transform2d<N, DST, false>(res[q]);
+        int* flat = &res[0][0][0];
+        // G2, G3: coefficient halves
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (a.coeff) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    sts128(chunk(s32h[h], e), make_uint4(flat[32 * h + 4 * e], flat[32 * h + 4 * e + 1],
+                                                         flat[32 * h + 4 * e + 2], flat[32 * h + 4 * e + 3]));
+                fence_async_smem();
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (a.coeff) tma_store_2d(&maps.coeff, 32 * h, unit0, s32h[h]);
+                bulk_commit();
+            }
+        }
+        // the previous reconstruction (3 groups back) has been read: its tile takes the prefetch
+        if (lane == 0) {
+            bulk_wait_read<3>();
+            if (tile + warp_stride < n_tiles) {
+                fence_async_smem();
+                issue_load(tile + warp_stride, cur ^ 1);
+            }
+        }
+        // -- quantise (levels out) and dequantise in place; G4, G5: level halves
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (lane == 0) bulk_wait_read<1>();  // the coefficient half that used this buffer has been read
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                int* r = flat + 32 * h + 4 * e;
+                int l[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    l[k] = quantize_fast(r[k], fq);
+                    r[k] = dequantize_fast(l[k], fq);
+                }
+                if (a.levels) sts128(chunk(s32h[h], e), make_uint4(l[0], l[1], l[2], l[3]));
+            }
+            if (a.levels) fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                if (a.levels) tma_store_2d(&maps.levels, 32 * h, unit0, s32h[h]);
+                bulk_commit();
+            }
+        }
+        // -- inverse transform, reconstruct against the prediction still in the pixel tile
+#pragma unroll
+        for (int q = 0; q < BPU; ++q) transform2d<N, DST, true>(res[q]);
+        // G1 (prediction) was forced complete by the waits above, the tile may be rewritten
+        if (a.recon) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t addr = chunk(s16[cur], c);
+                const uint4 pv = lds128(addr);
+                const int* r = flat + 8 * c;
+                uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w}, ow[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    ow[k] = pack16(recon_px(lo16(pw[k]), r[2 * k], a.maxv),
+                                   recon_px(hi16(pw[k]), r[2 * k + 1], a.maxv));
+                sts128(addr, make_uint4(ow[0], ow[1], ow[2], ow[3]));
+            }
+            fence_async_smem();
+        }
+        __syncwarp();
+        // G6: reconstruction
+        if (lane == 0) {
+            if (a.recon) tma_store_2d(&maps.recon, 0, unit0, s16[cur]);
+            bulk_commit();
+        }
+        // -- a lane whose inputs left the pixel domain recodes its unit exactly (cold path), after
+        //    the tile's TMA stores have been performed
+        if (__any_sync(0xffffffffu, !fast)) {
+            if (lane == 0) {
+                bulk_wait_all<0>();
+                fence_async_smem();
+            }
+            __syncwarp();
+            if (!fast) {
+                for (int q = 0; q < BPU; ++q) slow_block<N>(a, ub + q, DST);
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0) bulk_wait_read<0>();
+    __syncwarp();
+}
+
 // ------------------------------------------------------------ rows kernels
 constexpr int kRowsWarps = 4;  // 128 threads per CTA
 
@@ -634,20 +893,106 @@ static int launch_unit_v2(const FusedArgs& a, cudaStream_t st) {
     return NH_OK;
 }
 
-// Kernel generation used for N = 4, 8: 2 (default) or 1 (first generation, kept for A/B
-// profiling).  Set by nh_set_fused_impl() or the NH_FUSED_IMPL=v1 environment variable.
+// ---- tensor maps for generation 3 --------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// [n_units][64 elements] view of a block-major tensor; box = 32 units x 128 bytes, 128B swizzle.
+static int make_unit_map(CUtensorMap* m, const void* ptr, int64_t n_units, bool is32) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return NH_E_CUDA; }
+    const cuuint64_t gdim[2] = {64, (cuuint64_t)n_units};
+    const cuuint64_t gstride[1] = {(cuuint64_t)(is32 ? 256 : 128)};
+    const cuuint32_t box[2] = {(cuuint32_t)(is32 ? 32 : 64), 32};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, is32 ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2,
+                    const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return NH_E_CUDA; }
+    return NH_OK;
+}
+
+template <int N, bool DST>
+static int launch_unit_v3(const FusedArgs& a, cudaStream_t st) {
+    constexpr int BPU = 64 / (N * N);
+    constexpr int NN = N * N;
+    constexpr int kSmem = kV2Warps * 4 * 4096 + kV2Warps * 16 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(fused_unit_kernel_v3<N, DST>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fused_unit_kernel_v3)");
+        configured = true;
+    }
+    const int64_t n_units = a.n_blocks / BPU;  // whole units go through TMA
+    if (n_units > 0) {
+        TmaMaps maps;
+        int rc = make_unit_map(&maps.orig, a.orig, n_units, false);
+        // outputs that were not requested reuse the input map: the kernel never issues their stores
+        if (rc == NH_OK) rc = make_unit_map(&maps.pred, a.pred ? (const void*)a.pred : (const void*)a.orig, n_units, false);
+        if (rc == NH_OK) rc = make_unit_map(&maps.recon, a.recon ? (const void*)a.recon : (const void*)a.orig, n_units, false);
+        if (rc == NH_OK) rc = a.coeff ? make_unit_map(&maps.coeff, a.coeff, n_units, true) : make_unit_map(&maps.coeff, a.orig, n_units, false);
+        if (rc == NH_OK) rc = a.levels ? make_unit_map(&maps.levels, a.levels, n_units, true) : make_unit_map(&maps.levels, a.orig, n_units, false);
+        if (rc != NH_OK) return rc;
+        FusedArgs b = a;
+        b.n_blocks = n_units * BPU;
+        int grid = grid_for(n_units, (int64_t)kV2Warps * 32, 3);
+        fused_unit_kernel_v3<N, DST><<<grid, kV2Warps * 32, kSmem, st>>>(b, make_fast_quant(a.qp), maps, n_units);
+        NH_CHECK_LAUNCH("fused_unit_kernel_v3");
+    }
+    const int64_t done = n_units * BPU, tail = a.n_blocks - done;
+    if (tail > 0) {  // fewer than BPU trailing 4x4 blocks: not a whole 128-byte TMA row
+        FusedArgs t = a;
+        t.orig += done * NN; t.top += done * N; t.left += done * N;
+        t.top_right += done; t.bottom_left += done;
+        if (t.modes) t.modes += done;
+        if (t.pred) t.pred += done * NN;
+        if (t.coeff) t.coeff += done * NN;
+        if (t.levels) t.levels += done * NN;
+        if (t.recon) t.recon += done * NN;
+        t.n_blocks = tail;
+        return launch_unit_v2<N, DST>(t, st);
+    }
+    return NH_OK;
+}
+
+// Kernel generation used for N = 4, 8: 2 (default), 1 (first generation) or 3 (TMA tensor-map
+// staging); set by nh_set_fused_impl() or the NH_FUSED_IMPL=v1|v2|v3 environment variable.
 static int g_fused_impl = 0;
-static bool use_v1() {
+static int fused_impl() {
     if (g_fused_impl == 0) {
         const char* e = getenv("NH_FUSED_IMPL");
-        g_fused_impl = (e && e[0] == 'v' && e[1] == '1') ? 1 : 2;
+        g_fused_impl = (e && e[0] == 'v' && e[1] >= '1' && e[1] <= '3') ? e[1] - '0' : 2;
     }
-    return g_fused_impl == 1;
+    return g_fused_impl;
 }
 
 template <int N, bool DST>
 static int launch_unit(const FusedArgs& a, cudaStream_t st) {
-    return use_v1() ? launch_unit_v1<N, DST>(a, st) : launch_unit_v2<N, DST>(a, st);
+    switch (fused_impl()) {
+        case 1: return launch_unit_v1<N, DST>(a, st);
+        case 3: return launch_unit_v3<N, DST>(a, st);
+        default: return launch_unit_v2<N, DST>(a, st);
+    }
 }
 
 template <int N>
@@ -664,8 +1009,8 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 }  // namespace nh
 
 NH_API int nh_set_fused_impl(int generation) {
-    if (generation != 1 && generation != 2) {
-        nh::set_error("nh_set_fused_impl: generation must be 1 or 2, got %d", generation);
+    if (generation < 1 || generation > 3) {
+        nh::set_error("nh_set_fused_impl: generation must be 1, 2 or 3, got %d", generation);
         return NH_E_ARG;
     }
     nh::g_fused_impl = generation;

@@ -253,14 +253,14 @@ def test_fused_dcplanar_vs_oracle(Bt, n, B):
 
 
 @pytest.mark.parametrize("n", SIZES)
-@pytest.mark.parametrize("gen", (1, 2))
+@pytest.mark.parametrize("gen", (1, 2, 3))
 def test_fused_unit_generations_and_out_of_domain(Bt, n, gen):
     """Both kernel generations; blocks whose samples leave the pixel domain [0, 4095] (where the
     32-bit fast path of generation 2 is not exact) must still match the int64 reference arithmetic."""
     from nano_hevc_b200 import _lib
     rng = np.random.default_rng(77 + n)
     B = 999 if n <= 8 else 211
-    orig, top, left, tr, bl = _dcplanar_inputs(rng, B, n, 4096 if gen == 2 else 256)
+    orig, top, left, tr, bl = _dcplanar_inputs(rng, B, n, 4096 if gen >= 2 else 256)
     wild = rng.random(B) < 0.2
     orig[wild] = rng.integers(-32768, 32768, (int(wild.sum()), n, n))
     w2 = rng.random(B) < 0.1
