@@ -282,6 +282,53 @@ def fused_block_pipeline_modes(orig, top, left, top_left, mode, qp: int, is_intr
     return res
 
 
+def host_block_pipeline(orig, top, left, top_right, bottom_left, mode, qp: int, is_intra: bool = True,
+                        use_dst: bool = False, bit_depth: int = 8,
+                        outputs=("pred", "coeff", "levels", "recon"), chunk_blocks: int | None = None,
+                        device: torch.device | None = None, scratch: torch.Tensor | None = None,
+                        out: PipelineResult | None = None):
+    """K6 on HOST buffers (numpy arrays or CPU tensors, pinned memory recommended) through
+    ``nh_host_pipeline_dcplanar``: the library overlaps H2D, the kernel and D2H on internal streams
+    and returns CPU tensors.  This is the call behind the ``e2e`` number of bench.py."""
+    import numpy as np
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    as_cpu = lambda a, dt: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(dt).contiguous()
+    o = as_cpu(orig, torch.int16)
+    B, N = _blocks(o, "orig")
+    t, l = as_cpu(top, torch.int16), as_cpu(left, torch.int16)
+    tr, bl = as_cpu(top_right, torch.int16).reshape(-1), as_cpu(bottom_left, torch.int16).reshape(-1)
+    if t.shape != (B, N) or l.shape != (B, N) or tr.numel() != B or bl.numel() != B:
+        raise ValueError("refs must be top/left (B, N) and top_right/bottom_left (B,)")
+    for x in (o, t, l, tr, bl):
+        if x.is_cuda:
+            raise ValueError("host_block_pipeline takes host buffers; use fused_block_pipeline for CUDA tensors")
+    if isinstance(mode, (torch.Tensor, np.ndarray)):
+        m = as_cpu(mode, torch.uint8).reshape(-1)
+        if m.numel() != B:
+            raise ValueError(f"modes must have {B} entries")
+        ms = 0
+    else:
+        m, ms = None, int(mode)
+        if ms not in (0, 1):
+            raise ValueError("mode must be 0 (planar) or 1 (DC)")
+    if out is None:
+        want = set(outputs)
+        mk = lambda name, dt: torch.empty((B, N, N), dtype=dt).pin_memory() if name in want else None
+        out = PipelineResult(mk("pred", torch.int16), mk("coeff", torch.int32), mk("levels", torch.int32),
+                             mk("recon", torch.int16))
+    chunk = int(chunk_blocks) if chunk_blocks else max(1024, (1 << 22) // (N * N))
+    L = _lib.lib()
+    nbytes = int(L.nh_host_pipeline_scratch_bytes(N, chunk))
+    if scratch is None or scratch.numel() < nbytes:
+        scratch = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.nh_host_pipeline_dcplanar(
+            _ptr(o), _ptr(t), _ptr(l), _ptr(tr), _ptr(bl), _ptr(m), ms, B, N, int(qp), int(bool(is_intra)),
+            int(bool(use_dst)), int(bit_depth), _ptr(out.pred), _ptr(out.coeff), _ptr(out.levels),
+            _ptr(out.recon), _ptr(scratch), scratch.numel(), chunk))
+    return out
+
+
 # ------------------------------------------------------------------ frame level
 def _plane(plane):
     if plane.dim() != 2:

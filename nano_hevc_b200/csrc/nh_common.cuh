@@ -35,6 +35,14 @@ inline int grid_for(int64_t items, int64_t items_per_cta, int ctas_per_sm) {
     return (int)(need < cap ? need : cap);
 }
 
+// nh_fused.cu: K6 with int16 coefficient / level outputs, used by the host-buffer pipeline.
+int fused_pipeline_dcplanar_narrow(const int16_t* orig, const int16_t* top, const int16_t* left,
+                                   const int16_t* top_right, const int16_t* bottom_left,
+                                   const uint8_t* modes, int mode, int64_t n_blocks, int size, int qp,
+                                   int is_intra, int use_dst, int bit_depth, int16_t* pred,
+                                   int16_t* coeff16, int16_t* levels16, int16_t* recon, int* ood_flag,
+                                   cudaStream_t st);
+
 #define NH_CHECK_LAUNCH(what)                                  \
     do {                                                       \
         cudaError_t e__ = cudaGetLastError();                  \

@@ -37,6 +37,12 @@ struct FusedArgs {
     int32_t* coeff;
     int32_t* levels;
     int16_t* recon;
+    // "narrow" outputs of the host-buffer pipeline: coefficients / levels as int16 (they fit in the
+    // pixel domain: |coeff| <= 32394, |level| <= 13600), halving what has to cross PCIe.  A lane
+    // that leaves the pixel domain raises *ood_flag and the host redoes the chunk through int32.
+    int16_t* coeff16;
+    int16_t* levels16;
+    int* ood_flag;
 };
 
 // ------------------------------------------------------------ unit kernels
@@ -261,7 +267,7 @@ __device__ __noinline__ void slow_block(const FusedArgs& a, int64_t b, bool dst)
     }
 }
 
-template <int N, bool DST>
+template <int N, bool DST, bool NARROW>
 __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit_kernel_v2(const FusedArgs a, const FastQuant fq) {
     constexpr int NN = N * N;
     constexpr int BPU = 64 / NN;
@@ -411,7 +417,16 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit_kernel_v2(const F
         for (int q = 0; q < BPU; ++q) transform2d<N, DST, false>(res[q]);
         int* flat = &res[0][0][0];
         uint4* u32 = T32::unit(s32, lane);
-        if (a.coeff) {
+        uint4* n16 = T16::unit(s32, lane);  // the same tile viewed as 64 int16 per lane (narrow outputs)
+        if (NARROW) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                n16[e] = make_uint4(pack16(flat[8 * e], flat[8 * e + 1]), pack16(flat[8 * e + 2], flat[8 * e + 3]),
+                                    pack16(flat[8 * e + 4], flat[8 * e + 5]), pack16(flat[8 * e + 6], flat[8 * e + 7]));
+            __syncwarp();
+            T16::store(s32, reinterpret_cast<unsigned char*>(a.coeff16 + blk0 * NN), lane, chunks16);
+            __syncwarp();
+        } else if (a.coeff) {
 #pragma unroll
             for (int e = 0; e < 16; ++e)
                 u32[e] = make_uint4(flat[4 * e], flat[4 * e + 1], flat[4 * e + 2], flat[4 * e + 3]);
@@ -421,17 +436,25 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit_kernel_v2(const F
         }
         // -- quantise (levels out) and dequantise in place, 32-bit pixel-domain arithmetic
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            int* r = flat + 4 * e;
-            int l[4];
+        for (int e = 0; e < 8; ++e) {
+            int* r = flat + 8 * e;
+            int l[8];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 8; ++k) {
                 l[k] = quantize_fast(r[k], fq);
                 r[k] = dequantize_fast(l[k], fq);
             }
-            if (a.levels) u32[e] = make_uint4(l[0], l[1], l[2], l[3]);
+            if (NARROW) {
+                n16[e] = make_uint4(pack16(l[0], l[1]), pack16(l[2], l[3]), pack16(l[4], l[5]), pack16(l[6], l[7]));
+            } else if (a.levels) {
+                u32[2 * e] = make_uint4(l[0], l[1], l[2], l[3]);
+                u32[2 * e + 1] = make_uint4(l[4], l[5], l[6], l[7]);
+            }
         }
-        if (a.levels) {
+        if (NARROW) {
+            __syncwarp();
+            T16::store(s32, reinterpret_cast<unsigned char*>(a.levels16 + blk0 * NN), lane, chunks16);
+        } else if (a.levels) {
             __syncwarp();
             T32::store(s32, reinterpret_cast<unsigned char*>(a.levels + blk0 * NN), lane, chunks32);
         }
@@ -457,6 +480,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit_kernel_v2(const F
         // -- a lane whose inputs left the pixel domain recodes its unit exactly (cold path); the
         //    __syncwarp above orders the cooperative stores of its unit before these stores
         if (!fast) {
+            if (NARROW && ublocks > 0) *a.ood_flag = 1;
             for (int q = 0; q < ublocks; ++q) slow_block<N>(a, ub + q, DST);
         }
         __syncwarp();
@@ -829,13 +853,25 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 4) fused_rows_kernel(const Fu
             {
                 int c[N], lv[N], dq[N];
                 two_pass_transform<N, false, false, kDP>(M, r, true, c);
-                if (valid && a.coeff) store_row32<N>(a.coeff + b * NN + r * N, c);
+                if (valid && a.coeff16) {
+                    uint32_t cw[N / 2];
+                    pack_row<N>(c, cw);
+                    store_row16<N>(a.coeff16 + b * NN + r * N, cw);
+                } else if (valid && a.coeff) {
+                    store_row32<N>(a.coeff + b * NN + r * N, c);
+                }
 #pragma unroll
                 for (int k = 0; k < N; ++k) {
                     lv[k] = quantize_fast(c[k], fq);
                     dq[k] = dequantize_fast(lv[k], fq);
                 }
-                if (valid && a.levels) store_row32<N>(a.levels + b * NN + r * N, lv);
+                if (valid && a.levels16) {
+                    uint32_t lw2[N / 2];
+                    pack_row<N>(lv, lw2);
+                    store_row16<N>(a.levels16 + b * NN + r * N, lw2);
+                } else if (valid && a.levels) {
+                    store_row32<N>(a.levels + b * NN + r * N, lv);
+                }
                 __syncwarp();  // every lane has read its column of the second forward pass
                 store_row_smem<N>(M, r, dq);
             }
@@ -851,6 +887,7 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 4) fused_rows_kernel(const Fu
                 store_row16<N>(a.recon + b * NN + r * N, ow);
             }
         } else {
+            if (a.ood_flag && lane == 0) *a.ood_flag = 1;
             rows_tile_exact<N>(a, M, r, valid, b, pw);
         }
         __syncwarp();
@@ -875,20 +912,20 @@ static int launch_unit_v1(const FusedArgs& a, cudaStream_t st) {
     return NH_OK;
 }
 
-template <int N, bool DST>
+template <int N, bool DST, bool NARROW = false>
 static int launch_unit_v2(const FusedArgs& a, cudaStream_t st) {
     constexpr int BPU = 64 / (N * N);
     constexpr int kSmem = kV2Warps * (2 * WarpTile<128>::kBytes + WarpTile<256>::kBytes);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(fused_unit_kernel_v2<N, DST>,
+        cudaError_t e = cudaFuncSetAttribute(fused_unit_kernel_v2<N, DST, NARROW>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fused_unit_kernel_v2)");
         configured = true;
     }
     int64_t units = (a.n_blocks + BPU - 1) / BPU;
     int grid = grid_for(units, (int64_t)kV2Warps * 32, 3);
-    fused_unit_kernel_v2<N, DST><<<grid, kV2Warps * 32, kSmem, st>>>(a, make_fast_quant(a.qp));
+    fused_unit_kernel_v2<N, DST, NARROW><<<grid, kV2Warps * 32, kSmem, st>>>(a, make_fast_quant(a.qp));
     NH_CHECK_LAUNCH("fused_unit_kernel_v2");
     return NH_OK;
 }
@@ -988,6 +1025,7 @@ static int fused_impl() {
 
 template <int N, bool DST>
 static int launch_unit(const FusedArgs& a, cudaStream_t st) {
+    if (a.coeff16) return launch_unit_v2<N, DST, true>(a, st);  // narrow outputs: generation 2 only
     switch (fused_impl()) {
         case 1: return launch_unit_v1<N, DST>(a, st);
         case 3: return launch_unit_v3<N, DST>(a, st);
@@ -1005,6 +1043,15 @@ static int launch_rows(const FusedArgs& a, cudaStream_t st) {
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int dispatch_fused(const FusedArgs& a, int size, int use_dst, cudaStream_t st) {
+    switch (size) {
+        case 4: return use_dst ? launch_unit<4, true>(a, st) : launch_unit<4, false>(a, st);
+        case 8: return launch_unit<8, false>(a, st);
+        case 16: return launch_rows<16>(a, st);
+        default: return launch_rows<32>(a, st);
+    }
+}
 
 }  // namespace nh
 
@@ -1047,12 +1094,24 @@ NH_API int nh_fused_pipeline_dcplanar(const int16_t* orig, const int16_t* top, c
     if (n_blocks == 0) return NH_OK;
     FusedArgs a{orig, top, left, top_right, bottom_left, modes, mode, n_blocks,
                 make_quant_params(qp, l2, is_intra), (1 << bit_depth) - 1,
-                pred, coeff, levels, recon};
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    switch (size) {
-        case 4: return use_dst ? launch_unit<4, true>(a, st) : launch_unit<4, false>(a, st);
-        case 8: return launch_unit<8, false>(a, st);
-        case 16: return launch_rows<16>(a, st);
-        default: return launch_rows<32>(a, st);
-    }
+                pred, coeff, levels, recon, nullptr, nullptr, nullptr};
+    return nh::dispatch_fused(a, size, use_dst, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Internal entry of the host-buffer pipeline (nh_host.cu): same kernel, coefficients / levels
+// narrowed to int16 on the device side of the PCIe copy; *ood_flag is raised when a block left the
+// pixel domain (the narrow tensors are then not valid for that chunk).
+int nh::fused_pipeline_dcplanar_narrow(const int16_t* orig, const int16_t* top, const int16_t* left,
+                                       const int16_t* top_right, const int16_t* bottom_left,
+                                       const uint8_t* modes, int mode, int64_t n_blocks, int size, int qp,
+                                       int is_intra, int use_dst, int bit_depth, int16_t* pred,
+                                       int16_t* coeff16, int16_t* levels16, int16_t* recon, int* ood_flag,
+                                       cudaStream_t st) {
+    const int l2 = log2_size(size);
+    if (l2 < 0) { set_error("Unsupported transform size: %d", size); return NH_E_SIZE; }
+    if (n_blocks <= 0) return NH_OK;
+    FusedArgs a{orig, top, left, top_right, bottom_left, modes, mode, n_blocks,
+                make_quant_params(qp, l2, is_intra), (1 << bit_depth) - 1,
+                pred, nullptr, nullptr, recon, coeff16, levels16, ood_flag};
+    return dispatch_fused(a, size, use_dst, st);
 }

@@ -284,6 +284,32 @@ def test_fused_unit_generations_and_out_of_domain(Bt, n, gen):
         _lib.check(_lib.lib().nh_set_fused_impl(2))
 
 
+@pytest.mark.parametrize("n,B,chunk", [(4, 70001, 8192), (8, 20011, 4096), (16, 3001, 1024), (32, 1000, 300)])
+def test_host_pipeline_vs_oracle(Bt, n, B, chunk):
+    """The host-buffer C-ABI entry (chunked, three streams, int16 wire format for coefficients and
+    levels + host widening): bit-exact against the oracle, including a chunk that contains
+    out-of-domain blocks (redone through int32) and partial output sets."""
+    rng = np.random.default_rng(n * 13 + 1)
+    orig, top, left, tr, bl = _dcplanar_inputs(rng, B, n, 1024)
+    modes = rng.integers(0, 2, B).astype(np.uint8)
+    want = O.pipeline_dcplanar_batch(orig, top, left, tr, bl, modes, 24, use_dst=(n == 4), bit_depth=10,
+                                     threads=O.n_host_threads())
+    got = Bt.host_block_pipeline(orig, top, left, tr, bl, modes, 24, use_dst=(n == 4), bit_depth=10, chunk_blocks=chunk)
+    for name, w in zip(("pred", "coeff", "levels", "recon"), want):
+        eq(getattr(got, name).numpy(), w, f"{name} n={n}")
+    # second chunk leaves the pixel domain
+    lo = chunk + 5
+    orig[lo:lo + 7] = rng.integers(-32768, 32768, (7, n, n))
+    top[lo + 9] = -5
+    want = O.pipeline_dcplanar_batch(orig, top, left, tr, bl, 1, 31, threads=O.n_host_threads())
+    got = Bt.host_block_pipeline(orig, top, left, tr, bl, 1, 31, chunk_blocks=chunk, outputs=("coeff", "levels", "recon"))
+    assert got.pred is None
+    eq(got.coeff.numpy(), want[1], "ood coeff"); eq(got.levels.numpy(), want[2], "ood levels")
+    eq(got.recon.numpy(), want[3], "ood recon")
+    got = Bt.host_block_pipeline(orig, top, left, tr, bl, 0, 31, chunk_blocks=chunk, outputs=("levels",))
+    eq(got.levels.numpy(), O.pipeline_dcplanar_batch(orig, top, left, tr, bl, 0, 31, threads=O.n_host_threads())[2], "levels only")
+
+
 def test_fused_dcplanar_empty_and_errors(Bt):
     z = lambda *s: torch.zeros(s, dtype=torch.int16, device=DEV)
     got = Bt.fused_block_pipeline(z(0, 8, 8), z(0, 8), z(0, 8), z(0), z(0), 1, 27)
