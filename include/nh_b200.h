@@ -163,9 +163,9 @@ int nh_blocks_to_plane(const int16_t* blocks, int height, int width, int pitch, 
  * NULL except recon_plane when recon_neighbours == 1):
  *   modes (B,) u8; costs (B,) i32; pred (B,N,N) i16; coeff, levels (B,N,N) i32;
  *   recon_plane (H, pitch) i16 -- uncovered rows/columns are set to 0.
- * progress: device scratch of nh_encode_frame_scratch_bytes(height, size) bytes
+ * scratch: device scratch of nh_encode_frame_scratch_bytes(height, width, size) bytes
  *   (only used when recon_neighbours == 1; may be NULL otherwise). */
-int64_t nh_encode_frame_scratch_bytes(int height, int size);
+int64_t nh_encode_frame_scratch_bytes(int height, int width, int size);
 int nh_encode_frame(const int16_t* src, int height, int width, int pitch, int size, int cost_kind,
                     int qp, int recon_neighbours, int bit_depth, uint8_t* modes, int32_t* costs,
                     int16_t* pred, int32_t* coeff, int32_t* levels, int16_t* recon_plane,

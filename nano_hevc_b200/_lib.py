@@ -48,7 +48,7 @@ PROTOTYPES = {
     "nh_gather_refs": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "nh_plane_to_blocks": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "nh_blocks_to_plane": (_i, [_p, _i, _i, _i, _i, _p, _p]),
-    "nh_encode_frame_scratch_bytes": (_i64, [_i, _i]),
+    "nh_encode_frame_scratch_bytes": (_i64, [_i, _i, _i]),
     "nh_encode_frame": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i64,
                              _p]),
     "nh_reduce_sse_sad": (_i, [_p, _p, _i64, _p, _p]),

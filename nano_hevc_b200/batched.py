@@ -401,7 +401,7 @@ def encode_frame(plane, size: int, cost: str = "sad", qp: int = 27, recon_neighb
                       mk("levels", (B, size, size), torch.int32),
                       torch.empty((H, W), dtype=torch.int16, device=dev))
     L = _lib.lib()
-    nbytes = int(L.nh_encode_frame_scratch_bytes(H, size))
+    nbytes = int(L.nh_encode_frame_scratch_bytes(H, W, size))
     scratch = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         _lib.check(L.nh_encode_frame(_ptr(p), H, W, W, size, int(cost == "satd"), int(qp),

@@ -94,7 +94,8 @@ struct CoderArgs {
     const int16_t* src;    // (H, pitch)
     int H, W, pitch;
     int cost_kind;
-    int* progress;         // [bh] blocks finished per block row, then [bh] = row ticket counter
+    int* ticket;           // K8: row ticket counter
+    int16_t* bottom;       // K8: [bh][W] bottom rows of the reconstructed blocks, -1 = not yet written
     // common
     int64_t n_blocks;
     QuantParams qp;
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
     if constexpr (SRC == SRC_WAVEFRONT) {
         // One warp per block row, rows handed out in order by a ticket counter so that a
         // waiting warp only ever waits on a row that a resident warp already owns.
-        int* ticket = a.progress + bh;
+        int* ticket = a.ticket;
         for (;;) {
             int by = 0;
             if (lane == 0) by = atomicAdd(ticket, 1);
@@ -152,23 +153,36 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                     ood |= lv;
                 }
                 __syncwarp();  // O is about to be overwritten with the next block's pixels
-                if (by > 0) {  // above-right block (or the whole row above) must be reconstructed
-                    const int need = bx + 2 < bw ? bx + 2 : bw;
-                    if (lane == 0) {
-                        const volatile int* p = a.progress + (by - 1);
-                        while (*p < need) __nanosleep(20);
-                        __threadfence();
-                    }
-                    __syncwarp();
+                // Top references (corner, above, above-right) come from the exchange rows: every block
+                // publishes its reconstructed bottom row there and -1 marks "not written yet", so the
+                // data is its own flag -- one L2 round trip, no fence, no separate progress counter.
+                // Reconstructed samples are clipped to [0, 2^bit_depth - 1], never negative.
+                if (by == 0) {
+                    for (int k = gl; k < Cfg::REF_W; k += G) top[k] = 128;
+                    ood |= 0;
+                } else {
+                    const int16_t* up = a.bottom + (int64_t)(by - 1) * a.W;
+                    int last = x + 2 * N - 1;
+                    if (last > a.W - 1) last = a.W - 1;
+                    bool ready;
+                    do {
+                        ready = true;
+                        for (int k = gl; k < Cfg::REF_W; k += G) {
+                            int v;
+                            if (k == 0 && x == 0) {
+                                v = 128;
+                            } else {
+                                int col = x + k - 1;
+                                if (col > last) col = last;
+                                v = (int)__ldcg(up + col);
+                            }
+                            if (v < 0) ready = false;
+                            else top[k] = (int16_t)v;
+                        }
+                    } while (!__all_sync(0xffffffffu, ready));
+                    for (int k = gl; k < Cfg::REF_W; k += G) ood |= (int)top[k];
                 }
-                const int16_t* rp = a.out.recon_plane;
-                for (int k = gl; k < Cfg::REF_W; k += G) {
-                    const int kk = k <= 2 * N ? k : 2 * N;
-                    const int tv = top_ref<true>(rp, a.H, a.W, a.pitch, x, y, 2 * N, kk);
-                    top[k] = (int16_t)tv;
-                    ood |= tv;
-                    if (k == 0) left[0] = (int16_t)tv;
-                }
+                if (gl == 0) left[0] = top[0];
 #pragma unroll
                 for (int i = 0; i < OPL; ++i) {
                     const int e = gl + i * G;
@@ -194,14 +208,12 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                 }
                 code_block<N, G>(gl, true, b, mode, O, M, top, left, corner, dc, a.qp, a.fq, fast8, neg,
                                  a.maxv, a.use_dst != 0, a.out);
+                // publish the bottom row first (the row below is polling for it), then the plane
+                for (int e = gl; e < N; e += G)
+                    __stcg(a.bottom + (int64_t)by * a.W + x + e, O[(N - 1) * Cfg::O_PITCH + e]);
                 for (int e = gl; e < N * N; e += G)
                     a.out.recon_plane[(int64_t)(y + e / N) * a.pitch + x + e % N] = O[(e / N) * Cfg::O_PITCH + (e % N)];
-                __threadfence();
                 __syncwarp();
-                if (lane == 0) {
-                    volatile int* p = a.progress + by;
-                    *p = bx + 1;
-                }
             }
         }
         return;
@@ -279,6 +291,15 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
             __syncwarp();
         }
     }
+}
+
+// Exchange rows of the wavefront coder: -1 where a block will publish its bottom row, 0 in the
+// columns no full block covers (the reference reads the zero-initialised plane there).
+__global__ void __launch_bounds__(256) init_bottom_kernel(int16_t* bottom, int bh, int W, int covered, int* ticket) {
+    const int64_t total = (int64_t)bh * W;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x)
+        bottom[t] = (int)(t % W) < covered ? (int16_t)-1 : (int16_t)0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0;
 }
 
 template <int N, int G, int SRC>
@@ -396,9 +417,9 @@ NH_API int nh_fused_pipeline_modes(const int16_t* orig, const int16_t* top, cons
     return dispatch_coder<SRC_ARRAYS>(a, size, reinterpret_cast<cudaStream_t>(stream));
 }
 
-NH_API int64_t nh_encode_frame_scratch_bytes(int height, int size) {
-    if (log2_size(size) < 0 || height < 0) return 0;
-    return ((int64_t)(height / size) + 2) * 4;
+NH_API int64_t nh_encode_frame_scratch_bytes(int height, int width, int size) {
+    if (log2_size(size) < 0 || height < 0 || width < 0) return 0;
+    return 256 + (int64_t)(height / size) * width * 2;  // ticket counter + exchange rows
 }
 
 NH_API int nh_encode_frame(const int16_t* src, int height, int width, int pitch, int size,
@@ -436,14 +457,19 @@ NH_API int nh_encode_frame(const int16_t* src, int height, int width, int pitch,
     a.use_dst = size == 4;  // docs/frames_and_panes.md:328-329
     a.out = CoderOut{modes, costs, pred, coeff, levels, nullptr, recon_plane, pitch};
     if (!recon_neighbours) return dispatch_coder<SRC_PLANE>(a, size, st);
-    const int64_t need = nh_encode_frame_scratch_bytes(height, size);
+    const int64_t need = nh_encode_frame_scratch_bytes(height, width, size);
     if (!scratch || scratch_bytes < need) {
         set_error("nh_encode_frame: scratch of %lld bytes required, got %lld", (long long)need,
                   (long long)scratch_bytes);
         return NH_E_NOMEM;
     }
-    cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)need, st);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(scratch)");
-    a.progress = reinterpret_cast<int*>(scratch);
+    if ((reinterpret_cast<uintptr_t>(scratch) & 3) != 0) {
+        set_error("nh_encode_frame: scratch must be 4-byte aligned");
+        return NH_E_ARG;
+    }
+    a.ticket = reinterpret_cast<int*>(scratch);
+    a.bottom = reinterpret_cast<int16_t*>(reinterpret_cast<unsigned char*>(scratch) + 256);
+    init_bottom_kernel<<<grid_for((int64_t)bh * width, 256, 4), 256, 0, st>>>(a.bottom, bh, width, bw * size, a.ticket);
+    NH_CHECK_LAUNCH("init_bottom_kernel");
     return dispatch_coder<SRC_WAVEFRONT>(a, size, st);
 }
