@@ -20,7 +20,7 @@ struct CoderCfg {
     static constexpr int MS = SB >= G ? 1 : G / SB;     // mode splits (lanes sharing a sub-block)
     static constexpr int SBL = SB >= G ? G : SB;        // lanes that sum one mode's cost
     static constexpr int REF_W = 2 * N + 4;             // 2N+1 entries + padding read by the packed loads
-    static constexpr int NEG_W = N + 4;                 // projected extension (N) + ref[0..3]
+    static constexpr int NEG_W = N + 8;                 // projected extension (N) + ref[0..7] (9-sample windows)
     static constexpr int NEG_MODES = 15;                // modes 11..25 have a negative angle
     static constexpr int O_PITCH = N + 2;               // int16 elements; odd word pitch spreads banks
     static constexpr int REFS_BYTES = 2 * REF_W * 2;
@@ -172,6 +172,7 @@ template <int N, int G>
 __device__ __forceinline__ void build_neg_arrays(int gl, const int16_t* top, const int16_t* left,
                                                  int16_t* neg) {
     using Cfg = CoderCfg<N, G>;
+    constexpr int POS = Cfg::NEG_W - N;          // ref[0 .. POS-1] copied behind the projected part
     for (int t = gl; t < Cfg::NEG_MODES * N; t += G) {
         const int mi = t / N, j = t % N;         // mode 11 + mi, element k = j - N
         const int mode = 11 + mi;
@@ -181,33 +182,57 @@ __device__ __forceinline__ void build_neg_arrays(int gl, const int16_t* top, con
         // entries below (N*angle)>>5 are never read; clamp the index so the load stays in bounds
         neg[mi * Cfg::NEG_W + j] = sec[proj > 2 * N ? 2 * N : proj];
     }
-    for (int t = gl; t < Cfg::NEG_MODES * 4; t += G) {
-        const int mi = t >> 2, j = t & 3;
+    for (int t = gl; t < Cfg::NEG_MODES * POS; t += G) {
+        const int mi = t / POS, j = t % POS;
         const int16_t* pri = (11 + mi) >= 18 ? top : left;
         neg[mi * Cfg::NEG_W + N + j] = pri[j];   // pri[0] is the corner in the plane coders
     }
 }
 
-// Four predicted samples (bytes) of one scan line: R = halfword array (4-byte aligned), h = index of
-// the first sample's ref[k], f = fraction.
-__device__ __forceinline__ void pred_row4_pairs(const int16_t* R, int h, int f, uint32_t& lo, uint32_t& hi) {
+// SW predicted samples of one scan line as SW/2 words (bytes 0 and 2 of word i = samples 2i, 2i+1):
+// R = halfword array (4-byte aligned), h = index of the first sample's ref[k], f = fraction.
+template <int SW>
+__device__ __forceinline__ void pred_row_pairs(const int16_t* R, int h, int f, uint32_t (&out)[SW / 2]) {
     const uint32_t* W = reinterpret_cast<const uint32_t*>(R) + (h >> 1);
-    const uint32_t w0 = W[0], w1 = W[1], w2 = W[2];
+    uint32_t w[SW / 2 + 1];
+#pragma unroll
+    for (int i = 0; i <= SW / 2; ++i) w[i] = W[i];
     const uint32_t selA = (h & 1) ? 0x5432u : 0x3210u, selB = selA + 0x2222u;
-    const uint32_t a01 = __byte_perm(w0, w1, selA), a12 = __byte_perm(w0, w1, selB);
-    const uint32_t a23 = __byte_perm(w1, w2, selA), a34 = __byte_perm(w1, w2, selB);
     const uint32_t g = 32u - (uint32_t)f;
-    lo = (g * a01 + (uint32_t)f * a12 + 0x00100010u) >> 5;   // bytes 0 and 2 hold samples 0, 1
-    hi = (g * a23 + (uint32_t)f * a34 + 0x00100010u) >> 5;   // bytes 0 and 2 hold samples 2, 3
+#pragma unroll
+    for (int i = 0; i < SW / 2; ++i) {
+        const uint32_t a = __byte_perm(w[i], w[i + 1], selA);   // (R[k+2i],   R[k+2i+1])
+        const uint32_t b = __byte_perm(w[i], w[i + 1], selB);   // (R[k+2i+1], R[k+2i+2])
+        out[i] = (g * a + (uint32_t)f * b + 0x00100010u) >> 5;
+    }
 }
 
+// Strip geometry of the packed search: a lane owns 4 scan lines x SW samples (SW = 8 for N >= 8,
+// which amortises the per-scan-line address arithmetic over twice the pixels; 4 for N = 4).
 template <int N, int G>
-__device__ __forceinline__ int subblock_cost_u8(int mode, int sx, int sy, const uint32_t (&ow)[4],
-                                                const uint32_t (&owT)[4], const int16_t* top,
-                                                const int16_t* left, const int16_t* neg, int dc,
-                                                int cost_kind) {
+struct StripCfg {
+    static constexpr int SW = N >= 8 ? 8 : 4;
+    static constexpr int SB = N * N / (4 * SW);          // strips per block
+    static constexpr int SPL = SB >= G ? SB / G : 1;     // strips per lane
+    static constexpr int MS = SB >= G ? 1 : G / SB;      // mode splits
+    static constexpr int SBL = SB >= G ? G : SB;         // lanes that sum one mode's cost
+    static constexpr int SPR = N / SW;                   // strips per row of strips
+    static constexpr int WPS = SW / 4;                   // packed words per scan line
+};
+
+// Cost of one strip.  (b0, s0) = first base / first scan line of the strip in the orientation of the
+// mode: vertical modes use (x, y) of the image, horizontal modes (y, x) -- the strip is then the
+// transposed region and `oh` holds the transposed original samples.
+template <int N, int G>
+__device__ __forceinline__ int strip_cost_u8(int mode, int b0, int s0,
+                                             const uint32_t (&ov)[4][StripCfg<N, G>::WPS],
+                                             const uint32_t (&oh)[4][StripCfg<N, G>::WPS],
+                                             const int16_t* top, const int16_t* left,
+                                             const int16_t* neg, int dc, int cost_kind) {
     using Cfg = CoderCfg<N, G>;
-    uint32_t pr[4];        // predicted rows in scan order, 4 bytes each
+    using SC = StripCfg<N, G>;
+    constexpr int SW = SC::SW, WPS = SC::WPS;
+    uint32_t pr[4][WPS];   // predicted scan lines, 4 bytes per word
     bool transposed = false;
     if (mode >= 2) {
         const int angle = intra_angle(mode);
@@ -215,55 +240,68 @@ __device__ __forceinline__ int subblock_cost_u8(int mode, int sx, int sy, const 
         transposed = !vertical;
         const int16_t* pos = vertical ? top : left;
         const int16_t* ng = neg + (mode - 11) * Cfg::NEG_W + N;   // only dereferenced for modes 11..25
-        const int b0 = vertical ? sx : sy, s0 = vertical ? sy : sx;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int p = (s0 + j + 1) * angle;
             const int ip = p >> 5, f = p & 31;
             const int k = b0 + 1 + ip;
-            const int16_t* R = k < 0 ? ng : pos;
-            uint32_t lo, hi;
-            pred_row4_pairs(R, k, f, lo, hi);   // every array starts 4-byte aligned
-            pr[j] = __byte_perm(lo, hi, 0x6420);
+            const int16_t* R = k < 0 ? ng : pos;   // every array starts 4-byte aligned
+            uint32_t w[SW / 2];
+            pred_row_pairs<SW>(R, k, f, w);
+#pragma unroll
+            for (int q = 0; q < WPS; ++q) pr[j][q] = __byte_perm(w[2 * q], w[2 * q + 1], 0x6420);
         }
     } else if (mode == 1) {
         const uint32_t d4 = (uint32_t)dc * 0x01010101u;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) pr[j] = d4;
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < WPS; ++q) pr[j][q] = d4;
     } else {
+        // planar, image orientation: b0 = x, s0 = y
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int v[4];
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                v[i] = planar_px<N>(sx + i, sy + j, left[1 + sy + j], top[1 + sx + i], top[N + 1], left[N + 1]);
-            pr[j] = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
-        }
+            for (int q = 0; q < WPS; ++q) {
+                uint32_t word = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int x = b0 + 4 * q + i, y = s0 + j;
+                    word |= (uint32_t)planar_px<N>(x, y, left[1 + y], top[1 + x], top[N + 1], left[N + 1]) << (8 * i);
+                }
+                pr[j][q] = word;
+            }
     }
     int c = 0;
     if (cost_kind == NH_COST_SAD) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) c = (int)(__vsadu4(pr[j], transposed ? owT[j] : ow[j]) + (uint32_t)c);
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < WPS; ++q)
+                c = (int)(__vsadu4(pr[j][q], transposed ? oh[j][q] : ov[j][q]) + (uint32_t)c);
     } else {
-        int d[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t o4 = transposed ? owT[j] : ow[j];
+        for (int q = 0; q < WPS; ++q) {   // one 4x4 sub-block per packed word column
+            int d[16];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                d[4 * j + i] = (int)((o4 >> (8 * i)) & 0xff) - (int)((pr[j] >> (8 * i)) & 0xff);
-        }
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t o4 = transposed ? oh[j][q] : ov[j][q];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int a0 = d[j] + d[4 + j], a1 = d[j] - d[4 + j];
-            int a2 = d[8 + j] + d[12 + j], a3 = d[8 + j] - d[12 + j];
-            d[j] = a0 + a2; d[4 + j] = a1 + a3; d[8 + j] = a0 - a2; d[12 + j] = a1 - a3;
-        }
+                for (int i = 0; i < 4; ++i)
+                    d[4 * j + i] = (int)((o4 >> (8 * i)) & 0xff) - (int)((pr[j][q] >> (8 * i)) & 0xff);
+            }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            int a0 = d[4 * i] + d[4 * i + 1], a1 = d[4 * i] - d[4 * i + 1];
-            int a2 = d[4 * i + 2] + d[4 * i + 3], a3 = d[4 * i + 2] - d[4 * i + 3];
-            c += abs(a0 + a2) + abs(a1 + a3) + abs(a0 - a2) + abs(a1 - a3);
+            for (int j = 0; j < 4; ++j) {
+                int a0 = d[j] + d[4 + j], a1 = d[j] - d[4 + j];
+                int a2 = d[8 + j] + d[12 + j], a3 = d[8 + j] - d[12 + j];
+                d[j] = a0 + a2; d[4 + j] = a1 + a3; d[8 + j] = a0 - a2; d[12 + j] = a1 - a3;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int a0 = d[4 * i] + d[4 * i + 1], a1 = d[4 * i] - d[4 * i + 1];
+                int a2 = d[4 * i + 2] + d[4 * i + 3], a3 = d[4 * i + 2] - d[4 * i + 3];
+                c += abs(a0 + a2) + abs(a1 + a3) + abs(a0 - a2) + abs(a1 - a3);
+            }
         }
     }
     return c;
@@ -276,43 +314,51 @@ __device__ __forceinline__ int search_modes_u8(int gl, const int16_t* O, const i
                                                const int16_t* left, const int16_t* neg, int dc,
                                                int cost_kind) {
     using Cfg = CoderCfg<N, G>;
-    constexpr int SBW = N / 4;
-    uint32_t ow[Cfg::SPL][4], owT[Cfg::SPL][4];
-    int sx[Cfg::SPL], sy[Cfg::SPL];
+    using SC = StripCfg<N, G>;
+    constexpr int SW = SC::SW, WPS = SC::WPS;
+    // ov: the lane's strip for vertical / DC / planar modes (SW wide, 4 tall at (px, py));
+    // oh: its strip for horizontal modes, stored transposed (4 wide, SW tall at (py, px) mirrored:
+    //     scan line j = image column qx + j, base i = image row qy + i)
+    uint32_t ov[SC::SPL][4][WPS], oh[SC::SPL][4][WPS];
+    int px[SC::SPL], py[SC::SPL];
 #pragma unroll
-    for (int i = 0; i < Cfg::SPL; ++i) {
-        const int sb = (Cfg::MS == 1) ? gl + i * G : gl % Cfg::SB;
-        sx[i] = (sb % SBW) * 4;
-        sy[i] = (sb / SBW) * 4;
-        uint32_t v[4][4];
+    for (int s = 0; s < SC::SPL; ++s) {
+        const int st = (SC::MS == 1) ? gl + s * G : gl % SC::SB;
+        px[s] = (st % SC::SPR) * SW;   // base offset of the strip (x for vertical, y for horizontal)
+        py[s] = (st / SC::SPR) * 4;    // scan offset of the strip (y for vertical, x for horizontal)
 #pragma unroll
-        for (int y = 0; y < 4; ++y)
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int x = 0; x < 4; ++x) v[y][x] = (uint32_t)(uint16_t)O[(sy[i] + y) * Cfg::O_PITCH + sx[i] + x];
+            for (int q = 0; q < WPS; ++q) {
+                uint32_t wv = 0, wh = 0;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            ow[i][r] = v[r][0] | (v[r][1] << 8) | (v[r][2] << 16) | (v[r][3] << 24);
-            owT[i][r] = v[0][r] | (v[1][r] << 8) | (v[2][r] << 16) | (v[3][r] << 24);
-        }
+                for (int i = 0; i < 4; ++i) {
+                    const int b = px[s] + 4 * q + i, sc = py[s] + j;
+                    wv |= (uint32_t)(uint16_t)O[sc * Cfg::O_PITCH + b] << (8 * i);   // (y = sc, x = b)
+                    wh |= (uint32_t)(uint16_t)O[b * Cfg::O_PITCH + sc] << (8 * i);   // (y = b, x = sc)
+                }
+                ov[s][j][q] = wv;
+                oh[s][j][q] = wh;
+            }
     }
-    const int ms = (Cfg::MS == 1) ? 0 : gl / Cfg::SB;
+    const int ms = (SC::MS == 1) ? 0 : gl / SC::SB;
     int best = 0x7fffffff;
-    constexpr int ITERS = (35 + Cfg::MS - 1) / Cfg::MS;
+    constexpr int ITERS = (35 + SC::MS - 1) / SC::MS;
     for (int it = 0; it < ITERS; ++it) {
-        const int pos = it * Cfg::MS + ms;
+        const int pos = it * SC::MS + ms;
         const bool active = pos < 35;
         const int mode = !active ? 1 : (pos == 0 ? 1 : (pos == 1 ? 0 : pos));
         int c = 0;
 #pragma unroll
-        for (int i = 0; i < Cfg::SPL; ++i)
-            c += subblock_cost_u8<N, G>(mode, sx[i], sy[i], ow[i], owT[i], top, left, neg, dc, cost_kind);
+        for (int s = 0; s < SC::SPL; ++s)
+            c += strip_cost_u8<N, G>(mode, px[s], py[s], ov[s], oh[s], top, left, neg, dc, cost_kind);
 #pragma unroll
-        for (int off = Cfg::SBL / 2; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+        for (int off = SC::SBL / 2; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
         const int key = active ? ((c << 6) | pos) : 0x7fffffff;
         best = key < best ? key : best;
     }
 #pragma unroll
-    for (int off = G / 2; off >= Cfg::SBL; off >>= 1) {
+    for (int off = G / 2; off >= SC::SBL; off >>= 1) {
         int other = __shfl_xor_sync(0xffffffffu, best, off);
         best = other < best ? other : best;
     }
