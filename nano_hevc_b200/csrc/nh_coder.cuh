@@ -457,47 +457,42 @@ __device__ __forceinline__ void code_block(int gl, bool valid, int64_t b, int mo
         store_row_smem<N>(M, r, res);
     }
     __syncwarp();
-    if (rowlane) {
-        if (N == 4 && use_dst) col_pass<N, N == 4, false>(M, r);
-        else col_pass<N, false, false>(M, r);
-    }
-    __syncwarp();
-    if (rowlane) {
+    {
         int c[N], lv[N], dq[N];
-        if (N == 4 && use_dst) row_pass<N, N == 4, false>(M, r, c);
-        else row_pass<N, false, false>(M, r, c);
-        if (valid && out.coeff) store_row32<N>(out.coeff + b * NN + r * N, c);
-        if (fast8) {
+        if (N == 4 && use_dst) two_pass_transform<N, N == 4, false>(M, r, rowlane, c);
+        else two_pass_transform<N, false, false>(M, r, rowlane, c);
+        if (rowlane) {
+            if (valid && out.coeff) store_row32<N>(out.coeff + b * NN + r * N, c);
+            if (fast8) {
 #pragma unroll
-            for (int k = 0; k < N; ++k) {
-                lv[k] = quantize_fast(c[k], fq);
-                dq[k] = dequantize_fast(lv[k], fq);
+                for (int k = 0; k < N; ++k) {
+                    lv[k] = quantize_fast(c[k], fq);
+                    dq[k] = dequantize_fast(lv[k], fq);
+                }
+            } else {
+                quant_dequant_row<N>(c, qp, lv, dq);
             }
-        } else {
-            quant_dequant_row<N>(c, qp, lv, dq);
+            if (valid && out.levels) store_row32<N>(out.levels + b * NN + r * N, lv);
         }
-        if (valid && out.levels) store_row32<N>(out.levels + b * NN + r * N, lv);
-        store_row_smem<N>(M, r, dq);
+        __syncwarp();  // every lane has read its column of the second forward pass
+        if (rowlane) store_row_smem<N>(M, r, dq);
     }
     __syncwarp();
-    if (rowlane) {
-        if (N == 4 && use_dst) col_pass<N, N == 4, true>(M, r);
-        else col_pass<N, false, true>(M, r);
-    }
-    __syncwarp();
-    if (rowlane) {
+    {
         int res[N];
-        if (N == 4 && use_dst) row_pass<N, N == 4, true>(M, r, res);
-        else row_pass<N, false, true>(M, r, res);
-        uint32_t ow[N / 2];
+        if (N == 4 && use_dst) two_pass_transform<N, N == 4, true>(M, r, rowlane, res);
+        else two_pass_transform<N, false, true>(M, r, rowlane, res);
+        if (rowlane) {
+            uint32_t ow[N / 2];
 #pragma unroll
-        for (int k = 0; k < N / 2; ++k) {
-            const int a = recon_px(lo16(pw[k]), res[2 * k], maxv);
-            const int c2 = recon_px(hi16(pw[k]), res[2 * k + 1], maxv);
-            ow[k] = pack16(a, c2);
-            *reinterpret_cast<uint32_t*>(O + r * Cfg::O_PITCH + 2 * k) = ow[k];
+            for (int k = 0; k < N / 2; ++k) {
+                const int a = recon_px(lo16(pw[k]), res[2 * k], maxv);
+                const int c2 = recon_px(hi16(pw[k]), res[2 * k + 1], maxv);
+                ow[k] = pack16(a, c2);
+                *reinterpret_cast<uint32_t*>(O + r * Cfg::O_PITCH + 2 * k) = ow[k];
+            }
+            if (valid && out.recon) store_row16<N>(out.recon + b * NN + r * N, ow);
         }
-        if (valid && out.recon) store_row16<N>(out.recon + b * NN + r * N, ow);
     }
     __syncwarp();
 }

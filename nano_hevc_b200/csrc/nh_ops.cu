@@ -100,10 +100,8 @@ __global__ void __launch_bounds__(kRowsWarps * 32)
         }
         store_row_smem<N>(M, r, x);
         __syncwarp();
-        col_pass<N, false, INV>(M, r);
-        __syncwarp();
         int y[N];
-        row_pass<N, false, INV>(M, r, y);
+        two_pass_transform<N, false, INV>(M, r, true, y);  // one inlined butterfly for both passes
         if (valid) store_row32<N>(out + b * NN + r * N, y);
         __syncwarp();
     }
