@@ -124,6 +124,10 @@ int nh_fused_pipeline_dcplanar(const int16_t* orig, const int16_t* top, const in
  * 2 (default: cp.async prefetch + TMA bulk stores + 32-bit pixel-domain quant with an exact
  * fallback) or 1 (first generation, kept for A/B profiling).  Results are identical. */
 int nh_set_fused_impl(int generation);
+/* Selects the kernel behind nh_fused_pipeline_dcplanar for size 16 / 32: 2 (default: the four
+ * transform passes as warp-level f16 tensor-core MMAs, exact for 8-bit samples, exact CUDA-core
+ * fallback otherwise) or 1 (CUDA-core butterflies).  Results are identical. */
+int nh_set_rows_impl(int impl);
 /* Any of the 35 modes from padded (B, 2N+1) references (K1 convention). */
 int nh_fused_pipeline_modes(const int16_t* orig, const int16_t* top, const int16_t* left,
                             const int16_t* top_left, const uint8_t* modes, int mode,

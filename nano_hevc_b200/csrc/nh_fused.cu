@@ -894,6 +894,10 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 4) fused_rows_kernel(const Fu
     }
 }
 
+}  // namespace nh
+#include "nh_fused_mma.cuh"
+namespace nh {
+
 template <int N, bool DST>
 static int launch_unit_v1(const FusedArgs& a, cudaStream_t st) {
     constexpr int BPU = 64 / (N * N);
@@ -1042,14 +1046,32 @@ static int launch_rows(const FusedArgs& a, cudaStream_t st) {
     return NH_OK;
 }
 
+// Kernel behind N = 16, 32: 2 (default) = tensor-core passes (fused_mma_kernel), 1 = CUDA-core
+// butterflies (fused_rows_kernel); nh_set_rows_impl() or NH_ROWS_IMPL=1|2.  The int16-output variant
+// of the host pipeline always uses the CUDA-core kernel.
+static int g_rows_impl = 0;
+static int rows_impl() {
+    if (g_rows_impl == 0) {
+        const char* e = getenv("NH_ROWS_IMPL");
+        g_rows_impl = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 2;
+    }
+    return g_rows_impl;
+}
+
+template <int N>
+static int launch_16_32(const FusedArgs& a, cudaStream_t st) {
+    if (a.coeff16 || rows_impl() == 1) return launch_rows<N>(a, st);
+    return launch_mma<N>(a, st);
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static int dispatch_fused(const FusedArgs& a, int size, int use_dst, cudaStream_t st) {
     switch (size) {
         case 4: return use_dst ? launch_unit<4, true>(a, st) : launch_unit<4, false>(a, st);
         case 8: return launch_unit<8, false>(a, st);
-        case 16: return launch_rows<16>(a, st);
-        default: return launch_rows<32>(a, st);
+        case 16: return launch_16_32<16>(a, st);
+        default: return launch_16_32<32>(a, st);
     }
 }
 
@@ -1061,6 +1083,15 @@ NH_API int nh_set_fused_impl(int generation) {
         return NH_E_ARG;
     }
     nh::g_fused_impl = generation;
+    return NH_OK;
+}
+
+NH_API int nh_set_rows_impl(int impl) {
+    if (impl < 1 || impl > 2) {
+        nh::set_error("nh_set_rows_impl: impl must be 1 (CUDA-core) or 2 (tensor-core), got %d", impl);
+        return NH_E_ARG;
+    }
+    nh::g_rows_impl = impl;
     return NH_OK;
 }
 

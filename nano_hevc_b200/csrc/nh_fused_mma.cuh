@@ -1,0 +1,385 @@
+// nh_fused_mma.cuh -- K10: the fused DC / planar pipeline for N = 16, 32 with the four separable
+// transform passes on the tensor cores (included by nh_fused.cu).
+//
+// Why tensor cores here: ncu shows the CUDA-core 32x32 kernel limited by the integer pipe and by
+// shared-memory instruction issue (78 instr/px, 0.45 of the HBM peak) -- north_star's condition for
+// a tensor-core 32x32 transform.  Why warp-level HMMA (mma.sync m16n8k16, f16 x f16 -> f32) and not
+// tcgen05: the reference rounds and shifts between the passes (transform.py:180-194, :222-236), so
+// the four GEMMs of a block cannot be fused and every pass boundary needs the accumulators in
+// registers.  With mma.sync the accumulator fragment of one pass IS the operand fragment of the next
+// pass (C -> A directly; C -> B gives the transposed product), so the whole chain
+//     temp  = (T  X    + r) >> s      A = T      B = X (ldmatrix.trans)     -> (m = i, n = x)
+//     coefT = (T  temp^T + r) >> s    A = T      B = temp  (C -> B)         -> (m = v, n = i)
+//     tmp2  = (T^T dq  + r) >> s      A = T^T    B = dq^T  (C -> B)         -> (m = y, n = v)
+//     res   = (tmp2 T  + r) >> s      A = tmp2 (C -> A)   B = T             -> (m = y, n = x)
+// runs without a single shuffle or shared-memory round trip between passes; tcgen05 would need a
+// TMEM load, a rounding pass and a shared-memory store of the next operand at every boundary.
+//
+// Exactness: every MMA operand is an integer of magnitude <= 2048 (exact in f16) and every
+// accumulator stays below 2^24 (exact in f32) when all samples lie in [0, 255]:
+//     |residual| <= 255, |temp| <= 511, |coeff| <= 1023, |dequantised| <= 360 / 180 (N = 16 / 32, any
+//     QP, intra or inter), |tmp2| <= 661 / 328, accumulators <= 1.05e6
+// (tests/test_host_math.py::test_mma_operand_bounds recomputes these from the reference tables).
+// The rounding offset r rides in as the accumulator's initial value and the floor shift is one
+// FFMA.RM against 1.5 * 2^23 (the integer appears in the low mantissa bits).  Tiles with a sample
+// outside [0, 255] (or a clip bound above 1023) take the exact CUDA-core path (rows_tile_exact).
+#pragma once
+#include <cuda_fp16.h>
+
+namespace nh {
+
+constexpr int kMmaWarps = 4;
+constexpr float kMagicF = 12582912.0f;  // 1.5 * 2^23
+constexpr int kMagicI = 0x4B400000;     // its bit pattern: float(kMagicF + k) has bits kMagicI + k
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void stsm_x4(uint32_t addr, const uint32_t (&r)[4]) {
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};"
+                 :: "r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+// D += A(16x16, row) * B(16x8, col), f16 operands, f32 accumulate
+__device__ __forceinline__ void hmma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2,
+                                          uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ __half2 bits_h2(uint32_t w) { return *reinterpret_cast<__half2*>(&w); }
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) { return h2_bits(__floats2half2_rn(lo, hi)); }
+// quarter-wave table of nh_math.cuh's cos_q() in constant memory (runtime-indexed)
+static __constant__ signed char kc_cos_q[33] = {64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67, 64,
+                                                61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9,  4,  0};
+__device__ __forceinline__ int cosv_dev(int m) {
+    m &= 127;
+    const int q = m <= 32 ? m : m <= 64 ? 64 - m : m <= 96 ? m - 64 : 128 - m;
+    const int v = kc_cos_q[q];
+    return (m > 32 && m <= 96) ? -v : v;
+}
+// two entries of the N-point matrix (transform.py:28-135) as exact f16
+template <int N>
+__device__ __forceinline__ uint32_t t_pair(int r0, int c0, int r1, int c1) {
+    const int a = cosv_dev((r0 * (32 / N)) * (2 * c0 + 1)), b = cosv_dev((r1 * (32 / N)) * (2 * c1 + 1));
+    return pack_h2((float)a, (float)b);
+}
+// floor((acc) / 2^SH) of an accumulator that already holds the rounding offset, as kMagicF + k
+template <int SH>
+__device__ __forceinline__ float floor_shift_magic(float acc) {
+    return __fmaf_rd(acc, 1.0f / (float)(1 << SH), kMagicF);
+}
+
+// One pass boundary: accumulators -> rounded / shifted integers -> packed f16 operand fragments.
+template <int MT, int NT, int SH>
+__device__ __forceinline__ void round_to_operand(const float (&acc)[MT][NT][4], uint32_t (&h)[MT][NT][2]) {
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) {
+            const float v0 = floor_shift_magic<SH>(acc[mi][ni][0]) - kMagicF;
+            const float v1 = floor_shift_magic<SH>(acc[mi][ni][1]) - kMagicF;
+            const float v2 = floor_shift_magic<SH>(acc[mi][ni][2]) - kMagicF;
+            const float v3 = floor_shift_magic<SH>(acc[mi][ni][3]) - kMagicF;
+            h[mi][ni][0] = pack_h2(v0, v1);
+            h[mi][ni][1] = pack_h2(v2, v3);
+        }
+}
+
+template <int MT, int NT>
+__device__ __forceinline__ void init_acc(float (&acc)[MT][NT][4], float rnd) {
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[mi][ni][e] = rnd;
+}
+
+// acc(m, n) += A_const(m, k) * B(k, n) where B[k][n] = P[n][k] and P is the previous pass's result
+// held as packed C fragments `h` (C -> B: the product comes out transposed w.r.t. using P as A).
+template <int MT, int NT, int KT>
+__device__ __forceinline__ void mma_const_a(float (&acc)[MT][NT][4], const uint32_t (&ta)[MT][KT][4],
+                                            const uint32_t (&h)[MT][NT][2]) {
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni)
+#pragma unroll
+            for (int ki = 0; ki < KT; ++ki)
+                hmma16816(acc[mi][ni], ta[mi][ki][0], ta[mi][ki][1], ta[mi][ki][2], ta[mi][ki][3],
+                          h[ni >> 1][2 * ki][ni & 1], h[ni >> 1][2 * ki + 1][ni & 1]);
+}
+
+template <int N>
+__global__ void __launch_bounds__(kMmaWarps * 32, 3) fused_mma_kernel(const FusedArgs a, const FastQuant fq) {
+    constexpr int NN = N * N;
+    constexpr int BPW = 32 / N;  // blocks per warp tile
+    constexpr int MT = N / 16, NT = N / 8, KT = N / 16;
+    constexpr int SH = Log2<N>::v + 5;  // transform.py:173-175, :215-217
+    // int16 block tile in shared memory: row pitch N*2 + 16 bytes (an odd number of 16-byte groups),
+    // so the 8 rows of an ldmatrix / stmatrix 8x8 tile and the per-lane 128-bit row accesses are
+    // conflict-free.
+    constexpr int PITCH = N * 2 + 16;
+    constexpr int TILE = N * PITCH;
+    constexpr int EXACT_BYTES = BPW * RowsTile<N>::WORDS * 4;
+    constexpr int WARP_BYTES = 2 * BPW * TILE > EXACT_BYTES ? 2 * BPW * TILE : EXACT_BYTES;
+    __shared__ __align__(16) unsigned char smem[kMmaWarps][WARP_BYTES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane / N, r = lane % N;    // I/O mapping: lane = row r of block g
+    const int fg = lane >> 2, ft = lane & 3; // fragment mapping
+    unsigned char* sm = smem[warp];
+    unsigned char* my_o = sm + g * TILE + r * PITCH;          // this lane's row of the original tile
+    unsigned char* my_p = sm + (BPW + g) * TILE + r * PITCH;  // ... and of the prediction tile
+    // ldmatrix / stmatrix x4 row address of this lane: 8x8 tile j = lane >> 3 covers rows
+    // 8*(j&1).. and columns 8*(j>>1)..  of a 16x16 region
+    const int lane_off = (((lane >> 3) & 1) * 8 + (lane & 7)) * PITCH + (lane >> 4) * 16;
+
+    // transform matrix as constant operand fragments (exact small integers in f16)
+    uint32_t ta[MT][KT][4];  // A = T:    a0 = T[16mi+g][16ki+2t..], a1 = rows +8, a2 = cols +8, a3 = both
+    uint32_t tb[KT][NT][2];  // B = T:    b0 = {T[16ki+2t][8ni+g], T[16ki+2t+1][8ni+g]}, b1 = rows +8
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int ki = 0; ki < KT; ++ki) {
+            const int i0 = 16 * mi + fg, k0 = 16 * ki + 2 * ft;
+            ta[mi][ki][0] = t_pair<N>(i0, k0, i0, k0 + 1);
+            ta[mi][ki][1] = t_pair<N>(i0 + 8, k0, i0 + 8, k0 + 1);
+            ta[mi][ki][2] = t_pair<N>(i0, k0 + 8, i0, k0 + 9);
+            ta[mi][ki][3] = t_pair<N>(i0 + 8, k0 + 8, i0 + 8, k0 + 9);
+        }
+#pragma unroll
+    for (int ki = 0; ki < KT; ++ki)
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) {
+            const int k0 = 16 * ki + 2 * ft, x0 = 8 * ni + fg;
+            tb[ki][ni][0] = t_pair<N>(k0, x0, k0 + 1, x0);
+            tb[ki][ni][1] = t_pair<N>(k0 + 8, x0, k0 + 9, x0);
+        }
+
+    const float rnd = (float)(1 << (SH - 1));
+    const int clip_hi = a.maxv;
+    const bool clip_ok = a.maxv <= 1023;
+    const __half2 kBias = __floats2half2_rn(1024.0f, 1024.0f);
+    const float hi_f = 1024.0f + (float)(clip_ok ? clip_hi : 0);
+    const __half2 kHi = __floats2half2_rn(hi_f, hi_f);
+
+    const int64_t n_tiles = (a.n_blocks + BPW - 1) / BPW;
+    const int64_t warp_stride = (int64_t)gridDim.x * kMmaWarps;
+    int64_t tile = (int64_t)blockIdx.x * kMmaWarps + warp;
+
+    uint32_t nxt_ow[N / 2];  // this lane's row of original pixels, one tile ahead
+    auto load_orig = [&](int64_t t) {
+        const int64_t b = t * BPW + g;
+        if (b < a.n_blocks) {
+            load_row16<N>(a.orig + b * NN + r * N, nxt_ow);
+        } else {
+#pragma unroll
+            for (int k = 0; k < N / 2; ++k) nxt_ow[k] = 0;
+        }
+    };
+    if (tile < n_tiles) load_orig(tile);
+
+    for (; tile < n_tiles; tile += warp_stride) {
+        const int64_t b = tile * BPW + g;
+        const bool valid = b < a.n_blocks;
+        uint32_t ood = 0;  // any sample outside [0, 255]
+        {
+#pragma unroll
+            for (int q = 0; q < N / 8; ++q) {
+                *reinterpret_cast<uint4*>(my_o + 16 * q) =
+                    make_uint4(nxt_ow[4 * q], nxt_ow[4 * q + 1], nxt_ow[4 * q + 2], nxt_ow[4 * q + 3]);
+                ood |= (nxt_ow[4 * q] | nxt_ow[4 * q + 1] | nxt_ow[4 * q + 2] | nxt_ow[4 * q + 3]) & 0xFF00FF00u;
+            }
+            if (tile + warp_stride < n_tiles) load_orig(tile + warp_stride);
+            uint32_t pw[N / 2];
+            if (valid) {
+                const int mode = a.modes ? (int)a.modes[b] : a.mode;
+                uint32_t tw[N / 2], lw[N / 2];
+                load_row16<N>(a.top + b * N, tw);
+                load_row16<N>(a.left + b * N, lw);
+                const int tr = a.top_right[b], bl = a.bottom_left[b];
+#pragma unroll
+                for (int k = 0; k < N / 2; ++k) ood |= (tw[k] | lw[k]) & 0xFF00FF00u;
+                ood |= (uint32_t)(tr | bl) & 0xFFFFFF00u;
+                int p[N];
+                if (mode == 1) {
+                    const int dc = dc_value<N>(sum_row<N>(tw) + sum_row<N>(lw));
+#pragma unroll
+                    for (int x = 0; x < N; ++x) p[x] = dc;
+                } else {
+                    int top[N];
+                    unpack_row<N>(tw, top);
+                    planar_row<N>(r, (int)a.left[b * N + r], top, tr, bl, p);
+                }
+                pack_row<N>(p, pw);
+                if (a.pred) store_row16<N>(a.pred + b * NN + r * N, pw);
+            } else {
+#pragma unroll
+                for (int k = 0; k < N / 2; ++k) pw[k] = 0;
+            }
+#pragma unroll
+            for (int q = 0; q < N / 8; ++q)
+                *reinterpret_cast<uint4*>(my_p + 16 * q) =
+                    make_uint4(pw[4 * q], pw[4 * q + 1], pw[4 * q + 2], pw[4 * q + 3]);
+        }
+        const bool fast = clip_ok && !__any_sync(0xffffffffu, ood != 0);
+        __syncwarp();
+        if (fast) {
+#pragma unroll
+            for (int u = 0; u < BPW; ++u) {
+                const int64_t bu = tile * BPW + u;
+                const bool valid_u = bu < a.n_blocks;  // warp-uniform
+                const uint32_t so = smem_u32(sm + u * TILE) + lane_off;
+                const uint32_t sp = smem_u32(sm + (BPW + u) * TILE) + lane_off;
+                float acc[MT][NT][4];
+                uint32_t h[MT][NT][2];
+                // ---- forward, first pass: temp = (T X + r) >> s,  X = orig - pred as B fragments
+                {
+                    uint32_t xb[KT][NT][2];
+#pragma unroll
+                    for (int ki = 0; ki < KT; ++ki)
+#pragma unroll
+                        for (int np = 0; np < NT / 2; ++np) {
+                            uint32_t ro[4], rp[4];
+                            const uint32_t off = 16 * ki * PITCH + 32 * np;
+                            ldsm_x4_t(ro, so + off);
+                            ldsm_x4_t(rp, sp + off);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)  // (1024 + o) - (1024 + p), exact in f16
+                                xb[ki][2 * np + (j >> 1)][j & 1] = h2_bits(
+                                    __hsub2(bits_h2(ro[j] | 0x64006400u), bits_h2(rp[j] | 0x64006400u)));
+                        }
+                    init_acc<MT, NT>(acc, rnd);
+#pragma unroll
+                    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < NT; ++ni)
+#pragma unroll
+                            for (int ki = 0; ki < KT; ++ki)
+                                hmma16816(acc[mi][ni], ta[mi][ki][0], ta[mi][ki][1], ta[mi][ki][2],
+                                          ta[mi][ki][3], xb[ki][ni][0], xb[ki][ni][1]);
+                }
+                round_to_operand<MT, NT, SH>(acc, h);
+                // ---- forward, second pass (transposed): coeff^T(m = v, n = i) = (T temp^T + r) >> s
+                init_acc<MT, NT>(acc, rnd);
+                mma_const_a<MT, NT, KT>(acc, ta, h);
+                // ---- coefficients out, quant, levels out, dequant -> operand of the inverse
+#pragma unroll
+                for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < NT; ++ni) {
+                        float dqf[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int c = __float_as_int(floor_shift_magic<SH>(acc[mi][ni][e])) - kMagicI;
+                            const int i = 8 * ni + 2 * ft + (e & 1), v = 16 * mi + fg + 8 * (e >> 1);
+                            const int lv = quantize_fast(c, fq);
+                            const int dq = dequantize_fast(lv, fq);
+                            if (valid_u) {
+                                if (a.coeff) __stcs(a.coeff + bu * NN + i * N + v, c);
+                                if (a.levels) __stcs(a.levels + bu * NN + i * N + v, lv);
+                            }
+                            dqf[e] = __int_as_float(dq + kMagicI) - kMagicF;
+                        }
+                        h[mi][ni][0] = pack_h2(dqf[0], dqf[1]);
+                        h[mi][ni][1] = pack_h2(dqf[2], dqf[3]);
+                    }
+                // ---- inverse, first pass: tmp2(m = y, n = v) = (T^T dq + r) >> s,  A = T^T from tb
+                init_acc<MT, NT>(acc, rnd);
+                {
+                    uint32_t tat[MT][KT][4];
+#pragma unroll
+                    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+                        for (int ki = 0; ki < KT; ++ki) {
+                            tat[mi][ki][0] = tb[ki][2 * mi][0];
+                            tat[mi][ki][1] = tb[ki][2 * mi + 1][0];
+                            tat[mi][ki][2] = tb[ki][2 * mi][1];
+                            tat[mi][ki][3] = tb[ki][2 * mi + 1][1];
+                        }
+                    mma_const_a<MT, NT, KT>(acc, tat, h);
+                }
+                round_to_operand<MT, NT, SH>(acc, h);
+                // ---- inverse, second pass: res(m = y, n = x) = (tmp2 T + r) >> s,  A = tmp2 (C -> A)
+                init_acc<MT, NT>(acc, rnd);
+#pragma unroll
+                for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < NT; ++ni)
+#pragma unroll
+                        for (int ki = 0; ki < KT; ++ki)
+                            hmma16816(acc[mi][ni], h[mi][2 * ki][0], h[mi][2 * ki][1], h[mi][2 * ki + 1][0],
+                                      h[mi][2 * ki + 1][1], tb[ki][ni][0], tb[ki][ni][1]);
+                // ---- reconstruct + clip in f16 pairs: (1024 + p) + res clamped to [1024, 1024 + max]
+                // (anything beyond +-2048 is inexact in f16 but far outside the clamp), back to int16
+                // by masking the mantissa; the tile of original pixels is reused for the result.
+#pragma unroll
+                for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+                    for (int np = 0; np < NT / 2; ++np) {
+                        uint32_t rp[4], ro[4];
+                        const uint32_t off = 16 * mi * PITCH + 32 * np;
+                        ldsm_x4(rp, sp + off);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float(&c)[4] = acc[mi][2 * np + (j >> 1)];
+                            const float r0 = floor_shift_magic<SH>(c[2 * (j & 1)]) - kMagicF;
+                            const float r1 = floor_shift_magic<SH>(c[2 * (j & 1) + 1]) - kMagicF;
+                            __half2 s = __hadd2(bits_h2(rp[j] | 0x64006400u), __floats2half2_rn(r0, r1));
+                            s = __hmin2(__hmax2(s, kBias), kHi);
+                            ro[j] = h2_bits(s) & 0x03FF03FFu;
+                        }
+                        stsm_x4(so + off, ro);
+                    }
+            }
+            __syncwarp();
+            if (valid && a.recon) {
+#pragma unroll
+                for (int q = 0; q < N / 8; ++q)
+                    stg_stream(a.recon + b * NN + r * N + 8 * q, *reinterpret_cast<const uint4*>(my_o + 16 * q));
+            }
+        } else {
+            // exact CUDA-core path: residual rows into the int32 working matrix (aliases the tiles)
+            uint32_t ow[N / 2], pw[N / 2];
+#pragma unroll
+            for (int q = 0; q < N / 8; ++q) {
+                const uint4 vo = *reinterpret_cast<const uint4*>(my_o + 16 * q);
+                const uint4 vp = *reinterpret_cast<const uint4*>(my_p + 16 * q);
+                ow[4 * q] = vo.x; ow[4 * q + 1] = vo.y; ow[4 * q + 2] = vo.z; ow[4 * q + 3] = vo.w;
+                pw[4 * q] = vp.x; pw[4 * q + 1] = vp.y; pw[4 * q + 2] = vp.z; pw[4 * q + 3] = vp.w;
+            }
+            __syncwarp();
+            int* M = reinterpret_cast<int*>(sm) + g * RowsTile<N>::WORDS;
+            {
+                int res[N];
+#pragma unroll
+                for (int k = 0; k < N / 2; ++k) {
+                    res[2 * k] = sext16(lo16(ow[k]) - lo16(pw[k]));
+                    res[2 * k + 1] = sext16(hi16(ow[k]) - hi16(pw[k]));
+                }
+                store_row_smem<N>(M, r, res);
+            }
+            __syncwarp();
+            if (a.ood_flag && lane == 0) *a.ood_flag = 1;
+            rows_tile_exact<N>(a, M, r, valid, b, pw);
+        }
+        __syncwarp();
+    }
+}
+
+template <int N>
+static int launch_mma(const FusedArgs& a, cudaStream_t st) {
+    constexpr int BPW = 32 / N;
+    int grid = grid_for(a.n_blocks, (int64_t)kMmaWarps * BPW, 3);
+    fused_mma_kernel<N><<<grid, kMmaWarps * 32, 0, st>>>(a, make_fast_quant(a.qp));
+    NH_CHECK_LAUNCH("fused_mma_kernel");
+    return NH_OK;
+}
+
+}  // namespace nh

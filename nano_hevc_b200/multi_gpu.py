@@ -30,6 +30,19 @@ def _world(group=None):
     return 0, 1
 
 
+_STREAMS: dict = {}
+
+
+def _frame_streams(device, n):
+    """Per-device side streams, created once: the caching allocator keeps one pool per stream, so
+    fresh streams on every call would turn every output allocation into a cudaMalloc."""
+    key = str(torch.device(device))
+    have = _STREAMS.setdefault(key, [])
+    while len(have) < n:
+        have.append(torch.cuda.Stream(device=device))
+    return have[:n]
+
+
 def frame_stats(src: torch.Tensor, result) -> torch.Tensor:
     """(sse, n_samples, sum_sad_cost, nonzero_levels) of one coded frame as an int64 device tensor.
     sse / n_samples follow metrics.py:7-21 over the WHOLE plane (uncovered rows count, as in
@@ -44,7 +57,8 @@ def frame_stats(src: torch.Tensor, result) -> torch.Tensor:
 def encode_frames_sharded(frames: Sequence, size: int, cost: str = "sad", qp: int = 27,
                           recon_neighbours: bool = True, bit_depth: int = 8, group=None,
                           device: torch.device | None = None,
-                          encode_fn: Callable | None = None, stats_fn: Callable | None = None):
+                          encode_fn: Callable | None = None, stats_fn: Callable | None = None,
+                          max_concurrent_frames: int = 8):
     """Code ``frames`` (a sequence of (H, W) int16 arrays / tensors, identical on every rank) with
     frame i on rank ``i mod``-contiguous shard, then all-gather the per-frame statistics.
 
@@ -61,15 +75,31 @@ def encode_frames_sharded(frames: Sequence, size: int, cost: str = "sad", qp: in
                                                    bit_depth=bit_depth)
         stats_fn = frame_stats
     local, local_stats = [], []
-    for i in range(lo, hi):
+    # A wavefront frame occupies only a few hundred warps (one per block row), so the frames of this
+    # rank run concurrently on separate CUDA streams; the coders are independent (no shared state).
+    use_streams = (device is not None and torch.device(device).type == "cuda" and hi - lo > 1
+                   and max_concurrent_frames > 1)
+    streams = _frame_streams(device, min(hi - lo, max_concurrent_frames)) if use_streams else []
+    main = torch.cuda.current_stream(device) if use_streams else None
+    for n_done, i in enumerate(range(lo, hi)):
         f = frames[i]
         if not isinstance(f, torch.Tensor):
             f = torch.from_numpy(np.ascontiguousarray(f, dtype=np.int16))
         if device is not None:
             f = f.to(device, non_blocking=True)
-        r = encode_fn(f)
-        local.append(r)
-        local_stats.append(stats_fn(f, r).to(torch.int64))
+        if use_streams:
+            st = streams[n_done % len(streams)]
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                r = encode_fn(f)
+                local_stats.append(stats_fn(f, r).to(torch.int64))
+            local.append(r)
+        else:
+            r = encode_fn(f)
+            local.append(r)
+            local_stats.append(stats_fn(f, r).to(torch.int64))
+    for st in streams:
+        main.wait_stream(st)
     stat_dev = local_stats[0].device if local_stats else (device or torch.device("cpu"))
     # pad every rank's block to the largest shard so a single all_gather suffices
     per = -(-n // world) if world else n

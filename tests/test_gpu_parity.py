@@ -284,6 +284,74 @@ def test_fused_unit_generations_and_out_of_domain(Bt, n, gen):
         _lib.check(_lib.lib().nh_set_fused_impl(2))
 
 
+def _dct(n):
+    import math
+    c = [64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67, 64, 61, 57, 54, 50, 46, 43, 38, 36, 31, 25,
+         22, 18, 13, 9, 4, 0]
+    def cv(m):
+        m &= 127
+        return c[m] if m <= 32 else -c[64 - m] if m <= 64 else -c[m - 64] if m <= 96 else c[128 - m]
+    return np.array([[cv((i * (32 // n)) * (2 * j + 1)) for j in range(n)] for i in range(n)])
+
+
+@pytest.mark.parametrize("n", (16, 32))
+@pytest.mark.parametrize("impl", (1, 2))
+def test_fused_rows_impls_adversarial(Bt, n, impl):
+    """N = 16 / 32 behind both kernels (1 = CUDA-core butterflies, 2 = tensor-core passes).  The
+    tensor-core path is exact only because every operand stays a small integer: drive it with the
+    worst cases -- basis patterns 255*[sign(T[i] (x) T[j]) > 0] against pred 0 / 255 (largest
+    coefficients of either sign), impulses, checkerboards, every QP, intra and inter dead zone --
+    plus tiles that mix in-domain and out-of-domain blocks (exact fallback) and a clip bound > 1023."""
+    from nano_hevc_b200 import _lib
+    rng = np.random.default_rng(900 + n)
+    T = _dct(n)
+    blocks, tops = [], []
+    idx = [(0, 0), (1, 1), (n - 1, n - 1), (0, n - 1), (n - 1, 0), (1, 0), (n // 2, n // 2), (3, 5), (n - 1, 1)]
+    for (i, j) in idx:
+        s = np.sign(np.outer(T[i], T[j]))
+        for flip in (1, -1):
+            for ref in (0, 255):
+                blocks.append(np.where(flip * s > 0, 255, 0)); tops.append(ref)
+    for ref in (0, 255, 128):
+        imp = np.full((n, n), ref); imp[n // 3, n // 2] = 255 - ref
+        blocks.append(imp); tops.append(ref)
+        yy, xx = np.mgrid[0:n, 0:n]
+        blocks.append(np.where((yy + xx) % 2 == 0, 255, 0)); tops.append(ref)
+    nb = len(blocks)
+    B = nb + 200
+    orig, top, left, tr, bl = _dcplanar_inputs(rng, B, n)
+    orig[:nb] = np.array(blocks, np.int16)
+    for k, ref in enumerate(tops):
+        top[k] = ref; left[k] = ref; tr[k] = ref; bl[k] = ref
+    modes = rng.integers(0, 2, B).astype(np.uint8)
+    d = [dev(v) for v in (orig, top, left, tr, bl)]
+    _lib.check(_lib.lib().nh_set_rows_impl(impl))
+    try:
+        for qp in range(0, 52):
+            for intra in ((True, False) if qp % 7 == 0 else (True,)):
+                got = Bt.fused_block_pipeline(*d, dev(modes), qp, is_intra=intra)
+                want = O.pipeline_dcplanar_batch(orig, top, left, tr, bl, modes, qp, is_intra=intra,
+                                                 threads=O.n_host_threads())
+                for name, w in zip(("pred", "coeff", "levels", "recon"), want):
+                    eq(host(getattr(got, name)), w, f"{name} impl={impl} n={n} qp={qp} intra={intra}")
+        # out-of-domain samples sprinkled over the batch (256 is already outside the tensor-core domain)
+        o2, t2, l2 = orig.copy(), top.copy(), left.copy()
+        o2[3, 2, 1] = 256; o2[40] = rng.integers(-32768, 32768, (n, n)); t2[41, 0] = -1; l2[77, n - 1] = 4096
+        o2[100:110] = rng.integers(0, 1024, (10, n, n))
+        for qp, bd in ((22, 8), (37, 10), (4, 12)):
+            got = Bt.fused_block_pipeline(dev(o2), dev(t2), dev(l2), d[3], d[4], dev(modes), qp, bit_depth=bd)
+            want = O.pipeline_dcplanar_batch(o2, t2, l2, tr, bl, modes, qp, bit_depth=bd)
+            for name, w in zip(("pred", "coeff", "levels", "recon"), want):
+                eq(host(getattr(got, name)), w, f"ood {name} impl={impl} n={n} qp={qp} bd={bd}")
+        # partial outputs and a ragged single block
+        got = Bt.fused_block_pipeline(*[dev(v[:1]) for v in (orig, top, left, tr, bl)], 0, 30, outputs=("coeff", "recon"))
+        want = O.pipeline_dcplanar_batch(orig[:1], top[:1], left[:1], tr[:1], bl[:1], 0, 30)
+        assert got.pred is None and got.levels is None
+        eq(host(got.coeff), want[1]); eq(host(got.recon), want[3])
+    finally:
+        _lib.check(_lib.lib().nh_set_rows_impl(2))
+
+
 @pytest.mark.parametrize("n,B,chunk", [(4, 70001, 8192), (8, 20011, 4096), (16, 3001, 1024), (32, 1000, 300)])
 def test_host_pipeline_vs_oracle(Bt, n, B, chunk):
     """The host-buffer C-ABI entry (chunked, three streams, int16 wire format for coefficients and
