@@ -75,30 +75,22 @@ __device__ __forceinline__ float floor_shift_magic(float acc) {
     return __fmaf_rd(acc, 1.0f / (float)(1 << SH), kMagicF);
 }
 
-// One pass boundary: accumulators -> rounded / shifted integers -> packed f16 operand fragments.
-template <int MT, int NT, int SH>
-__device__ __forceinline__ void round_to_operand(const float (&acc)[MT][NT][4], uint32_t (&h)[MT][NT][2]) {
-#pragma unroll
-    for (int mi = 0; mi < MT; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < NT; ++ni) {
-            const float v0 = floor_shift_magic<SH>(acc[mi][ni][0]) - kMagicF;
-            const float v1 = floor_shift_magic<SH>(acc[mi][ni][1]) - kMagicF;
-            const float v2 = floor_shift_magic<SH>(acc[mi][ni][2]) - kMagicF;
-            const float v3 = floor_shift_magic<SH>(acc[mi][ni][3]) - kMagicF;
-            h[mi][ni][0] = pack_h2(v0, v1);
-            h[mi][ni][1] = pack_h2(v2, v3);
-        }
+// ---- pass boundaries ---------------------------------------------------------------------------
+// Plain form: accumulator -> floor shift -> f32 integer -> f16 pair.  2.5 instructions per value.
+template <int SH>
+__device__ __forceinline__ uint32_t round_pair_plain(float a0, float a1) {
+    return pack_h2(floor_shift_magic<SH>(a0) - kMagicF, floor_shift_magic<SH>(a1) - kMagicF);
 }
-
-template <int MT, int NT>
-__device__ __forceinline__ void init_acc(float (&acc)[MT][NT][4], float rnd) {
-#pragma unroll
-    for (int mi = 0; mi < MT; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < NT; ++ni)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[mi][ni][e] = rnd;
+// Biased form, for integers k in [-512, 511]: FFMA.RM against (magic + 512) leaves k + 512 in the low
+// 16 bits; PRMT packs two of them and OR 0x6400 turns each into the f16 number 1024 + (k + 512) =
+// k + 1536.  The operand fed to the next MMA is therefore k + 1536 and the constant 1536 * (row or
+// column sum of T) is taken out again through the next accumulator's initial value.  2 per value.
+constexpr float kOperandBias = 1536.0f;
+template <int SH>
+__device__ __forceinline__ uint32_t round_pair_biased(float a0, float a1) {
+    const uint32_t m0 = __float_as_uint(__fmaf_rd(a0, 1.0f / (float)(1 << SH), kMagicF + 512.0f));
+    const uint32_t m1 = __float_as_uint(__fmaf_rd(a1, 1.0f / (float)(1 << SH), kMagicF + 512.0f));
+    return __byte_perm(m0, m1, 0x5410) | 0x64006400u;
 }
 
 // acc(m, n) += A_const(m, k) * B(k, n) where B[k][n] = P[n][k] and P is the previous pass's result
@@ -121,14 +113,19 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) fused_mma_kernel(const Fuse
     constexpr int NN = N * N;
     constexpr int BPW = 32 / N;  // blocks per warp tile
     constexpr int MT = N / 16, NT = N / 8, KT = N / 16;
+    constexpr int S1 = Log2<N>::v + 1;
     constexpr int SH = Log2<N>::v + 5;  // transform.py:173-175, :215-217
+    // |tmp2| <= 328 at N = 32 fits the biased operand form, 661 at N = 16 does not
+    constexpr bool kBiasTmp2 = N == 32;
     // int16 block tile in shared memory: row pitch N*2 + 16 bytes (an odd number of 16-byte groups),
     // so the 8 rows of an ldmatrix / stmatrix 8x8 tile and the per-lane 128-bit row accesses are
     // conflict-free.
     constexpr int PITCH = N * 2 + 16;
     constexpr int TILE = N * PITCH;
+    constexpr int TOP_OFF = 2 * BPW * TILE;  // then one row of top references per block
+    constexpr int FAST_BYTES = TOP_OFF + BPW * N * 2;
     constexpr int EXACT_BYTES = BPW * RowsTile<N>::WORDS * 4;
-    constexpr int WARP_BYTES = 2 * BPW * TILE > EXACT_BYTES ? 2 * BPW * TILE : EXACT_BYTES;
+    constexpr int WARP_BYTES = FAST_BYTES > EXACT_BYTES ? FAST_BYTES : EXACT_BYTES;
     __shared__ __align__(16) unsigned char smem[kMmaWarps][WARP_BYTES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane / N, r = lane % N;    // I/O mapping: lane = row r of block g
@@ -136,6 +133,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) fused_mma_kernel(const Fuse
     unsigned char* sm = smem[warp];
     unsigned char* my_o = sm + g * TILE + r * PITCH;          // this lane's row of the original tile
     unsigned char* my_p = sm + (BPW + g) * TILE + r * PITCH;  // ... and of the prediction tile
+    int16_t* my_top = reinterpret_cast<int16_t*>(sm + TOP_OFF) + g * N;
     // ldmatrix / stmatrix x4 row address of this lane: 8x8 tile j = lane >> 3 covers rows
     // 8*(j&1).. and columns 8*(j>>1)..  of a 16x16 region
     const int lane_off = (((lane >> 3) & 1) * 8 + (lane & 7)) * PITCH + (lane >> 4) * 16;
@@ -161,80 +159,129 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) fused_mma_kernel(const Fuse
             tb[ki][ni][0] = t_pair<N>(k0, x0, k0 + 1, x0);
             tb[ki][ni][1] = t_pair<N>(k0 + 8, x0, k0 + 9, x0);
         }
-
+    // Accumulator start values: rounding offset, minus 1536 * (sum over the contracted index of the
+    // constant operand) where the data operand carries the +1536 bias.
     const float rnd = (float)(1 << (SH - 1));
-    const int clip_hi = a.maxv;
+    float init_f2[MT][2];  // rows v = 16mi + fg + 8h:  - 1536 * sum_x T[v][x]
+    float init_i1[MT][2];  // rows y = 16mi + fg + 8h:  - 1536 * sum_i T[i][y]
+    float init_i2[NT][2];  // cols x = 8ni + 2ft + p:   - 1536 * sum_v T[v][x]
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int v = 16 * mi + fg + 8 * hh;
+            int rs = 0, cs = 0;
+#pragma unroll 1
+            for (int k = 0; k < N; ++k) {
+                rs += cosv_dev((v * (32 / N)) * (2 * k + 1));
+                cs += cosv_dev((k * (32 / N)) * (2 * v + 1));
+            }
+            init_f2[mi][hh] = rnd - kOperandBias * (float)rs;
+            init_i1[mi][hh] = rnd - kOperandBias * (float)cs;
+        }
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni)
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int x = 8 * ni + 2 * ft + p;
+            int cs = 0;
+#pragma unroll 1
+            for (int k = 0; k < N; ++k) cs += cosv_dev((k * (32 / N)) * (2 * x + 1));
+            init_i2[ni][p] = kBiasTmp2 ? rnd - kOperandBias * (float)cs : rnd;
+        }
+
     const bool clip_ok = a.maxv <= 1023;
-    const __half2 kBias = __floats2half2_rn(1024.0f, 1024.0f);
-    const float hi_f = 1024.0f + (float)(clip_ok ? clip_hi : 0);
-    const __half2 kHi = __floats2half2_rn(hi_f, hi_f);
+    const uint32_t clip_lo2 = 0x08000800u;  // reconstruction carries a +2048 bias per 16-bit half
+    const uint32_t clip_hi2 = clip_lo2 + (uint32_t)(clip_ok ? a.maxv : 0) * 0x10001u;
+    const int dq_rnd_b = fq.dq_rnd + (512 << fq.dq_shift);  // dequantised value + 512
 
     const int64_t n_tiles = (a.n_blocks + BPW - 1) / BPW;
     const int64_t warp_stride = (int64_t)gridDim.x * kMmaWarps;
     int64_t tile = (int64_t)blockIdx.x * kMmaWarps + warp;
 
-    uint32_t nxt_ow[N / 2];  // this lane's row of original pixels, one tile ahead
-    auto load_orig = [&](int64_t t) {
+    // one tile ahead: this lane's row of original pixels and its reference samples
+    uint32_t nxt_ow[N / 2];
+    int nxt_top = 0, nxt_left = 0, nxt_tr = 0, nxt_bl = 0, nxt_mode = 0;
+    auto prefetch = [&](int64_t t) {
         const int64_t b = t * BPW + g;
         if (b < a.n_blocks) {
             load_row16<N>(a.orig + b * NN + r * N, nxt_ow);
+            nxt_top = a.top[b * N + r];
+            nxt_left = a.left[b * N + r];
+            nxt_tr = a.top_right[b];
+            nxt_bl = a.bottom_left[b];
+            nxt_mode = a.modes ? (int)a.modes[b] : a.mode;
         } else {
 #pragma unroll
             for (int k = 0; k < N / 2; ++k) nxt_ow[k] = 0;
+            nxt_top = nxt_left = nxt_tr = nxt_bl = 0;
+            nxt_mode = 1;
         }
     };
-    if (tile < n_tiles) load_orig(tile);
+    if (tile < n_tiles) prefetch(tile);
 
     for (; tile < n_tiles; tile += warp_stride) {
         const int64_t b = tile * BPW + g;
         const bool valid = b < a.n_blocks;
-        uint32_t ood = 0;  // any sample outside [0, 255]
-        {
+        uint32_t ood = (uint32_t)(nxt_top | nxt_left | nxt_tr | nxt_bl) & 0xFFFFFF00u;  // outside [0, 255]
 #pragma unroll
-            for (int q = 0; q < N / 8; ++q) {
-                *reinterpret_cast<uint4*>(my_o + 16 * q) =
-                    make_uint4(nxt_ow[4 * q], nxt_ow[4 * q + 1], nxt_ow[4 * q + 2], nxt_ow[4 * q + 3]);
-                ood |= (nxt_ow[4 * q] | nxt_ow[4 * q + 1] | nxt_ow[4 * q + 2] | nxt_ow[4 * q + 3]) & 0xFF00FF00u;
+        for (int q = 0; q < N / 8; ++q) {
+            *reinterpret_cast<uint4*>(my_o + 16 * q) =
+                make_uint4(nxt_ow[4 * q], nxt_ow[4 * q + 1], nxt_ow[4 * q + 2], nxt_ow[4 * q + 3]);
+            ood |= (nxt_ow[4 * q] | nxt_ow[4 * q + 1] | nxt_ow[4 * q + 2] | nxt_ow[4 * q + 3]) & 0xFF00FF00u;
+        }
+        my_top[r] = (int16_t)nxt_top;
+        const int left_r = nxt_left, tr = nxt_tr, bl = nxt_bl, mode = nxt_mode;
+        // sum of the block's 2N reference samples.  (A partial-mask __reduce_add_sync would split
+        // the warp -- WARPSYNC.EXCLUSIVE + REDUX into a uniform register -- and leave the halves
+        // diverged in front of the warp-collective instructions below.)
+        int ref_sum = nxt_top + nxt_left;
+        if constexpr (BPW == 1) {
+            ref_sum = __reduce_add_sync(0xffffffffu, ref_sum);
+        } else {
+#pragma unroll
+            for (int o = N / 2; o > 0; o >>= 1) ref_sum += __shfl_xor_sync(0xffffffffu, ref_sum, o);
+        }
+        const bool fast = clip_ok && !__any_sync(0xffffffffu, ood != 0);
+        if (tile + warp_stride < n_tiles) prefetch(tile + warp_stride);
+        __syncwarp();
+        // `fast` is warp-uniform and the ONLY branch around the warp-collective instructions
+        // (ldmatrix / mma / stmatrix .sync.aligned); the per-lane mode test is nested inside it and
+        // reconverges before them.
+        uint32_t pw[N / 2];  // this lane's prediction row, packed
+        uint32_t tw[N / 2];
+#pragma unroll
+        for (int q = 0; q < N / 8; ++q) {
+            const uint4 v = *reinterpret_cast<const uint4*>(my_top + 8 * q);
+            tw[4 * q] = v.x; tw[4 * q + 1] = v.y; tw[4 * q + 2] = v.z; tw[4 * q + 3] = v.w;
+        }
+        const uint32_t dc2 = (uint32_t)(dc_value<N>(ref_sum) & 0xffff) * 0x10001u;  // intra.py:46-62
+        if (fast) {
+            // intra.py:109-111 on 16-bit pairs: every term is non-negative and the sum of a pair
+            // member stays below 2^16, so one 32-bit multiply-add chain serves two pixels
+            const uint32_t wy = (uint32_t)(N - 1 - r);
+            const uint32_t c0 = (uint32_t)((r + 1) * bl + N) * 0x10001u;
+#pragma unroll
+            for (int k = 0; k < N / 2; ++k) {
+                const uint32_t ck1 = (uint32_t)(N - 1 - 2 * k) | ((uint32_t)(N - 2 - 2 * k) << 16);
+                const uint32_t ck2 = (uint32_t)(2 * k + 1) | ((uint32_t)(2 * k + 2) << 16);
+                const uint32_t t = tw[k] * wy + c0 + (uint32_t)left_r * ck1 + (uint32_t)tr * ck2;
+                pw[k] = mode == 1 ? dc2 : ((t >> S1) & 0x00FF00FFu);
             }
-            if (tile + warp_stride < n_tiles) load_orig(tile + warp_stride);
-            uint32_t pw[N / 2];
-            if (valid) {
-                const int mode = a.modes ? (int)a.modes[b] : a.mode;
-                uint32_t tw[N / 2], lw[N / 2];
-                load_row16<N>(a.top + b * N, tw);
-                load_row16<N>(a.left + b * N, lw);
-                const int tr = a.top_right[b], bl = a.bottom_left[b];
-#pragma unroll
-                for (int k = 0; k < N / 2; ++k) ood |= (tw[k] | lw[k]) & 0xFF00FF00u;
-                ood |= (uint32_t)(tr | bl) & 0xFFFFFF00u;
-                int p[N];
-                if (mode == 1) {
-                    const int dc = dc_value<N>(sum_row<N>(tw) + sum_row<N>(lw));
-#pragma unroll
-                    for (int x = 0; x < N; ++x) p[x] = dc;
-                } else {
-                    int top[N];
-                    unpack_row<N>(tw, top);
-                    planar_row<N>(r, (int)a.left[b * N + r], top, tr, bl, p);
-                }
-                pack_row<N>(p, pw);
-                if (a.pred) store_row16<N>(a.pred + b * NN + r * N, pw);
-            } else {
-#pragma unroll
-                for (int k = 0; k < N / 2; ++k) pw[k] = 0;
-            }
+            if (valid && a.pred) store_row16<N>(a.pred + b * NN + r * N, pw);
 #pragma unroll
             for (int q = 0; q < N / 8; ++q)
                 *reinterpret_cast<uint4*>(my_p + 16 * q) =
                     make_uint4(pw[4 * q], pw[4 * q + 1], pw[4 * q + 2], pw[4 * q + 3]);
-        }
-        const bool fast = clip_ok && !__any_sync(0xffffffffu, ood != 0);
-        __syncwarp();
-        if (fast) {
+            __syncwarp();
 #pragma unroll
             for (int u = 0; u < BPW; ++u) {
                 const int64_t bu = tile * BPW + u;
                 const bool valid_u = bu < a.n_blocks;  // warp-uniform
+                const bool want_c = valid_u && a.coeff != nullptr, want_l = valid_u && a.levels != nullptr;
+                // element (i = 2ft + ..., v = fg + ...) of the transposed coefficient fragments
+                int32_t* cp = a.coeff + bu * NN + (2 * ft) * N + fg;
+                int32_t* lp = a.levels + bu * NN + (2 * ft) * N + fg;
                 const uint32_t so = smem_u32(sm + u * TILE) + lane_off;
                 const uint32_t sp = smem_u32(sm + (BPW + u) * TILE) + lane_off;
                 float acc[MT][NT][4];
@@ -255,43 +302,58 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) fused_mma_kernel(const Fuse
                                 xb[ki][2 * np + (j >> 1)][j & 1] = h2_bits(
                                     __hsub2(bits_h2(ro[j] | 0x64006400u), bits_h2(rp[j] | 0x64006400u)));
                         }
-                    init_acc<MT, NT>(acc, rnd);
 #pragma unroll
                     for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
-                        for (int ni = 0; ni < NT; ++ni)
+                        for (int ni = 0; ni < NT; ++ni) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) acc[mi][ni][e] = rnd;
 #pragma unroll
                             for (int ki = 0; ki < KT; ++ki)
                                 hmma16816(acc[mi][ni], ta[mi][ki][0], ta[mi][ki][1], ta[mi][ki][2],
                                           ta[mi][ki][3], xb[ki][ni][0], xb[ki][ni][1]);
+                        }
                 }
-                round_to_operand<MT, NT, SH>(acc, h);
+#pragma unroll
+                for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < NT; ++ni) {  // |temp| <= 511: biased operand
+                        h[mi][ni][0] = round_pair_biased<SH>(acc[mi][ni][0], acc[mi][ni][1]);
+                        h[mi][ni][1] = round_pair_biased<SH>(acc[mi][ni][2], acc[mi][ni][3]);
+                    }
                 // ---- forward, second pass (transposed): coeff^T(m = v, n = i) = (T temp^T + r) >> s
-                init_acc<MT, NT>(acc, rnd);
+#pragma unroll
+                for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < NT; ++ni)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[mi][ni][e] = init_f2[mi][e >> 1];
                 mma_const_a<MT, NT, KT>(acc, ta, h);
-                // ---- coefficients out, quant, levels out, dequant -> operand of the inverse
+                // ---- coefficients out, quant, levels out, dequant -> biased operand of the inverse
 #pragma unroll
                 for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
                     for (int ni = 0; ni < NT; ++ni) {
-                        float dqf[4];
+                        int dqb[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int c = __float_as_int(floor_shift_magic<SH>(acc[mi][ni][e])) - kMagicI;
-                            const int i = 8 * ni + 2 * ft + (e & 1), v = 16 * mi + fg + 8 * (e >> 1);
+                            const int off = (8 * ni + (e & 1)) * N + 16 * mi + 8 * (e >> 1);
                             const int lv = quantize_fast(c, fq);
-                            const int dq = dequantize_fast(lv, fq);
-                            if (valid_u) {
-                                if (a.coeff) __stcs(a.coeff + bu * NN + i * N + v, c);
-                                if (a.levels) __stcs(a.levels + bu * NN + i * N + v, lv);
-                            }
-                            dqf[e] = __int_as_float(dq + kMagicI) - kMagicF;
+                            if (want_c) __stcs(cp + off, c);
+                            if (want_l) __stcs(lp + off, lv);
+                            dqb[e] = (lv * fq.dq_mult + dq_rnd_b) >> fq.dq_shift;  // |dq| <= 360
                         }
-                        h[mi][ni][0] = pack_h2(dqf[0], dqf[1]);
-                        h[mi][ni][1] = pack_h2(dqf[2], dqf[3]);
+                        h[mi][ni][0] = __byte_perm((uint32_t)dqb[0], (uint32_t)dqb[1], 0x5410) | 0x64006400u;
+                        h[mi][ni][1] = __byte_perm((uint32_t)dqb[2], (uint32_t)dqb[3], 0x5410) | 0x64006400u;
                     }
                 // ---- inverse, first pass: tmp2(m = y, n = v) = (T^T dq + r) >> s,  A = T^T from tb
-                init_acc<MT, NT>(acc, rnd);
+#pragma unroll
+                for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < NT; ++ni)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[mi][ni][e] = init_i1[mi][e >> 1];
                 {
                     uint32_t tat[MT][KT][4];
 #pragma unroll
@@ -305,20 +367,34 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) fused_mma_kernel(const Fuse
                         }
                     mma_const_a<MT, NT, KT>(acc, tat, h);
                 }
-                round_to_operand<MT, NT, SH>(acc, h);
-                // ---- inverse, second pass: res(m = y, n = x) = (tmp2 T + r) >> s,  A = tmp2 (C -> A)
-                init_acc<MT, NT>(acc, rnd);
 #pragma unroll
                 for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
-                    for (int ni = 0; ni < NT; ++ni)
+                    for (int ni = 0; ni < NT; ++ni) {
+                        if constexpr (kBiasTmp2) {
+                            h[mi][ni][0] = round_pair_biased<SH>(acc[mi][ni][0], acc[mi][ni][1]);
+                            h[mi][ni][1] = round_pair_biased<SH>(acc[mi][ni][2], acc[mi][ni][3]);
+                        } else {
+                            h[mi][ni][0] = round_pair_plain<SH>(acc[mi][ni][0], acc[mi][ni][1]);
+                            h[mi][ni][1] = round_pair_plain<SH>(acc[mi][ni][2], acc[mi][ni][3]);
+                        }
+                    }
+                // ---- inverse, second pass: res(m = y, n = x) = (tmp2 T + r) >> s,  A = tmp2 (C -> A)
+#pragma unroll
+                for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < NT; ++ni) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[mi][ni][e] = init_i2[ni][e & 1];
 #pragma unroll
                         for (int ki = 0; ki < KT; ++ki)
                             hmma16816(acc[mi][ni], h[mi][2 * ki][0], h[mi][2 * ki][1], h[mi][2 * ki + 1][0],
                                       h[mi][2 * ki + 1][1], tb[ki][ni][0], tb[ki][ni][1]);
-                // ---- reconstruct + clip in f16 pairs: (1024 + p) + res clamped to [1024, 1024 + max]
-                // (anything beyond +-2048 is inexact in f16 but far outside the clamp), back to int16
-                // by masking the mantissa; the tile of original pixels is reused for the result.
+                    }
+                // ---- reconstruct + clip (intra.py:70-78) on 16-bit pairs: FFMA.RM against magic + 2048
+                // leaves res + 2048 (> 0, |res| <= 1214) in the low 16 bits; add the prediction pair,
+                // clamp both halves to [2048, 2048 + max] and drop the bias.  The tile of original
+                // pixels is reused for the result.
 #pragma unroll
                 for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
@@ -329,11 +405,12 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) fused_mma_kernel(const Fuse
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float(&c)[4] = acc[mi][2 * np + (j >> 1)];
-                            const float r0 = floor_shift_magic<SH>(c[2 * (j & 1)]) - kMagicF;
-                            const float r1 = floor_shift_magic<SH>(c[2 * (j & 1) + 1]) - kMagicF;
-                            __half2 s = __hadd2(bits_h2(rp[j] | 0x64006400u), __floats2half2_rn(r0, r1));
-                            s = __hmin2(__hmax2(s, kBias), kHi);
-                            ro[j] = h2_bits(s) & 0x03FF03FFu;
+                            const uint32_t m0 = __float_as_uint(
+                                __fmaf_rd(c[2 * (j & 1)], 1.0f / (float)(1 << SH), kMagicF + 2048.0f));
+                            const uint32_t m1 = __float_as_uint(
+                                __fmaf_rd(c[2 * (j & 1) + 1], 1.0f / (float)(1 << SH), kMagicF + 2048.0f));
+                            const uint32_t s = __byte_perm(m0, m1, 0x5410) + rp[j];
+                            ro[j] = __vminu2(__vmaxu2(s, clip_lo2), clip_hi2) - clip_lo2;
                         }
                         stsm_x4(so + off, ro);
                     }
@@ -346,13 +423,20 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) fused_mma_kernel(const Fuse
             }
         } else {
             // exact CUDA-core path: residual rows into the int32 working matrix (aliases the tiles)
-            uint32_t ow[N / 2], pw[N / 2];
+            {
+                int top[N], p[N];
+                unpack_row<N>(tw, top);
+                planar_row<N>(r, left_r, top, tr, bl, p);
+                pack_row<N>(p, pw);
+#pragma unroll
+                for (int k = 0; k < N / 2; ++k) pw[k] = mode == 1 ? dc2 : pw[k];
+            }
+            if (valid && a.pred) store_row16<N>(a.pred + b * NN + r * N, pw);
+            uint32_t ow[N / 2];
 #pragma unroll
             for (int q = 0; q < N / 8; ++q) {
                 const uint4 vo = *reinterpret_cast<const uint4*>(my_o + 16 * q);
-                const uint4 vp = *reinterpret_cast<const uint4*>(my_p + 16 * q);
                 ow[4 * q] = vo.x; ow[4 * q + 1] = vo.y; ow[4 * q + 2] = vo.z; ow[4 * q + 3] = vo.w;
-                pw[4 * q] = vp.x; pw[4 * q + 1] = vp.y; pw[4 * q + 2] = vp.z; pw[4 * q + 3] = vp.w;
             }
             __syncwarp();
             int* M = reinterpret_cast<int*>(sm) + g * RowsTile<N>::WORDS;
