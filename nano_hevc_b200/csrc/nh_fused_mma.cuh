@@ -31,6 +31,12 @@ namespace nh {
 constexpr int kMmaWarps = 4;
 constexpr float kMagicF = 12582912.0f;  // 1.5 * 2^23
 constexpr int kMagicI = 0x4B400000;     // its bit pattern: float(kMagicF + k) has bits kMagicI + k
+// Operand bias: integers k in [-512, 511] travel as the f16 number k + 1536, whose bit pattern is
+// 0x6600 + k.  FFMA.RM against (magic + 0x6600) leaves exactly those 16 bits in the low half of the
+// f32 result, so one PRMT packs two operands; the constant 1536 * (row or column sum of T) is taken
+// out again through the next pass's accumulator start value.
+constexpr int kOperandBias = 1536;
+constexpr int kOperandBits = 0x6600;
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -44,79 +50,153 @@ __device__ __forceinline__ void stsm_x4(uint32_t addr, const uint32_t (&r)[4]) {
     asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};"
                  :: "r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
 }
-// D += A(16x16, row) * B(16x8, col), f16 operands, f32 accumulate
-__device__ __forceinline__ void hmma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2,
-                                          uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+// D = A(16x16, row) * B(16x8, col) + C, f16 operands, f32 accumulate.  C is a separate operand so
+// that a pass can start from constant registers without copying them into the accumulators first.
+__device__ __forceinline__ void hmma16816(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1,
+                                          float c0, float c1, float c2, float c3) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+        : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+        : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1), "f"(c0), "f"(c1), "f"(c2), "f"(c3));
 }
 __device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 __device__ __forceinline__ __half2 bits_h2(uint32_t w) { return *reinterpret_cast<__half2*>(&w); }
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) { return h2_bits(__floats2half2_rn(lo, hi)); }
-// quarter-wave table of nh_math.cuh's cos_q() in constant memory (runtime-indexed)
-static __constant__ signed char kc_cos_q[33] = {64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67, 64,
-                                                61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9,  4,  0};
-__device__ __forceinline__ int cosv_dev(int m) {
-    m &= 127;
-    const int q = m <= 32 ? m : m <= 64 ? 64 - m : m <= 96 ? m - 64 : 128 - m;
-    const int v = kc_cos_q[q];
-    return (m > 32 && m <= 96) ? -v : v;
-}
-// two entries of the N-point matrix (transform.py:28-135) as exact f16
-template <int N>
-__device__ __forceinline__ uint32_t t_pair(int r0, int c0, int r1, int c1) {
-    const int a = cosv_dev((r0 * (32 / N)) * (2 * c0 + 1)), b = cosv_dev((r1 * (32 / N)) * (2 * c1 + 1));
-    return pack_h2((float)a, (float)b);
-}
-// floor((acc) / 2^SH) of an accumulator that already holds the rounding offset, as kMagicF + k
+
+// floor(acc / 2^SH) of an accumulator that already holds the rounding offset, as kMagicF + k
 template <int SH>
 __device__ __forceinline__ float floor_shift_magic(float acc) {
     return __fmaf_rd(acc, 1.0f / (float)(1 << SH), kMagicF);
 }
-
-// ---- pass boundaries ---------------------------------------------------------------------------
-// Plain form: accumulator -> floor shift -> f32 integer -> f16 pair.  2.5 instructions per value.
+// Pass boundary, plain form: f32 integer -> f16 pair (FFMA.RM, FADD, half an F2FP per value).
 template <int SH>
 __device__ __forceinline__ uint32_t round_pair_plain(float a0, float a1) {
     return pack_h2(floor_shift_magic<SH>(a0) - kMagicF, floor_shift_magic<SH>(a1) - kMagicF);
 }
-// Biased form, for integers k in [-512, 511]: FFMA.RM against (magic + 512) leaves k + 512 in the low
-// 16 bits; PRMT packs two of them and OR 0x6400 turns each into the f16 number 1024 + (k + 512) =
-// k + 1536.  The operand fed to the next MMA is therefore k + 1536 and the constant 1536 * (row or
-// column sum of T) is taken out again through the next accumulator's initial value.  2 per value.
-constexpr float kOperandBias = 1536.0f;
+// Pass boundary, biased form for k in [-512, 511] (FFMA.RM + half a PRMT per value).
 template <int SH>
 __device__ __forceinline__ uint32_t round_pair_biased(float a0, float a1) {
-    const uint32_t m0 = __float_as_uint(__fmaf_rd(a0, 1.0f / (float)(1 << SH), kMagicF + 512.0f));
-    const uint32_t m1 = __float_as_uint(__fmaf_rd(a1, 1.0f / (float)(1 << SH), kMagicF + 512.0f));
-    return __byte_perm(m0, m1, 0x5410) | 0x64006400u;
+    const float m = kMagicF + (float)kOperandBits;
+    return __byte_perm(__float_as_uint(__fmaf_rd(a0, 1.0f / (float)(1 << SH), m)),
+                       __float_as_uint(__fmaf_rd(a1, 1.0f / (float)(1 << SH), m)), 0x5410);
 }
 
-// acc(m, n) += A_const(m, k) * B(k, n) where B[k][n] = P[n][k] and P is the previous pass's result
-// held as packed C fragments `h` (C -> B: the product comes out transposed w.r.t. using P as A).
-template <int MT, int NT, int KT>
-__device__ __forceinline__ void mma_const_a(float (&acc)[MT][NT][4], const uint32_t (&ta)[MT][KT][4],
-                                            const uint32_t (&h)[MT][NT][2]) {
-#pragma unroll
-    for (int mi = 0; mi < MT; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < NT; ++ni)
-#pragma unroll
-            for (int ki = 0; ki < KT; ++ki)
-                hmma16816(acc[mi][ni], ta[mi][ki][0], ta[mi][ki][1], ta[mi][ki][2], ta[mi][ki][3],
-                          h[ni >> 1][2 * ki][ni & 1], h[ni >> 1][2 * ki + 1][ni & 1]);
+// ---- per-lane constants, generated at compile time ------------------------------------------------
+// f16 bit pattern of a small integer (|v| <= 2048, exact)
+constexpr uint32_t f16_bits_of_int(int v) {
+    if (v == 0) return 0;
+    const uint32_t s = v < 0 ? 0x8000u : 0u;
+    const uint32_t m = (uint32_t)(v < 0 ? -v : v);
+    int e = 0;
+    while ((m >> e) > 1) ++e;
+    const uint32_t frac = e <= 10 ? (m << (10 - e)) : (m >> (e - 10));
+    return s | ((uint32_t)(e + 15) << 10) | (frac & 0x3ffu);
 }
-
 template <int N>
-__global__ void __launch_bounds__(kMmaWarps * 32, 3) fused_mma_kernel(const FusedArgs a, const FastQuant fq) {
+struct MmaConsts {
+    static constexpr int MT = N / 16, NT = N / 8, KT = N / 16;
+    // 128-bit vectors per lane:
+    //   V_TA + mi*KT + ki : A = T fragment    {T[16mi+g][16ki+2t..+1], rows +8, cols +8, both}
+    //   V_TB + ki*NT/2+np : B = T fragments   {b0, b1 of n-tile 2np, b0, b1 of n-tile 2np+1},
+    //                       b0 = {T[16ki+2t][8ni+g], T[16ki+2t+1][8ni+g]}, b1 = rows +8
+    //   accumulator start values (integers; converted to f32 when the CTA stages the table):
+    //   V_F2: r - 1536 * sum_x T[v][x], v = 16mi + g + 8h, at word 2mi + h   (forward, second pass)
+    //   V_I1: r - 1536 * sum_i T[i][y], y likewise                           (inverse, first pass)
+    //   V_I2: r - 1536 * sum_v T[v][x], x = 8ni + 2t + p, at word 2ni + p    (inverse, second pass;
+    //         plain r when the operand of that pass is not biased)
+    static constexpr int V_TA = 0, V_TB = MT * KT, V_F2 = V_TB + KT * NT / 2, V_I1 = V_F2 + (2 * MT + 3) / 4,
+                         V_I2 = V_I1 + (2 * MT + 3) / 4, V_END = V_I2 + (2 * NT + 3) / 4;
+    int32_t w[V_END][32][4];
+};
+template <int N>
+constexpr MmaConsts<N> make_mma_consts(bool bias_tmp2) {
+    using C = MmaConsts<N>;
+    C c{};
+    const int rnd = 1 << (Log2<N>::v + 4);
+    auto pair = [](int r0, int c0, int r1, int c1) -> int32_t {
+        return (int32_t)(f16_bits_of_int(dct<N>(r0, c0)) | (f16_bits_of_int(dct<N>(r1, c1)) << 16));
+    };
+    for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, t = lane & 3;
+        for (int mi = 0; mi < C::MT; ++mi)
+            for (int ki = 0; ki < C::KT; ++ki) {
+                const int i0 = 16 * mi + g, k0 = 16 * ki + 2 * t;
+                int32_t(&v)[4] = c.w[C::V_TA + mi * C::KT + ki][lane];
+                v[0] = pair(i0, k0, i0, k0 + 1);
+                v[1] = pair(i0 + 8, k0, i0 + 8, k0 + 1);
+                v[2] = pair(i0, k0 + 8, i0, k0 + 9);
+                v[3] = pair(i0 + 8, k0 + 8, i0 + 8, k0 + 9);
+            }
+        for (int ki = 0; ki < C::KT; ++ki)
+            for (int ni = 0; ni < C::NT; ++ni) {
+                const int k0 = 16 * ki + 2 * t, x0 = 8 * ni + g;
+                int32_t(&v)[4] = c.w[C::V_TB + ki * C::NT / 2 + ni / 2][lane];
+                v[2 * (ni & 1)] = pair(k0, x0, k0 + 1, x0);
+                v[2 * (ni & 1) + 1] = pair(k0 + 8, x0, k0 + 9, x0);
+            }
+        for (int mi = 0; mi < C::MT; ++mi)
+            for (int hh = 0; hh < 2; ++hh) {
+                const int v = 16 * mi + g + 8 * hh;
+                int rs = 0, cs = 0;
+                for (int k = 0; k < N; ++k) {
+                    rs += dct<N>(v, k);
+                    cs += dct<N>(k, v);
+                }
+                c.w[C::V_F2 + (2 * mi + hh) / 4][lane][(2 * mi + hh) % 4] = rnd - kOperandBias * rs;
+                c.w[C::V_I1 + (2 * mi + hh) / 4][lane][(2 * mi + hh) % 4] = rnd - kOperandBias * cs;
+            }
+        for (int ni = 0; ni < C::NT; ++ni)
+            for (int p = 0; p < 2; ++p) {
+                const int x = 8 * ni + 2 * t + p;
+                int cs = 0;
+                for (int k = 0; k < N; ++k) cs += dct<N>(k, x);
+                c.w[C::V_I2 + (2 * ni + p) / 4][lane][(2 * ni + p) % 4] = bias_tmp2 ? rnd - kOperandBias * cs : rnd;
+            }
+    }
+    return c;
+}
+// |tmp2| <= 328 at N = 32 fits the biased operand form, 661 at N = 16 does not
+template <int N> struct MmaBiasTmp2 { static constexpr bool v = N == 32; };
+__device__ constexpr MmaConsts<16> kMmaConsts16 = make_mma_consts<16>(MmaBiasTmp2<16>::v);
+__device__ constexpr MmaConsts<32> kMmaConsts32 = make_mma_consts<32>(MmaBiasTmp2<32>::v);
+template <int N>
+__device__ __forceinline__ const int32_t* mma_consts_words() {
+    if constexpr (N == 16) return &kMmaConsts16.w[0][0][0];
+    else return &kMmaConsts32.w[0][0][0];
+}
+
+// acc(m, n) = init(m) + A_const(m, k) * B(k, n) where B[k][n] = P[n][k] and P is the previous pass's
+// result held as packed C fragments `h` (C -> B: the product comes out transposed w.r.t. using P as
+// A).  `i4` holds this lane's start values (word 2mi + half), `afrag(mi, ki)` fetches an A fragment.
+template <int MT, int NT, int KT, class AFrag>
+__device__ __forceinline__ void mma_const_a(float (&acc)[MT][NT][4], const uint32_t (&h)[MT][NT][2],
+                                            const uint4& i4, AFrag afrag) {
+    const float init[4] = {__uint_as_float(i4.x), __uint_as_float(i4.y), __uint_as_float(i4.z), __uint_as_float(i4.w)};
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi) {
+#pragma unroll
+        for (int ki = 0; ki < KT; ++ki) {
+            const uint4 af = afrag(mi, ki);
+#pragma unroll
+            for (int ni = 0; ni < NT; ++ni) {
+                const uint32_t b0 = h[ni >> 1][2 * ki][ni & 1], b1 = h[ni >> 1][2 * ki + 1][ni & 1];
+                if (ki == 0)
+                    hmma16816(acc[mi][ni], af, b0, b1, init[2 * mi], init[2 * mi], init[2 * mi + 1], init[2 * mi + 1]);
+                else
+                    hmma16816(acc[mi][ni], af, b0, b1, acc[mi][ni][0], acc[mi][ni][1], acc[mi][ni][2], acc[mi][ni][3]);
+            }
+        }
+    }
+}
+
+template <int N, int OCC>
+__global__ void __launch_bounds__(kMmaWarps * 32, OCC) fused_mma_kernel(const FusedArgs a, const FastQuant fq) {
+    using C = MmaConsts<N>;
     constexpr int NN = N * N;
     constexpr int BPW = 32 / N;  // blocks per warp tile
     constexpr int MT = N / 16, NT = N / 8, KT = N / 16;
     constexpr int S1 = Log2<N>::v + 1;
     constexpr int SH = Log2<N>::v + 5;  // transform.py:173-175, :215-217
-    // |tmp2| <= 328 at N = 32 fits the biased operand form, 661 at N = 16 does not
-    constexpr bool kBiasTmp2 = N == 32;
+    constexpr bool kBiasTmp2 = MmaBiasTmp2<N>::v;
     // int16 block tile in shared memory: row pitch N*2 + 16 bytes (an odd number of 16-byte groups),
     // so the 8 rows of an ldmatrix / stmatrix 8x8 tile and the per-lane 128-bit row accesses are
     // conflict-free.
@@ -127,6 +207,20 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) fused_mma_kernel(const Fuse
     constexpr int EXACT_BYTES = BPW * RowsTile<N>::WORDS * 4;
     constexpr int WARP_BYTES = FAST_BYTES > EXACT_BYTES ? FAST_BYTES : EXACT_BYTES;
     __shared__ __align__(16) unsigned char smem[kMmaWarps][WARP_BYTES];
+    // Per-lane constants: staged once per CTA into shared memory (vector v of lane l at ctab[v][l]:
+    // a warp's 128-bit read is 512 contiguous bytes) and re-read where they are used.  Keeping the 48
+    // words in registers across the tile loop made the first version spill its prefetched pixels;
+    // the loads are volatile asm so that they stay inside the loop.
+    __shared__ __align__(16) uint4 ctab[C::V_END][32];
+    for (int i = threadIdx.x; i < C::V_END * 32; i += kMmaWarps * 32) {
+        const int4 v = reinterpret_cast<const int4*>(mma_consts_words<N>())[i];
+        uint4 o = make_uint4((uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w);
+        if (i >= C::V_F2 * 32)
+            o = make_uint4(__float_as_uint((float)v.x), __float_as_uint((float)v.y), __float_as_uint((float)v.z),
+                           __float_as_uint((float)v.w));
+        (&ctab[0][0])[i] = o;
+    }
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane / N, r = lane % N;    // I/O mapping: lane = row r of block g
     const int fg = lane >> 2, ft = lane & 3; // fragment mapping
@@ -137,63 +231,19 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) fused_mma_kernel(const Fuse
     // ldmatrix / stmatrix x4 row address of this lane: 8x8 tile j = lane >> 3 covers rows
     // 8*(j&1).. and columns 8*(j>>1)..  of a 16x16 region
     const int lane_off = (((lane >> 3) & 1) * 8 + (lane & 7)) * PITCH + (lane >> 4) * 16;
+    const uint32_t ctab_lane = smem_u32(&ctab[0][lane]);
+    auto cv = [&](int v) -> uint4 {  // vector v of this lane's constants
+        uint4 o;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(ctab_lane + 512u * (uint32_t)v));
+        return o;
+    };
 
-    // transform matrix as constant operand fragments (exact small integers in f16)
-    uint32_t ta[MT][KT][4];  // A = T:    a0 = T[16mi+g][16ki+2t..], a1 = rows +8, a2 = cols +8, a3 = both
-    uint32_t tb[KT][NT][2];  // B = T:    b0 = {T[16ki+2t][8ni+g], T[16ki+2t+1][8ni+g]}, b1 = rows +8
-#pragma unroll
-    for (int mi = 0; mi < MT; ++mi)
-#pragma unroll
-        for (int ki = 0; ki < KT; ++ki) {
-            const int i0 = 16 * mi + fg, k0 = 16 * ki + 2 * ft;
-            ta[mi][ki][0] = t_pair<N>(i0, k0, i0, k0 + 1);
-            ta[mi][ki][1] = t_pair<N>(i0 + 8, k0, i0 + 8, k0 + 1);
-            ta[mi][ki][2] = t_pair<N>(i0, k0 + 8, i0, k0 + 9);
-            ta[mi][ki][3] = t_pair<N>(i0 + 8, k0 + 8, i0 + 8, k0 + 9);
-        }
-#pragma unroll
-    for (int ki = 0; ki < KT; ++ki)
-#pragma unroll
-        for (int ni = 0; ni < NT; ++ni) {
-            const int k0 = 16 * ki + 2 * ft, x0 = 8 * ni + fg;
-            tb[ki][ni][0] = t_pair<N>(k0, x0, k0 + 1, x0);
-            tb[ki][ni][1] = t_pair<N>(k0 + 8, x0, k0 + 9, x0);
-        }
-    // Accumulator start values: rounding offset, minus 1536 * (sum over the contracted index of the
-    // constant operand) where the data operand carries the +1536 bias.
     const float rnd = (float)(1 << (SH - 1));
-    float init_f2[MT][2];  // rows v = 16mi + fg + 8h:  - 1536 * sum_x T[v][x]
-    float init_i1[MT][2];  // rows y = 16mi + fg + 8h:  - 1536 * sum_i T[i][y]
-    float init_i2[NT][2];  // cols x = 8ni + 2ft + p:   - 1536 * sum_v T[v][x]
-#pragma unroll
-    for (int mi = 0; mi < MT; ++mi)
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            const int v = 16 * mi + fg + 8 * hh;
-            int rs = 0, cs = 0;
-#pragma unroll 1
-            for (int k = 0; k < N; ++k) {
-                rs += cosv_dev((v * (32 / N)) * (2 * k + 1));
-                cs += cosv_dev((k * (32 / N)) * (2 * v + 1));
-            }
-            init_f2[mi][hh] = rnd - kOperandBias * (float)rs;
-            init_i1[mi][hh] = rnd - kOperandBias * (float)cs;
-        }
-#pragma unroll
-    for (int ni = 0; ni < NT; ++ni)
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            const int x = 8 * ni + 2 * ft + p;
-            int cs = 0;
-#pragma unroll 1
-            for (int k = 0; k < N; ++k) cs += cosv_dev((k * (32 / N)) * (2 * x + 1));
-            init_i2[ni][p] = kBiasTmp2 ? rnd - kOperandBias * (float)cs : rnd;
-        }
-
     const bool clip_ok = a.maxv <= 1023;
     const uint32_t clip_lo2 = 0x08000800u;  // reconstruction carries a +2048 bias per 16-bit half
     const uint32_t clip_hi2 = clip_lo2 + (uint32_t)(clip_ok ? a.maxv : 0) * 0x10001u;
-    const int dq_rnd_b = fq.dq_rnd + (512 << fq.dq_shift);  // dequantised value + 512
+    const int dq_rnd_b = fq.dq_rnd + (kOperandBits << fq.dq_shift);  // dequantised value + 0x6600
 
     const int64_t n_tiles = (a.n_blocks + BPW - 1) / BPW;
     const int64_t warp_stride = (int64_t)gridDim.x * kMmaWarps;
@@ -246,8 +296,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) fused_mma_kernel(const Fuse
         if (tile + warp_stride < n_tiles) prefetch(tile + warp_stride);
         __syncwarp();
         // `fast` is warp-uniform and the ONLY branch around the warp-collective instructions
-        // (ldmatrix / mma / stmatrix .sync.aligned); the per-lane mode test is nested inside it and
-        // reconverges before them.
+        // (ldmatrix / mma / stmatrix .sync.aligned); the per-lane mode test is a select inside it.
         uint32_t pw[N / 2];  // this lane's prediction row, packed
         uint32_t tw[N / 2];
 #pragma unroll
@@ -305,13 +354,16 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) fused_mma_kernel(const Fuse
 #pragma unroll
                     for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
-                        for (int ni = 0; ni < NT; ++ni) {
+                        for (int ki = 0; ki < KT; ++ki) {
+                            const uint4 af = cv(C::V_TA + mi * KT + ki);
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) acc[mi][ni][e] = rnd;
-#pragma unroll
-                            for (int ki = 0; ki < KT; ++ki)
-                                hmma16816(acc[mi][ni], ta[mi][ki][0], ta[mi][ki][1], ta[mi][ki][2],
-                                          ta[mi][ki][3], xb[ki][ni][0], xb[ki][ni][1]);
+                            for (int ni = 0; ni < NT; ++ni) {
+                                if (ki == 0)
+                                    hmma16816(acc[mi][ni], af, xb[ki][ni][0], xb[ki][ni][1], rnd, rnd, rnd, rnd);
+                                else
+                                    hmma16816(acc[mi][ni], af, xb[ki][ni][0], xb[ki][ni][1], acc[mi][ni][0],
+                                              acc[mi][ni][1], acc[mi][ni][2], acc[mi][ni][3]);
+                            }
                         }
                 }
 #pragma unroll
@@ -322,13 +374,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) fused_mma_kernel(const Fuse
                         h[mi][ni][1] = round_pair_biased<SH>(acc[mi][ni][2], acc[mi][ni][3]);
                     }
                 // ---- forward, second pass (transposed): coeff^T(m = v, n = i) = (T temp^T + r) >> s
-#pragma unroll
-                for (int mi = 0; mi < MT; ++mi)
-#pragma unroll
-                    for (int ni = 0; ni < NT; ++ni)
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) acc[mi][ni][e] = init_f2[mi][e >> 1];
-                mma_const_a<MT, NT, KT>(acc, ta, h);
+                mma_const_a<MT, NT, KT>(acc, h, cv(C::V_F2), [&](int mi, int ki) { return cv(C::V_TA + mi * KT + ki); });
                 // ---- coefficients out, quant, levels out, dequant -> biased operand of the inverse
 #pragma unroll
                 for (int mi = 0; mi < MT; ++mi)
@@ -342,31 +388,17 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) fused_mma_kernel(const Fuse
                             const int lv = quantize_fast(c, fq);
                             if (want_c) __stcs(cp + off, c);
                             if (want_l) __stcs(lp + off, lv);
-                            dqb[e] = (lv * fq.dq_mult + dq_rnd_b) >> fq.dq_shift;  // |dq| <= 360
+                            dqb[e] = (lv * fq.dq_mult + dq_rnd_b) >> fq.dq_shift;  // 0x6600 + dq, |dq| <= 360
                         }
-                        h[mi][ni][0] = __byte_perm((uint32_t)dqb[0], (uint32_t)dqb[1], 0x5410) | 0x64006400u;
-                        h[mi][ni][1] = __byte_perm((uint32_t)dqb[2], (uint32_t)dqb[3], 0x5410) | 0x64006400u;
+                        h[mi][ni][0] = __byte_perm((uint32_t)dqb[0], (uint32_t)dqb[1], 0x5410);
+                        h[mi][ni][1] = __byte_perm((uint32_t)dqb[2], (uint32_t)dqb[3], 0x5410);
                     }
-                // ---- inverse, first pass: tmp2(m = y, n = v) = (T^T dq + r) >> s,  A = T^T from tb
-#pragma unroll
-                for (int mi = 0; mi < MT; ++mi)
-#pragma unroll
-                    for (int ni = 0; ni < NT; ++ni)
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) acc[mi][ni][e] = init_i1[mi][e >> 1];
-                {
-                    uint32_t tat[MT][KT][4];
-#pragma unroll
-                    for (int mi = 0; mi < MT; ++mi)
-#pragma unroll
-                        for (int ki = 0; ki < KT; ++ki) {
-                            tat[mi][ki][0] = tb[ki][2 * mi][0];
-                            tat[mi][ki][1] = tb[ki][2 * mi + 1][0];
-                            tat[mi][ki][2] = tb[ki][2 * mi][1];
-                            tat[mi][ki][3] = tb[ki][2 * mi + 1][1];
-                        }
-                    mma_const_a<MT, NT, KT>(acc, tat, h);
-                }
+                // ---- inverse, first pass: tmp2(m = y, n = v) = (T^T dq + r) >> s.  A = T^T comes from
+                // the B = T fragments: a0 = b0 of n-tile 2mi, a1 = b0 of 2mi+1, a2 / a3 = their b1
+                mma_const_a<MT, NT, KT>(acc, h, cv(C::V_I1), [&](int mi, int ki) {
+                    const uint4 t = cv(C::V_TB + ki * NT / 2 + mi);
+                    return make_uint4(t.x, t.z, t.y, t.w);
+                });
 #pragma unroll
                 for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
@@ -381,16 +413,29 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) fused_mma_kernel(const Fuse
                     }
                 // ---- inverse, second pass: res(m = y, n = x) = (tmp2 T + r) >> s,  A = tmp2 (C -> A)
 #pragma unroll
-                for (int mi = 0; mi < MT; ++mi)
+                for (int np = 0; np < NT / 2; ++np) {
+                    const uint4 i4 = cv(C::V_I2 + np);  // start values of n-tiles 2np, 2np + 1
+                    const float i0 = __uint_as_float(i4.x), i1 = __uint_as_float(i4.y),
+                                i2 = __uint_as_float(i4.z), i3 = __uint_as_float(i4.w);
 #pragma unroll
-                    for (int ni = 0; ni < NT; ++ni) {
+                    for (int ki = 0; ki < KT; ++ki) {
+                        const uint4 t = cv(C::V_TB + ki * NT / 2 + np);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) acc[mi][ni][e] = init_i2[ni][e & 1];
-#pragma unroll
-                        for (int ki = 0; ki < KT; ++ki)
-                            hmma16816(acc[mi][ni], h[mi][2 * ki][0], h[mi][2 * ki][1], h[mi][2 * ki + 1][0],
-                                      h[mi][2 * ki + 1][1], tb[ki][ni][0], tb[ki][ni][1]);
+                        for (int mi = 0; mi < MT; ++mi) {
+                            const uint4 af = make_uint4(h[mi][2 * ki][0], h[mi][2 * ki][1], h[mi][2 * ki + 1][0],
+                                                        h[mi][2 * ki + 1][1]);
+                            float(&d0)[4] = acc[mi][2 * np];
+                            float(&d1)[4] = acc[mi][2 * np + 1];
+                            if (ki == 0) {
+                                hmma16816(d0, af, t.x, t.y, i0, i1, i0, i1);
+                                hmma16816(d1, af, t.z, t.w, i2, i3, i2, i3);
+                            } else {
+                                hmma16816(d0, af, t.x, t.y, d0[0], d0[1], d0[2], d0[3]);
+                                hmma16816(d1, af, t.z, t.w, d1[0], d1[1], d1[2], d1[3]);
+                            }
+                        }
                     }
+                }
                 // ---- reconstruct + clip (intra.py:70-78) on 16-bit pairs: FFMA.RM against magic + 2048
                 // leaves res + 2048 (> 0, |res| <= 1214) in the low 16 bits; add the prediction pair,
                 // clamp both halves to [2048, 2048 + max] and drop the bias.  The tile of original
@@ -451,7 +496,13 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) fused_mma_kernel(const Fuse
             }
             __syncwarp();
             if (a.ood_flag && lane == 0) *a.ood_flag = 1;
-            rows_tile_exact<N>(a, M, r, valid, b, pw);
+            // copies made HERE so that neither the kernel parameters nor pw have their address taken
+            // on the hot path (they would live in local memory for the whole loop otherwise)
+            const FusedArgs a_cold = a;
+            uint32_t pw_cold[N / 2];
+#pragma unroll
+            for (int k = 0; k < N / 2; ++k) pw_cold[k] = pw[k];
+            rows_tile_exact<N>(a_cold, M, r, valid, b, pw_cold);
         }
         __syncwarp();
     }
@@ -460,8 +511,14 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) fused_mma_kernel(const Fuse
 template <int N>
 static int launch_mma(const FusedArgs& a, cudaStream_t st) {
     constexpr int BPW = 32 / N;
-    int grid = grid_for(a.n_blocks, (int64_t)kMmaWarps * BPW, 3);
-    fused_mma_kernel<N><<<grid, kMmaWarps * 32, 0, st>>>(a, make_fast_quant(a.qp));
+    static int occ = 0;  // resident CTAs per SM the kernel is compiled for: NH_MMA_OCC=3|4 (A/B profiling)
+    if (occ == 0) {
+        const char* e = getenv("NH_MMA_OCC");
+        occ = (e && e[0] == '3') ? 3 : 4;
+    }
+    int grid = grid_for(a.n_blocks, (int64_t)kMmaWarps * BPW, occ);
+    if (occ == 3) fused_mma_kernel<N, 3><<<grid, kMmaWarps * 32, 0, st>>>(a, make_fast_quant(a.qp));
+    else fused_mma_kernel<N, 4><<<grid, kMmaWarps * 32, 0, st>>>(a, make_fast_quant(a.qp));
     NH_CHECK_LAUNCH("fused_mma_kernel");
     return NH_OK;
 }
