@@ -318,7 +318,7 @@ def run_ours(args, rank, world, local_rank):
                        "l2": f"inputs+outputs {alg_bytes / 1e9:.2f} GB per launch >> 126 MB L2 (no flush needed)",
                        "parallelism": f"frames sharded over {world} GPU(s), no collective on the hot path"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": {1: "fused_unit_kernel<8>", 2: "fused_unit_kernel_v2<8>", 3: "fused_unit_kernel_v3<8>"}[args.fused_impl], "bytes_per_px": BYTES_PER_PX,
+                         "traffic": traffic, "kernel": {1: "fused_unit_kernel<8>", 2: "fused_unit_kernel_v2<8>", 3: "fused_unit_kernel_v3<8>", 4: "fused_mma8_kernel"}[args.fused_impl], "bytes_per_px": BYTES_PER_PX,
                          "px_per_launch": px_launch, "launch_ms": launch_s * 1e3, "peak_source": peak_src,
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
@@ -339,7 +339,7 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--fused-impl", type=int, default=2, choices=[1, 2, 3],
+    ap.add_argument("--fused-impl", type=int, default=4, choices=[1, 2, 3, 4],
                     help="kernel generation of the fused 4x4/8x8 kernel (1 = first generation, for A/B runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -1016,13 +1016,14 @@ static int launch_unit_v3(const FusedArgs& a, cudaStream_t st) {
     return NH_OK;
 }
 
-// Kernel generation used for N = 4, 8: 2 (default), 1 (first generation) or 3 (TMA tensor-map
-// staging); set by nh_set_fused_impl() or the NH_FUSED_IMPL=v1|v2|v3 environment variable.
+// Kernel generation used for N = 4, 8: 4 (default: tensor-core passes at N = 8, generation 2 at
+// N = 4), 2 (cp.async + in-thread butterflies), 1 (first generation) or 3 (TMA tensor-map staging);
+// set by nh_set_fused_impl() or the NH_FUSED_IMPL=v1|v2|v3|v4 environment variable.
 static int g_fused_impl = 0;
 static int fused_impl() {
     if (g_fused_impl == 0) {
         const char* e = getenv("NH_FUSED_IMPL");
-        g_fused_impl = (e && e[0] == 'v' && e[1] >= '1' && e[1] <= '3') ? e[1] - '0' : 2;
+        g_fused_impl = (e && e[0] == 'v' && e[1] >= '1' && e[1] <= '4') ? e[1] - '0' : 4;
     }
     return g_fused_impl;
 }
@@ -1030,6 +1031,10 @@ static int fused_impl() {
 template <int N, bool DST>
 static int launch_unit(const FusedArgs& a, cudaStream_t st) {
     if (a.coeff16) return launch_unit_v2<N, DST, true>(a, st);  // narrow outputs: generation 2 only
+    if (N == 8 && fused_impl() == 4) {  // tensor-core passes (clip bound <= 1023), else generation 2
+        if (a.maxv <= 1023) return launch_mma8(a, st);
+        return launch_unit_v2<N, DST>(a, st);
+    }
     switch (fused_impl()) {
         case 1: return launch_unit_v1<N, DST>(a, st);
         case 3: return launch_unit_v3<N, DST>(a, st);
@@ -1078,8 +1083,8 @@ static int dispatch_fused(const FusedArgs& a, int size, int use_dst, cudaStream_
 }  // namespace nh
 
 NH_API int nh_set_fused_impl(int generation) {
-    if (generation < 1 || generation > 3) {
-        nh::set_error("nh_set_fused_impl: generation must be 1, 2 or 3, got %d", generation);
+    if (generation < 1 || generation > 4) {
+        nh::set_error("nh_set_fused_impl: generation must be 1, 2, 3 or 4, got %d", generation);
         return NH_E_ARG;
     }
     nh::g_fused_impl = generation;

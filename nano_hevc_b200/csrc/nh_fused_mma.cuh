@@ -508,13 +508,246 @@ __global__ void __launch_bounds__(kMmaWarps * 32, OCC) fused_mma_kernel(const Fu
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// N = 8 on the tensor cores.  Two 8x8 blocks share one m16n8k16 MMA through a block-diagonal
+// constant operand, so the chain of the 16 / 32 kernel carries over with every fragment full:
+//     temp   (m=(blk,i), n=x) = diag(T,T)     [X_a; X_b]            A = {tf, 0, 0, tf}   B = ldmatrix.trans
+//     coef^T (m=(blk,v), n=i) = diag(T,T)     [temp_a^T; temp_b^T]  B = previous C fragments
+//     tmp2   (m=(blk,y), n=v) = diag(T^T,T^T) [dq_a; dq_b]          A = {ttf, 0, 0, ttf}
+//     res    (m=(blk,y), n=x) = [tmp2_a; tmp2_b] T                  m16n8k8, A = previous C, B = {ttf}
+// with tf = {T[g][2t], T[g][2t+1]} and ttf = {T[2t][g], T[2t+1][g]}: the whole transform matrix is
+// two registers per lane.  Operand magnitudes for 8-bit samples: |temp| <= 511 (biased form),
+// |dq| <= 720, |tmp2| <= 1348 (plain f16), |res| <= 2523, accumulators <= 6.5e5.
+// Staging is the unit kernel's: a warp tile is 32 blocks, pixels arrive by cp.async one tile ahead
+// into padded shared tiles (block u at u * 144 bytes: the 8 rows of a block are one conflict-free
+// ldmatrix 8x8 tile), lane u predicts block u, pred / recon leave through the cooperative 128-bit
+// sweep.  Coefficients and levels are stored straight from the fragments (each STG.32 of a warp
+// fills four whole 32-byte sectors).  A tile with any sample outside [0, 255] is recoded afterwards,
+// one block per lane, with the exact reference arithmetic (slow_block).
+static __constant__ signed char kc_dct8[64] = {
+    64, 64, 64, 64, 64, 64, 64, 64, 89, 75, 50, 18, -18, -50, -75, -89, 83, 36, -36, -83, -83, -36, 36, 83,
+    75, -18, -89, -50, 50, 89, 18, -75, 64, -64, -64, 64, 64, -64, -64, 64, 50, -89, 18, 75, -75, -18, 89, -50,
+    36, -83, 83, -36, -36, 83, -83, 36, 18, -50, 75, -89, 89, -75, 50, -18};
+
+__device__ __forceinline__ void hmma1688(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0, float c0,
+                                         float c1, float c2, float c3) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%8,%9,%10};"
+        : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+        : "r"(a0), "r"(a1), "r"(b0), "f"(c0), "f"(c1), "f"(c2), "f"(c3));
+}
+
+template <int OCC>
+__global__ void __launch_bounds__(kV2Warps * 32, OCC) fused_mma8_kernel(const FusedArgs a, const FastQuant fq) {
+    constexpr int N = 8, NN = 64, SH = 8, S1 = 4;
+    using T16 = WarpTile<128>;
+    constexpr int kWarpBytes = 3 * T16::kBytes;  // 2 pixel tiles (double buffer) + 1 prediction tile
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int fg = lane >> 2, ft = lane & 3;
+    unsigned char* wbase = smem_raw + warp * kWarpBytes;
+    unsigned char* s16[2] = {wbase, wbase + T16::kBytes};
+    unsigned char* sP = wbase + 2 * T16::kBytes;
+    // ldmatrix / stmatrix x4: 8x8 tile j = lane >> 3 is block 4q + j, row lane & 7
+    const uint32_t lane_off = (uint32_t)((lane >> 3) * T16::kPitch + (lane & 7) * 16);
+
+    const uint4 tf4 = make_uint4(
+        pack_h2((float)kc_dct8[fg * 8 + 2 * ft], (float)kc_dct8[fg * 8 + 2 * ft + 1]), 0u, 0u, 0u);
+    const uint32_t tf = tf4.x;
+    const uint32_t ttf = pack_h2((float)kc_dct8[(2 * ft) * 8 + fg], (float)kc_dct8[(2 * ft + 1) * 8 + fg]);
+    const uint4 a_fwd = make_uint4(tf, 0u, 0u, tf), a_inv = make_uint4(ttf, 0u, 0u, ttf);
+    const float rnd = (float)(1 << (SH - 1));
+    // forward second pass takes temp + 1536: remove 1536 * sum_x T[v][x] (= 512 for v = 0, else 0)
+    const float init_f2 = fg == 0 ? rnd - (float)(kOperandBias * 512) : rnd;
+    const uint32_t clip_lo2 = 0x10001000u;  // reconstruction carries a +4096 bias per 16-bit half
+    const uint32_t clip_hi2 = clip_lo2 + (uint32_t)a.maxv * 0x10001u;  // launcher guarantees maxv <= 1023
+
+    const int64_t n_tiles = (a.n_blocks + 31) / 32;
+    const int64_t warp_stride = (int64_t)gridDim.x * kV2Warps;
+    int64_t tile = (int64_t)blockIdx.x * kV2Warps + warp;
+
+    auto prefetch = [&](int64_t t, unsigned char* dst) {
+        const int64_t blk0 = t * 32;
+        const int64_t rem = a.n_blocks - blk0;
+        const int chunks = (int)(rem < 32 ? rem : 32) * 8;
+        const unsigned char* gp = reinterpret_cast<const unsigned char*>(a.orig + blk0 * NN);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int c = it * 32 + lane;
+            if (c < chunks) cp_async16(smem_u32(dst + (c >> 3) * T16::kPitch + (c & 7) * 16), gp + (size_t)c * 16);
+        }
+    };
+    // references of lane u's block, one tile ahead like the pixels
+    uint32_t n_tw[4], n_lw[4];
+    int n_tr = 0, n_bl = 0, n_mode = 1;
+    auto load_refs = [&](int64_t t) {
+        const int64_t b = t * 32 + lane;
+        if (b < a.n_blocks) {
+            load_row16<N>(a.top + b * N, n_tw);
+            load_row16<N>(a.left + b * N, n_lw);
+            n_tr = a.top_right[b];
+            n_bl = a.bottom_left[b];
+            n_mode = a.modes ? (int)a.modes[b] : a.mode;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) n_tw[k] = n_lw[k] = 0;
+            n_tr = n_bl = 0;
+            n_mode = 1;
+        }
+    };
+    if (tile < n_tiles) {
+        prefetch(tile, s16[0]);
+        load_refs(tile);
+    }
+    cp_async_commit();
+    int cur = 0;
+    for (; tile < n_tiles; tile += warp_stride, cur ^= 1) {
+        const int64_t blk0 = tile * 32;
+        const int64_t trem = a.n_blocks - blk0;
+        const int blocks_valid = (int)(trem < 32 ? trem : 32);
+        const int chunks16 = blocks_valid * 8;
+        uint32_t ood = 0;  // any sample outside [0, 255]
+        // ---- lane u predicts block u (row layout, 16-bit pairs) into the prediction tile
+        {
+            uint32_t tw[4], lw[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { tw[k] = n_tw[k]; lw[k] = n_lw[k]; ood |= (tw[k] | lw[k]) & 0xFF00FF00u; }
+            const int tr = n_tr, bl = n_bl, mode = n_mode;
+            ood |= (uint32_t)(tr | bl) & 0xFFFFFF00u;
+            if (tile + warp_stride < n_tiles) load_refs(tile + warp_stride);
+            uint4* up = T16::unit(sP, lane);
+            if (mode == 1) {  // intra.py:46-62
+                int s = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s += lo16(tw[k]) + hi16(tw[k]) + lo16(lw[k]) + hi16(lw[k]);
+                const uint32_t dc2 = (uint32_t)(dc_value<N>(s) & 0xffff) * 0x10001u;
+#pragma unroll
+                for (int y = 0; y < 8; ++y) up[y] = make_uint4(dc2, dc2, dc2, dc2);
+            } else {  // intra.py:109-111, two pixels per multiply-add chain (exact for 8-bit samples)
+                uint32_t base[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    base[k] = (uint32_t)tr * ((uint32_t)(2 * k + 1) | ((uint32_t)(2 * k + 2) << 16)) + 0x00080008u;
+                const uint32_t bl2 = (uint32_t)bl * 0x10001u;
+#pragma unroll
+                for (int y = 0; y < 8; ++y) {
+                    const uint32_t ly = (y & 1) ? (lw[y >> 1] >> 16) : (lw[y >> 1] & 0xffffu);
+                    uint32_t p[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t ck1 = (uint32_t)(7 - 2 * k) | ((uint32_t)(6 - 2 * k) << 16);
+                        const uint32_t t = tw[k] * (uint32_t)(7 - y) + bl2 * (uint32_t)(y + 1) + ly * ck1 + base[k];
+                        p[k] = (t >> S1) & 0x00FF00FFu;
+                    }
+                    up[y] = make_uint4(p[0], p[1], p[2], p[3]);
+                }
+            }
+        }
+        // the other pixel tile is free: start fetching the next tile into it, then wait for this one
+        if (tile + warp_stride < n_tiles) prefetch(tile + warp_stride, s16[cur ^ 1]);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        if (a.pred) T16::store(sP, reinterpret_cast<unsigned char*>(a.pred + blk0 * NN), lane, chunks16);
+        const uint32_t sO = smem_u32(s16[cur]) + lane_off, sPa = smem_u32(sP) + lane_off;
+        uint32_t oodw = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            uint32_t ro[4], rp[4], pc[4], rr[4];
+            const uint32_t off = (uint32_t)(4 * q * T16::kPitch);
+            ldsm_x4_t(ro, sO + off);
+            ldsm_x4_t(rp, sPa + off);
+            ldsm_x4(pc, sPa + off);
+            oodw |= ro[0] | ro[1] | ro[2] | ro[3];
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const int ba = 4 * q + 2 * p;  // blocks ba, ba + 1 of the tile
+                const bool va = ba < blocks_valid, vb = ba + 1 < blocks_valid;
+                float acc[4];
+                // forward, first pass
+                const uint32_t x0 = h2_bits(__hsub2(bits_h2(ro[2 * p] | 0x64006400u), bits_h2(rp[2 * p] | 0x64006400u)));
+                const uint32_t x1 = h2_bits(__hsub2(bits_h2(ro[2 * p + 1] | 0x64006400u), bits_h2(rp[2 * p + 1] | 0x64006400u)));
+                hmma16816(acc, a_fwd, x0, x1, rnd, rnd, rnd, rnd);
+                uint32_t h0 = round_pair_biased<SH>(acc[0], acc[1]), h1 = round_pair_biased<SH>(acc[2], acc[3]);
+                // forward, second pass (transposed): acc[e] = coeff_blk[i = 2t + (e&1)][v = g], blk = e >> 1
+                hmma16816(acc, a_fwd, h0, h1, init_f2, init_f2, init_f2, init_f2);
+                float dqf[4];
+                int32_t* cp = a.coeff + (blk0 + ba) * NN + (2 * ft) * N + fg;
+                int32_t* lp = a.levels + (blk0 + ba) * NN + (2 * ft) * N + fg;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = __float_as_int(floor_shift_magic<SH>(acc[e])) - kMagicI;
+                    const int lv = quantize_fast(c, fq);
+                    const int dq = dequantize_fast(lv, fq);
+                    const bool v = (e >> 1) ? vb : va;
+                    const int o = (e & 1) * N + (e >> 1) * NN;
+                    if (v && a.coeff) __stcs(cp + o, c);
+                    if (v && a.levels) __stcs(lp + o, lv);
+                    dqf[e] = __int_as_float(dq + kMagicI) - kMagicF;
+                }
+                h0 = pack_h2(dqf[0], dqf[1]);
+                h1 = pack_h2(dqf[2], dqf[3]);
+                // inverse, first pass
+                hmma16816(acc, a_inv, h0, h1, rnd, rnd, rnd, rnd);
+                h0 = round_pair_plain<SH>(acc[0], acc[1]);
+                h1 = round_pair_plain<SH>(acc[2], acc[3]);
+                // inverse, second pass: acc[e] = res_blk[y = g][x = 2t + (e&1)], blk = e >> 1
+                hmma1688(acc, h0, h1, ttf, rnd, rnd, rnd, rnd);
+                // reconstruct + clip on 16-bit pairs carrying a +4096 bias (|res| <= 2523)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint32_t m0 = __float_as_uint(__fmaf_rd(acc[2 * j], 1.0f / (float)(1 << SH), kMagicF + 4096.0f));
+                    const uint32_t m1 = __float_as_uint(__fmaf_rd(acc[2 * j + 1], 1.0f / (float)(1 << SH), kMagicF + 4096.0f));
+                    const uint32_t s = __byte_perm(m0, m1, 0x5410) + pc[2 * p + j];
+                    rr[2 * p + j] = __vminu2(__vmaxu2(s, clip_lo2), clip_hi2) - clip_lo2;
+                }
+            }
+            stsm_x4(sO + off, rr);
+        }
+        ood |= oodw & 0xFF00FF00u;
+        __syncwarp();
+        if (a.recon) T16::store(s16[cur], reinterpret_cast<unsigned char*>(a.recon + blk0 * NN), lane, chunks16);
+        __syncwarp();
+        // any sample of the tile outside [0, 255]: recode it exactly, one block per lane (cold path;
+        // the __syncwarp above orders the cooperative stores before these)
+        if (__any_sync(0xffffffffu, ood != 0)) {
+            const FusedArgs a_cold = a;
+            if (lane < blocks_valid) slow_block<N>(a_cold, blk0 + lane, false);
+        }
+        __syncwarp();
+    }
+    cp_async_wait<0>();
+}
+
+template <int OCC>
+static int launch_mma8_occ(const FusedArgs& a, cudaStream_t st) {
+    constexpr int kSmem = kV2Warps * 3 * WarpTile<128>::kBytes;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(fused_mma8_kernel<OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fused_mma8_kernel)");
+        configured = true;
+    }
+    int grid = grid_for(a.n_blocks, (int64_t)kV2Warps * 32, OCC);
+    fused_mma8_kernel<OCC><<<grid, kV2Warps * 32, kSmem, st>>>(a, make_fast_quant(a.qp));
+    NH_CHECK_LAUNCH("fused_mma8_kernel");
+    return NH_OK;
+}
+static int launch_mma8(const FusedArgs& a, cudaStream_t st) {
+    static int occ = 0;
+    if (occ == 0) {
+        const char* e = getenv("NH_MMA_OCC");
+        occ = (e && e[0] == '4') ? 4 : 3;  // measured: 0.87 of the HBM peak at 3 CTAs / SM, 0.80 at 4
+    }
+    return occ == 3 ? launch_mma8_occ<3>(a, st) : launch_mma8_occ<4>(a, st);
+}
+
 template <int N>
 static int launch_mma(const FusedArgs& a, cudaStream_t st) {
     constexpr int BPW = 32 / N;
     static int occ = 0;  // resident CTAs per SM the kernel is compiled for: NH_MMA_OCC=3|4 (A/B profiling)
     if (occ == 0) {
         const char* e = getenv("NH_MMA_OCC");
-        occ = (e && e[0] == '3') ? 3 : 4;
+        occ = (e && e[0] == '4') ? 4 : 3;
     }
     int grid = grid_for(a.n_blocks, (int64_t)kMmaWarps * BPW, occ);
     if (occ == 3) fused_mma_kernel<N, 3><<<grid, kMmaWarps * 32, 0, st>>>(a, make_fast_quant(a.qp));

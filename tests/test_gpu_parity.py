@@ -13,6 +13,7 @@ from conftest import golden
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 
 SIZES = (4, 8, 16, 32)
+DEFAULT_FUSED_IMPL = 4  # kernel generation behind size 4 / 8 (nh_set_fused_impl)
 DEV = "cuda:0"
 
 
@@ -253,14 +254,14 @@ def test_fused_dcplanar_vs_oracle(Bt, n, B):
 
 
 @pytest.mark.parametrize("n", SIZES)
-@pytest.mark.parametrize("gen", (1, 2, 3))
+@pytest.mark.parametrize("gen", (1, 2, 3, 4))
 def test_fused_unit_generations_and_out_of_domain(Bt, n, gen):
     """Both kernel generations; blocks whose samples leave the pixel domain [0, 4095] (where the
     32-bit fast path of generation 2 is not exact) must still match the int64 reference arithmetic."""
     from nano_hevc_b200 import _lib
     rng = np.random.default_rng(77 + n)
     B = 999 if n <= 8 else 211
-    orig, top, left, tr, bl = _dcplanar_inputs(rng, B, n, 4096 if gen >= 2 else 256)
+    orig, top, left, tr, bl = _dcplanar_inputs(rng, B, n, 4096 if gen in (2, 3) else 256)
     wild = rng.random(B) < 0.2
     orig[wild] = rng.integers(-32768, 32768, (int(wild.sum()), n, n))
     w2 = rng.random(B) < 0.1
@@ -281,7 +282,7 @@ def test_fused_unit_generations_and_out_of_domain(Bt, n, gen):
         want = O.pipeline_dcplanar_batch(orig, top, left, tr, bl, 1, 30)
         eq(host(got.coeff), want[1]); eq(host(got.recon), want[3])
     finally:
-        _lib.check(_lib.lib().nh_set_fused_impl(2))
+        _lib.check(_lib.lib().nh_set_fused_impl(DEFAULT_FUSED_IMPL))
 
 
 def _dct(n):
@@ -294,10 +295,10 @@ def _dct(n):
     return np.array([[cv((i * (32 // n)) * (2 * j + 1)) for j in range(n)] for i in range(n)])
 
 
-@pytest.mark.parametrize("n", (16, 32))
+@pytest.mark.parametrize("n", (8, 16, 32))
 @pytest.mark.parametrize("impl", (1, 2))
 def test_fused_rows_impls_adversarial(Bt, n, impl):
-    """N = 16 / 32 behind both kernels (1 = CUDA-core butterflies, 2 = tensor-core passes).  The
+    """N = 8 / 16 / 32 behind both kernels (1 = CUDA-core butterflies, 2 = tensor-core passes).  The
     tensor-core path is exact only because every operand stays a small integer: drive it with the
     worst cases -- basis patterns 255*[sign(T[i] (x) T[j]) > 0] against pred 0 / 255 (largest
     coefficients of either sign), impulses, checkerboards, every QP, intra and inter dead zone --
@@ -326,6 +327,7 @@ def test_fused_rows_impls_adversarial(Bt, n, impl):
     modes = rng.integers(0, 2, B).astype(np.uint8)
     d = [dev(v) for v in (orig, top, left, tr, bl)]
     _lib.check(_lib.lib().nh_set_rows_impl(impl))
+    _lib.check(_lib.lib().nh_set_fused_impl(2 if impl == 1 else 4))
     try:
         for qp in range(0, 52):
             for intra in ((True, False) if qp % 7 == 0 else (True,)):
@@ -350,6 +352,7 @@ def test_fused_rows_impls_adversarial(Bt, n, impl):
         eq(host(got.coeff), want[1]); eq(host(got.recon), want[3])
     finally:
         _lib.check(_lib.lib().nh_set_rows_impl(2))
+        _lib.check(_lib.lib().nh_set_fused_impl(DEFAULT_FUSED_IMPL))
 
 
 @pytest.mark.parametrize("n,B,chunk", [(4, 70001, 8192), (8, 20011, 4096), (16, 3001, 1024), (32, 1000, 300)])

@@ -145,3 +145,40 @@ def test_dp2a_butterflies_exact_in_the_pixel_domain(shim, n):
     big = np.zeros((n, n), np.int32)
     big[0, 0], big[n - 1, 0] = 30000, -30000
     assert not np.array_equal(_xf_dp(shim, big, n, False), O.forward_transform(big))
+
+
+@pytest.mark.parametrize("n", (8, 16, 32))
+def test_mma_operand_bounds(n):
+    """The tensor-core kernels (csrc/nh_fused_mma.cuh) feed the four transform passes to f16 x f16 ->
+    f32 MMAs.  That is exact only while every operand is an integer of magnitude <= 2048 and every
+    accumulator stays below 2^24; the biased operand form additionally needs the value in
+    [-512, 511].  Recompute the worst cases for 8-bit samples from the reference's own tables and
+    quantiser (all QPs, intra and inter) and pin the numbers the kernels rely on."""
+    g = golden("tables.npz")
+    T = g[f"DCT{n}"].astype(np.int64)
+    sh = int(np.log2(n)) + 5
+    row_l1, col_l1 = int(np.abs(T).sum(1).max()), int(np.abs(T).sum(0).max())
+    # rows other than the DC row sum to zero: the forward second pass's bias correction is 1536 * 64N on v = 0 only
+    assert T.sum(1)[0] == 64 * n and not T.sum(1)[1:].any()
+    res_in = 255
+    temp = (row_l1 * res_in + (1 << (sh - 1))) >> sh           # first forward pass
+    coeff = (row_l1 * temp + (1 << (sh - 1))) >> sh             # second forward pass
+    c = np.arange(-coeff, coeff + 1, dtype=np.int32)
+    dq = 0
+    for qp in range(52):
+        for intra in (True, False):
+            dq = max(dq, int(np.abs(O.dequantize(O.quantize(c, qp, n, intra), qp, n)).max()))
+    tmp2 = (col_l1 * dq + (1 << (sh - 1))) >> sh                # first inverse pass
+    res = (col_l1 * tmp2 + (1 << (sh - 1))) >> sh               # second inverse pass
+    bias = 1536
+    acc_max = max(row_l1 * res_in, row_l1 * (temp + bias) + bias * 64 * n, col_l1 * (dq + bias) + bias * col_l1,
+                  col_l1 * (tmp2 + bias) + bias * col_l1) + (1 << (sh - 1))
+    assert acc_max < (1 << 24), acc_max
+    assert max(temp, dq, tmp2) + bias <= 2048 + bias and temp <= 511  # temp always travels biased
+    want = {8: (511, 1023, 720, 1348, 2523), 16: (511, 1023, 360, 661, 1214), 32: (511, 1023, 180, 328, 597)}[n]
+    got = (temp, coeff, dq, tmp2, res)
+    assert all(a <= b for a, b in zip(got, want)), (got, want)
+    # which operands may use the biased form (value + 512 must fit 10 bits), as coded in the kernels
+    assert (dq <= 511) == (n >= 16) and (tmp2 <= 511) == (n == 32)
+    # plain-form operands must still be exact f16 integers; reconstruction bias keeps res + bias > 0
+    assert max(dq, tmp2) <= 2048 and res < (4096 if n == 8 else 2048)

@@ -14,7 +14,7 @@ ap.add_argument("--size", type=int, default=32)
 ap.add_argument("--mpix", type=int, default=64)
 ap.add_argument("--mode", type=int, default=0)
 ap.add_argument("--reps", type=int, default=4)
-ap.add_argument("--impl", type=int, default=2)
+ap.add_argument("--impl", type=int, default=4)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 n = args.size
