@@ -3,6 +3,8 @@
 //   K6' nh_fused_pipeline_modes   (any of the 35 modes from given padded references)
 //   K7  nh_encode_frame, recon_neighbours = 0   (35-mode search + winner pipeline)
 //   K8  nh_encode_frame, recon_neighbours = 1   (anti-diagonal wavefront on the recon plane)
+#include <cstdlib>
+
 #include "nh_coder.cuh"
 
 namespace nh {
@@ -96,6 +98,7 @@ struct CoderArgs {
     int cost_kind;
     int* ticket;           // K8: row ticket counter
     int16_t* bottom;       // K8: [bh][W] bottom rows of the reconstructed blocks, -1 = not yet written
+    unsigned poll_sleep_ns;  // K8: back-off between two polls of a row that is not ready yet
     // common
     int64_t n_blocks;
     QuantParams qp;
@@ -179,7 +182,11 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                             if (v < 0) ready = false;
                             else top[k] = (int16_t)v;
                         }
-                    } while (!__all_sync(0xffffffffu, ready));
+                        ready = __all_sync(0xffffffffu, ready);
+                        // A spinning warp takes issue slots from the warps it waits for as soon as
+                        // several frames share the SMs (frames on concurrent streams): back off.
+                        if (!ready && a.poll_sleep_ns) __nanosleep(a.poll_sleep_ns);
+                    } while (!ready);
                     for (int k = gl; k < Cfg::REF_W; k += G) ood |= (int)top[k];
                 }
                 if (gl == 0) left[0] = top[0];
@@ -466,6 +473,15 @@ NH_API int nh_encode_frame(const int16_t* src, int height, int width, int pitch,
     if ((reinterpret_cast<uintptr_t>(scratch) & 3) != 0) {
         set_error("nh_encode_frame: scratch must be 4-byte aligned");
         return NH_E_ARG;
+    }
+    {
+        static int sleep_ns = -1;  // NH_WAVE_SLEEP_NS overrides the default back-off
+        if (sleep_ns < 0) {
+            const char* e = getenv("NH_WAVE_SLEEP_NS");
+            sleep_ns = e ? atoi(e) : 0;  // measured: polling without back-off is as fast or faster (profiles/r1_notes.md)
+            if (sleep_ns < 0) sleep_ns = 0;
+        }
+        a.poll_sleep_ns = (unsigned)sleep_ns;
     }
     a.ticket = reinterpret_cast<int*>(scratch);
     a.bottom = reinterpret_cast<int16_t*>(reinterpret_cast<unsigned char*>(scratch) + 256);

@@ -51,7 +51,10 @@ def frame_stats(src: torch.Tensor, result) -> torch.Tensor:
     ss = batched.sse_sad(src, result.recon_plane)
     nnz = batched.count_nonzero_batched(result.levels) if result.levels is not None else ss.new_zeros(())
     cost = result.costs.sum(dtype=torch.int64) if result.costs is not None else ss.new_zeros(())
-    return torch.stack([ss[0], ss.new_tensor(src.numel()), cost, nnz])
+    # torch.full, not new_tensor: a host scalar would be copied with a stream synchronisation, which
+    # serialises frames that are meant to overlap on separate streams
+    n = torch.full((), src.numel(), dtype=torch.int64, device=ss.device)
+    return torch.stack([ss[0], n, cost.to(torch.int64), nnz.to(torch.int64)])
 
 
 def encode_frames_sharded(frames: Sequence, size: int, cost: str = "sad", qp: int = 27,
