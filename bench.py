@@ -263,7 +263,7 @@ def run_ours(args, rank, world, local_rank):
         he = frame_to_cfg2_inputs(synth_frames(Fe, 100 + rank))
         h_in_p = [pin(a) for a in he]
         h_out = [torch.empty((Be, N, N), dtype=dt).pin_memory() for dt in (torch.int16, torch.int32, torch.int32, torch.int16)]
-        chunk = int(os.environ.get("NH_E2E_CHUNK", 64 * 1024))
+        chunk = int(os.environ.get("NH_E2E_CHUNK", 128 * 1024))  # measured best of 4K..128K (profiles/r1_notes.md)
         L = _lib.lib()
         sbytes = int(L.nh_host_pipeline_scratch_bytes(N, chunk))
         scratch = torch.empty((sbytes,), dtype=torch.uint8, device=dev)
@@ -287,14 +287,17 @@ def run_ours(args, rank, world, local_rank):
         dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        h2d = PASSES * sum(t.numel() * t.element_size() for t in h_in_p)
         delivered = PASSES * sum(t.numel() * t.element_size() for t in h_out)
-        # on the wire coefficients and levels travel as int16 and are widened on host threads
-        d2h = PASSES * sum(t.numel() * 2 for t in h_out)
+        # bytes that really crossed PCIe, counted by the library from its cudaMemcpyAsync calls (the
+        # output wire format is compact and data dependent); last call x PASSES calls per step
+        import ctypes
+        b_up, b_down = ctypes.c_int64(0), ctypes.c_int64(0)
+        _lib.check(L.nh_host_pipeline_last_transfer(ctypes.byref(b_up), ctypes.byref(b_down)))
+        h2d, d2h = PASSES * b_up.value, PASSES * b_down.value
         e2e = {"value": world * Fe * PX_PER_FRAME * PASSES * ksteps / float(dt.item()) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_bytes_delivered_per_step": delivered,
                "frames_per_pass": Fe, "steps": ksteps,
-               "api": "nh_host_pipeline_dcplanar (C ABI, pinned host buffers, 3-stream chunked overlap, int16 wire format for coeff/levels widened on host threads)",
+               "api": "nh_host_pipeline_dcplanar (C ABI, pinned host buffers, 3-stream chunked overlap; compact wire format: int8 coefficients + int16 exception segments, all-zero level segments elided, widened / zero-filled on host threads; d2h bytes are those of the last pass)",
                "host_threads": int(os.environ["NH_HOST_THREADS"])}
         # spot-check the e2e outputs against the device-resident path
         chk = batched.fused_block_pipeline(*[t.to(dev) for t in h_in_p], MODES[-1], QPS[-1])

@@ -208,6 +208,10 @@ int nh_level_stats(const int32_t* levels, int64_t n_elems, int64_t* nnz_out, dou
  * after the last byte has landed.  device_scratch is a caller-provided device
  * buffer of at least nh_host_pipeline_scratch_bytes(size, chunk_blocks) bytes. */
 int64_t nh_host_pipeline_scratch_bytes(int size, int64_t chunk_blocks);
+/* Bytes the most recent nh_host_pipeline_dcplanar call moved over PCIe in each direction (the
+ * output wire format is compact and data dependent: int8 coefficients with int16 exception
+ * segments, all-zero level segments elided; see csrc/nh_host.cu).  Either pointer may be NULL. */
+int nh_host_pipeline_last_transfer(int64_t* h2d_bytes, int64_t* d2h_bytes);
 int nh_host_pipeline_dcplanar(const int16_t* orig, const int16_t* top, const int16_t* left,
                               const int16_t* top_right, const int16_t* bottom_left,
                               const uint8_t* modes, int mode, int64_t n_blocks, int size, int qp,

@@ -58,6 +58,7 @@ PROTOTYPES = {
     "nh_count_nonzero": (_i, [_p, _i64, _p, _p]),
     "nh_level_stats": (_i, [_p, _i64, _p, _p, _p]),
     "nh_host_pipeline_scratch_bytes": (_i64, [_i, _i64]),
+    "nh_host_pipeline_last_transfer": (_i, [_p, _p]),
     "nh_host_pipeline_dcplanar": (_i, [_p, _p, _p, _p, _p, _p, _i, _i64, _i, _i, _i, _i, _i,
                                        _p, _p, _p, _p, _p, _i64, _i64]),
 }

@@ -316,7 +316,7 @@ def host_block_pipeline(orig, top, left, top_right, bottom_left, mode, qp: int, 
         mk = lambda name, dt: torch.empty((B, N, N), dtype=dt).pin_memory() if name in want else None
         out = PipelineResult(mk("pred", torch.int16), mk("coeff", torch.int32), mk("levels", torch.int32),
                              mk("recon", torch.int16))
-    chunk = int(chunk_blocks) if chunk_blocks else max(1024, (1 << 22) // (N * N))
+    chunk = int(chunk_blocks) if chunk_blocks else max(1024, (1 << 23) // (N * N))
     L = _lib.lib()
     nbytes = int(L.nh_host_pipeline_scratch_bytes(N, chunk))
     if scratch is None or scratch.numel() < nbytes:

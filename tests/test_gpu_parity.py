@@ -381,6 +381,44 @@ def test_host_pipeline_vs_oracle(Bt, n, B, chunk):
     eq(got.levels.numpy(), O.pipeline_dcplanar_batch(orig, top, left, tr, bl, 0, 31, threads=O.n_host_threads())[2], "levels only")
 
 
+@pytest.mark.parametrize("n,B,chunk", [(4, 70003, 8192), (8, 20011, 4096), (16, 3001, 1024), (32, 701, 300)])
+def test_host_pipeline_compact_wire(Bt, n, B, chunk):
+    """Compact wire format of the host pipeline (csrc/nh_host.cu): int8 coefficients with int16
+    exception segments, all-zero level segments elided.  Smooth content so that the format is taken,
+    a sprinkling of high-contrast blocks for both exception lists, one chunk that is all exceptions
+    (list overflow -> int16 format for that chunk), a ragged tail that is not a whole 64-element
+    segment (n = 4), partial output sets; bit-exact against the oracle, fewer bytes on the wire."""
+    import ctypes
+    from nano_hevc_b200 import _lib
+    rng = np.random.default_rng(n * 7 + 3)
+    yy, xx = np.mgrid[0:n, 0:n]
+    base = rng.integers(30, 200, (B, 1, 1))
+    orig = np.clip(base + xx[None] + 2 * yy[None] + rng.integers(-2, 3, (B, n, n)), 0, 255).astype(np.int16)
+    top = np.clip(base[:, :, 0] + np.arange(n)[None] + rng.integers(-2, 3, (B, n)), 0, 255).astype(np.int16)
+    left = np.clip(base[:, :, 0] + 2 * np.arange(n)[None] + rng.integers(-2, 3, (B, n)), 0, 255).astype(np.int16)
+    tr = top[:, -1].copy(); bl = left[:, -1].copy()
+    hot = rng.random(B) < 0.01                      # a few blocks with large coefficients and levels
+    orig[hot] = rng.integers(0, 256, (int(hot.sum()), n, n))
+    orig[-1] = rng.integers(0, 256, (n, n))         # the ragged tail segment is an exception too
+    lo = 2 * chunk                                  # third chunk: every block is an exception
+    orig[lo:lo + chunk] = rng.integers(0, 256, (min(chunk, B - lo), n, n))
+    modes = rng.integers(0, 2, B).astype(np.uint8)
+    L = _lib.lib()
+    for qp, outs in ((22, ("pred", "coeff", "levels", "recon")), (37, ("coeff", "levels")), (30, ("levels", "recon"))):
+        want = O.pipeline_dcplanar_batch(orig, top, left, tr, bl, modes, qp, use_dst=(n == 4), threads=O.n_host_threads())
+        got = Bt.host_block_pipeline(orig, top, left, tr, bl, modes, qp, use_dst=(n == 4), chunk_blocks=chunk, outputs=outs)
+        for name, w in zip(("pred", "coeff", "levels", "recon"), want):
+            if name in outs:
+                eq(getattr(got, name).numpy(), w, f"{name} n={n} qp={qp}")
+            else:
+                assert getattr(got, name) is None
+        up, down = ctypes.c_int64(0), ctypes.c_int64(0)
+        _lib.check(L.nh_host_pipeline_last_transfer(ctypes.byref(up), ctypes.byref(down)))
+        int16_format = sum(B * n * n * 2 for _ in outs)
+        assert 0 < down.value < int16_format, (down.value, int16_format)
+        assert up.value == orig.nbytes + top.nbytes + left.nbytes + tr.nbytes + bl.nbytes + modes.nbytes
+
+
 def test_fused_dcplanar_empty_and_errors(Bt):
     z = lambda *s: torch.zeros(s, dtype=torch.int16, device=DEV)
     got = Bt.fused_block_pipeline(z(0, 8, 8), z(0, 8), z(0, 8), z(0), z(0), 1, 27)
