@@ -51,6 +51,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner
+# on fd 1 when NCCL_DEBUG is set in the environment), so fd 1 is pointed at stderr for the whole run
+# and the JSON line goes to a duplicate of the original stdout.
+_JSON_FD = None
+
+
+def claim_stdout():
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def synth_frames(n_frames, seed):
     """SURVEY.md 8d (iii) 'smooth' synthetic luma: separable ramp + seeded low-amplitude noise."""
     rng = np.random.default_rng(4321 + seed)
@@ -172,7 +194,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 # ------------------------------------------------------------------- GPU leg
@@ -327,7 +349,7 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "stats": {"nonzero_levels_last_pass": int(stats[0].item()), "sse_last_pass": int(stats[1].item())},
         }
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -345,6 +367,7 @@ def main():
     ap.add_argument("--fused-impl", type=int, default=4, choices=[1, 2, 3, 4],
                     help="kernel generation of the fused 4x4/8x8 kernel (1 = first generation, for A/B runs)")
     args = ap.parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
