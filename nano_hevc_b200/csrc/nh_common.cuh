@@ -43,6 +43,10 @@ int fused_pipeline_dcplanar_narrow(const int16_t* orig, const int16_t* top, cons
                                    int16_t* coeff16, int16_t* levels16, int16_t* recon, int* ood_flag,
                                    cudaStream_t st);
 
+// nh_fused.cu: 2 = tensor-core kernels for N = 16 / 32 (default), 1 = CUDA-core butterflies
+// (nh_set_rows_impl / NH_ROWS_IMPL); also selects the single-stage transform kernels of nh_ops.cu.
+int rows_impl();
+
 #define NH_CHECK_LAUNCH(what)                                  \
     do {                                                       \
         cudaError_t e__ = cudaGetLastError();                  \

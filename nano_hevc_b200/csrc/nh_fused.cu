@@ -1055,7 +1055,7 @@ static int launch_rows(const FusedArgs& a, cudaStream_t st) {
 // butterflies (fused_rows_kernel); nh_set_rows_impl() or NH_ROWS_IMPL=1|2.  The int16-output variant
 // of the host pipeline always uses the CUDA-core kernel.
 static int g_rows_impl = 0;
-static int rows_impl() {
+int rows_impl() {
     if (g_rows_impl == 0) {
         const char* e = getenv("NH_ROWS_IMPL");
         g_rows_impl = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 2;

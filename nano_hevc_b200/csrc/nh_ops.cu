@@ -2,6 +2,7 @@
 // per-block functions: K2 predictors, K3 residual / reconstruct / clip,
 // K4 forward / inverse transforms, K5 quantize / dequantize.
 #include "nh_block.cuh"
+#include "nh_mma.cuh"
 
 namespace nh {
 
@@ -107,6 +108,218 @@ __global__ void __launch_bounds__(kRowsWarps * 32)
     }
 }
 
+// N = 16, 32 on the tensor cores: the two passes of ONE direction as register-chained HMMAs (see
+// nh_fused_mma.cuh for the fragment algebra).  pass 1: acc(m, n) = A1(m, k) X(k, n) with the constant
+// operand A1 = T (forward) or T^T (inverse) and X through ldmatrix.trans; pass 2: the rounded
+// accumulators are the A operand, B = T^T (forward) or T (inverse) comes from the same constant
+// table, and the result lands in the natural row layout.  Exact while every input sample lies in
+// [-1024, 1023]: |pass-1 result| <= 2048 (an exact f16 integer) and accumulators <= 4.2e6 < 2^24;
+// a warp tile with anything larger takes the CUDA-core butterflies.
+
+// int16 pair, each in [-1024, 1023] -> f16 pair, exactly: x + 1024 = 1024 b + l; (0x6400 | l) is the f16
+// number 1024 + l, from which 1024 (b = 1) or 2048 (b = 0) is subtracted.
+__device__ __forceinline__ uint32_t s16x2_to_h2(uint32_t w) {
+    const uint32_t v = __vadd2(w, 0x04000400u);
+    const uint32_t h = (v & 0x03ff03ffu) | 0x64006400u;
+    const uint32_t c = 0x68006800u - (v & 0x04000400u);
+    return h2_bits(__hsub2(bits_h2(h), bits_h2(c)));
+}
+
+template <int N, bool INV, bool IN32>
+__global__ void __launch_bounds__(kMmaWarps * 32, 3)
+    transform_mma_kernel(const void* __restrict__ in, int32_t* __restrict__ out, int64_t n_blocks) {
+    using C = MmaConsts<N>;
+    constexpr int NN = N * N;
+    constexpr int BPW = 32 / N;
+    constexpr int MT = N / 16, NT = N / 8, KT = N / 16;
+    constexpr int SH = Log2<N>::v + 5;
+    constexpr int PITCH = N * 2 + 16;
+    constexpr int TILE = N * PITCH;
+    constexpr int FAST_BYTES = BPW * TILE;
+    constexpr int EXACT_BYTES = BPW * RowsTile<N>::WORDS * 4;
+    constexpr int WARP_BYTES = FAST_BYTES > EXACT_BYTES ? FAST_BYTES : EXACT_BYTES;
+    constexpr int RW = IN32 ? N : N / 2;  // 32-bit words of one input row
+    __shared__ __align__(16) unsigned char smem[kMmaWarps][WARP_BYTES];
+    __shared__ __align__(16) uint4 ctab[C::V_END][32];
+    stage_mma_consts<N, kMmaWarps * 32>(&ctab[0][0]);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane / N, r = lane % N;
+    const int fg = lane >> 2, ft = lane & 3;
+    unsigned char* sm = smem[warp];
+    unsigned char* my_row = sm + g * TILE + r * PITCH;
+    int* M = reinterpret_cast<int*>(sm) + g * RowsTile<N>::WORDS;
+    const int lane_off = (((lane >> 3) & 1) * 8 + (lane & 7)) * PITCH + (lane >> 4) * 16;
+    const uint32_t ctab_lane = smem_u32(&ctab[0][lane]);
+    auto cv = [&](int v) -> uint4 { return ld_const_vec(ctab_lane, v); };
+    const float rnd = (float)(1 << (SH - 1));
+
+    const int64_t n_tiles = (n_blocks + BPW - 1) / BPW;
+    const int64_t warp_stride = (int64_t)gridDim.x * kMmaWarps;
+    int64_t tile = (int64_t)blockIdx.x * kMmaWarps + warp;
+    uint32_t nxt[RW];  // this lane's input row, one tile ahead
+    auto prefetch = [&](int64_t t) {
+        const int64_t b = t * BPW + g;
+        if (b < n_blocks) {
+            const unsigned char* p = reinterpret_cast<const unsigned char*>(in) + (b * NN + r * N) * (IN32 ? 4 : 2);
+#pragma unroll
+            for (int q = 0; q < RW / 4; ++q) {
+                const uint4 v = ldg_stream(p + 16 * q);
+                nxt[4 * q] = v.x; nxt[4 * q + 1] = v.y; nxt[4 * q + 2] = v.z; nxt[4 * q + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < RW; ++k) nxt[k] = 0;
+        }
+    };
+    if (tile < n_tiles) prefetch(tile);
+
+    for (; tile < n_tiles; tile += warp_stride) {
+        const int64_t b = tile * BPW + g;
+        const bool valid = b < n_blocks;
+        // pack the row to int16 pairs and test -1024 <= x <= 1023 on the way
+        uint32_t pw[N / 2];
+        uint32_t ood = 0;
+        if constexpr (IN32) {
+#pragma unroll
+            for (int k = 0; k < N / 2; ++k) {
+                const int x0 = (int)nxt[2 * k], x1 = (int)nxt[2 * k + 1];
+                ood |= (uint32_t)(x0 + 1024) | (uint32_t)(x1 + 1024);  // any bit >= 11 set: outside [-1024, 1023]
+                pw[k] = pack16(x0, x1);
+            }
+            ood &= 0xFFFFF800u;
+        } else {
+#pragma unroll
+            for (int k = 0; k < N / 2; ++k) {
+                pw[k] = nxt[k];
+                ood |= __vadd2(nxt[k], 0x04000400u);
+            }
+            ood &= 0xF800F800u;
+        }
+        const bool fast = !__any_sync(0xffffffffu, ood != 0);
+        if (fast) {
+#pragma unroll
+            for (int q = 0; q < N / 8; ++q)
+                *reinterpret_cast<uint4*>(my_row + 16 * q) = make_uint4(pw[4 * q], pw[4 * q + 1], pw[4 * q + 2], pw[4 * q + 3]);
+        } else {
+            int x[N];
+            if constexpr (IN32) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) x[k] = (int)nxt[k];
+            } else {
+                unpack_row<N>(pw, x);
+            }
+            store_row_smem<N>(M, r, x);
+        }
+        if (tile + warp_stride < n_tiles) prefetch(tile + warp_stride);
+        __syncwarp();
+        if (fast) {
+#pragma unroll
+            for (int u = 0; u < BPW; ++u) {
+                const int64_t bu = tile * BPW + u;
+                const bool valid_u = bu < n_blocks;
+                const uint32_t so = smem_u32(sm + u * TILE) + lane_off;
+                float acc[MT][NT][4];
+                uint32_t h[MT][NT][2];
+                {
+                    uint32_t xb[KT][NT][2];
+#pragma unroll
+                    for (int ki = 0; ki < KT; ++ki)
+#pragma unroll
+                        for (int np = 0; np < NT / 2; ++np) {
+                            uint32_t ro[4];
+                            ldsm_x4_t(ro, so + 16 * ki * PITCH + 32 * np);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) xb[ki][2 * np + (j >> 1)][j & 1] = s16x2_to_h2(ro[j]);
+                        }
+#pragma unroll
+                    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+                        for (int ki = 0; ki < KT; ++ki) {
+                            uint4 af;
+                            if constexpr (INV) {  // A = T^T from the B = T fragments
+                                const uint4 t = cv(C::V_TB + ki * NT / 2 + mi);
+                                af = make_uint4(t.x, t.z, t.y, t.w);
+                            } else {
+                                af = cv(C::V_TA + mi * KT + ki);
+                            }
+#pragma unroll
+                            for (int ni = 0; ni < NT; ++ni) {
+                                if (ki == 0)
+                                    hmma16816(acc[mi][ni], af, xb[ki][ni][0], xb[ki][ni][1], rnd, rnd, rnd, rnd);
+                                else
+                                    hmma16816(acc[mi][ni], af, xb[ki][ni][0], xb[ki][ni][1], acc[mi][ni][0],
+                                              acc[mi][ni][1], acc[mi][ni][2], acc[mi][ni][3]);
+                            }
+                        }
+                }
+#pragma unroll
+                for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < NT; ++ni) {
+                        h[mi][ni][0] = round_pair_plain<SH>(acc[mi][ni][0], acc[mi][ni][1]);
+                        h[mi][ni][1] = round_pair_plain<SH>(acc[mi][ni][2], acc[mi][ni][3]);
+                    }
+                // second pass: A = first-pass result (C -> A), B = T^T (forward) / T (inverse)
+#pragma unroll
+                for (int np = 0; np < NT / 2; ++np)
+#pragma unroll
+                    for (int ki = 0; ki < KT; ++ki) {
+                        uint32_t b00, b01, b10, b11;  // (b0, b1) of n-tiles 2np and 2np + 1
+                        if constexpr (INV) {
+                            const uint4 t = cv(C::V_TB + ki * NT / 2 + np);
+                            b00 = t.x; b01 = t.y; b10 = t.z; b11 = t.w;
+                        } else {  // B[k][n] = T[n][k]: the A = T fragment of m-tile np
+                            const uint4 t = cv(C::V_TA + np * KT + ki);
+                            b00 = t.x; b01 = t.z; b10 = t.y; b11 = t.w;
+                        }
+#pragma unroll
+                        for (int mi = 0; mi < MT; ++mi) {
+                            const uint4 af = make_uint4(h[mi][2 * ki][0], h[mi][2 * ki][1], h[mi][2 * ki + 1][0],
+                                                        h[mi][2 * ki + 1][1]);
+                            float(&d0)[4] = acc[mi][2 * np];
+                            float(&d1)[4] = acc[mi][2 * np + 1];
+                            if (ki == 0) {
+                                hmma16816(d0, af, b00, b01, rnd, rnd, rnd, rnd);
+                                hmma16816(d1, af, b10, b11, rnd, rnd, rnd, rnd);
+                            } else {
+                                hmma16816(d0, af, b00, b01, d0[0], d0[1], d0[2], d0[3]);
+                                hmma16816(d1, af, b10, b11, d1[0], d1[1], d1[2], d1[3]);
+                            }
+                        }
+                    }
+                if (valid_u) {
+                    int32_t* op = out + bu * NN + fg * N + 2 * ft;
+#pragma unroll
+                    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < NT; ++ni) {
+                            int v[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                v[e] = __float_as_int(floor_shift_magic<SH>(acc[mi][ni][e])) - kMagicI;
+                            __stcs(reinterpret_cast<int2*>(op + (16 * mi) * N + 8 * ni), make_int2(v[0], v[1]));
+                            __stcs(reinterpret_cast<int2*>(op + (16 * mi + 8) * N + 8 * ni), make_int2(v[2], v[3]));
+                        }
+                }
+            }
+        } else {
+            int y[N];
+            two_pass_transform<N, false, INV>(M, r, true, y);
+            if (valid) store_row32<N>(out + b * NN + r * N, y);
+        }
+        __syncwarp();
+    }
+}
+
+template <int N, bool INV, bool IN32>
+static int launch_transform_mma(const void* in, int32_t* out, int64_t n_blocks, cudaStream_t st) {
+    int grid = grid_for(n_blocks, kMmaWarps * (32 / N), 3);
+    transform_mma_kernel<N, INV, IN32><<<grid, kMmaWarps * 32, 0, st>>>(in, out, n_blocks);
+    NH_CHECK_LAUNCH("transform_mma_kernel");
+    return NH_OK;
+}
+
 template <int N, bool DST, bool INV, bool IN32>
 static int launch_transform_unit(const void* in, int32_t* out, int64_t n_blocks, cudaStream_t st) {
     constexpr int kSmem = kXfWarps * WarpTile<256>::kBytes;
@@ -140,8 +353,12 @@ static int dispatch_transform(const void* in, int32_t* out, int64_t n_blocks, in
             return use_dst ? launch_transform_unit<4, true, INV, IN32>(in, out, n_blocks, st)
                            : launch_transform_unit<4, false, INV, IN32>(in, out, n_blocks, st);
         case 8: return launch_transform_unit<8, false, INV, IN32>(in, out, n_blocks, st);
-        case 16: return launch_transform_rows<16, INV, IN32>(in, out, n_blocks, st);
-        case 32: return launch_transform_rows<32, INV, IN32>(in, out, n_blocks, st);
+        case 16:
+            return rows_impl() == 1 ? launch_transform_rows<16, INV, IN32>(in, out, n_blocks, st)
+                                    : launch_transform_mma<16, INV, IN32>(in, out, n_blocks, st);
+        case 32:
+            return rows_impl() == 1 ? launch_transform_rows<32, INV, IN32>(in, out, n_blocks, st)
+                                    : launch_transform_mma<32, INV, IN32>(in, out, n_blocks, st);
     }
     return NH_E_SIZE;
 }

@@ -355,6 +355,43 @@ def test_fused_rows_impls_adversarial(Bt, n, impl):
         _lib.check(_lib.lib().nh_set_fused_impl(DEFAULT_FUSED_IMPL))
 
 
+@pytest.mark.parametrize("n", (16, 32))
+@pytest.mark.parametrize("impl", (1, 2))
+def test_transform_impls_adversarial(Bt, n, impl):
+    """Single-stage forward / inverse transforms at N = 16 / 32 behind both kernels (1 = CUDA-core
+    butterflies, 2 = tensor-core passes, exact for inputs in [-1024, 1023]): extreme basis patterns at
+    the edge of the tensor-core domain, int16 and int32 inputs, values just outside the domain and
+    full-range values mixed into the batch (exact fallback per warp tile), ragged batch sizes."""
+    from nano_hevc_b200 import _lib
+    rng = np.random.default_rng(321 + n)
+    T = _dct(n)
+    pats = []
+    for (i, j) in [(0, 0), (1, 1), (n - 1, n - 1), (0, n - 1), (n - 1, 0), (2, 3), (n // 2, 1)]:
+        s = np.sign(np.outer(T[i], T[j]))
+        pats += [np.where(s > 0, 1023, -1024), np.where(s > 0, -1024, 1023), 255 * s, np.where(s > 0, 1023, 0)]
+        st = np.sign(np.outer(T[:, i], T[:, j]))          # worst case for the inverse (contracts over rows of T)
+        pats += [np.where(st > 0, 1023, -1024), np.where(st > 0, -1024, 1023)]
+    pats += [np.full((n, n), 1023), np.full((n, n), -1024), np.zeros((n, n))]
+    B = len(pats) + 301
+    x = rng.integers(-1024, 1024, (B, n, n)).astype(np.int32)
+    x[:len(pats)] = np.array(pats)
+    _lib.check(_lib.lib().nh_set_rows_impl(impl))
+    try:
+        for data in (x, x[:1], x[:len(pats) + 2]):
+            eq(host(Bt.forward_transform_batched(dev(data.astype(np.int16)))), O.forward_transform_batch(data.astype(np.int16)), f"fwd i16 n={n}")
+            eq(host(Bt.forward_transform_batched(dev(data))), O.forward_transform_batch(data), f"fwd i32 n={n}")
+            eq(host(Bt.inverse_transform_batched(dev(data))), O.inverse_transform_batch(data), f"inv n={n}")
+        y = x.copy()
+        y[7, 3, 2] = 1024; y[8, 0, 0] = -1025; y[100:140] = rng.integers(-32768, 32768, (40, n, n))
+        y[200, n - 1, n - 1] = 2 ** 31 - 1; y[201, 0, 1] = -2 ** 31
+        eq(host(Bt.forward_transform_batched(dev(y))), O.forward_transform_batch(y), f"fwd ood n={n}")
+        eq(host(Bt.inverse_transform_batched(dev(y))), O.inverse_transform_batch(y), f"inv ood n={n}")
+        y16 = np.clip(y, -32768, 32767).astype(np.int16)
+        eq(host(Bt.forward_transform_batched(dev(y16))), O.forward_transform_batch(y16), f"fwd ood i16 n={n}")
+    finally:
+        _lib.check(_lib.lib().nh_set_rows_impl(2))
+
+
 @pytest.mark.parametrize("n,B,chunk", [(4, 70001, 8192), (8, 20011, 4096), (16, 3001, 1024), (32, 1000, 300)])
 def test_host_pipeline_vs_oracle(Bt, n, B, chunk):
     """The host-buffer C-ABI entry (chunked, three streams, int16 wire format for coefficients and
