@@ -219,6 +219,14 @@ int nh_host_pipeline_dcplanar(const int16_t* orig, const int16_t* top, const int
                               int32_t* coeff, int32_t* levels, int16_t* recon,
                               void* device_scratch, int64_t scratch_bytes, int64_t chunk_blocks);
 
+/* ------------------------------------- device-side frame containers */
+/* Sample conversion for planes held on the device (nano_hevc/frame.py): uint8 -> int16 zero-extends
+ * (frame.py:45-51, Plane.from_buffer followed by the coder's astype(int16)); int16 -> uint8 keeps the
+ * low 8 bits, which is what numpy's astype(np.uint8) in Frame.to_yuv420p / PackedFrame.to_yuv420p
+ * does (frame.py:107-111, :172-178).  n samples, device pointers. */
+int nh_convert_u8_to_i16(const uint8_t* src, int16_t* dst, int64_t n, void* stream);
+int nh_convert_i16_to_u8(const int16_t* src, uint8_t* dst, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

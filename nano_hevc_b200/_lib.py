@@ -59,6 +59,8 @@ PROTOTYPES = {
     "nh_level_stats": (_i, [_p, _i64, _p, _p, _p]),
     "nh_host_pipeline_scratch_bytes": (_i64, [_i, _i64]),
     "nh_host_pipeline_last_transfer": (_i, [_p, _p]),
+    "nh_convert_u8_to_i16": (_i, [_p, _p, _i64, _p]),
+    "nh_convert_i16_to_u8": (_i, [_p, _p, _i64, _p]),
     "nh_host_pipeline_dcplanar": (_i, [_p, _p, _p, _p, _p, _p, _i, _i64, _i, _i, _i, _i, _i,
                                        _p, _p, _p, _p, _p, _i64, _i64]),
 }

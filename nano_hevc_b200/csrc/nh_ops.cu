@@ -529,6 +529,47 @@ static int launch_predict(const int16_t* top, const int16_t* left, const int16_t
     return NH_OK;
 }
 
+
+// =================================================================== frame containers
+// uint8 <-> int16 sample conversion for the device-side frame containers (frame.py:45-51 reads
+// uint8 planes, frame.py:107-111 / :172-178 write them back with numpy's astype(np.uint8), i.e.
+// the low 8 bits of every int16 sample).  16 samples per thread, scalar tail.
+template <bool TO_I16>
+__global__ void __launch_bounds__(256) convert_kernel(const void* __restrict__ in, void* __restrict__ out, int64_t n) {
+    const int64_t n16 = n / 16;
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(TO_I16 ? in : out);   // the uint8 side
+    const int16_t* w = reinterpret_cast<const int16_t*>(TO_I16 ? out : in);   // the int16 side
+    const bool vec = ((reinterpret_cast<uintptr_t>(b) & 15) | (reinterpret_cast<uintptr_t>(w) & 15)) == 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec) {
+        for (int64_t i = t0; i < n16; i += stride) {
+            if constexpr (TO_I16) {
+                const uint4 v = ldg_stream(reinterpret_cast<const uint4*>(in) + i);
+                const uint32_t s[4] = {v.x, v.y, v.z, v.w};
+                uint32_t o[8];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    o[2 * k] = __byte_perm(s[k], 0u, 0x4140);      // bytes 0, 1 zero-extended
+                    o[2 * k + 1] = __byte_perm(s[k], 0u, 0x4342);  // bytes 2, 3
+                }
+                uint4* d = reinterpret_cast<uint4*>(out) + 2 * i;
+                stg_stream(d, make_uint4(o[0], o[1], o[2], o[3]));
+                stg_stream(d + 1, make_uint4(o[4], o[5], o[6], o[7]));
+            } else {
+                const uint4 a = ldg_stream(reinterpret_cast<const uint4*>(in) + 2 * i);
+                const uint4 c = ldg_stream(reinterpret_cast<const uint4*>(in) + 2 * i + 1);
+                stg_stream(reinterpret_cast<uint4*>(out) + i,
+                           make_uint4(__byte_perm(a.x, a.y, 0x6420), __byte_perm(a.z, a.w, 0x6420),
+                                      __byte_perm(c.x, c.y, 0x6420), __byte_perm(c.z, c.w, 0x6420)));
+            }
+        }
+    }
+    for (int64_t i = (vec ? n16 * 16 : 0) + t0; i < n; i += stride) {
+        if constexpr (TO_I16) reinterpret_cast<int16_t*>(out)[i] = (int16_t)reinterpret_cast<const uint8_t*>(in)[i];
+        else reinterpret_cast<uint8_t*>(out)[i] = (uint8_t)reinterpret_cast<const int16_t*>(in)[i];
+    }
+}
+
 }  // namespace nh
 
 using namespace nh;
@@ -654,4 +695,20 @@ NH_API int nh_intra_predict_modes(const int16_t* top, const int16_t* left, const
     }
     return launch_predict<2>(top, left, top_left, nullptr, modes, mode, allow_dc_planar, pred, n_blocks,
                              size, reinterpret_cast<cudaStream_t>(stream));
+}
+
+NH_API int nh_convert_u8_to_i16(const uint8_t* src, int16_t* dst, int64_t n, void* stream) {
+    NH_REQUIRE(n >= 0 && (n == 0 || (src && dst)), "nh_convert_u8_to_i16: null pointer or negative count");
+    if (n == 0) return NH_OK;
+    convert_kernel<true><<<grid_for(n, 256 * 16, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, dst, n);
+    NH_CHECK_LAUNCH("convert_kernel");
+    return NH_OK;
+}
+
+NH_API int nh_convert_i16_to_u8(const int16_t* src, uint8_t* dst, int64_t n, void* stream) {
+    NH_REQUIRE(n >= 0 && (n == 0 || (src && dst)), "nh_convert_i16_to_u8: null pointer or negative count");
+    if (n == 0) return NH_OK;
+    convert_kernel<false><<<grid_for(n, 256 * 16, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, dst, n);
+    NH_CHECK_LAUNCH("convert_kernel");
+    return NH_OK;
 }

@@ -324,6 +324,55 @@ def g_cli():
     save("cli.npz", **out)
 
 
+def g_containers():
+    """Frame containers (frame.py:121-308): PackedFrame.from_yuv420p / to_yuv420p (astype(np.uint8)
+    wrap-around) and the FrameBufferPool acquire / release sequence."""
+    from nano_hevc.frame import PackedFrame, FrameBufferPool, Frame
+    out = {}
+    rng = np.random.default_rng(2024)
+    for (H, W) in ((6, 10), (18, 34), (64, 96)):
+        raw = rng.integers(0, 256, H * W + 2 * (H // 2) * (W // 2), dtype=np.uint8).tobytes()
+        pf = PackedFrame.from_yuv420p(raw, H, W)
+        tag = f"{H}x{W}"
+        out[f"raw_{tag}"] = np.frombuffer(raw, np.uint8)
+        out[f"y_{tag}"], out[f"u_{tag}"], out[f"v_{tag}"] = pf.y.copy(), pf.u.copy(), pf.v.copy()
+        assert pf.to_yuv420p() == raw and Frame.from_yuv420p(raw, H, W).to_yuv420p() == raw
+        # an int16 frame with samples outside 0..255: to_yuv420p keeps the low 8 bits
+        p16 = PackedFrame(H, W, dtype=np.int16)
+        vals = rng.integers(-32768, 32768, p16._buffer.size).astype(np.int16)
+        vals[:8] = [0, 255, 256, -1, -256, 300, 32767, -32768]
+        np.copyto(p16._buffer, vals)
+        out[f"i16_{tag}"] = vals
+        out[f"i16_bytes_{tag}"] = np.frombuffer(p16.to_yuv420p(), np.uint8)
+    # pool bookkeeping: a scripted sequence of operations and what the reference answers
+    pool = FrameBufferPool(8, 8, pool_size=3)
+    trace = []
+    def snap(tag, val):
+        trace.append((tag, val, pool.available_count, pool.in_use_count))
+    a, _ = pool.acquire(); snap("acquire", a)
+    b, fb = pool.acquire(); snap("acquire", b)
+    fb.y[:] = 7
+    pool.release(a); snap("release", a)
+    c, _ = pool.acquire(); snap("acquire", c)
+    d, _ = pool.acquire(); snap("acquire", d)
+    try:
+        pool.acquire()
+    except RuntimeError as e:
+        out["pool_exhausted_msg"] = np.array(str(e))
+    try:
+        pool.release(a + 100)
+    except ValueError as e:
+        out["pool_release_msg"] = np.array(str(e))
+    pool.release(b); snap("release", b)
+    e2, fe = pool.acquire(clear=False); snap("acquire", e2)
+    out["pool_kept_value"] = np.array(int(fe.y[0, 0]))      # clear=False keeps the 7 written above
+    e3 = pool.release(e2); snap("release", e2)
+    _, fz = pool.acquire(clear=True)
+    out["pool_cleared_value"] = np.array(int(fz.y[0, 0]))
+    out["pool_trace"] = np.array([[0 if t == "acquire" else 1, v, av, iu] for (t, v, av, iu) in trace], np.int64)
+    save("containers.npz", **out)
+
+
 if __name__ == "__main__":
     g_tables()
     g_predictors()
@@ -334,3 +383,4 @@ if __name__ == "__main__":
     g_cli()
     g_stats()
     g_frames()
+    g_containers()
