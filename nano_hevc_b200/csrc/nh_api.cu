@@ -2,6 +2,9 @@
 // libnh_b200.so (see include/nh_b200.h).
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
+#include <set>
+#include <utility>
 
 #include "nh_common.cuh"
 
@@ -34,6 +37,20 @@ int sm_count() {
         cached_sms = n;
     }
     return cached_sms;
+}
+
+int ensure_dynamic_smem_impl(const void* kernel, int bytes, const char* what) {
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.count({kernel, dev})) return NH_OK;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    done.insert({kernel, dev});
+    return NH_OK;
 }
 
 }  // namespace nh

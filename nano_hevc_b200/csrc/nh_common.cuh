@@ -47,6 +47,14 @@ int fused_pipeline_dcplanar_narrow(const int16_t* orig, const int16_t* top, cons
 // (nh_set_rows_impl / NH_ROWS_IMPL); also selects the single-stage transform kernels of nh_ops.cu.
 int rows_impl();
 
+// Opt a kernel into more than 48 KB of dynamic shared memory, once per (kernel, device): function
+// attributes are per context and a process may drive several GPUs.  nh_api.cu.
+int ensure_dynamic_smem_impl(const void* kernel, int bytes, const char* what);
+template <class Kernel>
+inline int ensure_dynamic_smem(Kernel kernel, int bytes, const char* what) {
+    return ensure_dynamic_smem_impl(reinterpret_cast<const void*>(kernel), bytes, what);
+}
+
 #define NH_CHECK_LAUNCH(what)                                  \
     do {                                                       \
         cudaError_t e__ = cudaGetLastError();                  \

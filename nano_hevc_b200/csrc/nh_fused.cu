@@ -902,12 +902,9 @@ template <int N, bool DST>
 static int launch_unit_v1(const FusedArgs& a, cudaStream_t st) {
     constexpr int BPU = 64 / (N * N);
     constexpr int kSmem = kUnitWarps * (WarpTile<128>::kBytes + WarpTile<256>::kBytes);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(fused_unit_kernel<N, DST>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fused_unit_kernel)");
-        configured = true;
+    {
+        const int rc = ensure_dynamic_smem(fused_unit_kernel<N, DST>, kSmem, "cudaFuncSetAttribute(fused_unit_kernel)");
+        if (rc != NH_OK) return rc;
     }
     int64_t units = (a.n_blocks + BPU - 1) / BPU;
     int grid = grid_for(units, (int64_t)kUnitWarps * 32, 2);
@@ -920,12 +917,9 @@ template <int N, bool DST, bool NARROW = false>
 static int launch_unit_v2(const FusedArgs& a, cudaStream_t st) {
     constexpr int BPU = 64 / (N * N);
     constexpr int kSmem = kV2Warps * (2 * WarpTile<128>::kBytes + WarpTile<256>::kBytes);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(fused_unit_kernel_v2<N, DST, NARROW>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fused_unit_kernel_v2)");
-        configured = true;
+    {
+        const int rc = ensure_dynamic_smem(fused_unit_kernel_v2<N, DST, NARROW>, kSmem, "cudaFuncSetAttribute(fused_unit_kernel_v2)");
+        if (rc != NH_OK) return rc;
     }
     int64_t units = (a.n_blocks + BPU - 1) / BPU;
     int grid = grid_for(units, (int64_t)kV2Warps * 32, 3);
@@ -977,12 +971,9 @@ static int launch_unit_v3(const FusedArgs& a, cudaStream_t st) {
     constexpr int BPU = 64 / (N * N);
     constexpr int NN = N * N;
     constexpr int kSmem = kV2Warps * 4 * 4096 + kV2Warps * 16 + 1024;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(fused_unit_kernel_v3<N, DST>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fused_unit_kernel_v3)");
-        configured = true;
+    {
+        const int rc = ensure_dynamic_smem(fused_unit_kernel_v3<N, DST>, kSmem, "cudaFuncSetAttribute(fused_unit_kernel_v3)");
+        if (rc != NH_OK) return rc;
     }
     const int64_t n_units = a.n_blocks / BPU;  // whole units go through TMA
     if (n_units > 0) {

@@ -573,11 +573,9 @@ __global__ void __launch_bounds__(kV2Warps * 32, OCC) fused_mma8_kernel(const Fu
 template <int OCC>
 static int launch_mma8_occ(const FusedArgs& a, cudaStream_t st) {
     constexpr int kSmem = kV2Warps * 3 * WarpTile<128>::kBytes;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(fused_mma8_kernel<OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fused_mma8_kernel)");
-        configured = true;
+    {
+        const int rc = ensure_dynamic_smem(fused_mma8_kernel<OCC>, kSmem, "cudaFuncSetAttribute(fused_mma8_kernel)");
+        if (rc != NH_OK) return rc;
     }
     int grid = grid_for(a.n_blocks, (int64_t)kV2Warps * 32, OCC);
     fused_mma8_kernel<OCC><<<grid, kV2Warps * 32, kSmem, st>>>(a, make_fast_quant(a.qp));

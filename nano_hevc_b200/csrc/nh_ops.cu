@@ -323,12 +323,9 @@ static int launch_transform_mma(const void* in, int32_t* out, int64_t n_blocks, 
 template <int N, bool DST, bool INV, bool IN32>
 static int launch_transform_unit(const void* in, int32_t* out, int64_t n_blocks, cudaStream_t st) {
     constexpr int kSmem = kXfWarps * WarpTile<256>::kBytes;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(transform_unit_kernel<N, DST, INV, IN32>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(transform_unit_kernel)");
-        configured = true;
+    {
+        const int rc = ensure_dynamic_smem(transform_unit_kernel<N, DST, INV, IN32>, kSmem, "cudaFuncSetAttribute(transform_unit_kernel)");
+        if (rc != NH_OK) return rc;
     }
     constexpr int BPU = 64 / (N * N);
     int grid = grid_for((n_blocks + BPU - 1) / BPU, kXfWarps * 32, 2);
