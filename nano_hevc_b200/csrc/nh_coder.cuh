@@ -116,7 +116,8 @@ __device__ __forceinline__ int subblock_cost(int mode, int sx, int sy, const int
 // every lane of the group.
 template <int N, int G>
 __device__ __forceinline__ int search_modes(int gl, const int16_t* O, const int16_t* top,
-                                            const int16_t* left, int corner, int dc, int cost_kind) {
+                                            const int16_t* left, int corner, int dc, int cost_kind,
+                                            int it0 = 0, int it_step = 1) {
     using Cfg = CoderCfg<N, G>;
     constexpr int SBW = N / 4;
     int o[Cfg::SPL][16];
@@ -132,7 +133,8 @@ __device__ __forceinline__ int search_modes(int gl, const int16_t* O, const int1
     const int ms = (Cfg::MS == 1) ? 0 : gl / Cfg::SB;
     int best = 0x7fffffff;
     constexpr int ITERS = (35 + Cfg::MS - 1) / Cfg::MS;
-    for (int it = 0; it < ITERS; ++it) {
+    // (it0, it_step): several warps may share one block, each taking every it_step-th iteration
+    for (int it = it0; it < ITERS; it += it_step) {
         const int pos = it * Cfg::MS + ms;          // position in the candidate order
         const bool active = pos < 35;
         const int mode = !active ? 1 : (pos == 0 ? 1 : (pos == 1 ? 0 : pos));
@@ -312,7 +314,7 @@ __device__ __forceinline__ int strip_cost_u8(int mode, int b0, int s0,
 template <int N, int G>
 __device__ __forceinline__ int search_modes_u8(int gl, const int16_t* O, const int16_t* top,
                                                const int16_t* left, const int16_t* neg, int dc,
-                                               int cost_kind) {
+                                               int cost_kind, int it0 = 0, int it_step = 1) {
     using Cfg = CoderCfg<N, G>;
     using SC = StripCfg<N, G>;
     constexpr int SW = SC::SW, WPS = SC::WPS;
@@ -344,7 +346,7 @@ __device__ __forceinline__ int search_modes_u8(int gl, const int16_t* O, const i
     const int ms = (SC::MS == 1) ? 0 : gl / SC::SB;
     int best = 0x7fffffff;
     constexpr int ITERS = (35 + SC::MS - 1) / SC::MS;
-    for (int it = 0; it < ITERS; ++it) {
+    for (int it = it0; it < ITERS; it += it_step) {
         const int pos = it * SC::MS + ms;
         const bool active = pos < 35;
         const int mode = !active ? 1 : (pos == 0 ? 1 : (pos == 1 ? 0 : pos));

@@ -300,6 +300,125 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
     }
 }
 
+// K8, N = 16 / 32: WPB warps per block row.  With one warp per row the critical path of the wavefront
+// is bw + 2 bh block times, and a 32x32 block is ~17 us of dependent work for a single warp, most of
+// it the 35-mode search.  Here a CTA owns the row: every warp searches a share of the candidate
+// modes (the argmin is merged through shared memory; the key order keeps the tie rule), warp 0 polls
+// the exchange row above and runs the winner pipeline, all threads move pixels.  Same exchange-row
+// protocol and ticket order as the one-warp kernel, so a waiting CTA only ever waits on a row that a
+// resident CTA owns.
+template <int N, int WPB>
+__global__ void __launch_bounds__(32 * WPB) coder_wave_mw_kernel(const CoderArgs a) {
+    using Cfg = CoderCfg<N, 32>;
+    constexpr int T = 32 * WPB;
+    __shared__ __align__(16) unsigned char smem[Cfg::GROUP_BYTES];
+    __shared__ int s_keys[WPB];
+    __shared__ int s_row;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int16_t* top = reinterpret_cast<int16_t*>(smem);
+    int16_t* left = top + Cfg::REF_W;
+    int16_t* neg = reinterpret_cast<int16_t*>(smem + Cfg::REFS_PAD);
+    int16_t* O = reinterpret_cast<int16_t*>(smem + Cfg::REFS_PAD + Cfg::NEG_BYTES);
+    int* M = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(O) + Cfg::O_BYTES);
+    const int bw = a.W / N, bh = a.H / N;
+    constexpr int OPL = (N * N + T - 1) / T;  // original samples per thread
+    for (;;) {
+        if (tid == 0) s_row = atomicAdd(a.ticket, 1);
+        __syncthreads();
+        const int by = s_row;
+        __syncthreads();  // everyone has read s_row before thread 0 draws the next ticket
+        if (by >= bh) break;
+        for (int bx = 0; bx < bw; ++bx) {
+            const int x = bx * N, y = by * N;
+            const int64_t b = (int64_t)by * bw + bx;
+            // original pixels do not depend on any neighbour: fetch them before the wait
+            int ov[OPL];
+#pragma unroll
+            for (int i = 0; i < OPL; ++i) {
+                const int e = tid + i * T;
+                ov[i] = e < N * N ? (int)__ldg(a.src + (int64_t)(y + e / N) * a.pitch + x + e % N) : 0;
+            }
+            int ood = 0;
+            // left references = right-most column of the block this CTA has just reconstructed (still
+            // in O); bottom-left is not reconstructed yet -> replicate (n_left = N)
+            for (int k = tid + 1; k < Cfg::REF_W; k += T) {
+                const int kk = k <= N ? k : N;
+                const int lv = bx == 0 ? 128 : (int)O[(kk - 1) * Cfg::O_PITCH + (N - 1)];
+                left[k] = (int16_t)lv;
+                ood |= lv;
+            }
+            // top references from the exchange row above (data-as-flag, -1 = not written yet): warp 0
+            // polls, the other warps wait at the barrier below without taking issue slots
+            if (warp == 0) {
+                if (by == 0) {
+                    for (int k = lane; k < Cfg::REF_W; k += 32) top[k] = 128;
+                } else {
+                    const int16_t* up = a.bottom + (int64_t)(by - 1) * a.W;
+                    int last = x + 2 * N - 1;
+                    if (last > a.W - 1) last = a.W - 1;
+                    bool ready;
+                    do {
+                        ready = true;
+                        for (int k = lane; k < Cfg::REF_W; k += 32) {
+                            int v;
+                            if (k == 0 && x == 0) {
+                                v = 128;
+                            } else {
+                                int col = x + k - 1;
+                                if (col > last) col = last;
+                                v = (int)__ldcg(up + col);
+                            }
+                            if (v < 0) ready = false;
+                            else top[k] = (int16_t)v;
+                        }
+                        ready = __all_sync(0xffffffffu, ready);
+                        if (!ready && a.poll_sleep_ns) __nanosleep(a.poll_sleep_ns);
+                    } while (!ready);
+                    for (int k = lane; k < Cfg::REF_W; k += 32) ood |= (int)top[k];
+                }
+            }
+            __syncthreads();  // O (previous reconstruction) has been consumed, top / left are in place
+            if (tid == 0) left[0] = top[0];
+#pragma unroll
+            for (int i = 0; i < OPL; ++i) {
+                const int e = tid + i * T;
+                if (e < N * N) O[(e / N) * Cfg::O_PITCH + (e % N)] = (int16_t)ov[i];
+                ood |= ov[i];
+            }
+            const bool fast8 = __syncthreads_or((ood & ~0xff) != 0) == 0;
+            const int corner = (int)top[0];
+            const int dc = dc_from_refs<N>(top, left);
+            if (fast8) {
+                build_neg_arrays<N, T>(tid, top, left, neg);
+                __syncthreads();
+            }
+            int key = fast8 ? search_modes_u8<N, 32>(lane, O, top, left, neg, dc, a.cost_kind, warp, WPB)
+                            : search_modes<N, 32>(lane, O, top, left, corner, dc, a.cost_kind, warp, WPB);
+            if (lane == 0) s_keys[warp] = key;
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < WPB; ++w) key = s_keys[w] < key ? s_keys[w] : key;
+            const int mode = mode_of_key(key);
+            if (warp == 0) {
+                if (lane == 0) {
+                    if (a.out.modes) a.out.modes[b] = (uint8_t)mode;
+                    if (a.out.costs) a.out.costs[b] = key >> 6;
+                }
+                code_block<N, 32>(lane, true, b, mode, O, M, top, left, corner, dc, a.qp, a.fq, fast8, neg,
+                                  a.maxv, a.use_dst != 0, a.out);
+                // publish the bottom row first: the row below is polling for it
+                for (int e = lane; e < N; e += 32)
+                    __stcg(a.bottom + (int64_t)by * a.W + x + e, O[(N - 1) * Cfg::O_PITCH + e]);
+            }
+            __syncthreads();  // the reconstruction is in O
+            for (int e = tid; e < N * N; e += T)
+                a.out.recon_plane[(int64_t)(y + e / N) * a.pitch + x + e % N] = O[(e / N) * Cfg::O_PITCH + (e % N)];
+            // no barrier needed here: the next block only reads O (left references) before the
+            // barrier that precedes its overwrite
+        }
+    }
+}
+
 // Exchange rows of the wavefront coder: -1 where a block will publish its bottom row, 0 in the
 // columns no full block covers (the reference reads the zero-initialised plane there).
 __global__ void __launch_bounds__(256) init_bottom_kernel(int16_t* bottom, int bh, int W, int covered, int* ticket) {
@@ -322,6 +441,25 @@ static int dispatch_coder(const CoderArgs& a, int size, cudaStream_t st) {
         int bh = a.H / size;
         int grid = bh < sm_count() * 16 ? bh : sm_count() * 16;
         if (grid < 1) grid = 1;
+        static int wave_warps = -1;  // warps per block row at N = 16 / 32: NH_WAVE_WARPS=1|2|4 (default 4)
+        if (wave_warps < 0) {
+            const char* e = getenv("NH_WAVE_WARPS");
+            wave_warps = (e && (e[0] == '1' || e[0] == '2' || e[0] == '8')) ? e[0] - '0' : 4;
+        }
+        if (size >= 16 && wave_warps > 1) {
+            if (grid > sm_count() * 4) grid = sm_count() * 4;
+            if (size == 16) {
+                if (wave_warps == 2) coder_wave_mw_kernel<16, 2><<<grid, 64, 0, st>>>(a);
+                else if (wave_warps == 8) coder_wave_mw_kernel<16, 8><<<grid, 256, 0, st>>>(a);
+                else coder_wave_mw_kernel<16, 4><<<grid, 128, 0, st>>>(a);
+            } else {
+                if (wave_warps == 2) coder_wave_mw_kernel<32, 2><<<grid, 64, 0, st>>>(a);
+                else if (wave_warps == 8) coder_wave_mw_kernel<32, 8><<<grid, 256, 0, st>>>(a);
+                else coder_wave_mw_kernel<32, 4><<<grid, 128, 0, st>>>(a);
+            }
+            NH_CHECK_LAUNCH("coder_wave_mw_kernel");
+            return NH_OK;
+        }
         switch (size) {
             case 4: return launch_coder<4, 32, SRC_WAVEFRONT>(a, grid, st);
             case 8: return launch_coder<8, 32, SRC_WAVEFRONT>(a, grid, st);

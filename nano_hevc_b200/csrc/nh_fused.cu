@@ -481,7 +481,8 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit_kernel_v2(const F
         //    __syncwarp above orders the cooperative stores of its unit before these stores
         if (!fast) {
             if (NARROW && ublocks > 0) *a.ood_flag = 1;
-            for (int q = 0; q < ublocks; ++q) slow_block<N>(a, ub + q, DST);
+            const FusedArgs a_cold = a;  // address taken here only, not on the hot path
+            for (int q = 0; q < ublocks; ++q) slow_block<N>(a_cold, ub + q, DST);
         }
         __syncwarp();
     }
@@ -736,7 +737,8 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3)
             }
             __syncwarp();
             if (!fast) {
-                for (int q = 0; q < BPU; ++q) slow_block<N>(a, ub + q, DST);
+                const FusedArgs a_cold = a;
+                for (int q = 0; q < BPU; ++q) slow_block<N>(a_cold, ub + q, DST);
             }
             __syncwarp();
         }
@@ -888,7 +890,11 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 4) fused_rows_kernel(const Fu
             }
         } else {
             if (a.ood_flag && lane == 0) *a.ood_flag = 1;
-            rows_tile_exact<N>(a, M, r, valid, b, pw);
+            const FusedArgs a_cold = a;  // copies made here so that nothing has its address taken on the hot path
+            uint32_t pw_cold[N / 2];
+#pragma unroll
+            for (int k = 0; k < N / 2; ++k) pw_cold[k] = pw[k];
+            rows_tile_exact<N>(a_cold, M, r, valid, b, pw_cold);
         }
         __syncwarp();
     }
