@@ -22,7 +22,10 @@ struct CoderCfg {
     static constexpr int REF_W = 2 * N + 4;             // 2N+1 entries + padding read by the packed loads
     static constexpr int NEG_W = N + 8;                 // projected extension (N) + ref[0..7] (9-sample windows)
     static constexpr int NEG_MODES = 15;                // modes 11..25 have a negative angle
-    static constexpr int O_PITCH = N + 2;               // int16 elements; odd word pitch spreads banks
+    // int16 elements.  Odd word pitch spreads banks; the latency-mode coders at N >= 16 (G = 32)
+    // use rows that are 16-byte aligned with an odd number of 16-byte groups instead, the layout
+    // ldmatrix / stmatrix need for the tensor-core winner pipeline
+    static constexpr int O_PITCH = (N >= 16 && G == 32) ? N + 8 : N + 2;
     static constexpr int REFS_BYTES = 2 * REF_W * 2;
     static constexpr int NEG_BYTES = ((NEG_MODES * NEG_W * 2 + 15) / 16) * 16;
     static constexpr int O_BYTES = ((N * O_PITCH * 2 + 15) / 16) * 16;

@@ -6,6 +6,7 @@
 #include <cstdlib>
 
 #include "nh_coder.cuh"
+#include "nh_mma.cuh"
 
 namespace nh {
 
@@ -84,6 +85,62 @@ __global__ void __launch_bounds__(256)
 // --------------------------------------------------------------- coder kernel
 enum { SRC_ARRAYS = 0, SRC_PLANE = 1, SRC_WAVEFRONT = 2 };
 
+// Winner pipeline of one N x N block (N = 16 / 32) on the tensor cores, for a whole warp whose
+// block sits in O with the ldmatrix pitch (CoderCfg<N, 32>::O_PITCH): the row lanes predict the
+// winning mode into `ptile` (same layout), then the register-chained passes of nh_mma.cuh code the
+// block and leave the reconstruction in O.  8-bit samples only (the callers' fast8 flag).
+struct MmaWinnerCtx {
+    uint32_t ctab_lane;  // shared-memory address of this lane's constant vectors (MmaConsts<N>)
+    int lane_off;        // this lane's ldmatrix / stmatrix row offset
+    int dq_rnd_b;
+    uint32_t clip_lo2, clip_hi2;
+};
+template <int N>
+__device__ __forceinline__ MmaWinnerCtx make_mma_winner_ctx(const uint4* ctab, int lane, const FastQuant& fq, int maxv) {
+    constexpr int PITCH = N * 2 + 16;
+    MmaWinnerCtx c;
+    c.ctab_lane = smem_u32(ctab + lane);
+    c.lane_off = (((lane >> 3) & 1) * 8 + (lane & 7)) * PITCH + (lane >> 4) * 16;
+    c.dq_rnd_b = fq.dq_rnd + (kOperandBits << fq.dq_shift);
+    c.clip_lo2 = 0x08000800u;
+    c.clip_hi2 = c.clip_lo2 + (uint32_t)(maxv <= 1023 ? maxv : 0) * 0x10001u;
+    return c;
+}
+template <int N>
+__device__ __forceinline__ void winner_mma(int lane, int64_t b, int mode, int16_t* O, unsigned char* ptile,
+                                           const int16_t* top, const int16_t* left, const int16_t* neg,
+                                           int dc, const FastQuant& fq, const MmaWinnerCtx& ctx,
+                                           const CoderOut& out) {
+    constexpr int PITCH = N * 2 + 16;
+    static_assert(PITCH == CoderCfg<N, 32>::O_PITCH * 2, "O tile must have the ldmatrix pitch");
+    if (lane < N) {
+        int p[N];
+        uint32_t pw[N / 2];
+        predict_row_u8<N, 32>(mode, lane, top, left, neg, dc, p);
+        pack_row<N>(p, pw);
+        if (out.pred) store_row16<N>(out.pred + b * N * N + lane * N, pw);
+#pragma unroll
+        for (int q = 0; q < N / 8; ++q)
+            *reinterpret_cast<uint4*>(ptile + lane * PITCH + 16 * q) =
+                make_uint4(pw[4 * q], pw[4 * q + 1], pw[4 * q + 2], pw[4 * q + 3]);
+    }
+    __syncwarp();
+    const int fg = lane >> 2, ft = lane & 3;
+    const uint32_t ctab_lane = ctx.ctab_lane;
+    auto cv = [&](int v) -> uint4 { return ld_const_vec(ctab_lane, v); };
+    mma_block_chain<N>(smem_u32(O) + ctx.lane_off, smem_u32(ptile) + ctx.lane_off, cv, out.coeff != nullptr,
+                       out.coeff + b * N * N + (2 * ft) * N + fg, out.levels != nullptr,
+                       out.levels + b * N * N + (2 * ft) * N + fg, fq, ctx.dq_rnd_b, ctx.clip_lo2, ctx.clip_hi2);
+    __syncwarp();
+    if (out.recon && lane < N) {  // block-major reconstruction (not requested by the plane coders)
+#pragma unroll
+        for (int q = 0; q < N / 8; ++q)
+            stg_stream(out.recon + b * N * N + lane * N + 8 * q,
+                       *reinterpret_cast<const uint4*>(reinterpret_cast<unsigned char*>(O) + lane * PITCH + 16 * q));
+    }
+}
+
+
 struct CoderArgs {
     // SRC_ARRAYS
     const int16_t* orig;   // (B,N,N)
@@ -125,6 +182,15 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
 
     const int bw = SRC == SRC_ARRAYS ? 1 : a.W / N;
     const int bh = SRC == SRC_ARRAYS ? 1 : a.H / N;
+    // 32x32 blocks (one per warp): the winner pipeline runs on the tensor cores when the block is 8-bit
+    constexpr bool kMmaWinner = N == 32 && G == 32 && SRC != SRC_ARRAYS;
+    __shared__ __align__(16) uint4 ctab[kMmaWinner ? MmaConsts<32>::V_END : 1][32];
+    MmaWinnerCtx mctx{};
+    if constexpr (kMmaWinner) {
+        stage_mma_consts<32, WARPS * 32>(&ctab[0][0]);
+        __syncthreads();
+        mctx = make_mma_winner_ctx<32>(&ctab[0][0], lane, a.fq, a.maxv);
+    }
 
     if constexpr (SRC == SRC_WAVEFRONT) {
         // One warp per block row, rows handed out in order by a ticket counter so that a
@@ -213,8 +279,17 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                     if (a.out.modes) a.out.modes[b] = (uint8_t)mode;
                     if (a.out.costs) a.out.costs[b] = key >> 6;
                 }
-                code_block<N, G>(gl, true, b, mode, O, M, top, left, corner, dc, a.qp, a.fq, fast8, neg,
-                                 a.maxv, a.use_dst != 0, a.out);
+                bool done = false;
+                if constexpr (kMmaWinner) {
+                    if (fast8 && a.maxv <= 1023) {
+                        winner_mma<32>(lane, b, mode, O, reinterpret_cast<unsigned char*>(M), top, left, neg, dc,
+                                       a.fq, mctx, a.out);
+                        done = true;
+                    }
+                }
+                if (!done)
+                    code_block<N, G>(gl, true, b, mode, O, M, top, left, corner, dc, a.qp, a.fq, fast8, neg,
+                                     a.maxv, a.use_dst != 0, a.out);
                 // publish the bottom row first (the row below is polling for it), then the plane
                 for (int e = gl; e < N; e += G)
                     __stcg(a.bottom + (int64_t)by * a.W + x + e, O[(N - 1) * Cfg::O_PITCH + e]);
@@ -287,8 +362,17 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                     if (a.out.costs) a.out.costs[b] = key >> 6;
                 }
             }
-            code_block<N, G>(gl, valid, b, mode, O, M, top, left, corner, dc, a.qp, a.fq,
-                             SRC != SRC_ARRAYS && fast8, neg, a.maxv, a.use_dst != 0, a.out);
+            bool done = false;
+            if constexpr (kMmaWinner) {
+                if (fast8 && valid && a.maxv <= 1023) {  // one block per warp: valid is warp-uniform
+                    winner_mma<32>(lane, b, mode, O, reinterpret_cast<unsigned char*>(M), top, left, neg, dc, a.fq,
+                                   mctx, a.out);
+                    done = true;
+                }
+            }
+            if (!done)
+                code_block<N, G>(gl, valid, b, mode, O, M, top, left, corner, dc, a.qp, a.fq,
+                                 SRC != SRC_ARRAYS && fast8, neg, a.maxv, a.use_dst != 0, a.out);
             if constexpr (SRC == SRC_PLANE) {
                 if (valid && a.out.recon_plane)
                     for (int e = gl; e < N * N; e += G)
@@ -311,10 +395,16 @@ template <int N, int WPB>
 __global__ void __launch_bounds__(32 * WPB) coder_wave_mw_kernel(const CoderArgs a) {
     using Cfg = CoderCfg<N, 32>;
     constexpr int T = 32 * WPB;
+    using MC = MmaConsts<N>;
+    static_assert(Cfg::M_BYTES >= N * (N * 2 + 16), "the prediction tile aliases the working matrix");
     __shared__ __align__(16) unsigned char smem[Cfg::GROUP_BYTES];
+    __shared__ __align__(16) uint4 ctab[MC::V_END][32];        // per-lane MMA constants
     __shared__ int s_keys[WPB];
     __shared__ int s_row;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    stage_mma_consts<N, T>(&ctab[0][0]);  // made visible by the first barrier of the row loop
+    const MmaWinnerCtx mctx = make_mma_winner_ctx<N>(&ctab[0][0], lane, a.fq, a.maxv);
+    const bool mma_ok = a.maxv <= 1023;
     int16_t* top = reinterpret_cast<int16_t*>(smem);
     int16_t* left = top + Cfg::REF_W;
     int16_t* neg = reinterpret_cast<int16_t*>(smem + Cfg::REFS_PAD);
@@ -404,8 +494,13 @@ __global__ void __launch_bounds__(32 * WPB) coder_wave_mw_kernel(const CoderArgs
                     if (a.out.modes) a.out.modes[b] = (uint8_t)mode;
                     if (a.out.costs) a.out.costs[b] = key >> 6;
                 }
-                code_block<N, 32>(lane, true, b, mode, O, M, top, left, corner, dc, a.qp, a.fq, fast8, neg,
-                                  a.maxv, a.use_dst != 0, a.out);
+                if (fast8 && mma_ok) {  // winner pipeline on the tensor cores (8-bit samples)
+                    winner_mma<N>(lane, b, mode, O, reinterpret_cast<unsigned char*>(M), top, left, neg, dc, a.fq,
+                                  mctx, a.out);
+                } else {
+                    code_block<N, 32>(lane, true, b, mode, O, M, top, left, corner, dc, a.qp, a.fq, fast8, neg,
+                                      a.maxv, a.use_dst != 0, a.out);
+                }
                 // publish the bottom row first: the row below is polling for it
                 for (int e = lane; e < N; e += 32)
                     __stcg(a.bottom + (int64_t)by * a.W + x + e, O[(N - 1) * Cfg::O_PITCH + e]);
@@ -441,10 +536,10 @@ static int dispatch_coder(const CoderArgs& a, int size, cudaStream_t st) {
         int bh = a.H / size;
         int grid = bh < sm_count() * 16 ? bh : sm_count() * 16;
         if (grid < 1) grid = 1;
-        static int wave_warps = -1;  // warps per block row at N = 16 / 32: NH_WAVE_WARPS=1|2|4 (default 4)
+        static int wave_warps = -1;  // warps per block row at N = 16 / 32: NH_WAVE_WARPS=1|2|4|8 (default 8)
         if (wave_warps < 0) {
             const char* e = getenv("NH_WAVE_WARPS");
-            wave_warps = (e && (e[0] == '1' || e[0] == '2' || e[0] == '8')) ? e[0] - '0' : 4;
+            wave_warps = (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 8;
         }
         if (size >= 16 && wave_warps > 1) {
             if (grid > sm_count() * 4) grid = sm_count() * 4;

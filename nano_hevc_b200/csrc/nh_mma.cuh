@@ -170,4 +170,172 @@ __device__ __forceinline__ uint4 ld_const_vec(uint32_t ctab_lane, int v) {
     return o;
 }
 
+// acc(m, n) = init(m) + A_const(m, k) * B(k, n) where B[k][n] = P[n][k] and P is the previous pass's
+// result held as packed C fragments `h` (C -> B: the product comes out transposed w.r.t. using P as
+// A).  `i4` holds this lane's start values (word 2mi + half), `afrag(mi, ki)` fetches an A fragment.
+template <int MT, int NT, int KT, class AFrag>
+__device__ __forceinline__ void mma_const_a(float (&acc)[MT][NT][4], const uint32_t (&h)[MT][NT][2],
+                                            const uint4& i4, AFrag afrag) {
+    const float init[4] = {__uint_as_float(i4.x), __uint_as_float(i4.y), __uint_as_float(i4.z), __uint_as_float(i4.w)};
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi) {
+#pragma unroll
+        for (int ki = 0; ki < KT; ++ki) {
+            const uint4 af = afrag(mi, ki);
+#pragma unroll
+            for (int ni = 0; ni < NT; ++ni) {
+                const uint32_t b0 = h[ni >> 1][2 * ki][ni & 1], b1 = h[ni >> 1][2 * ki + 1][ni & 1];
+                if (ki == 0)
+                    hmma16816(acc[mi][ni], af, b0, b1, init[2 * mi], init[2 * mi], init[2 * mi + 1], init[2 * mi + 1]);
+                else
+                    hmma16816(acc[mi][ni], af, b0, b1, acc[mi][ni][0], acc[mi][ni][1], acc[mi][ni][2], acc[mi][ni][3]);
+            }
+        }
+    }
+}
+
+// The register-chained pipeline of ONE N x N block (N = 16 / 32) for a whole warp: residual from
+// the original / prediction tiles in shared memory (`so` / `sp` = this lane's ldmatrix row address in
+// each, row pitch PITCH bytes), the four transform passes, quant / dequant in between, coefficients
+// and levels stored straight from the fragments (`cp` / `lp` already point at this lane's element
+// (i = 2 ft, v = fg)), reconstruction + clip written back over the original tile.  `cv(v)` fetches
+// vector v of the lane's constants (MmaConsts<N>).  Valid for 8-bit samples only (see above).
+template <int N, class CV>
+__device__ __forceinline__ void mma_block_chain(uint32_t so, uint32_t sp, CV cv, bool want_c, int32_t* cp,
+                                                bool want_l, int32_t* lp, const FastQuant& fq, int dq_rnd_b,
+                                                uint32_t clip_lo2, uint32_t clip_hi2) {
+    using C = MmaConsts<N>;
+    constexpr int MT = N / 16, NT = N / 8, KT = N / 16;
+    constexpr int SH = Log2<N>::v + 5;
+    constexpr int PITCH = N * 2 + 16;
+    constexpr bool kBiasTmp2 = MmaBiasTmp2<N>::v;
+    const float rnd = (float)(1 << (SH - 1));
+    float acc[MT][NT][4];
+    uint32_t h[MT][NT][2];
+    // ---- forward, first pass: temp = (T X + r) >> s,  X = orig - pred as B fragments
+    {
+        uint32_t xb[KT][NT][2];
+#pragma unroll
+        for (int ki = 0; ki < KT; ++ki)
+#pragma unroll
+            for (int np = 0; np < NT / 2; ++np) {
+                uint32_t ro[4], rp[4];
+                const uint32_t off = 16 * ki * PITCH + 32 * np;
+                ldsm_x4_t(ro, so + off);
+                ldsm_x4_t(rp, sp + off);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)  // (1024 + o) - (1024 + p), exact in f16
+                    xb[ki][2 * np + (j >> 1)][j & 1] = h2_bits(
+                        __hsub2(bits_h2(ro[j] | 0x64006400u), bits_h2(rp[j] | 0x64006400u)));
+            }
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+            for (int ki = 0; ki < KT; ++ki) {
+                const uint4 af = cv(C::V_TA + mi * KT + ki);
+#pragma unroll
+                for (int ni = 0; ni < NT; ++ni) {
+                    if (ki == 0)
+                        hmma16816(acc[mi][ni], af, xb[ki][ni][0], xb[ki][ni][1], rnd, rnd, rnd, rnd);
+                    else
+                        hmma16816(acc[mi][ni], af, xb[ki][ni][0], xb[ki][ni][1], acc[mi][ni][0],
+                                  acc[mi][ni][1], acc[mi][ni][2], acc[mi][ni][3]);
+                }
+            }
+    }
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) {  // |temp| <= 511: biased operand
+            h[mi][ni][0] = round_pair_biased<SH>(acc[mi][ni][0], acc[mi][ni][1]);
+            h[mi][ni][1] = round_pair_biased<SH>(acc[mi][ni][2], acc[mi][ni][3]);
+        }
+    // ---- forward, second pass (transposed): coeff^T(m = v, n = i) = (T temp^T + r) >> s
+    mma_const_a<MT, NT, KT>(acc, h, cv(C::V_F2), [&](int mi, int ki) { return cv(C::V_TA + mi * KT + ki); });
+    // ---- coefficients out, quant, levels out, dequant -> biased operand of the inverse
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) {
+            int dqb[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = __float_as_int(floor_shift_magic<SH>(acc[mi][ni][e])) - kMagicI;
+                const int off = (8 * ni + (e & 1)) * N + 16 * mi + 8 * (e >> 1);
+                const int lv = quantize_fast(c, fq);
+                if (want_c) __stcs(cp + off, c);
+                if (want_l) __stcs(lp + off, lv);
+                dqb[e] = (lv * fq.dq_mult + dq_rnd_b) >> fq.dq_shift;  // 0x6600 + dq, |dq| <= 360
+            }
+            h[mi][ni][0] = __byte_perm((uint32_t)dqb[0], (uint32_t)dqb[1], 0x5410);
+            h[mi][ni][1] = __byte_perm((uint32_t)dqb[2], (uint32_t)dqb[3], 0x5410);
+        }
+    // ---- inverse, first pass: tmp2(m = y, n = v) = (T^T dq + r) >> s.  A = T^T comes from
+    // the B = T fragments: a0 = b0 of n-tile 2mi, a1 = b0 of 2mi+1, a2 / a3 = their b1
+    mma_const_a<MT, NT, KT>(acc, h, cv(C::V_I1), [&](int mi, int ki) {
+        const uint4 t = cv(C::V_TB + ki * NT / 2 + mi);
+        return make_uint4(t.x, t.z, t.y, t.w);
+    });
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) {
+            if constexpr (kBiasTmp2) {
+                h[mi][ni][0] = round_pair_biased<SH>(acc[mi][ni][0], acc[mi][ni][1]);
+                h[mi][ni][1] = round_pair_biased<SH>(acc[mi][ni][2], acc[mi][ni][3]);
+            } else {
+                h[mi][ni][0] = round_pair_plain<SH>(acc[mi][ni][0], acc[mi][ni][1]);
+                h[mi][ni][1] = round_pair_plain<SH>(acc[mi][ni][2], acc[mi][ni][3]);
+            }
+        }
+    // ---- inverse, second pass: res(m = y, n = x) = (tmp2 T + r) >> s,  A = tmp2 (C -> A)
+#pragma unroll
+    for (int np = 0; np < NT / 2; ++np) {
+        const uint4 i4 = cv(C::V_I2 + np);  // start values of n-tiles 2np, 2np + 1
+        const float i0 = __uint_as_float(i4.x), i1 = __uint_as_float(i4.y),
+                    i2 = __uint_as_float(i4.z), i3 = __uint_as_float(i4.w);
+#pragma unroll
+        for (int ki = 0; ki < KT; ++ki) {
+            const uint4 t = cv(C::V_TB + ki * NT / 2 + np);
+#pragma unroll
+            for (int mi = 0; mi < MT; ++mi) {
+                const uint4 af = make_uint4(h[mi][2 * ki][0], h[mi][2 * ki][1], h[mi][2 * ki + 1][0],
+                                            h[mi][2 * ki + 1][1]);
+                float(&d0)[4] = acc[mi][2 * np];
+                float(&d1)[4] = acc[mi][2 * np + 1];
+                if (ki == 0) {
+                    hmma16816(d0, af, t.x, t.y, i0, i1, i0, i1);
+                    hmma16816(d1, af, t.z, t.w, i2, i3, i2, i3);
+                } else {
+                    hmma16816(d0, af, t.x, t.y, d0[0], d0[1], d0[2], d0[3]);
+                    hmma16816(d1, af, t.z, t.w, d1[0], d1[1], d1[2], d1[3]);
+                }
+            }
+        }
+    }
+    // ---- reconstruct + clip (intra.py:70-78) on 16-bit pairs: FFMA.RM against magic + 2048
+    // leaves res + 2048 (> 0, |res| <= 1214) in the low 16 bits; add the prediction pair,
+    // clamp both halves to [2048, 2048 + max] and drop the bias.  The tile of original
+    // pixels is reused for the result.
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int np = 0; np < NT / 2; ++np) {
+            uint32_t rp[4], ro[4];
+            const uint32_t off = 16 * mi * PITCH + 32 * np;
+            ldsm_x4(rp, sp + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float(&c)[4] = acc[mi][2 * np + (j >> 1)];
+                const uint32_t m0 = __float_as_uint(
+                    __fmaf_rd(c[2 * (j & 1)], 1.0f / (float)(1 << SH), kMagicF + 2048.0f));
+                const uint32_t m1 = __float_as_uint(
+                    __fmaf_rd(c[2 * (j & 1) + 1], 1.0f / (float)(1 << SH), kMagicF + 2048.0f));
+                const uint32_t s = __byte_perm(m0, m1, 0x5410) + rp[j];
+                ro[j] = __vminu2(__vmaxu2(s, clip_lo2), clip_hi2) - clip_lo2;
+            }
+            stsm_x4(so + off, ro);
+        }
+}
+
 }  // namespace nh
