@@ -595,6 +595,55 @@ def test_encode_frame_vs_oracle_medium(Bt, n, cost, rn):
         eq(host(getattr(r, name)), w[name], f"{name} n={n} {cost} rn={rn}")
 
 
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("rn", (0, 1))
+def test_config3_config5_4k_properties(Bt, n, rn):
+    """Configs 3 / 5 at the full 4K size, where the oracle is too slow to run the whole frame: the
+    coders' outputs must be self-consistent with the single-purpose kernels (each verified against the
+    oracle elsewhere) and a strided sample of blocks is re-coded by the oracle.
+      * references gathered from the plane the coder used (source plane, or the final reconstructed
+        plane for the wavefront: every neighbour it read was final when it was read) + the coder's
+        modes, pushed through nh_fused_pipeline_modes, reproduce pred / coeff / levels / recon;
+      * the reported cost is the SAD of the winning prediction, and no other mode is cheaper
+        (checked for a sample of the 35 modes; ties keep the order DC, planar, 2..34);
+      * the exchange of reconstructed neighbours between block rows (multi-warp rows at N = 16 / 32,
+        several hundred rows in flight) is therefore checked on every block of the frame;
+      * oracle spot check: 97 blocks spread over the frame, re-coded from the same references."""
+    H, W = 2160, 3840
+    src = _smooth(H, W, 40 + n)
+    src[H // 3: H // 2, W // 4: W // 2] = np.random.default_rng(n).integers(0, 256, (H // 2 - H // 3, W // 2 - W // 4))
+    d = dev(src)
+    r = Bt.encode_frame(d, n, cost="sad", qp=27, recon_neighbours=bool(rn))
+    bh, bw = H // n, W // n
+    B = bh * bw
+    plane = r.recon_plane if rn else d
+    top, left, corner = Bt.gather_refs(plane, n, 2 * n, n if rn else 2 * n)
+    orig = Bt.plane_to_blocks(d, n)
+    again = Bt.fused_block_pipeline_modes(orig, top, left, corner, r.modes, 27, use_dst=(n == 4))
+    for name in ("pred", "coeff", "levels"):
+        assert torch.equal(getattr(again, name), getattr(r, name)), f"{name} n={n} rn={rn}"
+    assert torch.equal(again.recon, Bt.plane_to_blocks(r.recon_plane, n)), f"recon n={n} rn={rn}"
+    # uncovered rows / columns stay zero (frame.py:41-43)
+    assert not r.recon_plane[bh * n:].any() and not r.recon_plane[:, bw * n:].any()
+    sad = Bt.block_costs(orig, r.pred, outputs=("sad",))[0]
+    assert torch.equal(sad, r.costs), f"costs n={n} rn={rn}"
+    order = {1: 0, 0: 1, **{m: m for m in range(2, 35)}}
+    pos_win = torch.tensor([order[m] for m in range(35)], device=DEV)[r.modes.long()]
+    for m in (1, 0, 2, 10, 18, 26, 34, 7, 23):
+        pm = Bt.intra_predict_modes_batched(top, left, corner, m, n)
+        c = Bt.block_costs(orig, pm, outputs=("sad",))[0]
+        worse = (c > r.costs) | ((c == r.costs) & (order[m] >= pos_win))
+        assert bool(worse.all()), f"mode {m} beats the winner somewhere, n={n} rn={rn}"
+    idx = np.linspace(0, B - 1, 97).astype(np.int64)
+    ti = torch.from_numpy(idx).to(DEV)
+    want = O.pipeline_modes_batch(host(orig[ti]), host(top[ti]), host(left[ti]), host(corner[ti]), host(r.modes[ti]), 27,
+                                  use_dst=(n == 4))
+    for name, w in zip(("pred", "coeff", "levels", "recon"), want):
+        got = getattr(r, name)[ti] if name != "recon" else again.recon[ti]
+        eq(host(got), w, f"oracle spot {name} n={n} rn={rn}")
+
+
 @pytest.mark.parametrize("n,cost", [(4, "satd"), (8, "sad"), (16, "satd"), (32, "sad")])
 @pytest.mark.parametrize("rn", (0, 1))
 def test_encode_frame_10bit_uses_generic_search(Bt, n, cost, rn):
