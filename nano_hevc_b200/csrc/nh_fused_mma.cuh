@@ -239,6 +239,10 @@ __device__ __forceinline__ void hmma1688(float (&d)[4], uint32_t a0, uint32_t a1
         : "r"(a0), "r"(a1), "r"(b0), "f"(c0), "f"(c1), "f"(c2), "f"(c3));
 }
 
+#ifndef NH_MMA8_UNROLL
+#define NH_MMA8_UNROLL 8
+#endif
+constexpr int kMma8Unroll = NH_MMA8_UNROLL;  // ldmatrix quads (4 blocks each) unrolled per loop trip
 template <int OCC>
 __global__ void __launch_bounds__(kV2Warps * 32, OCC) fused_mma8_kernel(const FusedArgs a, const FastQuant fq) {
     constexpr int N = 8, NN = 64, SH = 8, S1 = 4;
@@ -353,7 +357,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, OCC) fused_mma8_kernel(const Fu
         if (a.pred) T16::store(sP, reinterpret_cast<unsigned char*>(a.pred + blk0 * NN), lane, chunks16);
         const uint32_t sO = smem_u32(s16[cur]) + lane_off, sPa = smem_u32(sP) + lane_off;
         uint32_t oodw = 0;
-#pragma unroll
+#pragma unroll kMma8Unroll
         for (int q = 0; q < 8; ++q) {
             uint32_t ro[4], rp[4], pc[4], rr[4];
             const uint32_t off = (uint32_t)(4 * q * T16::kPitch);
