@@ -122,7 +122,8 @@ int nh_fused_pipeline_dcplanar(const int16_t* orig, const int16_t* top, const in
                                int32_t* coeff, int32_t* levels, int16_t* recon, void* stream);
 /* Selects the kernel generation behind nh_fused_pipeline_dcplanar for size 4 / 8:
  * 4 (default: at size 8 the four transform passes run as warp-level f16 tensor-core MMAs, exact
- * for 8-bit samples with an exact fallback otherwise; size 4 uses generation 2), 2 (cp.async
+ * for 8-bit samples with an exact fallback otherwise; size 4 uses a rolled one-block-per-lane
+ * variant of generation 2), 2 (cp.async
  * prefetch + in-thread butterflies + 32-bit pixel-domain quant with an exact fallback), 3 (2 with
  * TMA tensor-map staging) or 1 (first generation, kept for A/B profiling).  Results are identical. */
 int nh_set_fused_impl(int generation);

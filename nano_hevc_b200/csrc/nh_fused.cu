@@ -489,6 +489,180 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit_kernel_v2(const F
     cp_async_wait<0>();
 }
 
+// ------------------------------------------------------- 4x4 kernel, looped (generation 4 at N = 4)
+// Generation 2 keeps a lane's four 4x4 blocks (64 samples) in registers with everything unrolled: a
+// 64 KB hot loop that ncu shows waiting on instruction fetch (no-instruction 1.16 warps per issue,
+// profiles/r1_fused4_ncu_summary.json).  Here a lane codes ONE block at a time in two rolled loops
+// over four rounds (round q = block q*32 + lane of the 128-block warp tile), with the coefficients
+// parked in the int32 staging tile between the loops: a few more shared-memory reads, a hot loop of
+// about 10 KB.  Same tiles, same cooperative 128-bit sweeps, same exact cold path as generation 2.
+template <bool DST>
+__global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit4_kernel(const FusedArgs a, const FastQuant fq) {
+    constexpr int N = 4, NN = 16;
+    using T16 = WarpTile<128>;
+    using T32 = WarpTile<256>;
+    constexpr int kWarpBytes = 2 * T16::kBytes + T32::kBytes;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* wbase = smem_raw + warp * kWarpBytes;
+    unsigned char* s16[2] = {wbase, wbase + T16::kBytes};
+    unsigned char* s32 = wbase + 2 * T16::kBytes;
+    // block j of the tile lives in unit j >> 2 (padded pitch), slot j & 3
+    auto px_of = [&](unsigned char* tile, int j) { return reinterpret_cast<uint4*>(tile + (j >> 2) * T16::kPitch + (j & 3) * 32); };
+    auto i32_of = [&](int j) { return reinterpret_cast<uint4*>(s32 + (j >> 2) * T32::kPitch + (j & 3) * 64); };
+
+    const int64_t n_tiles = (a.n_blocks + 127) / 128;
+    const int64_t warp_stride = (int64_t)gridDim.x * kV2Warps;
+    int64_t tile = (int64_t)blockIdx.x * kV2Warps + warp;
+    auto prefetch = [&](int64_t t, unsigned char* dst) {
+        const int64_t blk0 = t * 128;
+        const int64_t rem = a.n_blocks - blk0;
+        const int chunks = (int)(rem < 128 ? rem : 128) * 2;
+        const unsigned char* g = reinterpret_cast<const unsigned char*>(a.orig + blk0 * NN);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int c = it * 32 + lane;
+            if (c < chunks) cp_async16(smem_u32(dst + (c >> 3) * T16::kPitch + (c & 7) * 16), g + (size_t)c * 16);
+        }
+    };
+    if (tile < n_tiles) prefetch(tile, s16[0]);
+    cp_async_commit();
+    int cur = 0;
+    for (; tile < n_tiles; tile += warp_stride, cur ^= 1) {
+        const int64_t blk0 = tile * 128;
+        const int64_t trem = a.n_blocks - blk0;
+        const int blocks_valid = (int)(trem < 128 ? trem : 128);
+        const int chunks16 = blocks_valid * 2, chunks32 = blocks_valid * 4;
+        if (tile + warp_stride < n_tiles) prefetch(tile + warp_stride, s16[cur ^ 1]);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        unsigned char* px = s16[cur];
+        uint32_t ood_mask = 0;  // bit q: this lane's block of round q left the pixel domain [0, 4095]
+        // ---- loop 1: predict, residual, forward transform; prediction and coefficients into the tiles
+        // references of the next round are fetched while this one is coded
+        uint2 tw, lw;
+        int tr, bl, mode;
+        auto load_refs = [&](int q, uint2& t2, uint2& l2, int& r2, int& b2, int& m2) {
+            const int j = q * 32 + lane;
+            if (q < 4 && j < blocks_valid) {
+                const int64_t b = blk0 + j;
+                t2 = __ldcs(reinterpret_cast<const uint2*>(a.top + b * N));
+                l2 = __ldcs(reinterpret_cast<const uint2*>(a.left + b * N));
+                r2 = a.top_right[b];
+                b2 = a.bottom_left[b];
+                m2 = a.modes ? (int)a.modes[b] : a.mode;
+            } else {
+                t2 = l2 = make_uint2(0u, 0u);
+                r2 = b2 = 0;
+                m2 = 1;
+            }
+        };
+        load_refs(0, tw, lw, tr, bl, mode);
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            const int j = q * 32 + lane;
+            uint2 ntw, nlw;
+            int ntr, nbl, nmode;
+            load_refs(q + 1, ntw, nlw, ntr, nbl, nmode);
+            uint4* p16 = px_of(px, j);
+            const uint4 v0 = p16[0], v1 = p16[1];
+            const uint32_t ow[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            uint32_t ood = (tw.x | tw.y | lw.x | lw.y) & 0xF000F000u;
+            ood |= (uint32_t)(tr | bl) & 0xFFFFF000u;
+            const int top[4] = {lo16(tw.x), hi16(tw.x), lo16(tw.y), hi16(tw.y)};
+            const int left[4] = {lo16(lw.x), hi16(lw.x), lo16(lw.y), hi16(lw.y)};
+            int p[16];
+            if (mode == 1) {
+                const int dc = dc_value<N>(top[0] + top[1] + top[2] + top[3] + left[0] + left[1] + left[2] + left[3]);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) p[e] = dc;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) p[e] = planar_px<N>(e & 3, e >> 2, left[e >> 2], top[e & 3], tr, bl);
+            }
+            int res[4][4];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                ood |= ow[k] & 0xF000F000u;
+                res[k >> 1][2 * (k & 1)] = lo16(ow[k]) - p[2 * k];
+                res[k >> 1][2 * (k & 1) + 1] = hi16(ow[k]) - p[2 * k + 1];
+            }
+            p16[0] = make_uint4(pack16(p[0], p[1]), pack16(p[2], p[3]), pack16(p[4], p[5]), pack16(p[6], p[7]));
+            p16[1] = make_uint4(pack16(p[8], p[9]), pack16(p[10], p[11]), pack16(p[12], p[13]), pack16(p[14], p[15]));
+            transform2d<N, DST, false>(res);
+            uint4* c32 = i32_of(j);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c32[i] = make_uint4(res[i][0], res[i][1], res[i][2], res[i][3]);
+            ood_mask |= (ood != 0 ? 1u : 0u) << q;
+            tw = ntw; lw = nlw; tr = ntr; bl = nbl; mode = nmode;
+        }
+        __syncwarp();
+        if (a.pred) T16::store(px, reinterpret_cast<unsigned char*>(a.pred + blk0 * NN), lane, chunks16);
+        if (a.coeff) T32::store(s32, reinterpret_cast<unsigned char*>(a.coeff + blk0 * NN), lane, chunks32);
+        __syncwarp();
+        // ---- loop 2: quantise (levels replace the coefficients in the tile), dequantise, inverse
+        // transform, reconstruct against the prediction still in the pixel tile
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            const int j = q * 32 + lane;
+            uint4* c32 = i32_of(j);
+            int res[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint4 c = c32[i];
+                const int cc[4] = {(int)c.x, (int)c.y, (int)c.z, (int)c.w};
+                int l[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    l[k] = quantize_fast(cc[k], fq);
+                    res[i][k] = dequantize_fast(l[k], fq);
+                }
+                c32[i] = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+            transform2d<N, DST, true>(res);
+            uint4* p16 = px_of(px, j);
+            const uint4 v0 = p16[0], v1 = p16[1];
+            const uint32_t pw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            uint32_t rw[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                rw[k] = pack16(recon_px(lo16(pw[k]), res[k >> 1][2 * (k & 1)], a.maxv),
+                               recon_px(hi16(pw[k]), res[k >> 1][2 * (k & 1) + 1], a.maxv));
+            p16[0] = make_uint4(rw[0], rw[1], rw[2], rw[3]);
+            p16[1] = make_uint4(rw[4], rw[5], rw[6], rw[7]);
+        }
+        __syncwarp();
+        if (a.levels) T32::store(s32, reinterpret_cast<unsigned char*>(a.levels + blk0 * NN), lane, chunks32);
+        if (a.recon) T16::store(px, reinterpret_cast<unsigned char*>(a.recon + blk0 * NN), lane, chunks16);
+        __syncwarp();
+        // -- blocks whose inputs left the pixel domain are recoded exactly (cold path; the __syncwarp
+        //    above orders the cooperative stores before these stores)
+        if (ood_mask) {
+            const FusedArgs a_cold = a;
+            for (int q = 0; q < 4; ++q) {
+                const int j = q * 32 + lane;
+                if (((ood_mask >> q) & 1u) && j < blocks_valid) slow_block<N>(a_cold, blk0 + j, DST);
+            }
+        }
+        __syncwarp();
+    }
+    cp_async_wait<0>();
+}
+
+template <bool DST>
+static int launch_unit4(const FusedArgs& a, cudaStream_t st) {
+    constexpr int kSmem = kV2Warps * (2 * WarpTile<128>::kBytes + WarpTile<256>::kBytes);
+    {
+        const int rc = ensure_dynamic_smem(fused_unit4_kernel<DST>, kSmem, "cudaFuncSetAttribute(fused_unit4_kernel)");
+        if (rc != NH_OK) return rc;
+    }
+    int grid = grid_for((a.n_blocks + 3) / 4, (int64_t)kV2Warps * 32, 3);
+    fused_unit4_kernel<DST><<<grid, kV2Warps * 32, kSmem, st>>>(a, make_fast_quant(a.qp));
+    NH_CHECK_LAUNCH("fused_unit4_kernel");
+    return NH_OK;
+}
+
 // ------------------------------------------------------- unit kernels, v3 (TMA)
 // Generation 2 with the staging sweeps replaced by tensor-map TMA copies issued by ONE elected lane:
 //   * the next pixel tile arrives through cp.async.bulk.tensor (UTMALDG) into a 128B-swizzled shared
@@ -1013,8 +1187,8 @@ static int launch_unit_v3(const FusedArgs& a, cudaStream_t st) {
     return NH_OK;
 }
 
-// Kernel generation used for N = 4, 8: 4 (default: tensor-core passes at N = 8, generation 2 at
-// N = 4), 2 (cp.async + in-thread butterflies), 1 (first generation) or 3 (TMA tensor-map staging);
+// Kernel generation used for N = 4, 8: 4 (default: tensor-core passes at N = 8, the rolled 4x4
+// kernel at N = 4), 2 (cp.async + in-thread butterflies), 1 (first generation) or 3 (TMA tensor-map staging);
 // set by nh_set_fused_impl() or the NH_FUSED_IMPL=v1|v2|v3|v4 environment variable.
 static int g_fused_impl = 0;
 static int fused_impl() {
@@ -1032,6 +1206,7 @@ static int launch_unit(const FusedArgs& a, cudaStream_t st) {
         if (a.maxv <= 1023) return launch_mma8(a, st);
         return launch_unit_v2<N, DST>(a, st);
     }
+    if (N == 4 && fused_impl() == 4) return launch_unit4<DST>(a, st);  // rolled 4x4 kernel
     switch (fused_impl()) {
         case 1: return launch_unit_v1<N, DST>(a, st);
         case 3: return launch_unit_v3<N, DST>(a, st);
