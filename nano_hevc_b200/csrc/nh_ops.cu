@@ -1,6 +1,8 @@
 // nh_ops.cu -- the batched single-stage operators behind the reference's
 // per-block functions: K2 predictors, K3 residual / reconstruct / clip,
 // K4 forward / inverse transforms, K5 quantize / dequantize.
+#include <cstdlib>
+
 #include "nh_block.cuh"
 #include "nh_mma.cuh"
 
@@ -125,8 +127,8 @@ __device__ __forceinline__ uint32_t s16x2_to_h2(uint32_t w) {
     return h2_bits(__hsub2(bits_h2(h), bits_h2(c)));
 }
 
-template <int N, bool INV, bool IN32>
-__global__ void __launch_bounds__(kMmaWarps * 32, 3)
+template <int N, bool INV, bool IN32, int OCC>
+__global__ void __launch_bounds__(kMmaWarps * 32, OCC)
     transform_mma_kernel(const void* __restrict__ in, int32_t* __restrict__ out, int64_t n_blocks) {
     using C = MmaConsts<N>;
     constexpr int NN = N * N;
@@ -157,19 +159,22 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3)
     const int64_t n_tiles = (n_blocks + BPW - 1) / BPW;
     const int64_t warp_stride = (int64_t)gridDim.x * kMmaWarps;
     int64_t tile = (int64_t)blockIdx.x * kMmaWarps + warp;
-    uint32_t nxt[RW];  // this lane's input row, one tile ahead
+    // The warp tile (BPW consecutive blocks) is contiguous in memory: lanes sweep it in 16-byte chunks
+    // (512 contiguous bytes per warp instruction), one tile ahead, and scatter the chunks into the
+    // int16 shared tile.  (Row-per-lane loads touched 32 different lines per instruction and left the
+    // kernel waiting on memory: long-scoreboard 9.6 warps per issue.)
+    constexpr int ESZ = IN32 ? 4 : 2;
+    constexpr int EPC = 16 / ESZ;                    // elements per chunk
+    constexpr int CPL = BPW * NN * ESZ / 16 / 32;    // chunks per lane
+    static_assert(CPL * 4 == RW, "chunk sweep and row sweep move the same number of words");
+    uint4 nxt[CPL];
     auto prefetch = [&](int64_t t) {
-        const int64_t b = t * BPW + g;
-        if (b < n_blocks) {
-            const unsigned char* p = reinterpret_cast<const unsigned char*>(in) + (b * NN + r * N) * (IN32 ? 4 : 2);
+        const int64_t e_valid = (n_blocks - t * BPW) * NN;  // elements of the tile that exist
+        const unsigned char* p = reinterpret_cast<const unsigned char*>(in) + t * BPW * NN * ESZ;
 #pragma unroll
-            for (int q = 0; q < RW / 4; ++q) {
-                const uint4 v = ldg_stream(p + 16 * q);
-                nxt[4 * q] = v.x; nxt[4 * q + 1] = v.y; nxt[4 * q + 2] = v.z; nxt[4 * q + 3] = v.w;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < RW; ++k) nxt[k] = 0;
+        for (int it = 0; it < CPL; ++it) {
+            const int c = it * 32 + lane;
+            nxt[it] = (int64_t)c * EPC < e_valid ? ldg_stream(p + 16 * c) : make_uint4(0u, 0u, 0u, 0u);
         }
     };
     if (tile < n_tiles) prefetch(tile);
@@ -177,39 +182,33 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3)
     for (; tile < n_tiles; tile += warp_stride) {
         const int64_t b = tile * BPW + g;
         const bool valid = b < n_blocks;
-        // pack the row to int16 pairs and test -1024 <= x <= 1023 on the way
-        uint32_t pw[N / 2];
+        // test -1024 <= x <= 1023 on the chunks as they are
         uint32_t ood = 0;
-        if constexpr (IN32) {
 #pragma unroll
-            for (int k = 0; k < N / 2; ++k) {
-                const int x0 = (int)nxt[2 * k], x1 = (int)nxt[2 * k + 1];
-                ood |= (uint32_t)(x0 + 1024) | (uint32_t)(x1 + 1024);  // any bit >= 11 set: outside [-1024, 1023]
-                pw[k] = pack16(x0, x1);
-            }
-            ood &= 0xFFFFF800u;
-        } else {
+        for (int it = 0; it < CPL; ++it) {
+            const uint32_t w[4] = {nxt[it].x, nxt[it].y, nxt[it].z, nxt[it].w};
 #pragma unroll
-            for (int k = 0; k < N / 2; ++k) {
-                pw[k] = nxt[k];
-                ood |= __vadd2(nxt[k], 0x04000400u);
-            }
-            ood &= 0xF800F800u;
+            for (int k = 0; k < 4; ++k) ood |= IN32 ? (w[k] + 1024u) & 0xFFFFF800u : __vadd2(w[k], 0x04000400u) & 0xF800F800u;
         }
         const bool fast = !__any_sync(0xffffffffu, ood != 0);
-        if (fast) {
 #pragma unroll
-            for (int q = 0; q < N / 8; ++q)
-                *reinterpret_cast<uint4*>(my_row + 16 * q) = make_uint4(pw[4 * q], pw[4 * q + 1], pw[4 * q + 2], pw[4 * q + 3]);
-        } else {
-            int x[N];
-            if constexpr (IN32) {
-#pragma unroll
-                for (int k = 0; k < N; ++k) x[k] = (int)nxt[k];
-            } else {
-                unpack_row<N>(pw, x);
+        for (int it = 0; it < CPL; ++it) {
+            const int e0 = (it * 32 + lane) * EPC;  // first element of the chunk within the tile
+            const int u = e0 / NN, row = (e0 % NN) / N, col = e0 % N;
+            const uint32_t w[4] = {nxt[it].x, nxt[it].y, nxt[it].z, nxt[it].w};
+            if (fast) {
+                unsigned char* dst = sm + u * TILE + row * PITCH + col * 2;
+                if constexpr (IN32) *reinterpret_cast<uint2*>(dst) = make_uint2(pack16((int)w[0], (int)w[1]), pack16((int)w[2], (int)w[3]));
+                else *reinterpret_cast<uint4*>(dst) = nxt[it];
+            } else {  // exact path: int32 working matrix of the block
+                int* mrow = reinterpret_cast<int*>(sm) + u * RowsTile<N>::WORDS + row * RowsTile<N>::PITCH + col;
+                if constexpr (IN32) {
+                    *reinterpret_cast<int4*>(mrow) = make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
+                } else {
+                    *reinterpret_cast<int4*>(mrow) = make_int4(lo16(w[0]), hi16(w[0]), lo16(w[1]), hi16(w[1]));
+                    *reinterpret_cast<int4*>(mrow + 4) = make_int4(lo16(w[2]), hi16(w[2]), lo16(w[3]), hi16(w[3]));
+                }
             }
-            store_row_smem<N>(M, r, x);
         }
         if (tile + warp_stride < n_tiles) prefetch(tile + warp_stride);
         __syncwarp();
@@ -314,8 +313,15 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3)
 
 template <int N, bool INV, bool IN32>
 static int launch_transform_mma(const void* in, int32_t* out, int64_t n_blocks, cudaStream_t st) {
-    int grid = grid_for(n_blocks, kMmaWarps * (32 / N), 3);
-    transform_mma_kernel<N, INV, IN32><<<grid, kMmaWarps * 32, 0, st>>>(in, out, n_blocks);
+    static int occ = 0;  // resident CTAs per SM the kernel is compiled for: NH_XF_OCC=3|4|5 (A/B runs)
+    if (occ == 0) {
+        const char* e = getenv("NH_XF_OCC");
+        occ = (e && e[0] >= '3' && e[0] <= '5') ? e[0] - '0' : 4;  // measured best overall (profiles/r1_notes.md)
+    }
+    int grid = grid_for(n_blocks, kMmaWarps * (32 / N), occ);
+    if (occ == 4) transform_mma_kernel<N, INV, IN32, 4><<<grid, kMmaWarps * 32, 0, st>>>(in, out, n_blocks);
+    else if (occ == 5) transform_mma_kernel<N, INV, IN32, 5><<<grid, kMmaWarps * 32, 0, st>>>(in, out, n_blocks);
+    else transform_mma_kernel<N, INV, IN32, 3><<<grid, kMmaWarps * 32, 0, st>>>(in, out, n_blocks);
     NH_CHECK_LAUNCH("transform_mma_kernel");
     return NH_OK;
 }
