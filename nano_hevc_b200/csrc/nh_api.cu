@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <mutex>
+#include <map>
 #include <set>
 #include <utility>
 
@@ -50,6 +51,40 @@ int ensure_dynamic_smem_impl(const void* kernel, int bytes, const char* what) {
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return cuda_fail(e, what);
     done.insert({kernel, dev});
+    return NH_OK;
+}
+
+constexpr int kTileCounters = 4096;
+__device__ unsigned int g_tile_counters[kTileCounters];
+
+int acquire_tile_counter(cudaStream_t stream, unsigned int** counter) {
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, int> slots;  // (device, stream) -> slot
+    static int next_slot[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    int slot;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = slots.find({dev, stream});
+        if (it == slots.end()) {
+            int& n = next_slot[dev & 63];
+            if (n >= kTileCounters) {  // more distinct streams than counters: recycle (streams come and go)
+                n = 0;
+                for (auto i = slots.begin(); i != slots.end();)
+                    i = i->first.first == dev ? slots.erase(i) : std::next(i);
+            }
+            it = slots.emplace(std::make_pair(dev, stream), n++).first;
+        }
+        slot = it->second;
+    }
+    void* base = nullptr;
+    e = cudaGetSymbolAddress(&base, g_tile_counters);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetSymbolAddress(g_tile_counters)");
+    *counter = reinterpret_cast<unsigned int*>(base) + slot;
+    e = cudaMemsetAsync(*counter, 0, sizeof(unsigned int), stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(tile counter)");
     return NH_OK;
 }
 

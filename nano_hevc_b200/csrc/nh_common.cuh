@@ -55,6 +55,12 @@ inline int ensure_dynamic_smem(Kernel kernel, int bytes, const char* what) {
     return ensure_dynamic_smem_impl(reinterpret_cast<const void*>(kernel), bytes, what);
 }
 
+// A zeroed 32-bit work counter for a kernel that hands out its tiles dynamically, valid for one
+// launch on `stream` (nh_api.cu).  Counters live in a static device array (nothing is allocated); a
+// stream keeps the slot it was first given, and the reset is enqueued on that stream in front of the
+// launch, so launches on one stream never interfere and different streams use different slots.
+int acquire_tile_counter(cudaStream_t stream, unsigned int** counter);
+
 #define NH_CHECK_LAUNCH(what)                                  \
     do {                                                       \
         cudaError_t e__ = cudaGetLastError();                  \
@@ -85,7 +91,11 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 // LDGSTS: 16 bytes global -> shared without a register round trip (L2 only, no L1 allocation).
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+#ifdef NH_CPASYNC_CA
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int PENDING>
