@@ -497,7 +497,8 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit_kernel_v2(const F
 // parked in the int32 staging tile between the loops: a few more shared-memory reads, a hot loop of
 // about 10 KB.  Same tiles, same cooperative 128-bit sweeps, same exact cold path as generation 2.
 template <bool DST>
-__global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit4_kernel(const FusedArgs a, const FastQuant fq) {
+__global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit4_kernel(const FusedArgs a, const FastQuant fq,
+                                                                        unsigned int* tile_counter) {
     constexpr int N = 4, NN = 16;
     using T16 = WarpTile<128>;
     using T32 = WarpTile<256>;
@@ -512,8 +513,14 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit4_kernel(const Fus
     auto i32_of = [&](int j) { return reinterpret_cast<uint4*>(s32 + (j >> 2) * T32::kPitch + (j & 3) * 64); };
 
     const int64_t n_tiles = (a.n_blocks + 127) / 128;
-    const int64_t warp_stride = (int64_t)gridDim.x * kV2Warps;
-    int64_t tile = (int64_t)blockIdx.x * kV2Warps + warp;
+    // tiles are handed out dynamically, one ticket ahead (a static partition waits for the slowest SM)
+    auto next_tile = [&]() -> int64_t {
+        unsigned int t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1u);
+        return (int64_t)__shfl_sync(0xffffffffu, t, 0);
+    };
+    int64_t tile = next_tile();
+    int64_t tile_next = tile < n_tiles ? next_tile() : n_tiles;
     auto prefetch = [&](int64_t t, unsigned char* dst) {
         const int64_t blk0 = t * 128;
         const int64_t rem = a.n_blocks - blk0;
@@ -528,12 +535,14 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit4_kernel(const Fus
     if (tile < n_tiles) prefetch(tile, s16[0]);
     cp_async_commit();
     int cur = 0;
-    for (; tile < n_tiles; tile += warp_stride, cur ^= 1) {
+    int64_t tile_after = n_tiles;
+    for (; tile < n_tiles; tile = tile_next, tile_next = tile_after, cur ^= 1) {
+        tile_after = tile_next < n_tiles ? next_tile() : n_tiles;
         const int64_t blk0 = tile * 128;
         const int64_t trem = a.n_blocks - blk0;
         const int blocks_valid = (int)(trem < 128 ? trem : 128);
         const int chunks16 = blocks_valid * 2, chunks32 = blocks_valid * 4;
-        if (tile + warp_stride < n_tiles) prefetch(tile + warp_stride, s16[cur ^ 1]);
+        if (tile_next < n_tiles) prefetch(tile_next, s16[cur ^ 1]);
         cp_async_commit();
         cp_async_wait<1>();
         __syncwarp();
@@ -658,7 +667,12 @@ static int launch_unit4(const FusedArgs& a, cudaStream_t st) {
         if (rc != NH_OK) return rc;
     }
     int grid = grid_for((a.n_blocks + 3) / 4, (int64_t)kV2Warps * 32, 3);
-    fused_unit4_kernel<DST><<<grid, kV2Warps * 32, kSmem, st>>>(a, make_fast_quant(a.qp));
+    unsigned int* counter = nullptr;
+    {
+        const int rc = acquire_tile_counter(st, &counter);
+        if (rc != NH_OK) return rc;
+    }
+    fused_unit4_kernel<DST><<<grid, kV2Warps * 32, kSmem, st>>>(a, make_fast_quant(a.qp), counter);
     NH_CHECK_LAUNCH("fused_unit4_kernel");
     return NH_OK;
 }

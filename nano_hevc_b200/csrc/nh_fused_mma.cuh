@@ -257,6 +257,9 @@ __device__ __forceinline__ void hmma1688(float (&d)[4], uint32_t a0, uint32_t a1
         : "r"(a0), "r"(a1), "r"(b0), "f"(c0), "f"(c1), "f"(c2), "f"(c3));
 }
 
+#ifndef NH_TILES_PER_TICKET
+#define NH_TILES_PER_TICKET 1
+#endif
 #ifndef NH_MMA8_UNROLL
 #define NH_MMA8_UNROLL 8
 #endif
@@ -291,10 +294,17 @@ __global__ void __launch_bounds__(kV2Warps * 32, OCC) fused_mma8_kernel(const Fu
     // Tiles are handed out dynamically (one atomic per tile, fetched one tile ahead): with a static
     // partition the kernel waits for its slowest SM -- ncu showed SM active cycles spread over
     // 1.02M .. 1.21M for an average of 1.09M.
+    constexpr int kTilesPerTicket = NH_TILES_PER_TICKET;
+    int64_t ticket_base = 0;
+    int ticket_left = 0;
     auto next_tile = [&]() -> int64_t {
-        unsigned int t = 0;
-        if (lane == 0) t = atomicAdd(tile_counter, 1u);
-        return (int64_t)__shfl_sync(0xffffffffu, t, 0);
+        if (ticket_left == 0) {
+            unsigned int t = 0;
+            if (lane == 0) t = atomicAdd(tile_counter, 1u);
+            ticket_base = (int64_t)__shfl_sync(0xffffffffu, t, 0) * kTilesPerTicket;
+            ticket_left = kTilesPerTicket;
+        }
+        return ticket_base + (kTilesPerTicket - ticket_left--);
     };
     int64_t tile = next_tile();
     int64_t tile_next = tile < n_tiles ? next_tile() : n_tiles;
