@@ -532,6 +532,27 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit4_kernel(const Fus
             if (c < chunks) cp_async16(smem_u32(dst + (c >> 3) * T16::kPitch + (c & 7) * 16), g + (size_t)c * 16);
         }
     };
+    struct Refs {
+        uint2 tw, lw;
+        int tr, bl, mode;
+    };
+    auto load_refs = [&](int64_t t, int q, Refs& rf) {  // block q*32 + lane of tile t
+        const int64_t b = t * 128 + q * 32 + lane;
+        if (t < n_tiles && b < a.n_blocks) {
+            rf.tw = __ldcs(reinterpret_cast<const uint2*>(a.top + b * N));
+            rf.lw = __ldcs(reinterpret_cast<const uint2*>(a.left + b * N));
+            rf.tr = a.top_right[b];
+            rf.bl = a.bottom_left[b];
+            rf.mode = a.modes ? (int)a.modes[b] : a.mode;
+        } else {
+            rf.tw = rf.lw = make_uint2(0u, 0u);
+            rf.tr = rf.bl = 0;
+            rf.mode = 1;
+        }
+    };
+    Refs rfA, rfB;  // references of the coming even / odd round
+    load_refs(tile, 0, rfA);
+    load_refs(tile, 1, rfB);
     if (tile < n_tiles) prefetch(tile, s16[0]);
     cp_async_commit();
     int cur = 0;
@@ -548,47 +569,26 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit4_kernel(const Fus
         __syncwarp();
         unsigned char* px = s16[cur];
         uint32_t ood_mask = 0;  // bit q: this lane's block of round q left the pixel domain [0, 4095]
-        // ---- loop 1: predict, residual, forward transform; prediction and coefficients into the tiles
-        // references of the next round are fetched while this one is coded
-        uint2 tw, lw;
-        int tr, bl, mode;
-        auto load_refs = [&](int q, uint2& t2, uint2& l2, int& r2, int& b2, int& m2) {
+        // ---- loop 1: predict, residual, forward transform; prediction and coefficients into the tiles.
+        // References travel two rounds ahead in two register sets (even / odd rounds); the sets for
+        // rounds 0 / 1 of the NEXT tile are fetched during rounds 2 / 3 of this one.
+        auto round1 = [&](int q, const Refs& rf) {
             const int j = q * 32 + lane;
-            if (q < 4 && j < blocks_valid) {
-                const int64_t b = blk0 + j;
-                t2 = __ldcs(reinterpret_cast<const uint2*>(a.top + b * N));
-                l2 = __ldcs(reinterpret_cast<const uint2*>(a.left + b * N));
-                r2 = a.top_right[b];
-                b2 = a.bottom_left[b];
-                m2 = a.modes ? (int)a.modes[b] : a.mode;
-            } else {
-                t2 = l2 = make_uint2(0u, 0u);
-                r2 = b2 = 0;
-                m2 = 1;
-            }
-        };
-        load_refs(0, tw, lw, tr, bl, mode);
-#pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-            const int j = q * 32 + lane;
-            uint2 ntw, nlw;
-            int ntr, nbl, nmode;
-            load_refs(q + 1, ntw, nlw, ntr, nbl, nmode);
             uint4* p16 = px_of(px, j);
             const uint4 v0 = p16[0], v1 = p16[1];
             const uint32_t ow[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-            uint32_t ood = (tw.x | tw.y | lw.x | lw.y) & 0xF000F000u;
-            ood |= (uint32_t)(tr | bl) & 0xFFFFF000u;
-            const int top[4] = {lo16(tw.x), hi16(tw.x), lo16(tw.y), hi16(tw.y)};
-            const int left[4] = {lo16(lw.x), hi16(lw.x), lo16(lw.y), hi16(lw.y)};
+            uint32_t ood = (rf.tw.x | rf.tw.y | rf.lw.x | rf.lw.y) & 0xF000F000u;
+            ood |= (uint32_t)(rf.tr | rf.bl) & 0xFFFFF000u;
+            const int top[4] = {lo16(rf.tw.x), hi16(rf.tw.x), lo16(rf.tw.y), hi16(rf.tw.y)};
+            const int left[4] = {lo16(rf.lw.x), hi16(rf.lw.x), lo16(rf.lw.y), hi16(rf.lw.y)};
             int p[16];
-            if (mode == 1) {
+            if (rf.mode == 1) {
                 const int dc = dc_value<N>(top[0] + top[1] + top[2] + top[3] + left[0] + left[1] + left[2] + left[3]);
 #pragma unroll
                 for (int e = 0; e < 16; ++e) p[e] = dc;
             } else {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) p[e] = planar_px<N>(e & 3, e >> 2, left[e >> 2], top[e & 3], tr, bl);
+                for (int e = 0; e < 16; ++e) p[e] = planar_px<N>(e & 3, e >> 2, left[e >> 2], top[e & 3], rf.tr, rf.bl);
             }
             int res[4][4];
 #pragma unroll
@@ -604,7 +604,13 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit4_kernel(const Fus
 #pragma unroll
             for (int i = 0; i < 4; ++i) c32[i] = make_uint4(res[i][0], res[i][1], res[i][2], res[i][3]);
             ood_mask |= (ood != 0 ? 1u : 0u) << q;
-            tw = ntw; lw = nlw; tr = ntr; bl = nbl; mode = nmode;
+        };
+#pragma unroll 1
+        for (int i = 0; i < 2; ++i) {
+            round1(2 * i, rfA);
+            load_refs(i == 0 ? tile : tile_next, i == 0 ? 2 : 0, rfA);
+            round1(2 * i + 1, rfB);
+            load_refs(i == 0 ? tile : tile_next, i == 0 ? 3 : 1, rfB);
         }
         __syncwarp();
         if (a.pred) T16::store(px, reinterpret_cast<unsigned char*>(a.pred + blk0 * NN), lane, chunks16);
