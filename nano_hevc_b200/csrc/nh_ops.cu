@@ -368,27 +368,46 @@ static int dispatch_transform(const void* in, int32_t* out, int64_t n_blocks, in
 
 // =================================================================== K5 / K3
 // Pure element-wise streams: 128-bit vector body plus a scalar tail.
+// Four independent 128-bit loads per thread and trip keep enough bytes in flight; F::fast is the
+// 32-bit form (exact while |x| <= 32768), F::exact the reference's int64 arithmetic.
 template <class F>
 __global__ void __launch_bounds__(256) map_i32_kernel(const int32_t* __restrict__ in,
                                                       int32_t* __restrict__ out, int64_t n, F f) {
+    constexpr int U = 4;
     const int64_t n4 = n / 4;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        uint4 v = ldg_stream(in + 4 * i);
-        stg_stream(out + 4 * i, make_uint4((uint32_t)f((int)v.x), (uint32_t)f((int)v.y),
-                                           (uint32_t)f((int)v.z), (uint32_t)f((int)v.w)));
+    auto apply = [&](uint4 v) -> uint4 {
+        const int x[4] = {(int)v.x, (int)v.y, (int)v.z, (int)v.w};
+        const uint32_t big = ((uint32_t)(x[0] + 32768) | (uint32_t)(x[1] + 32768) | (uint32_t)(x[2] + 32768) |
+                              (uint32_t)(x[3] + 32768)) & 0xFFFF0000u;
+        // x + 32768 in [0, 65535] for |x| <= 32767; x = 32768 itself is caught as "big" (bit 16)
+        if (big == 0)
+            return make_uint4((uint32_t)f.fast(x[0]), (uint32_t)f.fast(x[1]), (uint32_t)f.fast(x[2]), (uint32_t)f.fast(x[3]));
+        return make_uint4((uint32_t)f.exact(x[0]), (uint32_t)f.exact(x[1]), (uint32_t)f.exact(x[2]), (uint32_t)f.exact(x[3]));
+    };
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (U - 1) * stride < n4; i += U * stride) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = ldg_stream(in + 4 * (i + u * stride));
+#pragma unroll
+        for (int u = 0; u < U; ++u) stg_stream(out + 4 * (i + u * stride), apply(v[u]));
     }
-    for (int64_t i = 4 * n4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        out[i] = f(in[i]);
+    for (; i < n4; i += stride) stg_stream(out + 4 * i, apply(ldg_stream(in + 4 * i)));
+    for (int64_t k = 4 * n4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) out[k] = f.exact(in[k]);
 }
 
 struct QuantF {
     QuantParams p;
-    __device__ int operator()(int c) const { return quantize_one(c, p); }
+    FastQuant fq;
+    __device__ int fast(int c) const { return quantize_fast(c, fq); }
+    __device__ int exact(int c) const { return quantize_one(c, p); }
 };
 struct DequantF {
     QuantParams p;
-    __device__ int operator()(int l) const { return dequantize_one(l, p); }
+    FastQuant fq;
+    __device__ int fast(int l) const { return dequantize_fast(l, fq); }
+    __device__ int exact(int l) const { return dequantize_one(l, p); }
 };
 
 // kind 0: residual = orig - pred (intra.py:65-67); 1: clip (intra.py:75-78, b unused)
@@ -615,7 +634,8 @@ NH_API int nh_quantize(const int32_t* coeff, int32_t* level, int64_t n, int qp, 
     NH_REQUIRE(coeff && level && n >= 0, "nh_quantize: null pointer or negative count");
     NH_REQUIRE(aligned16(coeff) && aligned16(level), "nh_quantize: tensors must be 16-byte aligned");
     if (n == 0) return NH_OK;
-    QuantF f{make_quant_params(qp, log2_size(size), is_intra)};
+    QuantF f{make_quant_params(qp, log2_size(size), is_intra), {}};
+    f.fq = make_fast_quant(f.p);
     map_i32_kernel<<<grid_elems(n, 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(coeff, level, n, f);
     NH_CHECK_LAUNCH("nh_quantize");
     return NH_OK;
@@ -626,7 +646,8 @@ NH_API int nh_dequantize(const int32_t* level, int32_t* coeff, int64_t n, int qp
     NH_REQUIRE(coeff && level && n >= 0, "nh_dequantize: null pointer or negative count");
     NH_REQUIRE(aligned16(coeff) && aligned16(level), "nh_dequantize: tensors must be 16-byte aligned");
     if (n == 0) return NH_OK;
-    DequantF f{make_quant_params(qp, 2, 1)};
+    DequantF f{make_quant_params(qp, 2, 1), {}};
+    f.fq = make_fast_quant(f.p);
     map_i32_kernel<<<grid_elems(n, 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(level, coeff, n, f);
     NH_CHECK_LAUNCH("nh_dequantize");
     return NH_OK;
