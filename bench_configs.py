@@ -114,6 +114,17 @@ def main():
                 px = (H // n) * (W // n) * n * n
                 ms = time_ms(lambda: batched.encode_frame(plane, n, cost=cost, qp=27), max(2, args.reps // 2), warmup=1)
                 emit(f"encode_frame search N={n} {cost} (cfg3, one 4K frame)", px, 2 + 12 + 5 / (n * n), ms)
+    if "search" in which:
+        # SURVEY 8d asks for a batch of F >= 32 frames: 32 frames stacked into one tall plane (source
+        # neighbours, so only the first block row of each frame sees different references) show the
+        # steady-state rate without the per-launch tail of a single 4K frame
+        F = 32
+        tall = torch.cat([synth_plane(H, W, i, dev) for i in range(F)], dim=0)
+        for n in (4, 8, 16, 32):
+            px = (F * H // n) * (W // n) * n * n
+            ms = time_ms(lambda: batched.encode_frame(tall, n, cost="sad", qp=27), 2, warmup=1)
+            emit(f"encode_frame search N={n} sad (cfg3, {F} 4K frames in one launch)", px, 2 + 12 + 5 / (n * n), ms)
+        del tall
     if "wavefront" in which:
         for n in (4, 8, 16, 32):
             px = (H // n) * (W // n) * n * n

@@ -392,6 +392,36 @@ def test_transform_impls_adversarial(Bt, n, impl):
         _lib.check(_lib.lib().nh_set_rows_impl(2))
 
 
+@pytest.mark.parametrize("n", (4, 8))
+def test_fused_concurrent_streams(Bt, n):
+    """The 4x4 / 8x8 kernels hand out their warp tiles through a per-stream ticket counter
+    (csrc/nh_api.cu::acquire_tile_counter): launches that overlap on different streams, and
+    back-to-back launches on one stream, must not disturb each other."""
+    rng = np.random.default_rng(5 + n)
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    cases = []
+    for k, st in enumerate(streams):
+        B = 40000 + 1237 * k
+        ins = _dcplanar_inputs(rng, B, n)
+        modes = rng.integers(0, 2, B).astype(np.uint8)
+        cases.append((st, ins, modes, [dev(v) for v in ins], dev(modes)))
+    torch.cuda.synchronize()
+    outs = []
+    for rep in range(3):                      # several rounds so that launches really overlap
+        outs = []
+        for st, ins, modes, d, dm in cases:
+            with torch.cuda.stream(st):
+                outs.append((Bt.fused_block_pipeline(*d, dm, 22 + rep, use_dst=(n == 4)),
+                             Bt.fused_block_pipeline(*d, 1, 30, use_dst=(n == 4))))
+    torch.cuda.synchronize()
+    for (st, ins, modes, d, dm), (got, got2) in zip(cases, outs):
+        want = O.pipeline_dcplanar_batch(*ins, modes, 24, use_dst=(n == 4), threads=O.n_host_threads())
+        want2 = O.pipeline_dcplanar_batch(*ins, 1, 30, use_dst=(n == 4), threads=O.n_host_threads())
+        for name, w, w2 in zip(("pred", "coeff", "levels", "recon"), want, want2):
+            eq(host(getattr(got, name)), w, f"{name} n={n}")
+            eq(host(getattr(got2, name)), w2, f"{name} (second launch) n={n}")
+
+
 @pytest.mark.parametrize("n,B,chunk", [(4, 70001, 8192), (8, 20011, 4096), (16, 3001, 1024), (32, 1000, 300)])
 def test_host_pipeline_vs_oracle(Bt, n, B, chunk):
     """The host-buffer C-ABI entry (chunked, three streams, int16 wire format for coefficients and
