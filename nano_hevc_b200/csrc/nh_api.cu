@@ -79,9 +79,13 @@ int acquire_tile_counter(cudaStream_t stream, unsigned int** counter) {
         }
         slot = it->second;
     }
-    void* base = nullptr;
-    e = cudaGetSymbolAddress(&base, g_tile_counters);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaGetSymbolAddress(g_tile_counters)");
+    static void* bases[64] = {};  // device address of g_tile_counters, per device
+    void* base = bases[dev & 63];
+    if (!base) {
+        e = cudaGetSymbolAddress(&base, g_tile_counters);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaGetSymbolAddress(g_tile_counters)");
+        bases[dev & 63] = base;
+    }
     *counter = reinterpret_cast<unsigned int*>(base) + slot;
     e = cudaMemsetAsync(*counter, 0, sizeof(unsigned int), stream);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(tile counter)");

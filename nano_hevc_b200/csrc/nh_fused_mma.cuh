@@ -33,10 +33,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32, OCC) fused_mma_kernel(const Fu
     using C = MmaConsts<N>;
     constexpr int NN = N * N;
     constexpr int BPW = 32 / N;  // blocks per warp tile
-    constexpr int MT = N / 16, NT = N / 8, KT = N / 16;
     constexpr int S1 = Log2<N>::v + 1;
-    constexpr int SH = Log2<N>::v + 5;  // transform.py:173-175, :215-217
-    constexpr bool kBiasTmp2 = MmaBiasTmp2<N>::v;
     // int16 block tile in shared memory: row pitch N*2 + 16 bytes (an odd number of 16-byte groups),
     // so the 8 rows of an ldmatrix / stmatrix 8x8 tile and the per-lane 128-bit row accesses are
     // conflict-free.
@@ -67,7 +64,6 @@ __global__ void __launch_bounds__(kMmaWarps * 32, OCC) fused_mma_kernel(const Fu
     const uint32_t ctab_lane = smem_u32(&ctab[0][lane]);
     auto cv = [&](int v) -> uint4 { return ld_const_vec(ctab_lane, v); };
 
-    const float rnd = (float)(1 << (SH - 1));
     const bool clip_ok = a.maxv <= 1023;
     const uint32_t clip_lo2 = 0x08000800u;  // reconstruction carries a +2048 bias per 16-bit half
     const uint32_t clip_hi2 = clip_lo2 + (uint32_t)(clip_ok ? a.maxv : 0) * 0x10001u;

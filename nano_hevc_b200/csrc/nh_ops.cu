@@ -149,7 +149,6 @@ __global__ void __launch_bounds__(kMmaWarps * 32, OCC)
     const int g = lane / N, r = lane % N;
     const int fg = lane >> 2, ft = lane & 3;
     unsigned char* sm = smem[warp];
-    unsigned char* my_row = sm + g * TILE + r * PITCH;
     int* M = reinterpret_cast<int*>(sm) + g * RowsTile<N>::WORDS;
     const int lane_off = (((lane >> 3) & 1) * 8 + (lane & 7)) * PITCH + (lane >> 4) * 16;
     const uint32_t ctab_lane = smem_u32(&ctab[0][lane]);

@@ -78,10 +78,8 @@ __global__ void __launch_bounds__(256)
         c += (v.x != 0) + (v.y != 0) + (v.z != 0) + (v.w != 0);
     }
     for (int64_t i = 4 * n4 + tid; i < n; i += stride) c += lv[i] != 0;
-    long long zero = 0;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
-    (void)zero;
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(reinterpret_cast<unsigned long long*>(out), (unsigned long long)c);
 }
 
