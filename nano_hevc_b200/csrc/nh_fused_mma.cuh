@@ -1,5 +1,7 @@
-// nh_fused_mma.cuh -- K10: the fused DC / planar pipeline for N = 16, 32 with the four separable
-// transform passes on the tensor cores (included by nh_fused.cu).
+// nh_fused_mma.cuh -- K10: the fused DC / planar pipeline with the four separable transform passes
+// on the tensor cores (included by nh_fused.cu): fused_mma_kernel<N> for N = 16 / 32 and
+// fused_mma8_kernel for N = 8 (two blocks per MMA; its own comment below).  The chain of one block
+// lives in nh_mma.cuh (mma_block_chain), shared with the frame coders' winner pipeline.
 //
 // Why tensor cores here: ncu shows the CUDA-core 32x32 kernel limited by the integer pipe and by
 // shared-memory instruction issue (78 instr/px, 0.45 of the HBM peak) -- north_star's condition for

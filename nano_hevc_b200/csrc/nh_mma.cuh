@@ -1,7 +1,9 @@
 // nh_mma.cuh -- warp-level tensor-core building blocks shared by the fused pipeline kernels
-// (nh_fused_mma.cuh) and the single-stage transform kernels (nh_ops.cu): ldmatrix / stmatrix / HMMA
-// wrappers, the magic-number rounding helpers and the compile-time per-lane constant tables of the
-// 16- and 32-point transform matrices.  See nh_fused_mma.cuh for how the fragments chain.
+// (nh_fused_mma.cuh), the single-stage transform kernels (nh_ops.cu) and the winner pipeline of the
+// frame coders (nh_frame.cu): ldmatrix / stmatrix / HMMA wrappers, the magic-number rounding helpers,
+// the compile-time per-lane constant tables of the 16- and 32-point transform matrices and
+// mma_block_chain, the register-chained pipeline of one block.  See nh_fused_mma.cuh for how the
+// fragments chain and why the arithmetic is exact.
 #pragma once
 #include <cuda_fp16.h>
 
