@@ -66,6 +66,29 @@ def test_error_codes_without_device():
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_kernel_selection_and_accounting_entry_points():
+    """Entry points without a reference counterpart: argument validation works without a device."""
+    import ctypes as C
+    from nano_hevc_b200 import _lib
+    L = _lib.lib()
+    for good in (1, 2):
+        assert L.nh_set_rows_impl(good) == 0
+    for bad in (0, 3, -1):
+        assert L.nh_set_rows_impl(bad) != 0 and b"nh_set_rows_impl" in L.nh_last_error()
+    L.nh_set_rows_impl(2)
+    for good in (1, 2, 3, 4):
+        assert L.nh_set_fused_impl(good) == 0
+    assert L.nh_set_fused_impl(5) != 0
+    L.nh_set_fused_impl(4)
+    up, down = C.c_int64(-1), C.c_int64(-1)
+    assert L.nh_host_pipeline_last_transfer(C.byref(up), C.byref(down)) == 0 and up.value >= 0 and down.value >= 0
+    assert L.nh_host_pipeline_last_transfer(None, None) == 0
+    assert L.nh_host_pipeline_scratch_bytes(8, 1024) > 0 and L.nh_host_pipeline_scratch_bytes(12, 1024) == 0
+    assert L.nh_convert_u8_to_i16(None, None, 0, None) == 0       # empty is fine
+    assert L.nh_convert_u8_to_i16(None, None, 5, None) != 0       # null pointers are not
+    assert L.nh_convert_i16_to_u8(None, None, -1, None) != 0
+
+
 def test_compute_fails_loudly_without_gpu():
     import nano_hevc_b200 as P
     from nano_hevc_b200 import batched
