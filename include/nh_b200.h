@@ -115,6 +115,11 @@ int nh_clip_to_pixel_range(const int16_t* in, int16_t* out, int64_t n_elems, int
  * DC / planar from given N-sample references (config 2):
  *   orig (B,N,N); top,left (B,N); top_right,bottom_left (B,);
  *   modes (B,) uint8 with values 0/1, or NULL -> `mode` for all blocks. */
+/* Note on streams: the size 4 / 8 kernels hand out their work through a 32-bit counter that belongs
+ * to the stream of the call (a slot of a static device array, reset by a 4-byte memset enqueued in
+ * front of the launch).  Calls on one stream, and concurrent calls on different streams, are
+ * independent; a captured CUDA graph containing such a launch must not be replayed concurrently
+ * with itself. */
 int nh_fused_pipeline_dcplanar(const int16_t* orig, const int16_t* top, const int16_t* left,
                                const int16_t* top_right, const int16_t* bottom_left,
                                const uint8_t* modes, int mode, int64_t n_blocks, int size, int qp,
