@@ -1222,8 +1222,10 @@ static int fused_impl() {
 template <int N, bool DST>
 static int launch_unit(const FusedArgs& a, cudaStream_t st) {
     if (a.coeff16) return launch_unit_v2<N, DST, true>(a, st);  // narrow outputs: generation 2 only
-    if (N == 8 && fused_impl() == 4) {  // tensor-core passes (clip bound <= 1023), else generation 2
-        if (a.maxv <= 1023) return launch_mma8(a, st);
+    if (N == 8 && fused_impl() == 4) {
+        // tensor-core passes for 8-bit content; deeper content goes to generation 2, whose 32-bit fast
+        // path covers samples up to 4095 (the tensor-core kernel would recode every tile exactly)
+        if (a.maxv <= 255) return launch_mma8(a, st);
         return launch_unit_v2<N, DST>(a, st);
     }
     if (N == 4 && fused_impl() == 4) return launch_unit4<DST>(a, st);  // rolled 4x4 kernel
@@ -1257,7 +1259,8 @@ int rows_impl() {
 
 template <int N>
 static int launch_16_32(const FusedArgs& a, cudaStream_t st) {
-    if (a.coeff16 || rows_impl() == 1) return launch_rows<N>(a, st);
+    // tensor-core kernel for 8-bit content; the CUDA-core kernel keeps a fast path up to 12 bits
+    if (a.coeff16 || rows_impl() == 1 || a.maxv > 255) return launch_rows<N>(a, st);
     return launch_mma<N>(a, st);
 }
 
