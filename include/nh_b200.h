@@ -116,8 +116,8 @@ int nh_clip_to_pixel_range(const int16_t* in, int16_t* out, int64_t n_elems, int
  *   orig (B,N,N); top,left (B,N); top_right,bottom_left (B,);
  *   modes (B,) uint8 with values 0/1, or NULL -> `mode` for all blocks. */
 /* Note on streams: the size 4 / 8 kernels hand out their work through a 32-bit counter that belongs
- * to the stream of the call (a slot of a static device array, reset by a 4-byte memset enqueued in
- * front of the launch).  Calls on one stream, and concurrent calls on different streams, are
+ * to the stream of the call (a slot of a static device array that the last warp of a launch re-arms
+ * for the next one).  Calls on one stream, and concurrent calls on different streams, are
  * independent; a captured CUDA graph containing such a launch must not be replayed concurrently
  * with itself. */
 int nh_fused_pipeline_dcplanar(const int16_t* orig, const int16_t* top, const int16_t* left,

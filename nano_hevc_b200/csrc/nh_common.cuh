@@ -55,10 +55,12 @@ inline int ensure_dynamic_smem(Kernel kernel, int bytes, const char* what) {
     return ensure_dynamic_smem_impl(reinterpret_cast<const void*>(kernel), bytes, what);
 }
 
-// A zeroed 32-bit work counter for a kernel that hands out its tiles dynamically, valid for one
-// launch on `stream` (nh_api.cu).  Counters live in a static device array (nothing is allocated); a
-// stream keeps the slot it was first given, and the reset is enqueued on that stream in front of the
-// launch, so launches on one stream never interfere and different streams use different slots.
+// Work counters for a kernel that hands out its warp tiles dynamically: counter[0] = next ticket,
+// counter[1] = warps that have finished.  The pair is zero when a launch starts and the last warp to
+// finish zeroes it again (release_tile_counter), so no reset has to be enqueued between launches.
+// Counters live in a static device array (nothing is allocated); a stream keeps the slot it was
+// first given, so launches on one stream (serialised by the stream) and on different streams
+// (different slots) never interfere.  nh_api.cu.
 int acquire_tile_counter(cudaStream_t stream, unsigned int** counter);
 
 #define NH_CHECK_LAUNCH(what)                                  \
@@ -68,6 +70,18 @@ int acquire_tile_counter(cudaStream_t stream, unsigned int** counter);
     } while (0)
 
 #if defined(__CUDACC__)
+// Called by every warp (all lanes) after it has drawn its last ticket: the last of the launch's
+// `total_warps` warps re-arms the counter pair for the next launch.
+__device__ __forceinline__ void release_tile_counter(unsigned int* counter, unsigned int total_warps) {
+    if ((threadIdx.x & 31) == 0) {
+        const unsigned int done = atomicAdd(counter + 1, 1u);
+        if (done == total_warps - 1) {
+            counter[0] = 0;
+            counter[1] = 0;
+        }
+    }
+}
+
 // ----------------------------------------------------------- device helpers
 __device__ __forceinline__ int lo16(uint32_t w) { return (int)(short)(w & 0xffffu); }
 __device__ __forceinline__ int hi16(uint32_t w) { return (int)w >> 16; }

@@ -663,6 +663,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit4_kernel(const Fus
         __syncwarp();
     }
     cp_async_wait<0>();
+    release_tile_counter(tile_counter, gridDim.x * kV2Warps);
 }
 
 template <bool DST>

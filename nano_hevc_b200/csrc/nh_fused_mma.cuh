@@ -460,6 +460,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, OCC) fused_mma8_kernel(const Fu
         __syncwarp();
     }
     cp_async_wait<0>();
+    release_tile_counter(tile_counter, gridDim.x * kV2Warps);
 }
 
 template <int OCC>
