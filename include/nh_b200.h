@@ -178,6 +178,12 @@ int nh_blocks_to_plane(const int16_t* blocks, int height, int width, int pitch, 
  * scratch: device scratch of nh_encode_frame_scratch_bytes(height, width, size) bytes
  *   (only used when recon_neighbours == 1; may be NULL otherwise). */
 int64_t nh_encode_frame_scratch_bytes(int height, int width, int size);
+/* Selects how recon_neighbours == 0 runs on 8-bit content: 2 (default: a search kernel decides the
+ * modes -- every lane of a warp evaluates the same candidate mode on its own strip of pixels --
+ * and a second kernel codes the winners; needs the modes tensor, pitch % 4 == 0 and an 8-byte
+ * aligned plane, otherwise 1 is used) or 1 (search and winner pipeline in one kernel).  Results
+ * are identical. */
+int nh_set_search_impl(int impl);
 int nh_encode_frame(const int16_t* src, int height, int width, int pitch, int size, int cost_kind,
                     int qp, int recon_neighbours, int bit_depth, uint8_t* modes, int32_t* costs,
                     int16_t* pred, int32_t* coeff, int32_t* levels, int16_t* recon_plane,

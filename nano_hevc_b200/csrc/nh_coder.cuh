@@ -194,6 +194,29 @@ __device__ __forceinline__ void build_neg_arrays(int gl, const int16_t* top, con
     }
 }
 
+// The same for one mode only (the winner pipeline of a block whose mode is already decided).
+template <int N, int G>
+__device__ __forceinline__ void build_neg_array_of_mode(int gl, int mode, const int16_t* top, const int16_t* left,
+                                                        int16_t* neg) {
+    using Cfg = CoderCfg<N, G>;
+    constexpr int POS = Cfg::NEG_W - N;
+    if (mode < 11 || mode > 25) return;
+    const int mi = mode - 11;
+    const int16_t* sec = mode >= 18 ? left : top;
+    const int16_t* pri = mode >= 18 ? top : left;
+    const int inv = inv_angle_of_mode(mode);
+    for (int j = gl; j < N + POS; j += G) {
+        int16_t v;
+        if (j < N) {
+            const int proj = ((j - N + 1) * inv + 128) >> 8;
+            v = sec[proj > 2 * N ? 2 * N : proj];
+        } else {
+            v = pri[j - N];
+        }
+        neg[mi * Cfg::NEG_W + j] = v;
+    }
+}
+
 // SW predicted samples of one scan line as SW/2 words (bytes 0 and 2 of word i = samples 2i, 2i+1):
 // R = halfword array (4-byte aligned), h = index of the first sample's ref[k], f = fraction.
 template <int SW>

@@ -43,6 +43,11 @@ int fused_pipeline_dcplanar_narrow(const int16_t* orig, const int16_t* top, cons
                                    int16_t* coeff16, int16_t* levels16, int16_t* recon, int* ood_flag,
                                    cudaStream_t st);
 
+// nh_fused.cu (nh_coder8.cuh): K7 winner stage for 8x8 blocks of an 8-bit plane whose modes are decided.
+struct QuantParams;
+int coder8_plane_mma(const int16_t* src, int H, int W, int pitch, uint8_t* modes, int16_t* pred, int32_t* coeff,
+                     int32_t* levels, int16_t* recon_plane, const QuantParams& qp, int maxv, cudaStream_t st);
+
 // nh_fused.cu: 2 = tensor-core kernels for N = 16 / 32 (default), 1 = CUDA-core butterflies
 // (nh_set_rows_impl / NH_ROWS_IMPL); also selects the single-stage transform kernels of nh_ops.cu.
 int rows_impl();

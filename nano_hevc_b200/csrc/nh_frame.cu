@@ -7,41 +7,10 @@
 
 #include "nh_coder.cuh"
 #include "nh_mma.cuh"
+#include "nh_plane.cuh"
+#include "nh_search.cuh"
 
 namespace nh {
-
-// Neighbour fetch with the reference's substitution rules (block.py:38-55) and
-// replicate-last padding (intra.py:174-178) folded into an index clamp.
-// COHERENT: read through L2 (ld.cg) because another SM may just have written the sample.
-template <bool COHERENT>
-__device__ __forceinline__ int plane_px(const int16_t* plane, int64_t idx) {
-    if constexpr (COHERENT) return (int)__ldcg(plane + idx);
-    else return (int)__ldg(plane + idx);
-}
-
-template <bool COHERENT>
-__device__ __forceinline__ int top_ref(const int16_t* plane, int H, int W, int pitch, int x, int y,
-                                       int n_top, int k) {  // k = 0 .. 2N
-    if (k == 0) return (x == 0 || y == 0) ? 128 : plane_px<COHERENT>(plane, (int64_t)(y - 1) * pitch + x - 1);
-    if (y == 0) return 128;
-    int last = x + n_top - 1;
-    if (last > W - 1) last = W - 1;
-    int col = x + k - 1;
-    if (col > last) col = last;
-    return plane_px<COHERENT>(plane, (int64_t)(y - 1) * pitch + col);
-}
-
-template <bool COHERENT>
-__device__ __forceinline__ int left_ref(const int16_t* plane, int H, int W, int pitch, int x, int y,
-                                        int n_left, int k) {
-    if (k == 0) return (x == 0 || y == 0) ? 128 : plane_px<COHERENT>(plane, (int64_t)(y - 1) * pitch + x - 1);
-    if (x == 0) return 128;
-    int last = y + n_left - 1;
-    if (last > H - 1) last = H - 1;
-    int row = y + k - 1;
-    if (row > last) row = last;
-    return plane_px<COHERENT>(plane, (int64_t)row * pitch + x - 1);
-}
 
 // ------------------------------------------------------------------------ K1
 __global__ void __launch_bounds__(256)
@@ -149,6 +118,7 @@ struct CoderArgs {
     const int16_t* top_left;  // (B,)
     const uint8_t* modes_in;  // (B,) or NULL
     int mode;
+    int only_undecided;    // SRC_PLANE: skip the warp tiles whose modes_in are all decided (another kernel coded them)
     // SRC_PLANE / SRC_WAVEFRONT
     const int16_t* src;    // (H, pitch)
     int H, W, pitch;
@@ -183,13 +153,14 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
     const int bw = SRC == SRC_ARRAYS ? 1 : a.W / N;
     const int bh = SRC == SRC_ARRAYS ? 1 : a.H / N;
     // 32x32 blocks (one per warp): the winner pipeline runs on the tensor cores when the block is 8-bit
-    constexpr bool kMmaWinner = N == 32 && G == 32 && SRC != SRC_ARRAYS;
-    __shared__ __align__(16) uint4 ctab[kMmaWinner ? MmaConsts<32>::V_END : 1][32];
+    constexpr bool kMmaWinner = N >= 16 && G == 32 && SRC == SRC_PLANE || N == 32 && G == 32 && SRC == SRC_WAVEFRONT;
+    constexpr int NM = kMmaWinner ? N : 32;
+    __shared__ __align__(16) uint4 ctab[kMmaWinner ? MmaConsts<NM>::V_END : 1][32];
     MmaWinnerCtx mctx{};
     if constexpr (kMmaWinner) {
-        stage_mma_consts<32, WARPS * 32>(&ctab[0][0]);
+        stage_mma_consts<NM, WARPS * 32>(&ctab[0][0]);
         __syncthreads();
-        mctx = make_mma_winner_ctx<32>(&ctab[0][0], lane, a.fq, a.maxv);
+        mctx = make_mma_winner_ctx<NM>(&ctab[0][0], lane, a.fq, a.maxv);
     }
 
     if constexpr (SRC == SRC_WAVEFRONT) {
@@ -306,6 +277,15 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
             const int64_t b = tile * GPW + g;
             const bool valid = b < a.n_blocks;
             int corner = 0, x = 0, y = 0, ood = 0;
+            int mode_in = 0xFF;
+            bool given = false;
+            if constexpr (SRC == SRC_PLANE) {
+                // modes decided by search_plane_kernel (nh_search.cuh); 0xFF = not decided (the tile held a
+                // sample outside [0, 255]) -> the exact search below, for every block of this warp
+                if (a.modes_in) mode_in = valid ? (int)a.modes_in[b] : 1;
+                given = !__any_sync(0xffffffffu, mode_in > 34);
+                if (given && a.only_undecided) continue;
+            }
             if constexpr (SRC == SRC_ARRAYS) {
                 if (valid) {
                     for (int k = gl; k <= 2 * N; k += G) {
@@ -348,24 +328,32 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                 mode = (valid && a.modes_in) ? (int)a.modes_in[b] : a.mode;
                 if (mode > 34) mode = 34;  // launcher validates the scalar; clamp per-block garbage
             } else {
-                int key;
-                if (fast8) {  // warp-uniform: the shuffles inside both searches span the warp
-                    build_neg_arrays<N, G>(gl, top, left, neg);
-                    __syncwarp();
-                    key = search_modes_u8<N, G>(gl, O, top, left, neg, dc, a.cost_kind);
+                mode = mode_in;
+                if (given) {
+                    if (fast8) {
+                        build_neg_array_of_mode<N, G>(gl, mode, top, left, neg);
+                        __syncwarp();
+                    }
                 } else {
-                    key = search_modes<N, G>(gl, O, top, left, corner, dc, a.cost_kind);
-                }
-                mode = mode_of_key(key);
-                if (valid && gl == 0) {
-                    if (a.out.modes) a.out.modes[b] = (uint8_t)mode;
-                    if (a.out.costs) a.out.costs[b] = key >> 6;
+                    int key;
+                    if (fast8) {  // warp-uniform: the shuffles inside both searches span the warp
+                        build_neg_arrays<N, G>(gl, top, left, neg);
+                        __syncwarp();
+                        key = search_modes_u8<N, G>(gl, O, top, left, neg, dc, a.cost_kind);
+                    } else {
+                        key = search_modes<N, G>(gl, O, top, left, corner, dc, a.cost_kind);
+                    }
+                    mode = mode_of_key(key);
+                    if (valid && gl == 0) {
+                        if (a.out.modes) a.out.modes[b] = (uint8_t)mode;
+                        if (a.out.costs) a.out.costs[b] = key >> 6;
+                    }
                 }
             }
             bool done = false;
             if constexpr (kMmaWinner) {
                 if (fast8 && valid && a.maxv <= 1023) {  // one block per warp: valid is warp-uniform
-                    winner_mma<32>(lane, b, mode, O, reinterpret_cast<unsigned char*>(M), top, left, neg, dc, a.fq,
+                    winner_mma<NM>(lane, b, mode, O, reinterpret_cast<unsigned char*>(M), top, left, neg, dc, a.fq,
                                    mctx, a.out);
                     done = true;
                 }
@@ -573,6 +561,55 @@ static int dispatch_coder(const CoderArgs& a, int size, cudaStream_t st) {
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// K7 as two launches (8-bit content): search_plane_kernel decides the modes, coder_kernel codes the
+// winners (one block per warp and the tensor-core winner pipeline at N = 16 / 32).
+template <int N>
+static int launch_search(const CoderArgs& a, cudaStream_t st) {
+    using C = SearchCfg<N>;
+    int rc = ensure_dynamic_smem(search_plane_kernel<N>, C::SMEM_BYTES, "search_plane_kernel");
+    if (rc != NH_OK) return rc;
+    SearchArgs s{a.src, a.H, a.W, a.pitch, a.cost_kind, a.n_blocks, a.out.modes, a.out.costs};
+    const int per_sm = 5;  // __launch_bounds__(128, 5); 5 x SMEM_BYTES <= 140 KB for every N
+    const int grid = grid_for(a.n_blocks, (int64_t)C::WARPS * C::T, per_sm);
+    search_plane_kernel<N><<<grid, C::WARPS * 32, C::SMEM_BYTES, st>>>(s);
+    NH_CHECK_LAUNCH("search_plane_kernel");
+    return NH_OK;
+}
+
+// 2 (default) = search kernel + winner kernel, 1 = everything in the single coder kernel (A/B
+// profiling); nh_set_search_impl() or NH_SEARCH_IMPL=1|2.
+static int g_search_impl = 0;
+static int split_impl() {
+    if (g_search_impl == 0) {
+        const char* e = getenv("NH_SEARCH_IMPL");
+        g_search_impl = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 2;
+    }
+    return g_search_impl == 2;
+}
+
+static int dispatch_search_then_code(CoderArgs a, int size, cudaStream_t st) {
+    int rc;
+    switch (size) {
+        case 4: rc = launch_search<4>(a, st); break;
+        case 8: rc = launch_search<8>(a, st); break;
+        case 16: rc = launch_search<16>(a, st); break;
+        default: rc = launch_search<32>(a, st); break;
+    }
+    if (rc != NH_OK) return rc;
+    a.modes_in = a.out.modes;
+    if (size == 8 && (a.pitch % 8) == 0 && aligned16(a.src) && aligned16(a.out.recon_plane)) {
+        // winners on the tensor cores (nh_coder8.cuh); it hands the tiles it cannot take (undecided
+        // blocks) back by marking them 0xFF, and the exact coder below only touches marked blocks
+        rc = coder8_plane_mma(a.src, a.H, a.W, a.pitch, a.out.modes, a.out.pred, a.out.coeff, a.out.levels,
+                              a.out.recon_plane, a.qp, a.maxv, st);
+        if (rc != NH_OK) return rc;
+        a.only_undecided = 1;
+    }
+    if (size == 16) return launch_coder<16, 32, SRC_PLANE>(a, grid_for(a.n_blocks, 4, 8), st);
+    return dispatch_coder<SRC_PLANE>(a, size, st);
+}
+
+
 }  // namespace nh
 
 using namespace nh;
@@ -657,6 +694,15 @@ NH_API int nh_fused_pipeline_modes(const int16_t* orig, const int16_t* top, cons
     return dispatch_coder<SRC_ARRAYS>(a, size, reinterpret_cast<cudaStream_t>(stream));
 }
 
+NH_API int nh_set_search_impl(int impl) {
+    if (impl < 1 || impl > 2) {
+        set_error("nh_set_search_impl: impl must be 1 (single coder kernel) or 2 (search + winner kernels), got %d", impl);
+        return NH_E_ARG;
+    }
+    g_search_impl = impl;
+    return NH_OK;
+}
+
 NH_API int64_t nh_encode_frame_scratch_bytes(int height, int width, int size) {
     if (log2_size(size) < 0 || height < 0 || width < 0) return 0;
     return 256 + (int64_t)(height / size) * width * 2;  // ticket counter + exchange rows
@@ -696,7 +742,12 @@ NH_API int nh_encode_frame(const int16_t* src, int height, int width, int pitch,
     a.maxv = (1 << bit_depth) - 1;
     a.use_dst = size == 4;  // docs/frames_and_panes.md:328-329
     a.out = CoderOut{modes, costs, pred, coeff, levels, nullptr, recon_plane, pitch};
-    if (!recon_neighbours) return dispatch_coder<SRC_PLANE>(a, size, st);
+    if (!recon_neighbours) {
+        // the search kernel reads the plane in 8-byte pieces and needs the modes tensor as its output
+        const bool split_ok = split_impl() && bit_depth <= 8 && modes && (pitch % 4) == 0 &&
+                              (reinterpret_cast<uintptr_t>(src) & 7) == 0;
+        return split_ok ? dispatch_search_then_code(a, size, st) : dispatch_coder<SRC_PLANE>(a, size, st);
+    }
     const int64_t need = nh_encode_frame_scratch_bytes(height, width, size);
     if (!scratch || scratch_bytes < need) {
         set_error("nh_encode_frame: scratch of %lld bytes required, got %lld", (long long)need,

@@ -1097,6 +1097,7 @@ __global__ void __launch_bounds__(kRowsWarps * 32, 4) fused_rows_kernel(const Fu
 
 }  // namespace nh
 #include "nh_fused_mma.cuh"
+#include "nh_coder8.cuh"
 namespace nh {
 
 template <int N, bool DST>

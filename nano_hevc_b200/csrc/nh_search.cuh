@@ -1,0 +1,333 @@
+// nh_search.cuh -- K7 search stage for 8-bit planes: the exhaustive 35-mode decision of every full
+// block of a plane (source neighbours), written as modes (uint8) + costs (int32).  The winner
+// pipeline runs afterwards in coder_kernel, which is handed the modes (nh_frame.cu).
+//
+// Why a kernel of its own: in the one-kernel coder the candidate modes of a block are split across
+// the lanes that share it, so every mode-dependent quantity (angle, orientation, fraction, window
+// parity) is per-lane data and the hot loop spends more instructions selecting than interpolating
+// (ncu, 8x8 / SAD: 467 thread instructions per pixel, ALU pipe 73 %).  Here
+//   * a warp tile holds enough blocks that lane = one 4 x SW strip and ALL lanes evaluate the SAME
+//     modes (N = 4 / 8 / 16 / 32: 32 / 16 / 4 / 1 blocks per warp): angle and orientation are uniform;
+//   * horizontal mode m and vertical mode 36 - m share the angle, hence the integer part, fraction and
+//     window start of every scan line: they are evaluated together (left references against the
+//     transposed strip, top references against the strip);
+//   * references are kept as BYTES.  A first version held pair words (ref[t], ref[t+1]) for every t --
+//     no alignment work, but 8 shared-memory wavefronts per scan line, and ncu showed the kernel bound
+//     by the 128 B/clk shared-memory crossbar (LSU pipe 57 %, short-scoreboard 2.3 warps per issue,
+//     issue 53 %).  A scan line of 8 samples needs 9 consecutive bytes: three words, one funnel shift
+//     each, and PRMTs against RZ spread them into the 16-bit lanes (b0,b2) (b1,b3) (b2,b4) ...;
+//   * weights are scaled by 8: 8 * (32 * 255 + 16) = 65408 < 2^16, so the predicted sample is the HIGH
+//     BYTE of its 16-bit lane and one PRMT packs four of them -- no shift, no mask;
+//   * negative angles read the projected extension of _build_ref_array (intra.py:180-186, the (k+1)
+//     projection of SURVEY Q3) from per-mode byte arrays holding only the entries the reference itself
+//     fills (k >= (N * angle) >> 5) followed by a copy of the first bytes of the primary array, so that
+//     a window that starts below zero is one contiguous read.
+// Same candidate order and tie rule as search_modes(): positions 1, 0, 2 .. 34, first strict minimum.
+// A tile with any sample outside [0, 255] is not decided here: its blocks get mode 0xFF and the coder
+// kernel runs its own exact search for them.
+#pragma once
+#include "nh_coder.cuh"
+#include "nh_plane.cuh"
+
+namespace nh {
+
+constexpr int kNegAngle[15] = {-2, -5, -9, -13, -17, -21, -26, -32, -26, -21, -17, -13, -9, -5, -2};  // modes 11..25
+
+template <int N>
+struct SearchCfg {
+    static constexpr int SW = N >= 8 ? 8 : 4;          // strip width (a lane owns 4 scan lines x SW samples)
+    static constexpr int SB = N * N / (4 * SW);        // strips per block
+    static constexpr int T = 32 / SB;                  // blocks per warp tile
+    static constexpr int SPR = N / SW;                 // strips per row of strips
+    static constexpr int WPS = SW / 4;                 // packed words per scan line
+    static constexpr int PB = ((2 * N + 9) + 3) / 4 * 4;   // bytes of a positive array: ref[0 .. 2N+1] + word-read slack
+    static constexpr int CP = 4 * (WPS + 1);           // bytes of the primary array copied behind a projected extension
+    static constexpr int neg_len(int mi) { return -((N * kNegAngle[mi]) >> 5); }   // entries the reference fills
+    static constexpr int neg_bytes() {
+        int s = 0;
+        for (int mi = 0; mi < 15; ++mi) s += (neg_len(mi) + 3) / 4 * 4 + CP;
+        return s;
+    }
+    static constexpr int BLOCK_WORDS = ((2 * PB + neg_bytes()) / 4) | 1;   // odd: blocks spread over the banks
+    static constexpr int WARP_WORDS = T * BLOCK_WORDS;
+    static constexpr int GP = T >= 16 ? 1 : (T == 4 ? 4 : 8);   // build: groups of modes per orientation and block
+    static constexpr int MPG = 8 / GP;                 // modes per group
+    static constexpr int WARPS = 4;
+    static constexpr int SMEM_BYTES = (WARPS * WARP_WORDS + 16) * 4;
+};
+
+struct SearchArgs {
+    const int16_t* src;
+    int H, W, pitch;
+    int cost_kind;
+    int64_t n_blocks;
+    uint8_t* modes;
+    int32_t* costs;
+};
+
+// SAD (metrics.py:24-26) or the sum of satd_4x4 (metrics.py:29-43) of a strip held as packed bytes.
+template <int WPS>
+__device__ __forceinline__ int strip_cost_packed(const uint32_t (&pr)[4][WPS], const uint32_t (&o)[4][WPS],
+                                                 int cost_kind) {
+    int c = 0;
+    if (cost_kind == NH_COST_SAD) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < WPS; ++q) c = (int)(__vsadu4(pr[j][q], o[j][q]) + (uint32_t)c);
+    } else {
+#pragma unroll
+        for (int q = 0; q < WPS; ++q) {   // one 4x4 sub-block per packed word column
+            int d[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    d[4 * j + i] = (int)((o[j][q] >> (8 * i)) & 0xff) - (int)((pr[j][q] >> (8 * i)) & 0xff);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int a0 = d[j] + d[4 + j], a1 = d[j] - d[4 + j];
+                int a2 = d[8 + j] + d[12 + j], a3 = d[8 + j] - d[12 + j];
+                d[j] = a0 + a2; d[4 + j] = a1 + a3; d[8 + j] = a0 - a2; d[12 + j] = a1 - a3;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int a0 = d[4 * i] + d[4 * i + 1], a1 = d[4 * i] - d[4 * i + 1];
+                int a2 = d[4 * i + 2] + d[4 * i + 3], a3 = d[4 * i + 2] - d[4 * i + 3];
+                c += abs(a0 + a2) + abs(a1 + a3) + abs(a0 - a2) + abs(a1 - a3);
+            }
+        }
+    }
+    return c;
+}
+
+// One scan line of SW predicted samples (packed bytes) from the byte array at `bytes` + `ob`:
+//   ((32-f) ref[k+i] + f ref[k+i+1] + 16) >> 5  for i = 0 .. SW-1   (intra.py:191-207; f8 = 8 f, g8 = 8 (32 - f)).
+template <int WPS>
+__device__ __forceinline__ void predict_line_u8(const unsigned char* bytes, int ob, uint32_t f8, uint32_t g8,
+                                                uint32_t (&out)[WPS]) {
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(bytes + (ob & ~3));
+    const uint32_t sh = (uint32_t)(ob & 3) * 8u;
+    uint32_t w[WPS + 1], v[WPS + 1];
+#pragma unroll
+    for (int i = 0; i <= WPS; ++i) w[i] = wp[i];
+#pragma unroll
+    for (int i = 0; i < WPS; ++i) v[i] = __funnelshift_r(w[i], w[i + 1], sh);   // bytes k+4i .. k+4i+3
+    v[WPS] = w[WPS] >> sh;                                                        // byte k+SW in the low byte
+#pragma unroll
+    for (int q = 0; q < WPS; ++q) {
+        const uint32_t e0 = __byte_perm(v[q], 0u, 0x4240);        // (b0, b2)
+        const uint32_t o0 = __byte_perm(v[q], 0u, 0x4341);        // (b1, b3)
+        const uint32_t e1 = __byte_perm(e0, v[q + 1], 0x3412);    // (b2, b4)
+        const uint32_t t02 = g8 * e0 + 0x00800080u + f8 * o0;     // samples 0, 2 in the high bytes
+        const uint32_t t13 = g8 * o0 + 0x00800080u + f8 * e1;     // samples 1, 3
+        out[q] = __byte_perm(t02, t13, 0x7351);
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, 5) search_plane_kernel(const SearchArgs a) {
+    using C = SearchCfg<N>;
+    constexpr int SW = C::SW, SB = C::SB, T = C::T, WPS = C::WPS, S = Log2<N>::v;
+    extern __shared__ __align__(16) uint32_t smem_w[];
+    int* negT0 = reinterpret_cast<int*>(smem_w + C::WARPS * C::WARP_WORDS);   // byte t = 0 of mode 11+mi, from the block base
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 15) {
+        int off = 2 * C::PB;
+        for (int m = 0; m < (int)threadIdx.x; ++m) off += (-((N * intra_angle(11 + m)) >> 5) + 3) / 4 * 4 + C::CP;
+        negT0[threadIdx.x] = off + (-((N * intra_angle(11 + (int)threadIdx.x)) >> 5) + 3) / 4 * 4;
+    }
+    __syncthreads();
+
+    uint32_t* wbase = smem_w + warp * C::WARP_WORDS;
+    const int bi = lane / SB, st = lane % SB;        // block of the tile, strip of the block
+    const int px_ = (st % C::SPR) * SW;              // base offset of the strip  (x vertical / y horizontal)
+    const int py_ = (st / C::SPR) * 4;               // scan offset of the strip  (y vertical / x horizontal)
+    unsigned char* blk = reinterpret_cast<unsigned char*>(wbase + bi * C::BLOCK_WORDS);
+    const unsigned char* tb = blk;                   // top[0 .. 2N+1]   (index 0 = corner slot)
+    const unsigned char* lb = blk + C::PB;           // left[0 .. 2N+1]
+    const int bw = a.W / N;
+    const int64_t n_tiles = (a.n_blocks + T - 1) / T;
+
+    for (int64_t tile = (int64_t)blockIdx.x * C::WARPS + warp; tile < n_tiles;
+         tile += (int64_t)gridDim.x * C::WARPS) {
+        // ---- block coordinates (invalid blocks of a ragged tile recompute the last block; nothing is written)
+        int64_t b = tile * T + bi;
+        const bool valid = b < a.n_blocks;
+        if (!valid) b = a.n_blocks - 1;
+        const int x = (int)(b % bw) * N, y = (int)(b / bw) * N;
+        int ood = 0;
+        __syncwarp();   // the previous tile's arrays are no longer read
+
+        // ---- K1: references with the substitution rules of block.py:38-55, as bytes
+        constexpr int RE = T * (2 * N + 2);
+#pragma unroll
+        for (int e0 = 0; e0 < RE; e0 += 32) {   // uniform trip count (the shuffles need every lane), loads in flight together
+            const int e = e0 + lane < RE ? e0 + lane : RE - 1;
+            const int i = e / (2 * N + 2), k = e % (2 * N + 2);
+            const int xi = __shfl_sync(0xffffffffu, x, (i * SB) & 31), yi = __shfl_sync(0xffffffffu, y, (i * SB) & 31);
+            const int kk = k <= 2 * N ? k : 2 * N;   // entry 2N+1: replicate-last padding (only read with weight 0)
+            const int tv = top_ref<false>(a.src, a.H, a.W, a.pitch, xi, yi, 2 * N, kk);
+            const int lv = left_ref<false>(a.src, a.H, a.W, a.pitch, xi, yi, 2 * N, kk);
+            unsigned char* zb = reinterpret_cast<unsigned char*>(wbase + i * C::BLOCK_WORDS);
+            zb[k] = (unsigned char)tv;
+            zb[C::PB + k] = (unsigned char)lv;
+            ood |= tv | lv;
+        }
+
+        // ---- the lane's strip, packed bytes: ov = image orientation, oh = transposed (horizontal modes)
+        uint32_t ov[4][WPS], oh[4][WPS];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < WPS; ++q) {
+                const uint2 v = __ldg(reinterpret_cast<const uint2*>(a.src + (int64_t)(y + py_ + j) * a.pitch + x + px_ + 4 * q));
+                ood |= (int)((v.x | v.y) & 0xFF00FF00u);
+                ov[j][q] = __byte_perm(v.x, v.y, 0x6420);
+            }
+#pragma unroll
+        for (int q = 0; q < WPS; ++q) {
+            uint2 r[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                r[i] = __ldg(reinterpret_cast<const uint2*>(a.src + (int64_t)(y + px_ + 4 * q + i) * a.pitch + x + py_));
+                ood |= (int)((r[i].x | r[i].y) & 0xFF00FF00u);
+            }
+            // 4x4 byte transpose: oh[j][q] byte i = row i, column j
+            const uint32_t u0 = __byte_perm(r[0].x, r[1].x, 0x6240), v0 = __byte_perm(r[2].x, r[3].x, 0x6240);
+            const uint32_t u1 = __byte_perm(r[0].y, r[1].y, 0x6240), v1 = __byte_perm(r[2].y, r[3].y, 0x6240);
+            oh[0][q] = __byte_perm(u0, v0, 0x5410);
+            oh[1][q] = __byte_perm(u0, v0, 0x7632);
+            oh[2][q] = __byte_perm(u1, v1, 0x5410);
+            oh[3][q] = __byte_perm(u1, v1, 0x7632);
+        }
+        const bool fast8 = !__any_sync(0xffffffffu, (ood & ~0xff) != 0);
+        if (!fast8) {   // leave the tile to the coder kernel's exact search
+            if (valid && st == 0) a.modes[b] = 0xFF;
+            continue;
+        }
+        __syncwarp();
+
+        // ---- projected extensions of the negative-angle modes (intra.py:180-186).  Unit = (block,
+        // orientation, group of modes); the vertical modes run from 25 downwards so that the two
+        // orientations of a block walk through equal lengths side by side.
+        for (int u0 = 0; u0 < 2 * T * C::GP; u0 += 32) {
+            const int u = u0 + lane;
+            if (u < 2 * T * C::GP) {
+                const int i = u / (2 * C::GP), r = u % (2 * C::GP), o = r / C::GP, g = r % C::GP;
+                unsigned char* zb = reinterpret_cast<unsigned char*>(wbase + i * C::BLOCK_WORDS);
+                const unsigned char* pri = zb + (o ? 0 : C::PB);     // vertical: top
+                const unsigned char* sec = zb + (o ? C::PB : 0);
+                uint32_t pw[WPS + 1];
+#pragma unroll
+                for (int c = 0; c <= WPS; ++c) pw[c] = reinterpret_cast<const uint32_t*>(pri)[c];
+#pragma unroll 1
+                for (int q = 0; q < C::MPG; ++q) {
+                    const int midx = g * C::MPG + q;
+                    if (!o && midx >= 7) break;
+                    const int mode = o ? 25 - midx : 11 + midx;
+                    const int inv = inv_angle_of_mode(mode);
+                    const int len = -((N * intra_angle(mode)) >> 5);
+                    const int t0 = negT0[mode - 11];
+#pragma unroll
+                    for (int c = 0; c <= WPS; ++c) reinterpret_cast<uint32_t*>(zb + t0)[c] = pw[c];   // ref[t], t >= 0
+#pragma unroll 1
+                    for (int tt = 0; tt < len; ++tt) {                                               // t = -1 - tt
+                        int proj = (-tt * inv + 128) >> 8;                                           // (k+1) projection, Q3
+                        proj = proj > 2 * N ? 2 * N : proj;
+                        zb[t0 - 1 - tt] = sec[proj];
+                    }
+                }
+            }
+        }
+
+        // ---- DC (intra.py:46-62): top[1..N] + left[1..N], summed by the block's SB lanes
+        int rs = 0;
+#pragma unroll
+        for (int k = st; k < 2 * N; k += SB) rs += k < N ? (int)tb[1 + k] : (int)lb[1 + k - N];
+#pragma unroll
+        for (int off = SB / 2; off > 0; off >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, off);
+        const int dc = dc_value<N>(rs);
+        __syncwarp();
+
+        uint32_t pr[4][WPS], prh[4][WPS];
+        int best;
+        {   // position 0: DC
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int q = 0; q < WPS; ++q) pr[j][q] = (uint32_t)dc * 0x01010101u;
+            int c = strip_cost_packed<WPS>(pr, ov, a.cost_kind);
+#pragma unroll
+            for (int off = SB / 2; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+            best = c << 6;
+        }
+        {   // position 1: planar (intra.py:109-111), two samples per multiply-add chain; the weights carry a
+            // factor 2^(7-S) so that the sample is the high byte of its 16-bit lane (max 65408)
+            constexpr uint32_t SC = 1u << (7 - S);
+            const uint32_t tr = (uint32_t)tb[N + 1], bl = (uint32_t)lb[N + 1];
+            uint32_t kc[SW / 2], c1[SW / 2], zt[SW / 2];
+#pragma unroll
+            for (int i = 0; i < SW / 2; ++i) {
+                const uint32_t X = (uint32_t)(px_ + 2 * i);
+                c1[i] = (((uint32_t)(N - 1) - X) | (((uint32_t)(N - 2) - X) << 16)) * SC;
+                kc[i] = tr * (((X + 1) | ((X + 2) << 16)) * SC);
+                zt[i] = (uint32_t)tb[1 + px_ + 2 * i] | ((uint32_t)tb[2 + px_ + 2 * i] << 16);   // (top[1+X], top[2+X])
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int yy = py_ + j;
+                const uint32_t ly = (uint32_t)lb[1 + yy];
+                const uint32_t vy = (uint32_t)(N - 1 - yy) * SC;
+                const uint32_t by = ((uint32_t)(yy + 1) * bl + (uint32_t)N) * SC * 0x10001u;
+                uint32_t t[SW / 2];
+#pragma unroll
+                for (int i = 0; i < SW / 2; ++i) t[i] = ly * c1[i] + kc[i] + vy * zt[i] + by;
+#pragma unroll
+                for (int q = 0; q < WPS; ++q) pr[j][q] = __byte_perm(t[2 * q], t[2 * q + 1], 0x7531);
+            }
+            int c = strip_cost_packed<WPS>(pr, ov, a.cost_kind);
+#pragma unroll
+            for (int off = SB / 2; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+            const int key = (c << 6) | 1;
+            best = key < best ? key : best;
+        }
+        // ---- positions 2..34: angular modes (intra.py:116-207), the same modes on every lane: horizontal
+        // mode m together with its mirror, vertical mode 36 - m.  Mode 18 is its own mirror: its
+        // horizontal half is computed and dropped.
+#pragma unroll 1
+        for (int mode = 2; mode <= 18; ++mode) {
+            const int angle = intra_angle(mode);
+            const int vmode = 36 - mode;
+            const int mi_c = mode < 11 ? 0 : mode - 11;
+            const int negh = negT0[mi_c];          // only used when k < 0 (modes 11..25)
+            const int negv = negT0[14 - mi_c];
+            int p = (py_ + 1) * angle;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t f8 = ((uint32_t)p & 31u) << 3, g8 = 256u - f8;
+                const int k = px_ + 1 + (p >> 5);
+                predict_line_u8<WPS>(blk, (k < 0 ? negv : 0) + k, f8, g8, pr[j]);
+                predict_line_u8<WPS>(blk, (k < 0 ? negh : C::PB) + k, f8, g8, prh[j]);
+                p += angle;
+            }
+            int cv = strip_cost_packed<WPS>(pr, ov, a.cost_kind);
+            int ch = strip_cost_packed<WPS>(prh, oh, a.cost_kind);
+#pragma unroll
+            for (int off = SB / 2; off > 0; off >>= 1) {
+                cv += __shfl_xor_sync(0xffffffffu, cv, off);
+                ch += __shfl_xor_sync(0xffffffffu, ch, off);
+            }
+            const int keyv = (cv << 6) | vmode;
+            const int keyh = mode < 18 ? ((ch << 6) | mode) : 0x7fffffff;
+            best = keyv < best ? keyv : best;
+            best = keyh < best ? keyh : best;
+        }
+        if (valid && st == 0) {
+            a.modes[b] = (uint8_t)mode_of_key(best);
+            if (a.costs) a.costs[b] = best >> 6;
+        }
+    }
+}
+
+}  // namespace nh

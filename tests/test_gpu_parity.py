@@ -689,6 +689,35 @@ def test_encode_frame_10bit_uses_generic_search(Bt, n, cost, rn):
         eq(host(getattr(r, name)), w[name], f"{name} n={n} {cost} rn={rn}")
 
 
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("cost", ("sad", "satd"))
+def test_search_kernel_split_vs_single_kernel_vs_oracle(Bt, n, cost):
+    """Config 3 runs as search kernel + winner kernel on 8-bit content (nh_set_search_impl(2), default).
+    Ragged warp tiles (the block count is no multiple of the tile), frame edges on every side, and
+    a region with samples outside [0, 255] (those tiles are left to the coder kernel's exact search):
+    identical to the single-kernel path and to the C oracle."""
+    from nano_hevc_b200 import _lib
+    rng = np.random.default_rng(77 + n)
+    H, W = 5 * n + 3, 4 * ((13 * n + 8) // 4) + 4
+    src = _smooth(H, W, 3 * n)
+    src[: 2 * n] = rng.integers(0, 256, (2 * n, W))
+    bad = src.copy()
+    bad[3 * n + 1, 7 * n + 2] = 300
+    bad[n // 2, 2 * n] = -7
+    try:
+        for plane in (src, bad):
+            _lib.check(_lib.lib().nh_set_search_impl(2))
+            r2 = Bt.encode_frame(dev(plane), n, cost=cost, qp=26)
+            _lib.check(_lib.lib().nh_set_search_impl(1))
+            r1 = Bt.encode_frame(dev(plane), n, cost=cost, qp=26)
+            w = O.encode_frame(plane, n, cost=cost, qp=26, recon_neighbours=False)
+            for name in ("modes", "costs", "pred", "coeff", "levels", "recon_plane"):
+                eq(host(getattr(r2, name)), host(getattr(r1, name)), f"split vs single {name} n={n} {cost}")
+                eq(host(getattr(r2, name)), w[name], f"split vs oracle {name} n={n} {cost}")
+    finally:
+        _lib.check(_lib.lib().nh_set_search_impl(2))
+
+
 # ------------------------------------------- SURVEY 8f rank 2: level statistics
 def test_level_statistics_golden(P, Bt):
     g = golden("stats.npz")
