@@ -55,7 +55,7 @@ int ensure_dynamic_smem_impl(const void* kernel, int bytes, const char* what) {
 }
 
 constexpr int kTileCounters = 4096;
-__device__ unsigned int g_tile_counters[2 * kTileCounters];  // {ticket, finished warps} per slot, zero at load
+__device__ unsigned int g_tile_counters[4 * kTileCounters];  // {ticket, finished warps, undecided tiles, readers} per slot, zero at load
 
 int acquire_tile_counter(cudaStream_t stream, unsigned int** counter) {
     static std::mutex mu;
@@ -86,7 +86,7 @@ int acquire_tile_counter(cudaStream_t stream, unsigned int** counter) {
         if (e != cudaSuccess) return cuda_fail(e, "cudaGetSymbolAddress(g_tile_counters)");
         bases[dev & 63] = base;
     }
-    *counter = reinterpret_cast<unsigned int*>(base) + 2 * slot;
+    *counter = reinterpret_cast<unsigned int*>(base) + 4 * slot;
     return NH_OK;
 }
 

@@ -111,11 +111,28 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) coder8_plane_mma_kernel(cons
             // ---- K1 for block `lane` (an idle lane of a ragged tile gathers the last block again)
             const int bx = bx0 + (lane < blocks_valid ? lane : blocks_valid - 1);
             const int x = bx * N, y = by * N;
+            if (x > 0 && y > 0 && x + 2 * N <= a.W && y + 2 * N <= a.H) {   // no substitution, no truncation
+                const int16_t* c = a.src + (int64_t)(y - 1) * a.pitch + x - 1;
+                int tv[2 * N + 1], lv[2 * N + 1];
 #pragma unroll
-            for (int k = 0; k < 2 * N + 2; ++k) {
-                const int kk = k <= 2 * N ? k : 2 * N;
-                rb[k] = (unsigned char)top_ref<false>(a.src, a.H, a.W, a.pitch, x, y, 2 * N, kk);
-                rb[28 + k] = (unsigned char)left_ref<false>(a.src, a.H, a.W, a.pitch, x, y, 2 * N, kk);
+                for (int k = 0; k <= 2 * N; ++k) {
+                    tv[k] = __ldg(c + k);
+                    lv[k] = __ldg(c + (int64_t)k * a.pitch);
+                }
+#pragma unroll
+                for (int k = 0; k <= 2 * N; ++k) {
+                    rb[k] = (unsigned char)tv[k];
+                    rb[28 + k] = (unsigned char)lv[k];
+                }
+                rb[2 * N + 1] = (unsigned char)tv[2 * N];
+                rb[28 + 2 * N + 1] = (unsigned char)lv[2 * N];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 2 * N + 2; ++k) {
+                    const int kk = k <= 2 * N ? k : 2 * N;
+                    rb[k] = (unsigned char)top_ref<false>(a.src, a.H, a.W, a.pitch, x, y, 2 * N, kk);
+                    rb[28 + k] = (unsigned char)left_ref<false>(a.src, a.H, a.W, a.pitch, x, y, 2 * N, kk);
+                }
             }
             // ---- lane u predicts block u into the prediction tile (rows of 16-bit samples)
             uint4* up = T16::unit(sP, lane);
@@ -194,6 +211,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) coder8_plane_mma_kernel(cons
         __syncwarp();
         if (undecided) {  // warp-uniform
             if (lane < blocks_valid) a.modes[blk0 + lane] = 0xFF;
+            if (lane == 0) atomicAdd(tile_counter + 2, 1u);   // the exact coder kernel has work to do
             continue;
         }
         if (a.pred) T16::store(sP, reinterpret_cast<unsigned char*>(a.pred + blk0 * NN), lane, chunks16);
@@ -262,7 +280,8 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) coder8_plane_mma_kernel(cons
 
 // Declared in nh_common.cuh; called by nh_frame.cu.
 int coder8_plane_mma(const int16_t* src, int H, int W, int pitch, uint8_t* modes, int16_t* pred, int32_t* coeff,
-                     int32_t* levels, int16_t* recon_plane, const QuantParams& qp, int maxv, cudaStream_t st) {
+                     int32_t* levels, int16_t* recon_plane, const QuantParams& qp, int maxv, cudaStream_t st,
+                     unsigned int** handed_back) {
     constexpr int kSmem = kV2Warps * (3 * WarpTile<128>::kBytes + 32 * kC8RefBytes);
     int rc = ensure_dynamic_smem(coder8_plane_mma_kernel, kSmem, "cudaFuncSetAttribute(coder8_plane_mma_kernel)");
     if (rc != NH_OK) return rc;
@@ -272,6 +291,7 @@ int coder8_plane_mma(const int16_t* src, int H, int W, int pitch, uint8_t* modes
     unsigned int* counter = nullptr;
     rc = acquire_tile_counter(st, &counter);
     if (rc != NH_OK) return rc;
+    *handed_back = counter + 2;
     Coder8Args a{src, H, W, pitch, modes, pred, coeff, levels, recon_plane, maxv};
     coder8_plane_mma_kernel<<<grid, kV2Warps * 32, kSmem, st>>>(a, make_fast_quant(qp), counter);
     NH_CHECK_LAUNCH("coder8_plane_mma_kernel");

@@ -45,8 +45,10 @@ int fused_pipeline_dcplanar_narrow(const int16_t* orig, const int16_t* top, cons
 
 // nh_fused.cu (nh_coder8.cuh): K7 winner stage for 8x8 blocks of an 8-bit plane whose modes are decided.
 struct QuantParams;
+// *handed_back = device counter pair {tiles handed back to the exact coder, readers} of this stream.
 int coder8_plane_mma(const int16_t* src, int H, int W, int pitch, uint8_t* modes, int16_t* pred, int32_t* coeff,
-                     int32_t* levels, int16_t* recon_plane, const QuantParams& qp, int maxv, cudaStream_t st);
+                     int32_t* levels, int16_t* recon_plane, const QuantParams& qp, int maxv, cudaStream_t st,
+                     unsigned int** handed_back);
 
 // nh_fused.cu: 2 = tensor-core kernels for N = 16 / 32 (default), 1 = CUDA-core butterflies
 // (nh_set_rows_impl / NH_ROWS_IMPL); also selects the single-stage transform kernels of nh_ops.cu.
@@ -65,7 +67,8 @@ inline int ensure_dynamic_smem(Kernel kernel, int bytes, const char* what) {
 // finish zeroes it again (release_tile_counter), so no reset has to be enqueued between launches.
 // Counters live in a static device array (nothing is allocated); a stream keeps the slot it was
 // first given, so launches on one stream (serialised by the stream) and on different streams
-// (different slots) never interfere.  nh_api.cu.
+// (different slots) never interfere.  counter[2] / counter[3] belong to the frame coder (nh_coder8.cuh:
+// tiles handed back to the exact coder kernel, and the CTAs of that kernel that have looked).  nh_api.cu.
 int acquire_tile_counter(cudaStream_t stream, unsigned int** counter);
 
 #define NH_CHECK_LAUNCH(what)                                  \

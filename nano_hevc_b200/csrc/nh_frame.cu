@@ -119,6 +119,8 @@ struct CoderArgs {
     const uint8_t* modes_in;  // (B,) or NULL
     int mode;
     int only_undecided;    // SRC_PLANE: skip the warp tiles whose modes_in are all decided (another kernel coded them)
+    int vec_ok;            // SRC_PLANE: pitch % 8 == 0 and 16-byte aligned planes -> 128-bit pixel moves (N >= 16, G = 32)
+    unsigned int* handed_back;  // with only_undecided: {tiles the other kernel left to this one, CTAs that have looked}
     // SRC_PLANE / SRC_WAVEFRONT
     const int16_t* src;    // (H, pitch)
     int H, W, pitch;
@@ -163,6 +165,23 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
         mctx = make_mma_winner_ctx<NM>(&ctab[0][0], lane, a.fq, a.maxv);
     }
 
+    if constexpr (SRC == SRC_PLANE) {
+        // Called only to pick up what the tensor-core winner kernel handed back: usually nothing.  Every
+        // CTA looks at the count, and the last one to look re-arms the pair for the next call.
+        if (a.only_undecided && a.handed_back) {
+            __shared__ unsigned int s_count;
+            if (threadIdx.x == 0) {
+                s_count = *reinterpret_cast<volatile unsigned int*>(a.handed_back);
+                __threadfence();
+                if (atomicAdd(a.handed_back + 1, 1u) == gridDim.x - 1) {
+                    a.handed_back[0] = 0;
+                    a.handed_back[1] = 0;
+                }
+            }
+            __syncthreads();
+            if (s_count == 0) return;
+        }
+    }
     if constexpr (SRC == SRC_WAVEFRONT) {
         // One warp per block row, rows handed out in order by a ticket counter so that a
         // waiting warp only ever waits on a row that a resident warp already owns.
@@ -272,6 +291,21 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
         return;
     } else {
         const int64_t n_tiles = (a.n_blocks + GPW - 1) / GPW;
+        // One block per warp at N >= 16: the pixels move as 16-byte chunks (chunk c = row c / (N/8)), the
+        // next block's chunks are fetched while this one is coded.
+        constexpr bool kVec = SRC == SRC_PLANE && G == 32 && N >= 16;
+        constexpr int CPL = kVec ? N * N / 8 / 32 : 1;   // chunks per lane
+        const bool vec = kVec && a.vec_ok && !a.only_undecided;
+        uint4 nxt[CPL];
+        auto fetch = [&](int64_t t) {
+            const int fx = (int)(t % bw) * N, fy = (int)(t / bw) * N;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                const int c = lane + 32 * i, row = c / (N / 8), c8 = c % (N / 8);
+                nxt[i] = __ldg(reinterpret_cast<const uint4*>(a.src + (int64_t)(fy + row) * a.pitch + fx + 8 * c8));
+            }
+        };
+        if (vec && (int64_t)blockIdx.x * WARPS + warp < n_tiles) fetch((int64_t)blockIdx.x * WARPS + warp);
         for (int64_t tile = (int64_t)blockIdx.x * WARPS + warp; tile < n_tiles;
              tile += (int64_t)gridDim.x * WARPS) {
             const int64_t b = tile * GPW + g;
@@ -308,10 +342,21 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                         left[k] = (int16_t)lv;
                         ood |= tv | lv;
                     }
-                    for (int e = gl; e < N * N; e += G) {
-                        const int v = __ldg(a.src + (int64_t)(y + e / N) * a.pitch + x + e % N);
-                        O[(e / N) * Cfg::O_PITCH + (e % N)] = (int16_t)v;
-                        ood |= v;
+                    if (vec) {
+#pragma unroll
+                        for (int i = 0; i < CPL; ++i) {
+                            const int c = lane + 32 * i, row = c / (N / 8), c8 = c % (N / 8);
+                            *reinterpret_cast<uint4*>(O + row * Cfg::O_PITCH + 8 * c8) = nxt[i];
+                            ood |= (int)((nxt[i].x | nxt[i].y | nxt[i].z | nxt[i].w) & 0xFF00FF00u);
+                        }
+                        const int64_t tn = tile + (int64_t)gridDim.x * WARPS;
+                        if (tn < n_tiles) fetch(tn);
+                    } else {
+                        for (int e = gl; e < N * N; e += G) {
+                            const int v = __ldg(a.src + (int64_t)(y + e / N) * a.pitch + x + e % N);
+                            O[(e / N) * Cfg::O_PITCH + (e % N)] = (int16_t)v;
+                            ood |= v;
+                        }
                     }
                 }
             }
@@ -322,7 +367,13 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
             const bool fast8 = !__any_sync(0xffffffffu, (ood & ~0xff) != 0);
             __syncwarp();
             if constexpr (SRC == SRC_PLANE) corner = (int)top[0];
-            const int dc = dc_from_refs<N>(top, left);
+            int dc;
+            if constexpr (G == 32 && N >= 16) {   // one block per warp: lane k adds top[1+k] + left[1+k]
+                const int s = lane < N ? (int)top[1 + lane] + (int)left[1 + lane] : 0;
+                dc = dc_value<N>(__reduce_add_sync(0xffffffffu, s));
+            } else {
+                dc = dc_from_refs<N>(top, left);
+            }
             int mode;
             if constexpr (SRC == SRC_ARRAYS) {
                 mode = (valid && a.modes_in) ? (int)a.modes_in[b] : a.mode;
@@ -362,10 +413,20 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                 code_block<N, G>(gl, valid, b, mode, O, M, top, left, corner, dc, a.qp, a.fq,
                                  SRC != SRC_ARRAYS && fast8, neg, a.maxv, a.use_dst != 0, a.out);
             if constexpr (SRC == SRC_PLANE) {
-                if (valid && a.out.recon_plane)
-                    for (int e = gl; e < N * N; e += G)
-                        a.out.recon_plane[(int64_t)(y + e / N) * a.pitch + x + e % N] =
-                            O[(e / N) * Cfg::O_PITCH + (e % N)];
+                if (valid && a.out.recon_plane) {
+                    if (vec) {
+#pragma unroll
+                        for (int i = 0; i < CPL; ++i) {
+                            const int c = lane + 32 * i, row = c / (N / 8), c8 = c % (N / 8);
+                            stg_stream(a.out.recon_plane + (int64_t)(y + row) * a.pitch + x + 8 * c8,
+                                       *reinterpret_cast<const uint4*>(O + row * Cfg::O_PITCH + 8 * c8));
+                        }
+                    } else {
+                        for (int e = gl; e < N * N; e += G)
+                            a.out.recon_plane[(int64_t)(y + e / N) * a.pitch + x + e % N] =
+                                O[(e / N) * Cfg::O_PITCH + (e % N)];
+                    }
+                }
             }
             __syncwarp();
         }
@@ -601,7 +662,7 @@ static int dispatch_search_then_code(CoderArgs a, int size, cudaStream_t st) {
         // winners on the tensor cores (nh_coder8.cuh); it hands the tiles it cannot take (undecided
         // blocks) back by marking them 0xFF, and the exact coder below only touches marked blocks
         rc = coder8_plane_mma(a.src, a.H, a.W, a.pitch, a.out.modes, a.out.pred, a.out.coeff, a.out.levels,
-                              a.out.recon_plane, a.qp, a.maxv, st);
+                              a.out.recon_plane, a.qp, a.maxv, st, &a.handed_back);
         if (rc != NH_OK) return rc;
         a.only_undecided = 1;
     }
@@ -742,6 +803,7 @@ NH_API int nh_encode_frame(const int16_t* src, int height, int width, int pitch,
     a.maxv = (1 << bit_depth) - 1;
     a.use_dst = size == 4;  // docs/frames_and_panes.md:328-329
     a.out = CoderOut{modes, costs, pred, coeff, levels, nullptr, recon_plane, pitch};
+    a.vec_ok = (pitch % 8) == 0 && aligned16(src) && aligned16(recon_plane);
     if (!recon_neighbours) {
         // the search kernel reads the plane in 8-byte pieces and needs the modes tensor as its output
         const bool split_ok = split_impl() && bit_depth <= 8 && modes && (pitch % 4) == 0 &&

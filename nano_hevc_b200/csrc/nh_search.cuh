@@ -125,6 +125,18 @@ __device__ __forceinline__ void predict_line_u8(const unsigned char* bytes, int 
     }
 }
 
+// The same for a scan line whose fraction is 0 (angles 0 and +-32): the samples are the bytes themselves.
+template <int WPS>
+__device__ __forceinline__ void copy_line_u8(const unsigned char* bytes, int ob, uint32_t (&out)[WPS]) {
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(bytes + (ob & ~3));
+    const uint32_t sh = (uint32_t)(ob & 3) * 8u;
+    uint32_t w[WPS + 1];
+#pragma unroll
+    for (int i = 0; i <= WPS; ++i) w[i] = wp[i];
+#pragma unroll
+    for (int i = 0; i < WPS; ++i) out[i] = __funnelshift_r(w[i], w[i + 1], sh);
+}
+
 template <int N>
 __global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, 5) search_plane_kernel(const SearchArgs a) {
     using C = SearchCfg<N>;
@@ -303,13 +315,23 @@ __global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, 5) search_plane_kern
             const int negh = negT0[mi_c];          // only used when k < 0 (modes 11..25)
             const int negv = negT0[14 - mi_c];
             int p = (py_ + 1) * angle;
+            if ((angle & 31) == 0) {   // modes 2 / 34, 10 / 26, 18: every fraction is 0
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t f8 = ((uint32_t)p & 31u) << 3, g8 = 256u - f8;
-                const int k = px_ + 1 + (p >> 5);
-                predict_line_u8<WPS>(blk, (k < 0 ? negv : 0) + k, f8, g8, pr[j]);
-                predict_line_u8<WPS>(blk, (k < 0 ? negh : C::PB) + k, f8, g8, prh[j]);
-                p += angle;
+                for (int j = 0; j < 4; ++j) {
+                    const int k = px_ + 1 + (p >> 5);
+                    copy_line_u8<WPS>(blk, (k < 0 ? negv : 0) + k, pr[j]);
+                    copy_line_u8<WPS>(blk, (k < 0 ? negh : C::PB) + k, prh[j]);
+                    p += angle;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t f8 = ((uint32_t)p & 31u) << 3, g8 = 256u - f8;
+                    const int k = px_ + 1 + (p >> 5);
+                    predict_line_u8<WPS>(blk, (k < 0 ? negv : 0) + k, f8, g8, pr[j]);
+                    predict_line_u8<WPS>(blk, (k < 0 ? negh : C::PB) + k, f8, g8, prh[j]);
+                    p += angle;
+                }
             }
             int cv = strip_cost_packed<WPS>(pr, ov, a.cost_kind);
             int ch = strip_cost_packed<WPS>(prh, oh, a.cost_kind);

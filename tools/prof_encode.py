@@ -15,9 +15,10 @@ ap.add_argument("--size", type=int, default=16)
 ap.add_argument("--cost", default="sad")
 ap.add_argument("--wavefront", action="store_true")
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--frames", type=int, default=1, help="frames stacked into one tall plane (config 3 batch)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
-plane = synth_plane(2160, 3840, 0, dev)
+plane = torch.cat([synth_plane(2160, 3840, i, dev) for i in range(args.frames)], dim=0)
 for _ in range(args.reps):
     r = batched.encode_frame(plane, args.size, cost=args.cost, qp=27, recon_neighbours=args.wavefront)
 torch.cuda.synchronize()
