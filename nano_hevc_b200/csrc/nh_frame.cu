@@ -296,13 +296,21 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
         constexpr bool kVec = SRC == SRC_PLANE && G == 32 && N >= 16;
         constexpr int CPL = kVec ? N * N / 8 / 32 : 1;   // chunks per lane
         const bool vec = kVec && a.vec_ok && !a.only_undecided;
+        constexpr int RPL = (Cfg::REF_W + 31) / 32;      // reference entries per lane
         uint4 nxt[CPL];
+        int ntv[RPL], nlv[RPL];
         auto fetch = [&](int64_t t) {
             const int fx = (int)(t % bw) * N, fy = (int)(t / bw) * N;
 #pragma unroll
             for (int i = 0; i < CPL; ++i) {
                 const int c = lane + 32 * i, row = c / (N / 8), c8 = c % (N / 8);
                 nxt[i] = __ldg(reinterpret_cast<const uint4*>(a.src + (int64_t)(fy + row) * a.pitch + fx + 8 * c8));
+            }
+#pragma unroll
+            for (int i = 0; i < RPL; ++i) {
+                const int k = lane + 32 * i, kk = k <= 2 * N ? k : 2 * N;
+                ntv[i] = top_ref<false>(a.src, a.H, a.W, a.pitch, fx, fy, 2 * N, kk);
+                nlv[i] = left_ref<false>(a.src, a.H, a.W, a.pitch, fx, fy, 2 * N, kk);
             }
         };
         if (vec && (int64_t)blockIdx.x * WARPS + warp < n_tiles) fetch((int64_t)blockIdx.x * WARPS + warp);
@@ -334,13 +342,25 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                 if (valid) {
                     x = (int)(b % bw) * N;
                     y = (int)(b / bw) * N;
-                    for (int k = gl; k < Cfg::REF_W; k += G) {
-                        const int kk = k <= 2 * N ? k : 2 * N;
-                        const int tv = top_ref<false>(a.src, a.H, a.W, a.pitch, x, y, 2 * N, kk);
-                        const int lv = left_ref<false>(a.src, a.H, a.W, a.pitch, x, y, 2 * N, kk);
-                        top[k] = (int16_t)tv;
-                        left[k] = (int16_t)lv;
-                        ood |= tv | lv;
+                    if (vec) {
+#pragma unroll
+                        for (int i = 0; i < RPL; ++i) {
+                            const int k = lane + 32 * i;
+                            if (k < Cfg::REF_W) {
+                                top[k] = (int16_t)ntv[i];
+                                left[k] = (int16_t)nlv[i];
+                                ood |= ntv[i] | nlv[i];
+                            }
+                        }
+                    } else {
+                        for (int k = gl; k < Cfg::REF_W; k += G) {
+                            const int kk = k <= 2 * N ? k : 2 * N;
+                            const int tv = top_ref<false>(a.src, a.H, a.W, a.pitch, x, y, 2 * N, kk);
+                            const int lv = left_ref<false>(a.src, a.H, a.W, a.pitch, x, y, 2 * N, kk);
+                            top[k] = (int16_t)tv;
+                            left[k] = (int16_t)lv;
+                            ood |= tv | lv;
+                        }
                     }
                     if (vec) {
 #pragma unroll
