@@ -353,7 +353,8 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                             }
                         }
                     } else {
-                        for (int k = gl; k < Cfg::REF_W; k += G) {
+#pragma unroll
+                        for (int k = gl; k < Cfg::REF_W; k += G) {   // unrolled: all loads in flight together
                             const int kk = k <= 2 * N ? k : 2 * N;
                             const int tv = top_ref<false>(a.src, a.H, a.W, a.pitch, x, y, 2 * N, kk);
                             const int lv = left_ref<false>(a.src, a.H, a.W, a.pitch, x, y, 2 * N, kk);
@@ -372,6 +373,7 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                         const int64_t tn = tile + (int64_t)gridDim.x * WARPS;
                         if (tn < n_tiles) fetch(tn);
                     } else {
+#pragma unroll (N <= 8 ? N : 4)
                         for (int e = gl; e < N * N; e += G) {
                             const int v = __ldg(a.src + (int64_t)(y + e / N) * a.pitch + x + e % N);
                             O[(e / N) * Cfg::O_PITCH + (e % N)] = (int16_t)v;
