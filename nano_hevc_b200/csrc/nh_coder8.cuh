@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) coder8_plane_mma_kernel(cons
         }
         if (a.pred) T16::store(sP, reinterpret_cast<unsigned char*>(a.pred + blk0 * NN), lane, chunks16);
         const uint32_t sO = smem_u32(s16[cur]) + lane_off, sPa = smem_u32(sP) + lane_off;
-#pragma unroll kMma8Unroll
+#pragma unroll 2
         for (int q = 0; q < 8; ++q) {
             uint32_t ro[4], rp[4], pc[4], rr[4];
             const uint32_t off = (uint32_t)(4 * q * T16::kPitch);

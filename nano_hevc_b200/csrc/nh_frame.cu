@@ -652,7 +652,7 @@ static int launch_search(const CoderArgs& a, cudaStream_t st) {
     int rc = ensure_dynamic_smem(search_plane_kernel<N>, C::SMEM_BYTES, "search_plane_kernel");
     if (rc != NH_OK) return rc;
     SearchArgs s{a.src, a.H, a.W, a.pitch, a.cost_kind, a.n_blocks, a.out.modes, a.out.costs};
-    const int per_sm = 5;  // __launch_bounds__(128, 5); 5 x SMEM_BYTES <= 140 KB for every N
+    const int per_sm = 6;  // __launch_bounds__(128, 6); 6 x SMEM_BYTES <= 170 KB for every N
     const int grid = grid_for(a.n_blocks, (int64_t)C::WARPS * C::T, per_sm);
     search_plane_kernel<N><<<grid, C::WARPS * 32, C::SMEM_BYTES, st>>>(s);
     NH_CHECK_LAUNCH("search_plane_kernel");

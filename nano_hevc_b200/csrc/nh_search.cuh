@@ -138,7 +138,7 @@ __device__ __forceinline__ void copy_line_u8(const unsigned char* bytes, int ob,
 }
 
 template <int N>
-__global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, 5) search_plane_kernel(const SearchArgs a) {
+__global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, 6) search_plane_kernel(const SearchArgs a) {
     using C = SearchCfg<N>;
     constexpr int SW = C::SW, SB = C::SB, T = C::T, WPS = C::WPS, S = Log2<N>::v;
     extern __shared__ __align__(16) uint32_t smem_w[];
