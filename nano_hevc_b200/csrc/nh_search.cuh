@@ -101,35 +101,39 @@ __device__ __forceinline__ int strip_cost_packed(const uint32_t (&pr)[4][WPS], c
     return c;
 }
 
-// One scan line of SW predicted samples (packed bytes) from the byte array at `bytes` + `ob`:
+// One scan line of SW predicted samples (packed bytes):
 //   ((32-f) ref[k+i] + f ref[k+i+1] + 16) >> 5  for i = 0 .. SW-1   (intra.py:191-207; f8 = 8 f, g8 = 8 (32 - f)).
+// wp = word that holds ref[k], sh = 8 (k & 3), sel_last = 0x3412 + ((k & 3) << 8): the three depend on k
+// only, so the two halves of a mirror pair share them.
 template <int WPS>
-__device__ __forceinline__ void predict_line_u8(const unsigned char* bytes, int ob, uint32_t f8, uint32_t g8,
-                                                uint32_t (&out)[WPS]) {
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(bytes + (ob & ~3));
-    const uint32_t sh = (uint32_t)(ob & 3) * 8u;
-    uint32_t w[WPS + 1], v[WPS + 1];
+__device__ __forceinline__ void predict_line_w(const uint32_t* wp, uint32_t sh, uint32_t sel_last, uint32_t f8,
+                                               uint32_t g8, uint32_t (&out)[WPS]) {
+    uint32_t w[WPS + 1], v[WPS];
 #pragma unroll
     for (int i = 0; i <= WPS; ++i) w[i] = wp[i];
 #pragma unroll
     for (int i = 0; i < WPS; ++i) v[i] = __funnelshift_r(w[i], w[i + 1], sh);   // bytes k+4i .. k+4i+3
-    v[WPS] = w[WPS] >> sh;                                                        // byte k+SW in the low byte
 #pragma unroll
     for (int q = 0; q < WPS; ++q) {
         const uint32_t e0 = __byte_perm(v[q], 0u, 0x4240);        // (b0, b2)
         const uint32_t o0 = __byte_perm(v[q], 0u, 0x4341);        // (b1, b3)
-        const uint32_t e1 = __byte_perm(e0, v[q + 1], 0x3412);    // (b2, b4)
+        const uint32_t e1 = q + 1 < WPS ? __byte_perm(e0, v[q + 1], 0x3412)      // (b2, b4)
+                                        : __byte_perm(e0, w[WPS], sel_last);     // b4 = byte k & 3 of the last word
         const uint32_t t02 = g8 * e0 + 0x00800080u + f8 * o0;     // samples 0, 2 in the high bytes
         const uint32_t t13 = g8 * o0 + 0x00800080u + f8 * e1;     // samples 1, 3
         out[q] = __byte_perm(t02, t13, 0x7351);
     }
 }
+template <int WPS>
+__device__ __forceinline__ void predict_line_u8(const unsigned char* bytes, int ob, uint32_t f8, uint32_t g8,
+                                                uint32_t (&out)[WPS]) {
+    const uint32_t k3 = (uint32_t)ob & 3u;
+    predict_line_w<WPS>(reinterpret_cast<const uint32_t*>(bytes + (ob & ~3)), k3 * 8u, 0x3412u + (k3 << 8), f8, g8, out);
+}
 
 // The same for a scan line whose fraction is 0 (angles 0 and +-32): the samples are the bytes themselves.
 template <int WPS>
-__device__ __forceinline__ void copy_line_u8(const unsigned char* bytes, int ob, uint32_t (&out)[WPS]) {
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(bytes + (ob & ~3));
-    const uint32_t sh = (uint32_t)(ob & 3) * 8u;
+__device__ __forceinline__ void copy_line_w(const uint32_t* wp, uint32_t sh, uint32_t (&out)[WPS]) {
     uint32_t w[WPS + 1];
 #pragma unroll
     for (int i = 0; i <= WPS; ++i) w[i] = wp[i];
@@ -319,8 +323,10 @@ __global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, 6) search_plane_kern
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int k = px_ + 1 + (p >> 5);
-                    copy_line_u8<WPS>(blk, (k < 0 ? negv : 0) + k, pr[j]);
-                    copy_line_u8<WPS>(blk, (k < 0 ? negh : C::PB) + k, prh[j]);
+                    const int k4 = k & ~3;
+                    const uint32_t sh = (uint32_t)(k & 3) * 8u;
+                    copy_line_w<WPS>(reinterpret_cast<const uint32_t*>(blk + (k < 0 ? negv : 0) + k4), sh, pr[j]);
+                    copy_line_w<WPS>(reinterpret_cast<const uint32_t*>(blk + (k < 0 ? negh : C::PB) + k4), sh, prh[j]);
                     p += angle;
                 }
             } else {
@@ -328,8 +334,14 @@ __global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, 6) search_plane_kern
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t f8 = ((uint32_t)p & 31u) << 3, g8 = 256u - f8;
                     const int k = px_ + 1 + (p >> 5);
-                    predict_line_u8<WPS>(blk, (k < 0 ? negv : 0) + k, f8, g8, pr[j]);
-                    predict_line_u8<WPS>(blk, (k < 0 ? negh : C::PB) + k, f8, g8, prh[j]);
+                    // every array starts on a word: the word offset, the byte shift and the selector of the
+                    // last byte depend on k only and serve both halves
+                    const int k4 = k & ~3;
+                    const uint32_t k3 = (uint32_t)k & 3u, sh = k3 * 8u, sel_last = 0x3412u + (k3 << 8);
+                    predict_line_w<WPS>(reinterpret_cast<const uint32_t*>(blk + (k < 0 ? negv : 0) + k4), sh, sel_last, f8,
+                                        g8, pr[j]);
+                    predict_line_w<WPS>(reinterpret_cast<const uint32_t*>(blk + (k < 0 ? negh : C::PB) + k4), sh, sel_last,
+                                        f8, g8, prh[j]);
                     p += angle;
                 }
             }
