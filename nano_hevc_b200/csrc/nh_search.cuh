@@ -71,10 +71,18 @@ __device__ __forceinline__ int strip_cost_packed(const uint32_t (&pr)[4][WPS], c
                                                  int cost_kind) {
     int c = 0;
     if (cost_kind == NH_COST_SAD) {
+        // two accumulate chains (VABSDIFF4.U8.ACC with a live accumulator): written as asm because the
+        // compiler otherwise starts every instruction from RZ and adds the partial sums on the ALU pipe,
+        // which is the pipe that bounds this kernel
+        uint32_t c0 = 0, c1 = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < 2; ++j)
 #pragma unroll
-            for (int q = 0; q < WPS; ++q) c = (int)(__vsadu4(pr[j][q], o[j][q]) + (uint32_t)c);
+            for (int q = 0; q < WPS; ++q) {
+                asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(c0) : "r"(pr[j][q]), "r"(o[j][q]));
+                asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(c1) : "r"(pr[j + 2][q]), "r"(o[j + 2][q]));
+            }
+        c = (int)(c0 + c1);
     } else {
 #pragma unroll
         for (int q = 0; q < WPS; ++q) {   // one 4x4 sub-block per packed word column
