@@ -299,8 +299,10 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
         constexpr int RPL = (Cfg::REF_W + 31) / 32;      // reference entries per lane
         uint4 nxt[CPL];
         int ntv[RPL], nlv[RPL];
+        int nmode = 0xFF;
         auto fetch = [&](int64_t t) {
             const int fx = (int)(t % bw) * N, fy = (int)(t / bw) * N;
+            if (a.modes_in) nmode = (int)a.modes_in[t];   // one block per warp: block index = tile index
 #pragma unroll
             for (int i = 0; i < CPL; ++i) {
                 const int c = lane + 32 * i, row = c / (N / 8), c8 = c % (N / 8);
@@ -324,7 +326,8 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
             if constexpr (SRC == SRC_PLANE) {
                 // modes decided by search_plane_kernel (nh_search.cuh); 0xFF = not decided (the tile held a
                 // sample outside [0, 255]) -> the exact search below, for every block of this warp
-                if (a.modes_in) mode_in = valid ? (int)a.modes_in[b] : 1;
+                if (vec) mode_in = nmode;   // fetched with the pixels during the previous block
+                else if (a.modes_in) mode_in = valid ? (int)a.modes_in[b] : 1;
                 given = !__any_sync(0xffffffffu, mode_in > 34);
                 if (given && a.only_undecided) continue;
             }
