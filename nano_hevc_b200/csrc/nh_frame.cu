@@ -316,6 +316,14 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
             }
         };
         if (vec && (int64_t)blockIdx.x * WARPS + warp < n_tiles) fetch((int64_t)blockIdx.x * WARPS + warp);
+        // several blocks per warp: at least the decided mode of the next tile is fetched a tile ahead
+        auto load_mode = [&](int64_t t) -> int {
+            const int64_t bb = t * GPW + g;
+            return (a.modes_in && bb < a.n_blocks) ? (int)a.modes_in[bb] : (a.modes_in ? 1 : 0xFF);
+        };
+        int pmode = 0xFF;
+        if (SRC == SRC_PLANE && !vec && (int64_t)blockIdx.x * WARPS + warp < n_tiles)
+            pmode = load_mode((int64_t)blockIdx.x * WARPS + warp);
         for (int64_t tile = (int64_t)blockIdx.x * WARPS + warp; tile < n_tiles;
              tile += (int64_t)gridDim.x * WARPS) {
             const int64_t b = tile * GPW + g;
@@ -326,8 +334,13 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
             if constexpr (SRC == SRC_PLANE) {
                 // modes decided by search_plane_kernel (nh_search.cuh); 0xFF = not decided (the tile held a
                 // sample outside [0, 255]) -> the exact search below, for every block of this warp
-                if (vec) mode_in = nmode;   // fetched with the pixels during the previous block
-                else if (a.modes_in) mode_in = valid ? (int)a.modes_in[b] : 1;
+                if (vec) {
+                    mode_in = nmode;   // fetched with the pixels during the previous block
+                } else {
+                    mode_in = pmode;
+                    const int64_t tn = tile + (int64_t)gridDim.x * WARPS;
+                    if (tn < n_tiles) pmode = load_mode(tn);
+                }
                 given = !__any_sync(0xffffffffu, mode_in > 34);
                 if (given && a.only_undecided) continue;
             }
