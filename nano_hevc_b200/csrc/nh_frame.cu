@@ -321,6 +321,29 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
             const int64_t bb = t * GPW + g;
             return (a.modes_in && bb < a.n_blocks) ? (int)a.modes_in[bb] : (a.modes_in ? 1 : 0xFF);
         };
+        // ... and at N <= 8 its references and pixels too (scalar loads, a handful of registers per lane)
+        constexpr bool kSp = SRC == SRC_PLANE && N <= 8;
+        constexpr int RS = kSp ? (Cfg::REF_W + G - 1) / G : 1, PS = kSp ? N * N / G : 1;
+        const bool sp = kSp && !a.only_undecided;
+        int stv[RS], slv[RS], spx[PS];
+        auto sfetch = [&](int64_t t) {
+            const int64_t bb = t * GPW + g;
+            if (bb < a.n_blocks) {
+                const int fx = (int)(bb % bw) * N, fy = (int)(bb / bw) * N;
+#pragma unroll
+                for (int i = 0; i < RS; ++i) {
+                    const int k = gl + i * G, kk = k <= 2 * N ? k : 2 * N;
+                    stv[i] = top_ref<false>(a.src, a.H, a.W, a.pitch, fx, fy, 2 * N, kk);
+                    slv[i] = left_ref<false>(a.src, a.H, a.W, a.pitch, fx, fy, 2 * N, kk);
+                }
+#pragma unroll
+                for (int i = 0; i < PS; ++i) {
+                    const int e = gl + i * G;
+                    spx[i] = __ldg(a.src + (int64_t)(fy + e / N) * a.pitch + fx + e % N);
+                }
+            }
+        };
+        if (sp && (int64_t)blockIdx.x * WARPS + warp < n_tiles) sfetch((int64_t)blockIdx.x * WARPS + warp);
         int pmode = 0xFF;
         if (SRC == SRC_PLANE && !vec && (int64_t)blockIdx.x * WARPS + warp < n_tiles)
             pmode = load_mode((int64_t)blockIdx.x * WARPS + warp);
@@ -368,6 +391,22 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                                 ood |= ntv[i] | nlv[i];
                             }
                         }
+                    } else if (sp) {
+#pragma unroll
+                        for (int i = 0; i < RS; ++i) {
+                            const int k = gl + i * G;
+                            if (k < Cfg::REF_W) {
+                                top[k] = (int16_t)stv[i];
+                                left[k] = (int16_t)slv[i];
+                                ood |= stv[i] | slv[i];
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < PS; ++i) {
+                            const int e = gl + i * G;
+                            O[(e / N) * Cfg::O_PITCH + (e % N)] = (int16_t)spx[i];
+                            ood |= spx[i];
+                        }
                     } else {
 #pragma unroll
                         for (int k = gl; k < Cfg::REF_W; k += G) {   // unrolled: all loads in flight together
@@ -388,7 +427,7 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                         }
                         const int64_t tn = tile + (int64_t)gridDim.x * WARPS;
                         if (tn < n_tiles) fetch(tn);
-                    } else {
+                    } else if (!sp) {
 #pragma unroll (N <= 8 ? N : 4)
                         for (int e = gl; e < N * N; e += G) {
                             const int v = __ldg(a.src + (int64_t)(y + e / N) * a.pitch + x + e % N);
@@ -396,6 +435,12 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                             ood |= v;
                         }
                     }
+                }
+            }
+            if constexpr (kSp) {
+                if (sp) {
+                    const int64_t tn = tile + (int64_t)gridDim.x * WARPS;
+                    if (tn < n_tiles) sfetch(tn);
                 }
             }
             if (!valid) {  // keep shared memory defined for the idle groups of a ragged tile
