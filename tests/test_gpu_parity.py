@@ -691,19 +691,26 @@ def test_encode_frame_10bit_uses_generic_search(Bt, n, cost, rn):
 
 @pytest.mark.parametrize("n", SIZES)
 @pytest.mark.parametrize("cost", ("sad", "satd"))
-def test_search_kernel_split_vs_single_kernel_vs_oracle(Bt, n, cost):
+@pytest.mark.parametrize("wmul", (4, 8))
+def test_search_kernel_split_vs_single_kernel_vs_oracle(Bt, n, cost, wmul):
     """Config 3 runs as search kernel + winner kernel on 8-bit content (nh_set_search_impl(2), default).
     Ragged warp tiles (the block count is no multiple of the tile), frame edges on every side, and
     a region with samples outside [0, 255] (those tiles are left to the coder kernel's exact search):
     identical to the single-kernel path and to the C oracle."""
     from nano_hevc_b200 import _lib
     rng = np.random.default_rng(77 + n)
-    H, W = 5 * n + 3, 4 * ((13 * n + 8) // 4) + 4
+    # wmul = 4: the 128-bit paths (tensor-core 8x8 winners, vectorised 16 / 32 winners) are off;
+    # wmul = 8: they are on, and the out-of-range samples make the 8x8 tensor-core kernel hand whole
+    # tiles back to the exact coder
+    H, W = 5 * n + 3, wmul * ((13 * n + 8) // wmul) + wmul
+    if wmul == 8:
+        H, W = 6 * n + 3, 8 * ((45 * n) // 8) + 8   # more than one 32-block tile per row at N = 8
     src = _smooth(H, W, 3 * n)
     src[: 2 * n] = rng.integers(0, 256, (2 * n, W))
     bad = src.copy()
     bad[3 * n + 1, 7 * n + 2] = 300
     bad[n // 2, 2 * n] = -7
+    bad[H - 2, W - 3] = 256   # in the columns / rows no full block covers, or the last block: a reference of nobody
     try:
         for plane in (src, bad):
             _lib.check(_lib.lib().nh_set_search_impl(2))
@@ -714,6 +721,12 @@ def test_search_kernel_split_vs_single_kernel_vs_oracle(Bt, n, cost):
             for name in ("modes", "costs", "pred", "coeff", "levels", "recon_plane"):
                 eq(host(getattr(r2, name)), host(getattr(r1, name)), f"split vs single {name} n={n} {cost}")
                 eq(host(getattr(r2, name)), w[name], f"split vs oracle {name} n={n} {cost}")
+            # optional outputs: only what was asked for is written, and it is the same
+            _lib.check(_lib.lib().nh_set_search_impl(2))
+            r3 = Bt.encode_frame(dev(plane), n, cost=cost, qp=26, outputs=("modes", "levels"))
+            assert r3.pred is None and r3.coeff is None and r3.costs is None
+            eq(host(r3.modes), w["modes"], "modes (subset)"); eq(host(r3.levels), w["levels"], "levels (subset)")
+            eq(host(r3.recon_plane), w["recon_plane"], "recon_plane (subset)")
     finally:
         _lib.check(_lib.lib().nh_set_search_impl(2))
 
