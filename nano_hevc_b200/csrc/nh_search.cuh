@@ -31,7 +31,12 @@
 
 namespace nh {
 
-constexpr int kNegAngle[15] = {-2, -5, -9, -13, -17, -21, -26, -32, -26, -21, -17, -13, -9, -5, -2};  // modes 11..25
+// INTRA_PRED_ANGLE of mode 11 + mi (the negative angles), as a function so that device code can fold it
+// after unrolling: -2, -5, -9, -13, -17, -21, -26, -32, -26, ..., -2
+__host__ __device__ constexpr int neg_angle_at(int mi) {
+    const int d = mi <= 7 ? mi : 14 - mi;
+    return d == 0 ? -2 : d == 1 ? -5 : d == 2 ? -9 : d == 3 ? -13 : d == 4 ? -17 : d == 5 ? -21 : d == 6 ? -26 : -32;
+}
 
 template <int N>
 struct SearchCfg {
@@ -42,7 +47,12 @@ struct SearchCfg {
     static constexpr int WPS = SW / 4;                 // packed words per scan line
     static constexpr int PB = ((2 * N + 9) + 3) / 4 * 4;   // bytes of a positive array: ref[0 .. 2N+1] + word-read slack
     static constexpr int CP = 4 * (WPS + 1);           // bytes of the primary array copied behind a projected extension
-    static constexpr int neg_len(int mi) { return -((N * kNegAngle[mi]) >> 5); }   // entries the reference fills
+    __host__ __device__ static constexpr int neg_len(int mi) { return -((N * neg_angle_at(mi)) >> 5); }   // entries the reference fills
+    __host__ __device__ static constexpr int neg_t0(int mi) {   // byte t = 0 of mode 11 + mi, from the block base
+        int off = 2 * PB;
+        for (int m = 0; m < mi; ++m) off += (neg_len(m) + 3) / 4 * 4 + CP;
+        return off + (neg_len(mi) + 3) / 4 * 4;
+    }
     static constexpr int neg_bytes() {
         int s = 0;
         for (int mi = 0; mi < 15; ++mi) s += (neg_len(mi) + 3) / 4 * 4 + CP;
@@ -156,11 +166,7 @@ __global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, 6) search_plane_kern
     extern __shared__ __align__(16) uint32_t smem_w[];
     int* negT0 = reinterpret_cast<int*>(smem_w + C::WARPS * C::WARP_WORDS);   // byte t = 0 of mode 11+mi, from the block base
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x < 15) {
-        int off = 2 * C::PB;
-        for (int m = 0; m < (int)threadIdx.x; ++m) off += (-((N * intra_angle(11 + m)) >> 5) + 3) / 4 * 4 + C::CP;
-        negT0[threadIdx.x] = off + (-((N * intra_angle(11 + (int)threadIdx.x)) >> 5) + 3) / 4 * 4;
-    }
+    if (threadIdx.x < 15) negT0[threadIdx.x] = C::neg_t0((int)threadIdx.x);
     __syncthreads();
 
     uint32_t* wbase = smem_w + warp * C::WARP_WORDS;
@@ -235,6 +241,37 @@ __global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, 6) search_plane_kern
         // ---- projected extensions of the negative-angle modes (intra.py:180-186).  Unit = (block,
         // orientation, group of modes); the vertical modes run from 25 downwards so that the two
         // orientations of a block walk through equal lengths side by side.
+        if constexpr (C::GP == 1) {
+            // N = 4 / 8: unit = (block, orientation).  Horizontal mode 11 + q and vertical mode 25 - q share the
+            // angle, hence the length and every projected index: unrolled, each entry is one byte load and one
+            // byte store at constant offsets (the loop form below cost 15 % of the kernel at N = 8).
+            for (int u0 = 0; u0 < 2 * T; u0 += 32) {
+                const int u = u0 + lane;
+                if (u < 2 * T) {
+                    const int i = u >> 1, o = u & 1;
+                    unsigned char* zb = reinterpret_cast<unsigned char*>(wbase + i * C::BLOCK_WORDS);
+                    const unsigned char* sec = zb + (o ? C::PB : 0);
+                    uint32_t pw[WPS + 1];
+#pragma unroll
+                    for (int c = 0; c <= WPS; ++c) pw[c] = reinterpret_cast<const uint32_t*>(zb + (o ? 0 : C::PB))[c];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int len = C::neg_len(14 - q);
+                        const int inv = inv_angle(neg_angle_at(14 - q));
+                        if (q < 7 || o) {   // mode 18 (q = 7) is vertical only
+                            unsigned char* dst = zb + (o ? C::neg_t0(14 - q) : C::neg_t0(q < 7 ? q : 6));
+#pragma unroll
+                            for (int c = 0; c <= WPS; ++c) reinterpret_cast<uint32_t*>(dst)[c] = pw[c];   // ref[t], t >= 0
+#pragma unroll
+                            for (int tt = 0; tt < len; ++tt) {                                           // t = -1 - tt
+                                const int proj = (-tt * inv + 128) >> 8;                                 // (k+1) projection, Q3
+                                dst[-1 - tt] = sec[proj > 2 * N ? 2 * N : proj];
+                            }
+                        }
+                    }
+                }
+            }
+        } else
         for (int u0 = 0; u0 < 2 * T * C::GP; u0 += 32) {
             const int u = u0 + lane;
             if (u < 2 * T * C::GP) {
