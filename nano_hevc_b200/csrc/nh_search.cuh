@@ -239,64 +239,31 @@ __global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, 6) search_plane_kern
         __syncwarp();
 
         // ---- projected extensions of the negative-angle modes (intra.py:180-186).  Unit = (block,
-        // orientation, group of modes); the vertical modes run from 25 downwards so that the two
-        // orientations of a block walk through equal lengths side by side.
-        if constexpr (C::GP == 1) {
-            // N = 4 / 8: unit = (block, orientation).  Horizontal mode 11 + q and vertical mode 25 - q share the
-            // angle, hence the length and every projected index: unrolled, each entry is one byte load and one
-            // byte store at constant offsets (the loop form below cost 15 % of the kernel at N = 8).
-            for (int u0 = 0; u0 < 2 * T; u0 += 32) {
-                const int u = u0 + lane;
-                if (u < 2 * T) {
-                    const int i = u >> 1, o = u & 1;
-                    unsigned char* zb = reinterpret_cast<unsigned char*>(wbase + i * C::BLOCK_WORDS);
-                    const unsigned char* sec = zb + (o ? C::PB : 0);
-                    uint32_t pw[WPS + 1];
-#pragma unroll
-                    for (int c = 0; c <= WPS; ++c) pw[c] = reinterpret_cast<const uint32_t*>(zb + (o ? 0 : C::PB))[c];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int len = C::neg_len(14 - q);
-                        const int inv = inv_angle(neg_angle_at(14 - q));
-                        if (q < 7 || o) {   // mode 18 (q = 7) is vertical only
-                            unsigned char* dst = zb + (o ? C::neg_t0(14 - q) : C::neg_t0(q < 7 ? q : 6));
-#pragma unroll
-                            for (int c = 0; c <= WPS; ++c) reinterpret_cast<uint32_t*>(dst)[c] = pw[c];   // ref[t], t >= 0
-#pragma unroll
-                            for (int tt = 0; tt < len; ++tt) {                                           // t = -1 - tt
-                                const int proj = (-tt * inv + 128) >> 8;                                 // (k+1) projection, Q3
-                                dst[-1 - tt] = sec[proj > 2 * N ? 2 * N : proj];
-                            }
-                        }
-                    }
-                }
-            }
-        } else
+        // orientation, group of MPG modes).  Horizontal mode 11 + q and vertical mode 25 - q share the angle,
+        // hence the length and every projected index: unrolled over q, each entry is one byte load and one
+        // byte store at constant offsets (a loop over table-driven items cost 15 % of the kernel at N = 8).
         for (int u0 = 0; u0 < 2 * T * C::GP; u0 += 32) {
             const int u = u0 + lane;
             if (u < 2 * T * C::GP) {
                 const int i = u / (2 * C::GP), r = u % (2 * C::GP), o = r / C::GP, g = r % C::GP;
                 unsigned char* zb = reinterpret_cast<unsigned char*>(wbase + i * C::BLOCK_WORDS);
-                const unsigned char* pri = zb + (o ? 0 : C::PB);     // vertical: top
-                const unsigned char* sec = zb + (o ? C::PB : 0);
+                const unsigned char* sec = zb + (o ? C::PB : 0);     // vertical: secondary = left, primary = top
                 uint32_t pw[WPS + 1];
 #pragma unroll
-                for (int c = 0; c <= WPS; ++c) pw[c] = reinterpret_cast<const uint32_t*>(pri)[c];
-#pragma unroll 1
-                for (int q = 0; q < C::MPG; ++q) {
-                    const int midx = g * C::MPG + q;
-                    if (!o && midx >= 7) break;
-                    const int mode = o ? 25 - midx : 11 + midx;
-                    const int inv = inv_angle_of_mode(mode);
-                    const int len = -((N * intra_angle(mode)) >> 5);
-                    const int t0 = negT0[mode - 11];
+                for (int c = 0; c <= WPS; ++c) pw[c] = reinterpret_cast<const uint32_t*>(zb + (o ? 0 : C::PB))[c];
 #pragma unroll
-                    for (int c = 0; c <= WPS; ++c) reinterpret_cast<uint32_t*>(zb + t0)[c] = pw[c];   // ref[t], t >= 0
-#pragma unroll 1
-                    for (int tt = 0; tt < len; ++tt) {                                               // t = -1 - tt
-                        int proj = (-tt * inv + 128) >> 8;                                           // (k+1) projection, Q3
-                        proj = proj > 2 * N ? 2 * N : proj;
-                        zb[t0 - 1 - tt] = sec[proj];
+                for (int q = 0; q < 8; ++q) {
+                    const int len = C::neg_len(14 - q);
+                    const int inv = inv_angle(neg_angle_at(14 - q));
+                    if (q / C::MPG == g && (q < 7 || o)) {   // mode 18 (q = 7) is vertical only
+                        unsigned char* dst = zb + (o ? C::neg_t0(14 - q) : C::neg_t0(q < 7 ? q : 6));
+#pragma unroll
+                        for (int c = 0; c <= WPS; ++c) reinterpret_cast<uint32_t*>(dst)[c] = pw[c];   // ref[t], t >= 0
+#pragma unroll
+                        for (int tt = 0; tt < len; ++tt) {                                           // t = -1 - tt
+                            const int proj = (-tt * inv + 128) >> 8;                                 // (k+1) projection, Q3
+                            dst[-1 - tt] = sec[proj > 2 * N ? 2 * N : proj];
+                        }
                     }
                 }
             }
