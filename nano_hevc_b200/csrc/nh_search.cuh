@@ -190,6 +190,8 @@ __global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, 6) search_plane_kern
         __syncwarp();   // the previous tile's arrays are no longer read
 
         // ---- K1: references with the substitution rules of block.py:38-55, as bytes
+        // every block of the tile away from the frame edges (warp-uniform): the common case
+        const bool interior = __all_sync(0xffffffffu, x > 0 && y > 0 && x + 2 * N <= a.W && y + 2 * N <= a.H);
         constexpr int RE = T * (2 * N + 2);
 #pragma unroll
         for (int e0 = 0; e0 < RE; e0 += 32) {   // uniform trip count (the shuffles need every lane), loads in flight together
@@ -197,8 +199,15 @@ __global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, 6) search_plane_kern
             const int i = e / (2 * N + 2), k = e % (2 * N + 2);
             const int xi = __shfl_sync(0xffffffffu, x, (i * SB) & 31), yi = __shfl_sync(0xffffffffu, y, (i * SB) & 31);
             const int kk = k <= 2 * N ? k : 2 * N;   // entry 2N+1: replicate-last padding (only read with weight 0)
-            const int tv = top_ref<false>(a.src, a.H, a.W, a.pitch, xi, yi, 2 * N, kk);
-            const int lv = left_ref<false>(a.src, a.H, a.W, a.pitch, xi, yi, 2 * N, kk);
+            int tv, lv;
+            if (interior) {   // no substitution, no truncation: top[k] = plane[y-1][x-1+k], left[k] = plane[y-1+k][x-1]
+                const int16_t* c = a.src + (int64_t)(yi - 1) * a.pitch + xi - 1;
+                tv = __ldg(c + kk);
+                lv = __ldg(c + (int64_t)kk * a.pitch);
+            } else {
+                tv = top_ref<false>(a.src, a.H, a.W, a.pitch, xi, yi, 2 * N, kk);
+                lv = left_ref<false>(a.src, a.H, a.W, a.pitch, xi, yi, 2 * N, kk);
+            }
             unsigned char* zb = reinterpret_cast<unsigned char*>(wbase + i * C::BLOCK_WORDS);
             zb[k] = (unsigned char)tv;
             zb[C::PB + k] = (unsigned char)lv;
