@@ -295,6 +295,7 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
         // next block's chunks are fetched while this one is coded.
         constexpr bool kVec = SRC == SRC_PLANE && G == 32 && N >= 16;
         constexpr int CPL = kVec ? N * N / 8 / 32 : 1;   // chunks per lane
+        constexpr int CW = N >= 8 ? N / 8 : 1;           // chunks per row
         const bool vec = kVec && a.vec_ok && !a.only_undecided;
         constexpr int RPL = (Cfg::REF_W + 31) / 32;      // reference entries per lane
         uint4 nxt[CPL];
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
             if (a.modes_in) nmode = (int)a.modes_in[t];   // one block per warp: block index = tile index
 #pragma unroll
             for (int i = 0; i < CPL; ++i) {
-                const int c = lane + 32 * i, row = c / (N / 8), c8 = c % (N / 8);
+                const int c = lane + 32 * i, row = c / CW, c8 = c % CW;
                 nxt[i] = __ldg(reinterpret_cast<const uint4*>(a.src + (int64_t)(fy + row) * a.pitch + fx + 8 * c8));
             }
 #pragma unroll
@@ -421,7 +422,7 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                     if (vec) {
 #pragma unroll
                         for (int i = 0; i < CPL; ++i) {
-                            const int c = lane + 32 * i, row = c / (N / 8), c8 = c % (N / 8);
+                            const int c = lane + 32 * i, row = c / CW, c8 = c % CW;
                             *reinterpret_cast<uint4*>(O + row * Cfg::O_PITCH + 8 * c8) = nxt[i];
                             ood |= (int)((nxt[i].x | nxt[i].y | nxt[i].z | nxt[i].w) & 0xFF00FF00u);
                         }
@@ -500,7 +501,7 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                     if (vec) {
 #pragma unroll
                         for (int i = 0; i < CPL; ++i) {
-                            const int c = lane + 32 * i, row = c / (N / 8), c8 = c % (N / 8);
+                            const int c = lane + 32 * i, row = c / CW, c8 = c % CW;
                             stg_stream(a.out.recon_plane + (int64_t)(y + row) * a.pitch + x + 8 * c8,
                                        *reinterpret_cast<const uint4*>(O + row * Cfg::O_PITCH + 8 * c8));
                         }
