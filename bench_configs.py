@@ -122,8 +122,9 @@ def main():
         tall = torch.cat([synth_plane(H, W, i, dev) for i in range(F)], dim=0)
         for n in (4, 8, 16, 32):
             px = (F * H // n) * (W // n) * n * n
-            ms = time_ms(lambda: batched.encode_frame(tall, n, cost="sad", qp=27), 2, warmup=1)
-            emit(f"encode_frame search N={n} sad (cfg3, {F} 4K frames in one launch)", px, 2 + 12 + 5 / (n * n), ms)
+            for cost in ("sad", "satd"):
+                ms = time_ms(lambda: batched.encode_frame(tall, n, cost=cost, qp=27), 2, warmup=1)
+                emit(f"encode_frame search N={n} {cost} (cfg3, {F} 4K frames in one launch)", px, 2 + 12 + 5 / (n * n), ms)
         del tall
     if "wavefront" in which:
         for n in (4, 8, 16, 32):

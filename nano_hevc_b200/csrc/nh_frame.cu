@@ -708,17 +708,21 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 // K7 as two launches (8-bit content): search_plane_kernel decides the modes, coder_kernel codes the
 // winners (one block per warp and the tensor-core winner pipeline at N = 16 / 32).
-template <int N>
-static int launch_search(const CoderArgs& a, cudaStream_t st) {
+template <int N, int COST>
+static int launch_search_cost(const CoderArgs& a, cudaStream_t st) {
     using C = SearchCfg<N>;
-    int rc = ensure_dynamic_smem(search_plane_kernel<N>, C::SMEM_BYTES, "search_plane_kernel");
+    int rc = ensure_dynamic_smem(search_plane_kernel<N, COST>, C::SMEM_BYTES, "search_plane_kernel");
     if (rc != NH_OK) return rc;
     SearchArgs s{a.src, a.H, a.W, a.pitch, a.cost_kind, a.n_blocks, a.out.modes, a.out.costs};
-    const int per_sm = 6;  // __launch_bounds__(128, 6); 6 x SMEM_BYTES <= 170 KB for every N
+    const int per_sm = COST == NH_COST_SAD ? 6 : 5;  // the kernel's __launch_bounds__; 6 x SMEM_BYTES <= 170 KB for every N
     const int grid = grid_for(a.n_blocks, (int64_t)C::WARPS * C::T, per_sm);
-    search_plane_kernel<N><<<grid, C::WARPS * 32, C::SMEM_BYTES, st>>>(s);
+    search_plane_kernel<N, COST><<<grid, C::WARPS * 32, C::SMEM_BYTES, st>>>(s);
     NH_CHECK_LAUNCH("search_plane_kernel");
     return NH_OK;
+}
+template <int N>
+static int launch_search(const CoderArgs& a, cudaStream_t st) {
+    return a.cost_kind == NH_COST_SAD ? launch_search_cost<N, NH_COST_SAD>(a, st) : launch_search_cost<N, NH_COST_SATD>(a, st);
 }
 
 // 2 (default) = search kernel + winner kernel, 1 = everything in the single coder kernel (A/B

@@ -94,27 +94,38 @@ __device__ __forceinline__ int strip_cost_packed(const uint32_t (&pr)[4][WPS], c
             }
         c = (int)(c0 + c1);
     } else {
+        // Sum of satd_4x4 on 16-bit pairs.  Every lane carries a bias of 0x4000, restored by the constant of
+        // each three-input add, so lanes stay in [0x4000 - 2040, 0x4000 + 2040] and nothing crosses between
+        // them.  Lanes = columns (0, 2) and (1, 3): the column pass is lane-wise; the row pass stops one stage
+        // early because |a + c| + |a - c| = 2 max(|a|, |c|).
+        constexpr uint32_t B2 = 0x40004000u;
+        uint32_t acc = 0;
 #pragma unroll
         for (int q = 0; q < WPS; ++q) {   // one 4x4 sub-block per packed word column
-            int d[16];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    d[4 * j + i] = (int)((o[j][q] >> (8 * i)) & 0xff) - (int)((pr[j][q] >> (8 * i)) & 0xff);
+            uint32_t e[4], f[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                int a0 = d[j] + d[4 + j], a1 = d[j] - d[4 + j];
-                int a2 = d[8 + j] + d[12 + j], a3 = d[8 + j] - d[12 + j];
-                d[j] = a0 + a2; d[4 + j] = a1 + a3; d[8 + j] = a0 - a2; d[12 + j] = a1 - a3;
+                e[j] = __byte_perm(o[j][q], 0u, 0x4240) + B2 - __byte_perm(pr[j][q], 0u, 0x4240);   // (d0, d2)
+                f[j] = __byte_perm(o[j][q], 0u, 0x4341) + B2 - __byte_perm(pr[j][q], 0u, 0x4341);   // (d1, d3)
             }
+            auto had4 = [&](uint32_t (&x)[4]) {   // 4-point Hadamard down the rows, two columns per word
+                const uint32_t u0 = x[0] + x[1] - B2, u1 = x[0] - x[1] + B2, u2 = x[2] + x[3] - B2, u3 = x[2] - x[3] + B2;
+                x[0] = u0 + u2 - B2; x[1] = u1 + u3 - B2; x[2] = u0 - u2 + B2; x[3] = u1 - u3 + B2;
+            };
+            had4(e);
+            had4(f);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                int a0 = d[4 * i] + d[4 * i + 1], a1 = d[4 * i] - d[4 * i + 1];
-                int a2 = d[4 * i + 2] + d[4 * i + 3], a3 = d[4 * i + 2] - d[4 * i + 3];
-                c += abs(a0 + a2) + abs(a1 + a3) + abs(a0 - a2) + abs(a1 - a3);
+            for (int r = 0; r < 4; ++r) {
+                const uint32_t sd[2] = {e[r] + f[r] - B2, e[r] - f[r] + B2};   // (a, c) and (b, e')
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t m = __vmaxu2(sd[h], 0x80008000u - sd[h]);   // |.| + bias in both lanes
+                    const uint32_t mx = __vmaxu2(m, __byte_perm(m, m, 0x1032));   // max of the two lanes, in both
+                    acc = acc + mx - B2;
+                }
             }
         }
+        c = (int)(2u * (acc & 0xffffu));
     }
     return c;
 }
@@ -159,8 +170,10 @@ __device__ __forceinline__ void copy_line_w(const uint32_t* wp, uint32_t sh, uin
     for (int i = 0; i < WPS; ++i) out[i] = __funnelshift_r(w[i], w[i + 1], sh);
 }
 
-template <int N>
-__global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, 6) search_plane_kernel(const SearchArgs a) {
+// COST is a template parameter so that the SAD instance is not compiled around the registers of the SATD code
+// (6 resident CTAs per SM without spills; the SATD instance runs at 5).
+template <int N, int COST>
+__global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, COST == NH_COST_SAD ? 6 : 5) search_plane_kernel(const SearchArgs a) {
     using C = SearchCfg<N>;
     constexpr int SW = C::SW, SB = C::SB, T = C::T, WPS = C::WPS, S = Log2<N>::v;
     extern __shared__ __align__(16) uint32_t smem_w[];
@@ -294,7 +307,7 @@ __global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, 6) search_plane_kern
             for (int j = 0; j < 4; ++j)
 #pragma unroll
                 for (int q = 0; q < WPS; ++q) pr[j][q] = (uint32_t)dc * 0x01010101u;
-            int c = strip_cost_packed<WPS>(pr, ov, a.cost_kind);
+            int c = strip_cost_packed<WPS>(pr, ov, COST);
 #pragma unroll
             for (int off = SB / 2; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
             best = c << 6;
@@ -323,7 +336,7 @@ __global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, 6) search_plane_kern
 #pragma unroll
                 for (int q = 0; q < WPS; ++q) pr[j][q] = __byte_perm(t[2 * q], t[2 * q + 1], 0x7531);
             }
-            int c = strip_cost_packed<WPS>(pr, ov, a.cost_kind);
+            int c = strip_cost_packed<WPS>(pr, ov, COST);
 #pragma unroll
             for (int off = SB / 2; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
             const int key = (c << 6) | 1;
@@ -366,8 +379,8 @@ __global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, 6) search_plane_kern
                     p += angle;
                 }
             }
-            int cv = strip_cost_packed<WPS>(pr, ov, a.cost_kind);
-            int ch = strip_cost_packed<WPS>(prh, oh, a.cost_kind);
+            int cv = strip_cost_packed<WPS>(pr, ov, COST);
+            int ch = strip_cost_packed<WPS>(prh, oh, COST);
 #pragma unroll
             for (int off = SB / 2; off > 0; off >>= 1) {
                 cv += __shfl_xor_sync(0xffffffffu, cv, off);
