@@ -235,6 +235,44 @@ __device__ __forceinline__ void pred_row_pairs(const int16_t* R, int h, int f, u
     }
 }
 
+// Sum of satd_4x4 (metrics.py:29-43) over the 4x4 sub-blocks of a strip held as packed bytes (pr = predicted,
+// o = original; 4 scan lines x WPS words).
+template <int WPS>
+__device__ __forceinline__ int satd_strip_packed(const uint32_t (&pr)[4][WPS], const uint32_t (&o)[4][WPS]) {
+    // Sum of satd_4x4 on 16-bit pairs.  Every lane carries a bias of 0x4000, restored by the constant of
+    // each three-input add, so lanes stay in [0x4000 - 2040, 0x4000 + 2040] and nothing crosses between
+    // them.  Lanes = columns (0, 2) and (1, 3): the column pass is lane-wise; the row pass stops one stage
+    // early because |a + c| + |a - c| = 2 max(|a|, |c|).
+    constexpr uint32_t B2 = 0x40004000u;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int q = 0; q < WPS; ++q) {   // one 4x4 sub-block per packed word column
+        uint32_t e[4], f[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            e[j] = __byte_perm(o[j][q], 0u, 0x4240) + B2 - __byte_perm(pr[j][q], 0u, 0x4240);   // (d0, d2)
+            f[j] = __byte_perm(o[j][q], 0u, 0x4341) + B2 - __byte_perm(pr[j][q], 0u, 0x4341);   // (d1, d3)
+        }
+        auto had4 = [&](uint32_t (&x)[4]) {   // 4-point Hadamard down the rows, two columns per word
+            const uint32_t u0 = x[0] + x[1] - B2, u1 = x[0] - x[1] + B2, u2 = x[2] + x[3] - B2, u3 = x[2] - x[3] + B2;
+            x[0] = u0 + u2 - B2; x[1] = u1 + u3 - B2; x[2] = u0 - u2 + B2; x[3] = u1 - u3 + B2;
+        };
+        had4(e);
+        had4(f);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t sd[2] = {e[r] + f[r] - B2, e[r] - f[r] + B2};   // (a, c) and (b, e')
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t m = __vmaxu2(sd[h], 0x80008000u - sd[h]);   // |.| + bias in both lanes
+                const uint32_t mx = __vmaxu2(m, __byte_perm(m, m, 0x1032));   // max of the two lanes, in both
+                acc = acc + mx - B2;
+            }
+        }
+    }
+    return (int)(2u * (acc & 0xffffu));
+}
+
 // Strip geometry of the packed search: a lane owns 4 scan lines x SW samples (SW = 8 for N >= 8,
 // which amortises the per-scan-line address arithmetic over twice the pixels; 4 for N = 4).
 template <int N, int G>
@@ -308,29 +346,7 @@ __device__ __forceinline__ int strip_cost_u8(int mode, int b0, int s0,
             for (int q = 0; q < WPS; ++q)
                 c = (int)(__vsadu4(pr[j][q], transposed ? oh[j][q] : ov[j][q]) + (uint32_t)c);
     } else {
-#pragma unroll
-        for (int q = 0; q < WPS; ++q) {   // one 4x4 sub-block per packed word column
-            int d[16];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t o4 = transposed ? oh[j][q] : ov[j][q];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    d[4 * j + i] = (int)((o4 >> (8 * i)) & 0xff) - (int)((pr[j][q] >> (8 * i)) & 0xff);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                int a0 = d[j] + d[4 + j], a1 = d[j] - d[4 + j];
-                int a2 = d[8 + j] + d[12 + j], a3 = d[8 + j] - d[12 + j];
-                d[j] = a0 + a2; d[4 + j] = a1 + a3; d[8 + j] = a0 - a2; d[12 + j] = a1 - a3;
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                int a0 = d[4 * i] + d[4 * i + 1], a1 = d[4 * i] - d[4 * i + 1];
-                int a2 = d[4 * i + 2] + d[4 * i + 3], a3 = d[4 * i + 2] - d[4 * i + 3];
-                c += abs(a0 + a2) + abs(a1 + a3) + abs(a0 - a2) + abs(a1 - a3);
-            }
-        }
+        c = transposed ? satd_strip_packed<WPS>(pr, oh) : satd_strip_packed<WPS>(pr, ov);
     }
     return c;
 }

@@ -94,38 +94,7 @@ __device__ __forceinline__ int strip_cost_packed(const uint32_t (&pr)[4][WPS], c
             }
         c = (int)(c0 + c1);
     } else {
-        // Sum of satd_4x4 on 16-bit pairs.  Every lane carries a bias of 0x4000, restored by the constant of
-        // each three-input add, so lanes stay in [0x4000 - 2040, 0x4000 + 2040] and nothing crosses between
-        // them.  Lanes = columns (0, 2) and (1, 3): the column pass is lane-wise; the row pass stops one stage
-        // early because |a + c| + |a - c| = 2 max(|a|, |c|).
-        constexpr uint32_t B2 = 0x40004000u;
-        uint32_t acc = 0;
-#pragma unroll
-        for (int q = 0; q < WPS; ++q) {   // one 4x4 sub-block per packed word column
-            uint32_t e[4], f[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                e[j] = __byte_perm(o[j][q], 0u, 0x4240) + B2 - __byte_perm(pr[j][q], 0u, 0x4240);   // (d0, d2)
-                f[j] = __byte_perm(o[j][q], 0u, 0x4341) + B2 - __byte_perm(pr[j][q], 0u, 0x4341);   // (d1, d3)
-            }
-            auto had4 = [&](uint32_t (&x)[4]) {   // 4-point Hadamard down the rows, two columns per word
-                const uint32_t u0 = x[0] + x[1] - B2, u1 = x[0] - x[1] + B2, u2 = x[2] + x[3] - B2, u3 = x[2] - x[3] + B2;
-                x[0] = u0 + u2 - B2; x[1] = u1 + u3 - B2; x[2] = u0 - u2 + B2; x[3] = u1 - u3 + B2;
-            };
-            had4(e);
-            had4(f);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const uint32_t sd[2] = {e[r] + f[r] - B2, e[r] - f[r] + B2};   // (a, c) and (b, e')
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t m = __vmaxu2(sd[h], 0x80008000u - sd[h]);   // |.| + bias in both lanes
-                    const uint32_t mx = __vmaxu2(m, __byte_perm(m, m, 0x1032));   // max of the two lanes, in both
-                    acc = acc + mx - B2;
-                }
-            }
-        }
-        c = (int)(2u * (acc & 0xffffu));
+        c = satd_strip_packed<WPS>(pr, o);
     }
     return c;
 }
