@@ -216,6 +216,8 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) coder8_plane_mma_kernel(cons
         }
         if (a.pred) T16::store(sP, reinterpret_cast<unsigned char*>(a.pred + blk0 * NN), lane, chunks16);
         const uint32_t sO = smem_u32(s16[cur]) + lane_off, sPa = smem_u32(sP) + lane_off;
+        // unrolled 2x, not 8x as in fused_mma8_kernel: with the 35-mode prediction code in front of it the
+        // kernel waited on instruction fetch (ncu: no-instruction 1.08 warps per issue -> 0.08)
 #pragma unroll 2
         for (int q = 0; q < 8; ++q) {
             uint32_t ro[4], rp[4], pc[4], rr[4];
