@@ -14,11 +14,20 @@ predict -> residual -> forward -> quant -> dequant -> inverse -> recon.
             host inputs -> H2D -> kernel -> D2H of all four outputs, every pass, inside the timing.
   roofline  fused 8x8 kernel: algorithmic bytes (14.5625 B/px) / mean launch time
             against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
-  cpu_baseline  the CPU oracle port (oracle/nh_oracle.c) on the host cores, bounded sample.
+  e2e_noise the same call on SURVEY 8d's `noise` frames (every level segment non-zero: the compact
+            wire format does not apply and everything crosses PCIe as int16) -- brackets `e2e`.
+  cpu_baseline  the CPU oracle port (oracle/nh_oracle.c) on the host cores, bounded sample, plus
+            `reference_numpy`: the reference's OWN numpy functions (imported from
+            $NANO_HEVC_REFERENCE, baseline/_ref or /root/reference when one of them is there) on a
+            fixed-seed subsample of the same workload, 1 core and all cores.
+  secondary BASELINE configs 3 (32 x 4K 35-mode search), 5 (4K wavefront coder, F frames per GPU in one
+            nh_encode_frames call + the NCCL gather of the per-frame statistics) and 4 (2^20-block
+            transform microbench on rotating buffers > 4x L2): Gpix/s, algorithmic B/px, fraction of
+            the measured HBM bandwidth and the limiting pipe (from the ncu captures in profiles/).
 
 --impl reference times the reference's CPU implementation of the same path (the oracle port of
-its numpy functions; the reference itself is pure Python and does not travel to the GPU box) on
-all host threads and prints the same JSON line with "impl": "reference".
+its numpy functions, all host threads; `cpu_baseline.reference_numpy` carries the reference's own
+numpy code when it is importable) and prints the same JSON line with "impl": "reference".
 """
 from __future__ import annotations
 
@@ -81,6 +90,14 @@ def synth_frames(n_frames, seed):
     out = np.empty((n_frames, H, W), np.int16)
     for f in range(n_frames):
         out[f] = np.clip(base + rng.integers(-12, 13, (H, W), dtype=np.int16), 0, 255)
+    return out
+
+
+def noise_frames(n_frames, seed):
+    """SURVEY.md 8d (i) 'noise': default_rng(1234 + frame_idx).integers(0, 256, (H, W))."""
+    out = np.empty((n_frames, H, W), np.int16)
+    for f in range(n_frames):
+        out[f] = np.random.default_rng(1234 + seed + f).integers(0, 256, (H, W), dtype=np.uint8)
     return out
 
 
@@ -152,6 +169,16 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
+def cfg2_config(frames_per_gpu, world):
+    """config of the headline workload: identical in both arms (the driver compares them)."""
+    px_launch = frames_per_gpu * PX_PER_FRAME
+    return {"workload": "cfg2", "frame": f"{W}x{H}", "block": N, "frames_per_gpu": frames_per_gpu,
+            "blocks_per_gpu": frames_per_gpu * BLOCKS_PER_FRAME, "modes": ["dc", "planar"], "qps": list(QPS),
+            "passes_per_step": PASSES,
+            "l2": f"inputs+outputs {BYTES_PER_PX * px_launch / 1e9:.2f} GB per launch >> 126 MB L2 (no flush needed)",
+            "parallelism": f"frames sharded over {world} GPU(s), no collective on the hot path"}
+
+
 # ------------------------------------------------------------------ CPU legs
 def cpu_port_rate(n_frames, threads):
     """Oracle port (oracle/nh_oracle.c) over `n_frames` frames x 8 passes on `threads` host threads."""
@@ -165,6 +192,61 @@ def cpu_port_rate(n_frames, threads):
             O.pipeline_dcplanar_batch(orig, top, left, tr, bl, mode, qp, threads=threads)
     dt = time.perf_counter() - t0
     return n_frames * PX_PER_FRAME * PASSES / dt / 1e6, dt
+
+
+# The reference's own numpy functions (never copied into this repository): importable when the driver or
+# the builder has placed the unmodified package under one of these roots.
+def _reference_root():
+    for root in (os.environ.get("NANO_HEVC_REFERENCE"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if root and os.path.isdir(os.path.join(root, "nano_hevc")):
+            return root
+    return None
+
+
+def _numpy_ref_worker(job):
+    """One process: the cfg2 composition (README.md:55-71) on `n` 8x8 blocks with the reference's functions."""
+    root, seed, n = job
+    sys.path.insert(0, root)
+    import nano_hevc as R
+    frames = synth_frames(1, seed)
+    orig, top, left, tr, bl = frame_to_cfg2_inputs(frames)
+    idx = np.random.default_rng(seed).choice(orig.shape[0], n, replace=False)
+    t0 = time.perf_counter()
+    for b in idx:
+        for mode in MODES:
+            pred = (R.intra_dc_predict(top[b], left[b], N) if mode == 1 else
+                    R.intra_planar_predict(top[b], left[b], int(tr[b]), int(bl[b]), N))
+            res = R.residual_block(orig[b], pred)
+            co = R.forward_transform(res)
+            for qp in QPS:
+                lv = R.quantize_block(co, qp)
+                rr = R.inverse_transform(R.dequantize_block(lv, qp))
+                R.clip_to_pixel_range(R.reconstruct_block(pred, rr))
+    return time.perf_counter() - t0
+
+
+def reference_numpy_rate(blocks_per_proc=384):
+    """The reference's own numpy code on a fixed-seed subsample of cfg2:
+    Mpix/s on 1 core and on all cores (one process per core).  Note the composition shares the prediction and
+    the forward transform between the four QPs of a mode, as a caller of the reference would."""
+    root = _reference_root()
+    if root is None:
+        return {"reference_numpy": None, "why": "the reference package is not present on this box "
+                                                "(NANO_HEVC_REFERENCE, baseline/_ref and /root/reference probed)"}
+    import multiprocessing as mp
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    px = blocks_per_proc * N * N * PASSES
+    t1 = _numpy_ref_worker((root, 0, blocks_per_proc))
+    with mp.get_context("spawn").Pool(cores) as pool:
+        times = pool.map(_numpy_ref_worker, [(root, 1 + i, blocks_per_proc) for i in range(cores)])
+    wall = max(times)   # the processes run concurrently; each times its own compute loop
+    return {"reference_numpy": {"kind": "reference", "value_1core": px / t1 / 1e6, "value_allcores": cores * px / wall / 1e6,
+                                "unit": UNIT, "cores": cores, "root": os.path.relpath(root, ROOT) if root.startswith(ROOT) else root,
+                                "sample": f"{blocks_per_proc} blocks x {PASSES} passes per process (fixed seed), 1 process "
+                                          f"({t1:.1f} s) then {cores} concurrent processes (slowest {wall:.1f} s)"}}
 
 
 def run_reference(args, rank, world):
@@ -187,14 +269,120 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
         "data": "synthetic",
-        "config": {"workload": "cfg2", "frame": f"{W}x{H}", "block": N, "modes": ["dc", "planar"], "qps": list(QPS),
-                   "note": "reference's CPU implementation of the path = oracle port of its numpy functions "
-                           "(the pure-Python reference does not travel to the GPU box)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": cfg2_config(args.frames, world),
+        "note": "reference's CPU implementation of the path = oracle port of its numpy functions on all host "
+                "threads; each step is a bounded sample of the cfg2 batch (see cpu_baseline.sample)",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         **reference_numpy_rate()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit_json(line)
+
+
+# ------------------------------------------------------------------- secondary configs (GPU)
+def _synth_plane_dev(torch, Hh, Ww, seed, dev):
+    g = torch.Generator(device=dev).manual_seed(4321 + seed)
+    yy = torch.arange(Hh, device=dev).view(Hh, 1)
+    xx = torch.arange(Ww, device=dev).view(1, Ww)
+    base = 40 + (150 * xx) // (Ww - 1) + (60 * yy) // (Hh - 1)
+    return (base + torch.randint(-12, 13, (Hh, Ww), generator=g, device=dev)).clamp(0, 255).to(torch.int16)
+
+
+def run_secondary(torch, dist, batched, dev, rank, world, peak):
+    """BASELINE configs 3, 5 and 4 on every rank (weak scaling: per-GPU work fixed), CUDA events, max over
+    ranks; value = work of all ranks / that time.  Limiting pipes are the ncu findings in profiles/."""
+    H4, W4 = 2160, 3840
+
+    def timed(fn, reps, warmup=1):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def entry(px_per_gpu, bpp, ms, **extra):
+        gpix = world * px_per_gpu / (ms / 1e3) / 1e9
+        gbs = px_per_gpu * bpp / (ms / 1e3) / 1e9          # per GPU
+        return {"Gpix_s": gpix, "ms": ms, "bytes_per_px": bpp, "GBs_per_gpu": gbs, "frac_hbm": gbs / peak, **extra}
+
+    out = {"n_gpus": world, "peak_hbm_gbs": peak,
+           "note": "per-GPU work fixed (weak scaling); Gpix_s is the aggregate over all ranks, frac_hbm per GPU"}
+    # ---- cfg3: 32 4K frames per GPU, one nh_encode_frames call (search + winner pipeline, all outputs)
+    F3 = 32
+    planes = torch.stack([_synth_plane_dev(torch, H4, W4, 100 * rank + i, dev) for i in range(F3)])
+    cfg3 = {}
+    for n in (8, 32):
+        px = F3 * (H4 // n) * (W4 // n) * n * n
+        res = batched.encode_frames(planes, n, cost="sad", qp=27, stats=False)
+        for cost in ("sad", "satd"):
+            ms = timed(lambda: batched.encode_frames(planes, n, cost=cost, qp=27, stats=False, out=res), 2)
+            cfg3[f"N{n}_{cost}"] = entry(px, 2 + 12 + 5 / (n * n), ms, frames_per_gpu=F3,
+                                         limiter="ALU pipe (search kernel), see profiles/")
+        del res
+    out["cfg3"] = cfg3
+    # ---- cfg5: wavefront coder, F 4K frames per GPU in one call + one frame alone (latency); stats by NCCL
+    cfg5 = {}
+    for n in (8, 32):
+        px1 = (H4 // n) * (W4 // n) * n * n
+        for F in (1, 8):
+            sub = planes[:F]
+            res = batched.encode_frames(sub, n, cost="sad", qp=27, recon_neighbours=True)
+            scratch = torch.empty((int(1 << 26),), dtype=torch.uint8, device=dev)
+            ms = timed(lambda: batched.encode_frames(sub, n, cost="sad", qp=27, recon_neighbours=True, out=res,
+                                                     scratch=scratch), 2)
+            e = entry(F * px1, 2 + 12 + 5 / (n * n), ms, frames_per_gpu=F,
+                      limiter="dependency latency (anti-diagonal wavefront)")
+            if F == 8:   # final gather of the per-frame statistics: the only collective of the config
+                st = res.stats.clone()
+                if world > 1:
+                    g = [torch.empty_like(st) for _ in range(world)]
+                    dist.all_gather(g, st)
+                    st = torch.cat(g)
+                sse = st[:, 0].double() / st[:, 1].double()
+                e["psnr_first_frames"] = [float(v) for v in (10 * torch.log10(255.0 ** 2 / sse))[:2].tolist()]
+                e["frames_total"] = int(st.shape[0])
+            cfg5[f"N{n}_F{F}"] = e
+            del res, scratch
+    out["cfg5"] = cfg5
+    del planes
+    # ---- cfg4: 2^20 blocks per size, forward / inverse alone, rotating over buffers > 4x the 126 MB L2
+    cfg4 = {}
+    Bn = 1 << 20
+    g = torch.Generator(device=dev).manual_seed(99)
+    for n, dst in ((4, False), (4, True), (8, False), (16, False), (32, False)):
+        per_call = Bn * n * n * 6                      # int16 in + int32 out
+        rot = max(2, -(-(4 * 126 * (1 << 20)) // per_call) + 1)
+        xs = [torch.randint(-255, 256, (Bn, n, n), generator=g, device=dev, dtype=torch.int16) for _ in range(rot)]
+        L = __import__("nano_hevc_b200")._lib.lib()
+        co = [torch.empty((Bn, n, n), dtype=torch.int32, device=dev) for _ in range(rot)]
+        rs = [torch.empty((Bn, n, n), dtype=torch.int32, device=dev) for _ in range(rot)]
+        st = torch.cuda.current_stream().cuda_stream
+
+        def fwd():
+            for x, c in zip(xs, co):
+                L.nh_forward_transform(x.data_ptr(), 0, c.data_ptr(), Bn, n, int(dst), st)
+
+        def inv():
+            for c, r in zip(co, rs):
+                L.nh_inverse_transform(c.data_ptr(), r.data_ptr(), Bn, n, int(dst), st)
+
+        tag = f"N{n}{'dst' if dst else ''}"
+        cfg4[f"{tag}_forward"] = entry(rot * Bn * n * n, 6, timed(fwd, 3), rotating_buffers=rot)
+        cfg4[f"{tag}_inverse"] = entry(rot * Bn * n * n, 8, timed(inv, 3), rotating_buffers=rot)
+        del xs, co, rs
+    out["cfg4"] = cfg4
+    return out
 
 
 # ------------------------------------------------------------------- GPU leg
@@ -205,6 +393,9 @@ def run_ours(args, rank, world, local_rank):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    # pinned buffers and the library's host threads stay on the NUMA node of this rank's GPU
+    from nano_hevc_b200 import hostbind
+    numa = hostbind.bind_to_gpu_numa_node(local_rank) if world > 1 else {"bound": False, "note": "single rank: not bound"}
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -266,64 +457,89 @@ def run_ours(args, rank, world, local_rank):
     launch_s = total_ms / 1e3 / launches
     achieved = alg_bytes / launch_s / 1e9
     peak, peak_src = measured_peak()
-    traffic = None
+    traffic, traffic_source = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic_fused8.json")
     if os.path.exists(tpath):
         try:
             t = json.load(open(tpath))
             traffic = t["dram_bytes_per_px"] * px_launch
+            traffic_source = "ncu capture profiles/traffic_fused8.json (dram bytes per px of an earlier run x this run's px per launch; not measured in this run)"
         except Exception:
             traffic = None
 
     # ---- e2e: host buffers through the C ABI, H2D + kernel + D2H inside the timed region
-    e2e = None
+    e2e = e2e_noise = None
     if not args.no_e2e:
-        os.environ.setdefault("NH_HOST_THREADS", str(max(2, min(8, (os.cpu_count() or 8) // max(world, 1)))))
-        Fe = min(F, args.e2e_frames)
-        Be = Fe * BLOCKS_PER_FRAME
+        try:
+            avail = len(os.sched_getaffinity(0))
+        except AttributeError:
+            avail = os.cpu_count() or 8
+        # host threads of the widening pass: this rank's share of the cores the job may use
+        share = numa.get("cpus_before", avail) // max(world, 1) if world > 1 else avail - 1
+        os.environ.setdefault("NH_HOST_THREADS", str(max(2, min(16, share))))
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        he = frame_to_cfg2_inputs(synth_frames(Fe, 100 + rank))
-        h_in_p = [pin(a) for a in he]
-        h_out = [torch.empty((Be, N, N), dtype=dt).pin_memory() for dt in (torch.int16, torch.int32, torch.int32, torch.int16)]
         chunk = int(os.environ.get("NH_E2E_CHUNK", 128 * 1024))  # measured best of 4K..128K (profiles/r1_notes.md)
         L = _lib.lib()
         sbytes = int(L.nh_host_pipeline_scratch_bytes(N, chunk))
         scratch = torch.empty((sbytes,), dtype=torch.uint8, device=dev)
-
-        def e2e_step():
-            for mode in MODES:
-                for qp in QPS:
-                    _lib.check(L.nh_host_pipeline_dcplanar(
-                        *[t.data_ptr() for t in h_in_p], None, mode, Be, N, qp, 1, 0, 8,
-                        *[t.data_ptr() for t in h_out], scratch.data_ptr(), sbytes, chunk))
-
-        e2e_step()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ksteps = max(1, min(args.steps, 5))
-        t0 = time.perf_counter()
-        for _ in range(ksteps):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        delivered = PASSES * sum(t.numel() * t.element_size() for t in h_out)
-        # bytes that really crossed PCIe, counted by the library from its cudaMemcpyAsync calls (the
-        # output wire format is compact and data dependent); last call x PASSES calls per step
         import ctypes
-        b_up, b_down = ctypes.c_int64(0), ctypes.c_int64(0)
-        _lib.check(L.nh_host_pipeline_last_transfer(ctypes.byref(b_up), ctypes.byref(b_down)))
-        h2d, d2h = PASSES * b_up.value, PASSES * b_down.value
-        e2e = {"value": world * Fe * PX_PER_FRAME * PASSES * ksteps / float(dt.item()) / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_bytes_delivered_per_step": delivered,
-               "frames_per_pass": Fe, "steps": ksteps,
-               "api": "nh_host_pipeline_dcplanar (C ABI, pinned host buffers, 3-stream chunked overlap; compact wire format: int8 coefficients + int16 exception segments, all-zero level segments elided, widened / zero-filled on host threads; d2h bytes are those of the last pass)",
-               "host_threads": int(os.environ["NH_HOST_THREADS"])}
-        # spot-check the e2e outputs against the device-resident path
-        chk = batched.fused_block_pipeline(*[t.to(dev) for t in h_in_p], MODES[-1], QPS[-1])
-        assert torch.equal(chk.levels.cpu(), h_out[2]) and torch.equal(chk.recon.cpu(), h_out[3]), "e2e mismatch"
+
+        def e2e_leg(frames_np, ksteps, what):
+            Fe = frames_np.shape[0]
+            Be = Fe * BLOCKS_PER_FRAME
+            h_in_p = [pin(a) for a in frame_to_cfg2_inputs(frames_np)]
+            h_out = [torch.empty((Be, N, N), dtype=dt).pin_memory() for dt in (torch.int16, torch.int32, torch.int32, torch.int16)]
+
+            def e2e_step():
+                for mode in MODES:
+                    for qp in QPS:
+                        _lib.check(L.nh_host_pipeline_dcplanar(
+                            *[t.data_ptr() for t in h_in_p], None, mode, Be, N, qp, 1, 0, 8,
+                            *[t.data_ptr() for t in h_out], scratch.data_ptr(), sbytes, chunk))
+
+            e2e_step()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(ksteps):
+                e2e_step()
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            delivered = PASSES * sum(t.numel() * t.element_size() for t in h_out)
+            # bytes that really crossed PCIe, counted by the library from its cudaMemcpyAsync calls (the
+            # output wire format is compact and data dependent); last call x PASSES calls per step
+            b_up, b_down = ctypes.c_int64(0), ctypes.c_int64(0)
+            _lib.check(L.nh_host_pipeline_last_transfer(ctypes.byref(b_up), ctypes.byref(b_down)))
+            res = {"value": world * Fe * PX_PER_FRAME * PASSES * ksteps / float(dt.item()) / 1e6, "unit": UNIT,
+                   "h2d_bytes_per_step": PASSES * b_up.value, "d2h_bytes_per_step": PASSES * b_down.value,
+                   "host_bytes_delivered_per_step": delivered, "frames_per_pass": Fe, "steps": ksteps, "content": what,
+                   "host_threads": int(os.environ["NH_HOST_THREADS"]), "host_cores_available": avail, "numa": numa}
+            # spot-check the e2e outputs against the device-resident path (first 8 frames)
+            nb = min(Be, 8 * BLOCKS_PER_FRAME)
+            chk = batched.fused_block_pipeline(*[t[:nb].to(dev) for t in h_in_p], MODES[-1], QPS[-1])
+            assert torch.equal(chk.levels.cpu(), h_out[2][:nb]) and torch.equal(chk.recon.cpu(), h_out[3][:nb]), "e2e mismatch"
+            assert torch.equal(chk.coeff.cpu(), h_out[1][:nb]) and torch.equal(chk.pred.cpu(), h_out[0][:nb]), "e2e mismatch"
+            return res
+
+        Fe = min(F, args.e2e_frames)
+        base_e = synth_frames(min(Fe, 16), 100 + rank)
+        frames_e = np.concatenate([base_e] * (-(-Fe // base_e.shape[0])))[:Fe]
+        e2e = e2e_leg(frames_e, max(1, min(args.steps, 3)), "smooth (SURVEY 8d iii), the frames of the headline config")
+        e2e["api"] = ("nh_host_pipeline_dcplanar (C ABI, pinned host buffers, 3-stream chunked overlap; compact wire format: "
+                      "int8 coefficients + int16 exception segments, all-zero level segments elided, widened / zero-filled "
+                      "on host threads into the reference's int32 arrays; d2h bytes are those of the last pass)")
+        e2e["bound"] = ("host DRAM + PCIe: 12 B/px of int32 / int16 results are written to host memory per pass on top of the DMA "
+                        "traffic (tools/ubench_pcie.py: 46 GB/s per direction under duplex load)")
+        Fn = min(Fe, 32)
+        e2e_noise = e2e_leg(noise_frames(Fn, 1000 * rank), 1, "noise (SURVEY 8d i): every level segment non-zero, int16 wire format")
+        del scratch
+
+    secondary = None
+    if not args.no_secondary:
+        secondary = run_secondary(torch, dist, batched, dev, rank, world, peak)
 
     if rank == 0:
         cpu = None
@@ -333,22 +549,21 @@ def run_ours(args, rank, world, local_rank):
             frames_cpu = max(2, min(128, 4 * thr))  # ~15-30 core-seconds of CPU work
             rate, dt = cpu_port_rate(frames_cpu, thr)
             cpu = {"value": rate, "unit": UNIT, "cores": thr, "kind": "port",
-                   "sample": f"{frames_cpu} frames x {PASSES} passes of the same workload, {dt:.1f} s wall"}
+                   "sample": f"{frames_cpu} frames x {PASSES} passes of the same workload, {dt:.1f} s wall",
+                   **reference_numpy_rate()}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "cfg2", "frame": f"{W}x{H}", "block": N, "frames_per_gpu": F,
-                       "blocks_per_gpu": B, "modes": ["dc", "planar"], "qps": list(QPS), "passes_per_step": PASSES,
-                       "l2": f"inputs+outputs {alg_bytes / 1e9:.2f} GB per launch >> 126 MB L2 (no flush needed)",
-                       "parallelism": f"frames sharded over {world} GPU(s), no collective on the hot path"},
+            "config": cfg2_config(F, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": {1: "fused_unit_kernel<8>", 2: "fused_unit_kernel_v2<8>", 3: "fused_unit_kernel_v3<8>", 4: "fused_mma8_kernel"}[args.fused_impl], "bytes_per_px": BYTES_PER_PX,
+                         "traffic": traffic, "traffic_source": traffic_source, "kernel": {1: "fused_unit_kernel<8>", 2: "fused_unit_kernel_v2<8>", 3: "fused_unit_kernel_v3<8>", 4: "fused_mma8_kernel"}[args.fused_impl], "bytes_per_px": BYTES_PER_PX,
                          "px_per_launch": px_launch, "launch_ms": launch_s * 1e3, "peak_source": peak_src,
                          "frac_of_nominal_8TBs": achieved / 8000.0,
                          "note": "peak is the driver's b.copy_(a) probe (1 read : 1 write); this write-dominated "
                                  "stream can run marginally faster than that probe, so frac may exceed 1"},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "e2e_noise": e2e_noise, "gpu_launches": launches, "clocks": clocks,
+            "secondary": secondary,
             "stats": {"nonzero_levels_last_pass": int(stats[0].item()), "sse_last_pass": int(stats[1].item())},
         }
         emit_json(line)
@@ -363,7 +578,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=128, help="1080p frames per GPU per pass")
-    ap.add_argument("--e2e-frames", type=int, default=16)
+    ap.add_argument("--e2e-frames", type=int, default=128, help="frames per pass of the e2e leg (default: the full config)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the cfg3 / cfg5 / cfg4 measurements")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--fused-impl", type=int, default=4, choices=[1, 2, 3, 4],

@@ -70,7 +70,8 @@ int nh_inverse_transform(const int32_t* coeff, int32_t* residual, int64_t n_bloc
                          int use_dst, void* stream);
 
 /* ---------------------------------------------- K5: quant (batched) */
-/* nano_hevc/quant.py:41-79 quantize(coeff, qp, size, is_intra) / :126-137 quantize_block */
+/* nano_hevc/quant.py:41-79 quantize(coeff, qp, size, is_intra) / :126-137 quantize_block.
+ * Like the reference, any size is taken through int(log2(size)); 1..63 is accepted. */
 int nh_quantize(const int32_t* coeff, int32_t* level, int64_t n_elems, int qp, int size,
                 int is_intra, void* stream);
 /* nano_hevc/quant.py:82-123 dequantize(level, qp, size) / :140-150 dequantize_block
@@ -82,6 +83,10 @@ int nh_dequantize(const int32_t* level, int32_t* coeff, int64_t n_elems, int qp,
 /* nano_hevc/intra.py:46-62 intra_dc_predict(top, left, size); top,left (B,N) */
 int nh_intra_dc_predict(const int16_t* top, const int16_t* left, int16_t* pred, int64_t n_blocks,
                         int size, void* stream);
+/* The same function for reference arrays of another length than `size`: intra.py:61 adds top.sum() and
+ * left.sum() of whatever it is given.  top (B, n_top), left (B, n_left). */
+int nh_intra_dc_predict_ragged(const int16_t* top, int n_top, const int16_t* left, int n_left,
+                               int16_t* pred, int64_t n_blocks, int size, void* stream);
 /* nano_hevc/intra.py:81-113 intra_planar_predict(top, left, top_right, bottom_left, size);
  * top,left (B,N); top_right, bottom_left (B,) */
 int nh_intra_planar_predict(const int16_t* top, const int16_t* left, const int16_t* top_right,
@@ -118,14 +123,18 @@ int nh_clip_to_pixel_range(const int16_t* in, int16_t* out, int64_t n_elems, int
 /* Note on streams: the size 4 / 8 kernels hand out their work through a 32-bit counter that belongs
  * to the stream of the call (a slot of a static device array that the last warp of a launch re-arms
  * for the next one).  Calls on one stream, and concurrent calls on different streams, are
- * independent; a captured CUDA graph containing such a launch must not be replayed concurrently
- * with itself. */
+ * independent; a slot only moves to another stream after an event recorded behind its last launch
+ * has completed (more than 4096 distinct streams per device).  A captured CUDA graph containing such
+ * a launch must not be replayed concurrently with itself. */
 int nh_fused_pipeline_dcplanar(const int16_t* orig, const int16_t* top, const int16_t* left,
                                const int16_t* top_right, const int16_t* bottom_left,
                                const uint8_t* modes, int mode, int64_t n_blocks, int size, int qp,
                                int is_intra, int use_dst, int bit_depth, int16_t* pred,
                                int32_t* coeff, int32_t* levels, int16_t* recon, void* stream);
-/* Selects the kernel generation behind nh_fused_pipeline_dcplanar for size 4 / 8:
+/* The three nh_set_*_impl selectors below exist for A/B profiling.  They are PER CALLING THREAD
+ * (thread-local): a selection affects the later calls of the thread that made it and nothing else, so
+ * the library keeps no mutable state shared between callers.
+ * Selects the kernel generation behind nh_fused_pipeline_dcplanar for size 4 / 8:
  * 4 (default: at size 8 the four transform passes run as warp-level f16 tensor-core MMAs, exact
  * for 8-bit samples with an exact fallback otherwise; size 4 uses a rolled one-block-per-lane
  * variant of generation 2), 2 (cp.async
@@ -189,6 +198,25 @@ int nh_encode_frame(const int16_t* src, int height, int width, int pitch, int si
                     int16_t* pred, int32_t* coeff, int32_t* levels, int16_t* recon_plane,
                     void* scratch, int64_t scratch_bytes, void* stream);
 
+/* The same coders over a BATCH of frames in one call (BASELINE configs 3 and 5: "32 x 4K", "8-frame 4K
+ * batch"): frame f is the (height, pitch) plane at src + f * frame_stride (frame_stride >= height * pitch,
+ * in samples; recon_planes uses the same strides) and every block-major output holds frame f at block
+ * offset f * (height / size) * (width / size).  Frames are independent -- each is coded exactly as
+ * nh_encode_frame would code it -- but one launch covers all of them: with recon_neighbours != 0 the block
+ * rows of all frames share the wavefront scheduler (tickets interleave the frames), so F frames fill the
+ * GPU where one frame occupies a few hundred warps.
+ * stats: optional (F, 4) int64 device tensor, written by this call:
+ *   { sum (src - recon)^2 over the whole plane (numerator of metrics.py:7-21; uncovered rows count as in
+ *     __main__.py:135-137), height * width, sum of the winners' costs, number of non-zero levels };
+ *   needs recon_planes, and costs / levels for the last two entries (0 otherwise).
+ * scratch: nh_encode_frames_scratch_bytes(n_frames, height, width, size) bytes (recon_neighbours != 0 only). */
+int64_t nh_encode_frames_scratch_bytes(int n_frames, int height, int width, int size);
+int nh_encode_frames(const int16_t* src, int n_frames, int64_t frame_stride, int height, int width,
+                     int pitch, int size, int cost_kind, int qp, int recon_neighbours, int bit_depth,
+                     uint8_t* modes, int32_t* costs, int16_t* pred, int32_t* coeff, int32_t* levels,
+                     int16_t* recon_planes, int64_t* stats, void* scratch, int64_t scratch_bytes,
+                     void* stream);
+
 /* -------------------------------------------------- K9: reductions */
 /* Integer numerators of nano_hevc/metrics.py: out[0] = sum (a-b)^2  (mse/psnr, :7-21),
  * out[1] = sum |a-b| (sad, :24-26).  a, b int16, n_elems elements; out: 2 x int64 on the
@@ -198,6 +226,21 @@ int nh_reduce_sse_sad(const int16_t* a, const int16_t* b, int64_t n_elems, int64
 /* Same over a (height, width) window of two pitched planes. */
 int nh_reduce_sse_sad_2d(const int16_t* a, int pitch_a, const int16_t* b, int pitch_b, int height,
                          int width, int64_t* out, void* stream);
+/* Wide-input reductions behind the per-block metric wrappers: the reference widens before it reduces
+ * (metrics.py:9 float64, :26 / :33 int32, :48 int64), so uint16 samples and the int32 output of
+ * inverse_transform must not be narrowed to int16.  a, b int32 (b may be NULL = zeros), n elements.
+ *   out[0] = sum (a-b)^2, difference in int64, accumulated modulo 2^64   (residual_energy, metrics.py:46-48)
+ *   out[1] = sum |a-b| with the int32 wrap-around of metrics.py:26, summed in int64   (sad)
+ *   *fsum  = sum of float64 (a-b)^2                                       (mse for sums beyond 2^53)
+ * out: 2 x int64, fsum: 1 x double, device, zeroed by this call. */
+int nh_reduce_metrics_i32(const int32_t* a, const int32_t* b, int64_t n_elems, int64_t* out, double* fsum,
+                          void* stream);
+/* metrics.py:7-10 mse for float64 inputs: *fsum = sum (a-b)^2 in float64 (summation order differs from
+ * numpy's pairwise sum: equal to ~1e-15 relative). */
+int nh_reduce_sse_f64(const double* a, const double* b, int64_t n_elems, double* fsum, void* stream);
+/* metrics.py:29-43 satd_4x4 on int32 inputs with the reference's int32 arithmetic: a, b (B,4,4) int32,
+ * out (B,) int64. */
+int nh_satd_4x4_i32(const int32_t* a, const int32_t* b, int64_t n_blocks, int64_t* out, void* stream);
 /* Per-block costs of (B,N,N) pairs: sad (B,) i32 and satd (B,) i32 (sum of satd_4x4 over the
  * 4x4 sub-blocks, metrics.py:29-43), energy (B,) i64 = sum (a-b)^2 (residual_energy, :46-48).
  * Any output may be NULL. */

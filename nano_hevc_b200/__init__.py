@@ -192,9 +192,17 @@ def intra_dc_predict(top: np.ndarray, left: np.ndarray, size: int) -> np.ndarray
     """intra.py:46-62."""
     from . import batched
     _check_pred_size(size)
-    t = _dev(np.asarray(top).reshape(-1)[:size], np.int16).reshape(1, -1)
-    l = _dev(np.asarray(left).reshape(-1)[:size], np.int16).reshape(1, -1)
-    return _host(batched.intra_dc_predict_batched(t, l, size)[0])
+    t = _dev(np.asarray(top).reshape(-1), np.int16).reshape(1, -1)
+    l = _dev(np.asarray(left).reshape(-1), np.int16).reshape(1, -1)
+    if t.shape[1] == size and l.shape[1] == size:
+        return _host(batched.intra_dc_predict_batched(t, l, size)[0])
+    # intra.py:61 sums the whole arrays whatever their length
+    torch = _torch()
+    out = torch.empty((1, size, size), dtype=torch.int16, device=t.device)
+    _lib.check(_lib.lib().nh_intra_dc_predict_ragged(t.data_ptr(), t.shape[1], l.data_ptr(), l.shape[1],
+                                                     out.data_ptr(), 1, size,
+                                                     torch.cuda.current_stream().cuda_stream))
+    return _host(out[0])
 
 
 def intra_dc_predict_4x4(top: np.ndarray, left: np.ndarray) -> np.ndarray:
@@ -277,23 +285,72 @@ def clip_to_pixel_range(block: np.ndarray, bit_depth: int = 8) -> np.ndarray:
 
 
 # -------------------------------------------------------------------- metrics
+# The reference widens before it reduces (metrics.py:9 float64, :26 / :33 int32, :48 int64).  Inputs whose
+# dtype fits int16 take the int16 kernels; anything wider (uint16 samples, the int32 output of
+# inverse_transform, int64) goes through the int32 kernels after the same astype(int32) wrap-around as
+# metrics.py:26, or -- for mse on values an int32 cannot hold -- through the float64 kernel.
+_NARROW = (np.dtype(np.int8), np.dtype(np.uint8), np.dtype(np.int16), np.dtype(np.bool_))
+
+
+def _is_narrow(*arrs):
+    return all(a.dtype in _NARROW for a in arrs)
+
+
+def _wide_reduce(a32, b32):
+    """(sum d^2 mod 2^64, sum |d| int32-wrap, float64 sum d^2) of int32 arrays on the device."""
+    torch = _torch()
+    x = _dev(a32, np.int32).reshape(-1)
+    y = _dev(b32, np.int32).reshape(-1) if b32 is not None else None
+    out = torch.empty((2,), dtype=torch.int64, device=x.device)
+    fs = torch.empty((1,), dtype=torch.float64, device=x.device)
+    _lib.check(_lib.lib().nh_reduce_metrics_i32(x.data_ptr(), None if y is None else y.data_ptr(), x.numel(),
+                                                out.data_ptr(), fs.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream))
+    o = out.cpu().numpy()
+    return int(o[0]), int(o[1]), float(fs.item())
+
+
 def _pair16(a, b):
-    a, b = np.asarray(a), np.asarray(b)
-    return _dev(a, np.int16).reshape(-1), _dev(b, np.int16).reshape(-1), a.size
+    return _dev(a, np.int16).reshape(-1), _dev(b, np.int16).reshape(-1)
 
 
 def sad(a: np.ndarray, b: np.ndarray) -> int:
     """metrics.py:24-26."""
     from . import batched
-    x, y, _ = _pair16(a, b)
-    return int(batched.sse_sad(x, y)[1].item())
+    a, b = np.asarray(a), np.asarray(b)
+    if _is_narrow(a, b):
+        x, y = _pair16(a, b)
+        return int(batched.sse_sad(x, y)[1].item())
+    return _wide_reduce(a.astype(np.int32), b.astype(np.int32))[1]
+
+
+def _sum_sq(a, b):
+    """Sum of squared differences as the float64 value np.sum(diff ** 2) has (metrics.py:9-10)."""
+    from . import batched
+    torch = _torch()
+    if _is_narrow(a, b):
+        x, y = _pair16(a, b)
+        return np.float64(int(batched.sse_sad(x, y)[0].item()))
+    fits32 = all(np.issubdtype(v.dtype, np.integer) and
+                 (v.dtype.itemsize < 4 or v.dtype == np.int32 or
+                  (v.size == 0 or (int(v.min()) >= -2**31 and int(v.max()) < 2**31))) for v in (a, b))
+    if fits32:
+        sse, _, fsum = _wide_reduce(a.astype(np.int32), b.astype(np.int32))
+        # below 2^53 every square and every partial sum is an exactly representable integer, so the
+        # float64 sum of the reference equals the integer sum whatever its order
+        return np.float64(sse) if fsum < 2.0 ** 53 else np.float64(fsum)
+    x = _dev(a, np.float64).reshape(-1)
+    y = _dev(b, np.float64).reshape(-1)
+    fs = torch.empty((1,), dtype=torch.float64, device=x.device)
+    _lib.check(_lib.lib().nh_reduce_sse_f64(x.data_ptr(), y.data_ptr(), x.numel(), fs.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream))
+    return np.float64(fs.item())
 
 
 def mse(original: np.ndarray, reconstructed: np.ndarray) -> float:
     """metrics.py:7-10 (exact integer SSE on the device, float64 mean on the host)."""
-    from . import batched
-    x, y, n = _pair16(original, reconstructed)
-    return float(np.float64(int(batched.sse_sad(x, y)[0].item())) / np.float64(n))
+    a, b = np.asarray(original), np.asarray(reconstructed)
+    return float(_sum_sq(a, b) / np.float64(a.size))
 
 
 def psnr(original: np.ndarray, reconstructed: np.ndarray, peak: int = 255) -> float:
@@ -307,17 +364,28 @@ def psnr(original: np.ndarray, reconstructed: np.ndarray, peak: int = 255) -> fl
 def satd_4x4(a: np.ndarray, b: np.ndarray) -> int:
     """metrics.py:29-43."""
     from . import batched
-    x = _dev(np.asarray(a).reshape(4, 4), np.int16).reshape(1, 4, 4)
-    y = _dev(np.asarray(b).reshape(4, 4), np.int16).reshape(1, 4, 4)
-    return int(batched.block_costs(x, y, outputs=("satd",))[1][0].item())
+    a, b = np.asarray(a).reshape(4, 4), np.asarray(b).reshape(4, 4)
+    if _is_narrow(a, b):
+        x, y = _dev(a, np.int16).reshape(1, 4, 4), _dev(b, np.int16).reshape(1, 4, 4)
+        return int(batched.block_costs(x, y, outputs=("satd",))[1][0].item())
+    torch = _torch()
+    x, y = _dev(a.astype(np.int32), np.int32), _dev(b.astype(np.int32), np.int32)
+    out = torch.empty((1,), dtype=torch.int64, device=x.device)
+    _lib.check(_lib.lib().nh_satd_4x4_i32(x.data_ptr(), y.data_ptr(), 1, out.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream))
+    return int(out.item())
 
 
 def residual_energy(residual: np.ndarray) -> int:
     """metrics.py:46-48."""
     from . import batched
-    r = _dev(np.asarray(residual), np.int16).reshape(-1)
-    z = _torch().zeros_like(r)
-    return int(batched.sse_sad(r, z)[0].item())
+    r = np.asarray(residual)
+    if _is_narrow(r):
+        x = _dev(r, np.int16).reshape(-1)
+        return int(batched.sse_sad(x, _torch().zeros_like(x))[0].item())
+    if r.dtype == np.int32 or r.dtype == np.uint16:
+        return _wide_reduce(r.astype(np.int32), None)[0]
+    raise ValueError(f"residual_energy: dtype {r.dtype} is outside the supported domain (int8 .. int32)")
 
 
 __all__ = [

@@ -35,6 +35,7 @@ PROTOTYPES = {
     "nh_quantize": (_i, [_p, _p, _i64, _i, _i, _i, _p]),
     "nh_dequantize": (_i, [_p, _p, _i64, _i, _i, _p]),
     "nh_intra_dc_predict": (_i, [_p, _p, _p, _i64, _i, _p]),
+    "nh_intra_dc_predict_ragged": (_i, [_p, _i, _p, _i, _p, _i64, _i, _p]),
     "nh_intra_planar_predict": (_i, [_p, _p, _p, _p, _p, _i64, _i, _p]),
     "nh_intra_predict_modes": (_i, [_p, _p, _p, _p, _i, _i, _p, _i64, _i, _p]),
     "nh_residual_block": (_i, [_p, _p, _p, _i64, _p]),
@@ -53,8 +54,14 @@ PROTOTYPES = {
     "nh_encode_frame_scratch_bytes": (_i64, [_i, _i, _i]),
     "nh_encode_frame": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i64,
                              _p]),
+    "nh_encode_frames_scratch_bytes": (_i64, [_i, _i, _i, _i]),
+    "nh_encode_frames": (_i, [_p, _i, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p,
+                              _i64, _p]),
     "nh_reduce_sse_sad": (_i, [_p, _p, _i64, _p, _p]),
     "nh_reduce_sse_sad_2d": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),
+    "nh_reduce_metrics_i32": (_i, [_p, _p, _i64, _p, _p, _p]),
+    "nh_reduce_sse_f64": (_i, [_p, _p, _i64, _p, _p]),
+    "nh_satd_4x4_i32": (_i, [_p, _p, _i64, _p, _p]),
     "nh_block_costs": (_i, [_p, _p, _i64, _i, _p, _p, _p, _p]),
     "nh_count_nonzero": (_i, [_p, _i64, _p, _p]),
     "nh_level_stats": (_i, [_p, _i64, _p, _p, _p]),

@@ -17,6 +17,7 @@ SIZES = (4, 8, 16, 32)
 
 PipelineResult = namedtuple("PipelineResult", "pred coeff levels recon")
 FrameResult = namedtuple("FrameResult", "modes costs pred coeff levels recon_plane")
+FramesResult = namedtuple("FramesResult", "modes costs pred coeff levels recon_planes stats")
 
 
 def _require_cuda(*tensors):
@@ -92,7 +93,8 @@ def quantize_batched(coeff: torch.Tensor, qp: int, size: int | None = None, is_i
     """quant.py:41-79 element-wise; ``size`` defaults to the last dimension (quantize_block)."""
     dev = _require_cuda(coeff)
     size = int(coeff.shape[-1]) if size is None else int(size)
-    _check_size(size)
+    if not 1 <= size <= 63:   # quant.py:72 takes int(log2(size)) of anything; the kernel covers 1..63
+        raise ValueError(f"Unsupported block size: {size}")
     c = _c(coeff, torch.int32)
     out = torch.empty_like(c)
     with torch.cuda.device(dev):
@@ -409,6 +411,49 @@ def encode_frame(plane, size: int, cost: str = "sad", qp: int = 27, recon_neighb
                                      _ptr(res.costs), _ptr(res.pred), _ptr(res.coeff), _ptr(res.levels),
                                      _ptr(res.recon_plane), _ptr(scratch), scratch.numel(), _stream()))
     return res
+
+
+def encode_frames(planes, size: int, cost: str = "sad", qp: int = 27, recon_neighbours: bool = False,
+                  bit_depth: int = 8, outputs=("modes", "costs", "pred", "coeff", "levels"), stats: bool = True,
+                  out: FramesResult | None = None, scratch: torch.Tensor | None = None):
+    """K7 / K8 over a batch of frames in ONE call (``nh_encode_frames``): ``planes`` is an (F, H, W) int16
+    tensor; frame f is coded exactly as ``encode_frame(planes[f], ...)`` would code it.  With
+    ``recon_neighbours`` the block rows of all frames share the wavefront scheduler, so a batch fills the
+    GPU (BASELINE config 5), without it every block of every frame is independent (config 3).
+
+    Returns FramesResult with leading frame dimension: modes / costs (F, B), pred / coeff / levels
+    (F, B, N, N), recon_planes (F, H, W) and, with ``stats``, an (F, 4) int64 device tensor
+    [sse over the whole plane, H * W, sum of winner costs, non-zero levels] (metrics.py:7-21 numerators;
+    ``psnr_from_sse`` finishes PSNR on the host).  ``out`` / ``scratch`` let a caller reuse buffers."""
+    dev = _require_cuda(planes)
+    _check_size(size)
+    if cost not in ("sad", "satd"):
+        raise ValueError("cost must be 'sad' or 'satd'")
+    if planes.dim() != 3:
+        raise ValueError(f"planes must be (F, H, W), got {tuple(planes.shape)}")
+    p = _c(planes, torch.int16)
+    F, H, W = p.shape
+    B = (H // size) * (W // size)
+    if out is None:
+        want = set(outputs)
+        if stats:
+            want |= {"costs", "levels"}
+        mk = lambda name, shape, dt: torch.empty(shape, dtype=dt, device=dev) if name in want else None
+        out = FramesResult(mk("modes", (F, B), torch.uint8), mk("costs", (F, B), torch.int32),
+                           mk("pred", (F, B, size, size), torch.int16), mk("coeff", (F, B, size, size), torch.int32),
+                           mk("levels", (F, B, size, size), torch.int32),
+                           torch.empty((F, H, W), dtype=torch.int16, device=dev),
+                           torch.empty((F, 4), dtype=torch.int64, device=dev) if stats else None)
+    L = _lib.lib()
+    nbytes = int(L.nh_encode_frames_scratch_bytes(F, H, W, size)) if recon_neighbours else 16
+    if scratch is None or scratch.numel() < nbytes:
+        scratch = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.nh_encode_frames(_ptr(p), F, H * W, H, W, W, size, int(cost == "satd"), int(qp),
+                                      int(bool(recon_neighbours)), int(bit_depth), _ptr(out.modes), _ptr(out.costs),
+                                      _ptr(out.pred), _ptr(out.coeff), _ptr(out.levels), _ptr(out.recon_planes),
+                                      _ptr(out.stats), _ptr(scratch), scratch.numel(), _stream()))
+    return out
 
 
 # ------------------------------------------------------------------ reductions

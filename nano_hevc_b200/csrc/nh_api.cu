@@ -57,37 +57,82 @@ int ensure_dynamic_smem_impl(const void* kernel, int bytes, const char* what) {
 constexpr int kTileCounters = 4096;
 __device__ unsigned int g_tile_counters[4 * kTileCounters];  // {ticket, finished warps, undecided tiles, readers} per slot, zero at load
 
+// A stream keeps the slot it was first given.  When every slot is taken, a new stream takes over the slot
+// of a stream whose last launch has provably finished (the event recorded behind that launch by
+// tile_counter_launched() has completed), one slot at a time: a counter pair that a launch still in
+// flight is using is never handed to anyone else.
+namespace {
+struct CounterSlot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;   // recorded behind the last launch that used the slot
+    bool pending = false;         // acquired, launch not yet recorded
+};
+struct DeviceCounters {
+    void* base = nullptr;         // device address of g_tile_counters
+    int used = 0;
+    std::map<cudaStream_t, int> by_stream;
+    CounterSlot slots[kTileCounters];
+};
+std::mutex g_counter_mu;
+std::map<int, DeviceCounters*> g_counter_devs;
+}  // namespace
+
 int acquire_tile_counter(cudaStream_t stream, unsigned int** counter) {
-    static std::mutex mu;
-    static std::map<std::pair<int, cudaStream_t>, int> slots;  // (device, stream) -> slot
-    static int next_slot[64] = {};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
-    int slot;
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        auto it = slots.find({dev, stream});
-        if (it == slots.end()) {
-            int& n = next_slot[dev & 63];
-            if (n >= kTileCounters) {  // more distinct streams than counters: recycle (streams come and go)
-                n = 0;
-                for (auto i = slots.begin(); i != slots.end();)
-                    i = i->first.first == dev ? slots.erase(i) : std::next(i);
-            }
-            it = slots.emplace(std::make_pair(dev, stream), n++).first;
-        }
-        slot = it->second;
-    }
-    static void* bases[64] = {};  // device address of g_tile_counters, per device
-    void* base = bases[dev & 63];
-    if (!base) {
-        e = cudaGetSymbolAddress(&base, g_tile_counters);
+    std::lock_guard<std::mutex> lk(g_counter_mu);
+    DeviceCounters*& dc = g_counter_devs[dev];
+    if (!dc) dc = new DeviceCounters();
+    if (!dc->base) {
+        e = cudaGetSymbolAddress(&dc->base, g_tile_counters);
         if (e != cudaSuccess) return cuda_fail(e, "cudaGetSymbolAddress(g_tile_counters)");
-        bases[dev & 63] = base;
     }
-    *counter = reinterpret_cast<unsigned int*>(base) + 4 * slot;
+    int slot = -1;
+    auto it = dc->by_stream.find(stream);
+    if (it != dc->by_stream.end()) {
+        slot = it->second;
+    } else if (dc->used < kTileCounters) {
+        slot = dc->used++;
+    } else {
+        for (int i = 0; i < kTileCounters && slot < 0; ++i) {
+            CounterSlot& c = dc->slots[i];
+            if (c.pending) continue;
+            if (c.done && cudaEventQuery(c.done) != cudaSuccess) {   // still running (or captured): leave it alone
+                cudaGetLastError();
+                continue;
+            }
+            dc->by_stream.erase(c.stream);
+            slot = i;
+        }
+        if (slot < 0) {
+            set_error("all %d work-counter slots of device %d belong to streams with launches in flight", kTileCounters, dev);
+            return NH_E_CUDA;
+        }
+    }
+    dc->by_stream[stream] = slot;
+    dc->slots[slot].stream = stream;
+    dc->slots[slot].pending = true;
+    *counter = reinterpret_cast<unsigned int*>(dc->base) + 4 * slot;
     return NH_OK;
+}
+
+void tile_counter_launched(cudaStream_t stream) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    std::lock_guard<std::mutex> lk(g_counter_mu);
+    auto d = g_counter_devs.find(dev);
+    if (d == g_counter_devs.end()) return;
+    auto it = d->second->by_stream.find(stream);
+    if (it == d->second->by_stream.end()) return;
+    CounterSlot& c = d->second->slots[it->second];
+    if (!c.done && cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        c.done = nullptr;
+        return;   // without an event the slot simply stays with its stream (pending is never cleared)
+    }
+    if (cudaEventRecord(c.done, stream) == cudaSuccess) c.pending = false;
+    else cudaGetLastError();
 }
 
 }  // namespace nh

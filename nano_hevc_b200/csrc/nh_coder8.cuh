@@ -25,6 +25,8 @@ struct Coder8Args {
     int32_t* levels;
     int16_t* recon_plane;  // pitch as src
     int maxv;
+    int n_frames;          // frames stacked `frame_stride` samples apart (src and recon_plane alike);
+    int64_t frame_stride;  // block-major tensors hold frame f at block offset f * (bw * bh)
 };
 
 // 4x4 byte transpose: c[j] byte i = r[i] byte j
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) coder8_plane_mma_kernel(cons
 
     const int bw = a.W / N, bh = a.H / N;
     const int tpr = (bw + 31) / 32;                 // tiles per block row
-    const int64_t n_tiles = (int64_t)tpr * bh;
+    const int64_t n_tiles = (int64_t)tpr * bh * a.n_frames;   // block rows of all frames, frame after frame
     auto next_tile = [&]() -> int64_t {
         unsigned int t = 0;
         if (lane == 0) t = atomicAdd(tile_counter, 1u);
@@ -74,9 +76,10 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) coder8_plane_mma_kernel(cons
     int64_t tile_next = tile < n_tiles ? next_tile() : n_tiles;
 
     auto prefetch = [&](int64_t t, unsigned char* dst) {   // row `it` of block `lane`: 512 contiguous bytes per warp
-        const int by = (int)(t / tpr), bx0 = (int)(t % tpr) * 32;
+        const int byg = (int)(t / tpr), bx0 = (int)(t % tpr) * 32;
+        const int fr = byg / bh, by = byg - fr * bh;
         if (bx0 + lane < bw) {
-            const int16_t* gp = a.src + (int64_t)by * N * a.pitch + (bx0 + lane) * N;
+            const int16_t* gp = a.src + fr * a.frame_stride + (int64_t)by * N * a.pitch + (bx0 + lane) * N;
 #pragma unroll
             for (int it = 0; it < 8; ++it) cp_async16(smem_u32(dst + lane * T16::kPitch + it * 16), gp + (int64_t)it * a.pitch);
         } else {
@@ -88,8 +91,8 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) coder8_plane_mma_kernel(cons
     };
     int n_mode = 1;
     auto load_mode = [&](int64_t t) {
-        const int by = (int)(t / tpr), bx0 = (int)(t % tpr) * 32;
-        n_mode = bx0 + lane < bw ? (int)a.modes[(int64_t)by * bw + bx0 + lane] : 1;
+        const int byg = (int)(t / tpr), bx0 = (int)(t % tpr) * 32;   // frame f, row by = block row f * bh + by
+        n_mode = bx0 + lane < bw ? (int)a.modes[(int64_t)byg * bw + bx0 + lane] : 1;
     };
     if (tile < n_tiles) {
         prefetch(tile, s16[0]);
@@ -99,8 +102,10 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) coder8_plane_mma_kernel(cons
     int cur = 0;
     int64_t tile_after = n_tiles;
     for (; tile < n_tiles; tile = tile_next, tile_next = tile_after, cur ^= 1) {
-        const int by = (int)(tile / tpr), bx0 = (int)(tile % tpr) * 32;
-        const int64_t blk0 = (int64_t)by * bw + bx0;
+        const int byg = (int)(tile / tpr), bx0 = (int)(tile % tpr) * 32;
+        const int fr = byg / bh, by = byg - fr * bh;
+        const int16_t* srcf = a.src + fr * a.frame_stride;
+        const int64_t blk0 = (int64_t)byg * bw + bx0;
         const int blocks_valid = bw - bx0 < 32 ? bw - bx0 : 32;
         const int chunks16 = blocks_valid * 8;
         tile_after = tile_next < n_tiles ? next_tile() : n_tiles;
@@ -112,7 +117,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) coder8_plane_mma_kernel(cons
             const int bx = bx0 + (lane < blocks_valid ? lane : blocks_valid - 1);
             const int x = bx * N, y = by * N;
             if (x > 0 && y > 0 && x + 2 * N <= a.W && y + 2 * N <= a.H) {   // no substitution, no truncation
-                const int16_t* c = a.src + (int64_t)(y - 1) * a.pitch + x - 1;
+                const int16_t* c = srcf + (int64_t)(y - 1) * a.pitch + x - 1;
                 int tv[2 * N + 1], lv[2 * N + 1];
 #pragma unroll
                 for (int k = 0; k <= 2 * N; ++k) {
@@ -130,8 +135,8 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) coder8_plane_mma_kernel(cons
 #pragma unroll
                 for (int k = 0; k < 2 * N + 2; ++k) {
                     const int kk = k <= 2 * N ? k : 2 * N;
-                    rb[k] = (unsigned char)top_ref<false>(a.src, a.H, a.W, a.pitch, x, y, 2 * N, kk);
-                    rb[28 + k] = (unsigned char)left_ref<false>(a.src, a.H, a.W, a.pitch, x, y, 2 * N, kk);
+                    rb[k] = (unsigned char)top_ref<false>(srcf, a.H, a.W, a.pitch, x, y, 2 * N, kk);
+                    rb[28 + k] = (unsigned char)left_ref<false>(srcf, a.H, a.W, a.pitch, x, y, 2 * N, kk);
                 }
             }
             // ---- lane u predicts block u into the prediction tile (rows of 16-bit samples)
@@ -267,7 +272,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) coder8_plane_mma_kernel(cons
         }
         __syncwarp();
         if (a.recon_plane && lane < blocks_valid) {   // row `it` of block `lane`: 512 contiguous bytes per warp
-            int16_t* gp = a.recon_plane + (int64_t)by * N * a.pitch + (bx0 + lane) * N;
+            int16_t* gp = a.recon_plane + fr * a.frame_stride + (int64_t)by * N * a.pitch + (bx0 + lane) * N;
             uint4 v[8];
 #pragma unroll
             for (int it = 0; it < 8; ++it) v[it] = *reinterpret_cast<const uint4*>(s16[cur] + lane * T16::kPitch + it * 16);
@@ -281,20 +286,20 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) coder8_plane_mma_kernel(cons
 }
 
 // Declared in nh_common.cuh; called by nh_frame.cu.
-int coder8_plane_mma(const int16_t* src, int H, int W, int pitch, uint8_t* modes, int16_t* pred, int32_t* coeff,
-                     int32_t* levels, int16_t* recon_plane, const QuantParams& qp, int maxv, cudaStream_t st,
-                     unsigned int** handed_back) {
+int coder8_plane_mma(const int16_t* src, int n_frames, int64_t frame_stride, int H, int W, int pitch, uint8_t* modes,
+                     int16_t* pred, int32_t* coeff, int32_t* levels, int16_t* recon_plane, const QuantParams& qp,
+                     int maxv, cudaStream_t st, unsigned int** handed_back) {
     constexpr int kSmem = kV2Warps * (3 * WarpTile<128>::kBytes + 32 * kC8RefBytes);
     int rc = ensure_dynamic_smem(coder8_plane_mma_kernel, kSmem, "cudaFuncSetAttribute(coder8_plane_mma_kernel)");
     if (rc != NH_OK) return rc;
     const int bw = W / 8, bh = H / 8;
-    const int64_t n_tiles = (int64_t)((bw + 31) / 32) * bh;
+    const int64_t n_tiles = (int64_t)((bw + 31) / 32) * bh * n_frames;
     const int grid = grid_for(n_tiles, kV2Warps, 3);
     unsigned int* counter = nullptr;
     rc = acquire_tile_counter(st, &counter);
     if (rc != NH_OK) return rc;
     *handed_back = counter + 2;
-    Coder8Args a{src, H, W, pitch, modes, pred, coeff, levels, recon_plane, maxv};
+    Coder8Args a{src, H, W, pitch, modes, pred, coeff, levels, recon_plane, maxv, n_frames, frame_stride};
     coder8_plane_mma_kernel<<<grid, kV2Warps * 32, kSmem, st>>>(a, make_fast_quant(qp), counter);
     NH_CHECK_LAUNCH("coder8_plane_mma_kernel");
     return NH_OK;

@@ -46,9 +46,9 @@ int fused_pipeline_dcplanar_narrow(const int16_t* orig, const int16_t* top, cons
 // nh_fused.cu (nh_coder8.cuh): K7 winner stage for 8x8 blocks of an 8-bit plane whose modes are decided.
 struct QuantParams;
 // *handed_back = device counter pair {tiles handed back to the exact coder, readers} of this stream.
-int coder8_plane_mma(const int16_t* src, int H, int W, int pitch, uint8_t* modes, int16_t* pred, int32_t* coeff,
-                     int32_t* levels, int16_t* recon_plane, const QuantParams& qp, int maxv, cudaStream_t st,
-                     unsigned int** handed_back);
+int coder8_plane_mma(const int16_t* src, int n_frames, int64_t frame_stride, int H, int W, int pitch, uint8_t* modes,
+                     int16_t* pred, int32_t* coeff, int32_t* levels, int16_t* recon_plane, const QuantParams& qp,
+                     int maxv, cudaStream_t st, unsigned int** handed_back);
 
 // nh_fused.cu: 2 = tensor-core kernels for N = 16 / 32 (default), 1 = CUDA-core butterflies
 // (nh_set_rows_impl / NH_ROWS_IMPL); also selects the single-stage transform kernels of nh_ops.cu.
@@ -68,8 +68,12 @@ inline int ensure_dynamic_smem(Kernel kernel, int bytes, const char* what) {
 // Counters live in a static device array (nothing is allocated); a stream keeps the slot it was
 // first given, so launches on one stream (serialised by the stream) and on different streams
 // (different slots) never interfere.  counter[2] / counter[3] belong to the frame coder (nh_coder8.cuh:
-// tiles handed back to the exact coder kernel, and the CTAs of that kernel that have looked).  nh_api.cu.
+// tiles handed back to the exact coder kernel, and the CTAs of that kernel that have looked).
+// tile_counter_launched() is called behind the LAST launch that uses the pair: it records the event
+// that lets the slot move to another stream once that launch has finished (only needed after more
+// than 4096 distinct streams).  nh_api.cu.
 int acquire_tile_counter(cudaStream_t stream, unsigned int** counter);
+void tile_counter_launched(cudaStream_t stream);
 
 #define NH_CHECK_LAUNCH(what)                                  \
     do {                                                       \

@@ -128,8 +128,13 @@ struct CoderArgs {
     int* ticket;           // K8: row ticket counter
     int16_t* bottom;       // K8: [bh][W] bottom rows of the reconstructed blocks, -1 = not yet written
     unsigned poll_sleep_ns;  // K8: back-off between two polls of a row that is not ready yet
+    // SRC_PLANE / SRC_WAVEFRONT: frames stacked `frame_stride` samples apart (src and recon_plane alike);
+    // block-major outputs hold frame f at block offset f * blocks_per_frame, exchange rows at f * bh * W
+    int n_frames;
+    int64_t frame_stride;
+    int64_t blocks_per_frame;
     // common
-    int64_t n_blocks;
+    int64_t n_blocks;   // blocks of all frames
     QuantParams qp;
     FastQuant fq;
     int maxv;
@@ -185,22 +190,28 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
     if constexpr (SRC == SRC_WAVEFRONT) {
         // One warp per block row, rows handed out in order by a ticket counter so that a
         // waiting warp only ever waits on a row that a resident warp already owns.
+        // Tickets interleave the frames (ticket t = row t / F of frame t % F), so all frames advance
+        // together and the row above always holds a smaller ticket.
         int* ticket = a.ticket;
         for (;;) {
-            int by = 0;
-            if (lane == 0) by = atomicAdd(ticket, 1);
-            by = __shfl_sync(0xffffffffu, by, 0);
+            int tk = 0;
+            if (lane == 0) tk = atomicAdd(ticket, 1);
+            tk = __shfl_sync(0xffffffffu, tk, 0);
+            const int by = tk / a.n_frames, fr = tk - by * a.n_frames;
             if (by >= bh) break;
+            const int16_t* srcf = a.src + fr * a.frame_stride;
+            int16_t* reconf = a.out.recon_plane + fr * a.frame_stride;
+            int16_t* bottomf = a.bottom + (int64_t)fr * bh * a.W;
             for (int bx = 0; bx < bw; ++bx) {
                 const int x = bx * N, y = by * N;
-                const int64_t b = (int64_t)by * bw + bx;
+                const int64_t b = fr * a.blocks_per_frame + (int64_t)by * bw + bx;
                 // original pixels do not depend on any neighbour: fetch them before the wait
                 constexpr int OPL = (N * N + G - 1) / G;  // orig samples per lane
                 int ov[OPL];
 #pragma unroll
                 for (int i = 0; i < OPL; ++i) {
                     const int e = gl + i * G;
-                    ov[i] = e < N * N ? (int)__ldg(a.src + (int64_t)(y + e / N) * a.pitch + x + e % N) : 0;
+                    ov[i] = e < N * N ? (int)__ldg(srcf + (int64_t)(y + e / N) * a.pitch + x + e % N) : 0;
                 }
                 int ood = 0;  // any sample outside [0, 255] disables the packed 8-bit search
                 // left references = right-most column of the block this warp has just reconstructed
@@ -220,7 +231,7 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                     for (int k = gl; k < Cfg::REF_W; k += G) top[k] = 128;
                     ood |= 0;
                 } else {
-                    const int16_t* up = a.bottom + (int64_t)(by - 1) * a.W;
+                    const int16_t* up = bottomf + (int64_t)(by - 1) * a.W;
                     int last = x + 2 * N - 1;
                     if (last > a.W - 1) last = a.W - 1;
                     bool ready;
@@ -282,9 +293,9 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                                      a.maxv, a.use_dst != 0, a.out);
                 // publish the bottom row first (the row below is polling for it), then the plane
                 for (int e = gl; e < N; e += G)
-                    __stcg(a.bottom + (int64_t)by * a.W + x + e, O[(N - 1) * Cfg::O_PITCH + e]);
+                    __stcg(bottomf + (int64_t)by * a.W + x + e, O[(N - 1) * Cfg::O_PITCH + e]);
                 for (int e = gl; e < N * N; e += G)
-                    a.out.recon_plane[(int64_t)(y + e / N) * a.pitch + x + e % N] = O[(e / N) * Cfg::O_PITCH + (e % N)];
+                    reconf[(int64_t)(y + e / N) * a.pitch + x + e % N] = O[(e / N) * Cfg::O_PITCH + (e % N)];
                 __syncwarp();
             }
         }
@@ -301,19 +312,28 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
         uint4 nxt[CPL];
         int ntv[RPL], nlv[RPL];
         int nmode = 0xFF;
+        // plane sources: block b -> frame b / blocks_per_frame, raster position inside the frame
+        auto locate = [&](int64_t bb, int& fx, int& fy) -> const int16_t* {
+            const int fr = (int)(bb / a.blocks_per_frame);
+            const int64_t lb = bb - fr * a.blocks_per_frame;
+            fx = (int)(lb % bw) * N;
+            fy = (int)(lb / bw) * N;
+            return a.src + fr * a.frame_stride;
+        };
         auto fetch = [&](int64_t t) {
-            const int fx = (int)(t % bw) * N, fy = (int)(t / bw) * N;
+            int fx, fy;
+            const int16_t* srcf = locate(t, fx, fy);
             if (a.modes_in) nmode = (int)a.modes_in[t];   // one block per warp: block index = tile index
 #pragma unroll
             for (int i = 0; i < CPL; ++i) {
                 const int c = lane + 32 * i, row = c / CW, c8 = c % CW;
-                nxt[i] = __ldg(reinterpret_cast<const uint4*>(a.src + (int64_t)(fy + row) * a.pitch + fx + 8 * c8));
+                nxt[i] = __ldg(reinterpret_cast<const uint4*>(srcf + (int64_t)(fy + row) * a.pitch + fx + 8 * c8));
             }
 #pragma unroll
             for (int i = 0; i < RPL; ++i) {
                 const int k = lane + 32 * i, kk = k <= 2 * N ? k : 2 * N;
-                ntv[i] = top_ref<false>(a.src, a.H, a.W, a.pitch, fx, fy, 2 * N, kk);
-                nlv[i] = left_ref<false>(a.src, a.H, a.W, a.pitch, fx, fy, 2 * N, kk);
+                ntv[i] = top_ref<false>(srcf, a.H, a.W, a.pitch, fx, fy, 2 * N, kk);
+                nlv[i] = left_ref<false>(srcf, a.H, a.W, a.pitch, fx, fy, 2 * N, kk);
             }
         };
         if (vec && (int64_t)blockIdx.x * WARPS + warp < n_tiles) fetch((int64_t)blockIdx.x * WARPS + warp);
@@ -330,17 +350,18 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
         auto sfetch = [&](int64_t t) {
             const int64_t bb = t * GPW + g;
             if (bb < a.n_blocks) {
-                const int fx = (int)(bb % bw) * N, fy = (int)(bb / bw) * N;
+                int fx, fy;
+                const int16_t* srcf = locate(bb, fx, fy);
 #pragma unroll
                 for (int i = 0; i < RS; ++i) {
                     const int k = gl + i * G, kk = k <= 2 * N ? k : 2 * N;
-                    stv[i] = top_ref<false>(a.src, a.H, a.W, a.pitch, fx, fy, 2 * N, kk);
-                    slv[i] = left_ref<false>(a.src, a.H, a.W, a.pitch, fx, fy, 2 * N, kk);
+                    stv[i] = top_ref<false>(srcf, a.H, a.W, a.pitch, fx, fy, 2 * N, kk);
+                    slv[i] = left_ref<false>(srcf, a.H, a.W, a.pitch, fx, fy, 2 * N, kk);
                 }
 #pragma unroll
                 for (int i = 0; i < PS; ++i) {
                     const int e = gl + i * G;
-                    spx[i] = __ldg(a.src + (int64_t)(fy + e / N) * a.pitch + fx + e % N);
+                    spx[i] = __ldg(srcf + (int64_t)(fy + e / N) * a.pitch + fx + e % N);
                 }
             }
         };
@@ -353,6 +374,8 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
             const int64_t b = tile * GPW + g;
             const bool valid = b < a.n_blocks;
             int corner = 0, x = 0, y = 0, ood = 0;
+            const int16_t* srcf = a.src;
+            int16_t* reconf = a.out.recon_plane;
             int mode_in = 0xFF;
             bool given = false;
             if constexpr (SRC == SRC_PLANE) {
@@ -380,8 +403,8 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                 }
             } else {
                 if (valid) {
-                    x = (int)(b % bw) * N;
-                    y = (int)(b / bw) * N;
+                    srcf = locate(b, x, y);
+                    if (reconf) reconf += srcf - a.src;
                     if (vec) {
 #pragma unroll
                         for (int i = 0; i < RPL; ++i) {
@@ -412,8 +435,8 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
 #pragma unroll
                         for (int k = gl; k < Cfg::REF_W; k += G) {   // unrolled: all loads in flight together
                             const int kk = k <= 2 * N ? k : 2 * N;
-                            const int tv = top_ref<false>(a.src, a.H, a.W, a.pitch, x, y, 2 * N, kk);
-                            const int lv = left_ref<false>(a.src, a.H, a.W, a.pitch, x, y, 2 * N, kk);
+                            const int tv = top_ref<false>(srcf, a.H, a.W, a.pitch, x, y, 2 * N, kk);
+                            const int lv = left_ref<false>(srcf, a.H, a.W, a.pitch, x, y, 2 * N, kk);
                             top[k] = (int16_t)tv;
                             left[k] = (int16_t)lv;
                             ood |= tv | lv;
@@ -431,7 +454,7 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
                     } else if (!sp) {
 #pragma unroll (N <= 8 ? N : 4)
                         for (int e = gl; e < N * N; e += G) {
-                            const int v = __ldg(a.src + (int64_t)(y + e / N) * a.pitch + x + e % N);
+                            const int v = __ldg(srcf + (int64_t)(y + e / N) * a.pitch + x + e % N);
                             O[(e / N) * Cfg::O_PITCH + (e % N)] = (int16_t)v;
                             ood |= v;
                         }
@@ -502,13 +525,12 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(
 #pragma unroll
                         for (int i = 0; i < CPL; ++i) {
                             const int c = lane + 32 * i, row = c / CW, c8 = c % CW;
-                            stg_stream(a.out.recon_plane + (int64_t)(y + row) * a.pitch + x + 8 * c8,
+                            stg_stream(reconf + (int64_t)(y + row) * a.pitch + x + 8 * c8,
                                        *reinterpret_cast<const uint4*>(O + row * Cfg::O_PITCH + 8 * c8));
                         }
                     } else {
                         for (int e = gl; e < N * N; e += G)
-                            a.out.recon_plane[(int64_t)(y + e / N) * a.pitch + x + e % N] =
-                                O[(e / N) * Cfg::O_PITCH + (e % N)];
+                            reconf[(int64_t)(y + e / N) * a.pitch + x + e % N] = O[(e / N) * Cfg::O_PITCH + (e % N)];
                     }
                 }
             }
@@ -548,18 +570,22 @@ __global__ void __launch_bounds__(32 * WPB) coder_wave_mw_kernel(const CoderArgs
     for (;;) {
         if (tid == 0) s_row = atomicAdd(a.ticket, 1);
         __syncthreads();
-        const int by = s_row;
+        const int tk = s_row;   // frames interleaved: ticket t = row t / F of frame t % F
         __syncthreads();  // everyone has read s_row before thread 0 draws the next ticket
+        const int by = tk / a.n_frames, fr = tk - by * a.n_frames;
         if (by >= bh) break;
+        const int16_t* srcf = a.src + fr * a.frame_stride;
+        int16_t* reconf = a.out.recon_plane + fr * a.frame_stride;
+        int16_t* bottomf = a.bottom + (int64_t)fr * bh * a.W;
         for (int bx = 0; bx < bw; ++bx) {
             const int x = bx * N, y = by * N;
-            const int64_t b = (int64_t)by * bw + bx;
+            const int64_t b = fr * a.blocks_per_frame + (int64_t)by * bw + bx;
             // original pixels do not depend on any neighbour: fetch them before the wait
             int ov[OPL];
 #pragma unroll
             for (int i = 0; i < OPL; ++i) {
                 const int e = tid + i * T;
-                ov[i] = e < N * N ? (int)__ldg(a.src + (int64_t)(y + e / N) * a.pitch + x + e % N) : 0;
+                ov[i] = e < N * N ? (int)__ldg(srcf + (int64_t)(y + e / N) * a.pitch + x + e % N) : 0;
             }
             int ood = 0;
             // left references = right-most column of the block this CTA has just reconstructed (still
@@ -576,7 +602,7 @@ __global__ void __launch_bounds__(32 * WPB) coder_wave_mw_kernel(const CoderArgs
                 if (by == 0) {
                     for (int k = lane; k < Cfg::REF_W; k += 32) top[k] = 128;
                 } else {
-                    const int16_t* up = a.bottom + (int64_t)(by - 1) * a.W;
+                    const int16_t* up = bottomf + (int64_t)(by - 1) * a.W;
                     int last = x + 2 * N - 1;
                     if (last > a.W - 1) last = a.W - 1;
                     bool ready;
@@ -636,11 +662,11 @@ __global__ void __launch_bounds__(32 * WPB) coder_wave_mw_kernel(const CoderArgs
                 }
                 // publish the bottom row first: the row below is polling for it
                 for (int e = lane; e < N; e += 32)
-                    __stcg(a.bottom + (int64_t)by * a.W + x + e, O[(N - 1) * Cfg::O_PITCH + e]);
+                    __stcg(bottomf + (int64_t)by * a.W + x + e, O[(N - 1) * Cfg::O_PITCH + e]);
             }
             __syncthreads();  // the reconstruction is in O
             for (int e = tid; e < N * N; e += T)
-                a.out.recon_plane[(int64_t)(y + e / N) * a.pitch + x + e % N] = O[(e / N) * Cfg::O_PITCH + (e % N)];
+                reconf[(int64_t)(y + e / N) * a.pitch + x + e % N] = O[(e / N) * Cfg::O_PITCH + (e % N)];
             // no barrier needed here: the next block only reads O (left references) before the
             // barrier that precedes its overwrite
         }
@@ -649,11 +675,78 @@ __global__ void __launch_bounds__(32 * WPB) coder_wave_mw_kernel(const CoderArgs
 
 // Exchange rows of the wavefront coder: -1 where a block will publish its bottom row, 0 in the
 // columns no full block covers (the reference reads the zero-initialised plane there).
-__global__ void __launch_bounds__(256) init_bottom_kernel(int16_t* bottom, int bh, int W, int covered, int* ticket) {
-    const int64_t total = (int64_t)bh * W;
+__global__ void __launch_bounds__(256) init_bottom_kernel(int16_t* bottom, int64_t rows, int W, int covered, int* ticket) {
+    const int64_t total = rows * W;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x)
         bottom[t] = (int)(t % W) < covered ? (int16_t)-1 : (int16_t)0;
     if (blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0;
+}
+
+// Per-frame statistics of coded frames, one launch for all of them (grid.y = frame):
+//   stats[f] = { sum (src - recon)^2 over the WHOLE plane (metrics.py:7-21 numerator; uncovered rows count,
+//               __main__.py:135-137), H * W, sum of the winners' costs, number of non-zero levels }.
+__global__ void __launch_bounds__(256)
+    frame_stats_kernel(const int16_t* __restrict__ src, const int16_t* __restrict__ recon, int64_t frame_stride, int H,
+                       int W, int pitch, int vec_ok, const int32_t* __restrict__ costs,
+                       const int32_t* __restrict__ levels, int64_t blocks_per_frame, int nn, int64_t* __restrict__ stats) {
+    const int fr = blockIdx.y;
+    const int16_t* a = src + fr * frame_stride;
+    const int16_t* b = recon + fr * frame_stride;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    long long sse = 0, nnz = 0, cost = 0;
+    auto acc2 = [&](uint32_t wa, uint32_t wb) {
+        const int d0 = lo16(wa) - lo16(wb), d1 = hi16(wa) - hi16(wb);
+        sse += (long long)d0 * d0 + (long long)d1 * d1;
+    };
+    if (vec_ok) {
+        const int w8 = W / 8;
+        for (int64_t t = tid; t < (int64_t)H * w8; t += stride) {
+            const int64_t o = (t / w8) * pitch + (t % w8) * 8;
+            const uint4 va = ldg_stream(a + o), vb = ldg_stream(b + o);
+            acc2(va.x, vb.x); acc2(va.y, vb.y); acc2(va.z, vb.z); acc2(va.w, vb.w);
+        }
+        const int tail = W - w8 * 8;
+        for (int64_t t = tid; t < (int64_t)H * tail; t += stride) {
+            const int64_t o = (t / tail) * pitch + w8 * 8 + t % tail;
+            const int d = (int)a[o] - (int)b[o];
+            sse += (long long)d * d;
+        }
+    } else {
+        for (int64_t t = tid; t < (int64_t)H * W; t += stride) {
+            const int64_t o = (t / W) * pitch + t % W;
+            const int d = (int)a[o] - (int)b[o];
+            sse += (long long)d * d;
+        }
+    }
+    if (levels) {
+        const int32_t* lv = levels + fr * blocks_per_frame * nn;   // 16-byte aligned: nn >= 16
+        const int64_t n4 = blocks_per_frame * nn / 4;
+        for (int64_t i = tid; i < n4; i += stride) {
+            const uint4 v = ldg_stream(lv + 4 * i);
+            nnz += (v.x != 0) + (v.y != 0) + (v.z != 0) + (v.w != 0);
+        }
+    }
+    if (costs)
+        for (int64_t i = tid; i < blocks_per_frame; i += stride) cost += costs[fr * blocks_per_frame + i];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        sse += __shfl_xor_sync(0xffffffffu, sse, off);
+        nnz += __shfl_xor_sync(0xffffffffu, nnz, off);
+        cost += __shfl_xor_sync(0xffffffffu, cost, off);
+    }
+    __shared__ long long sh[3][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sh[0][warp] = sse; sh[1][warp] = cost; sh[2][warp] = nnz; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t0 = 0, t1 = 0, t2 = 0;
+        for (int w = 0; w < 8; ++w) { t0 += sh[0][w]; t1 += sh[1][w]; t2 += sh[2][w]; }
+        unsigned long long* o = reinterpret_cast<unsigned long long*>(stats + 4 * fr);
+        atomicAdd(o, (unsigned long long)t0);
+        atomicAdd(o + 2, (unsigned long long)t1);
+        atomicAdd(o + 3, (unsigned long long)t2);
+        if (blockIdx.x == 0) stats[4 * fr + 1] = (int64_t)H * W;
+    }
 }
 
 template <int N, int G, int SRC>
@@ -666,14 +759,13 @@ static int launch_coder(const CoderArgs& a, int grid, cudaStream_t st) {
 template <int SRC>
 static int dispatch_coder(const CoderArgs& a, int size, cudaStream_t st) {
     if (SRC == SRC_WAVEFRONT) {
-        int bh = a.H / size;
-        int grid = bh < sm_count() * 16 ? bh : sm_count() * 16;
+        const int64_t rows = (int64_t)(a.H / size) * a.n_frames;
+        int grid = rows < sm_count() * 16 ? (int)rows : sm_count() * 16;
         if (grid < 1) grid = 1;
-        static int wave_warps = -1;  // warps per block row at N = 16 / 32: NH_WAVE_WARPS=1|2|4|8 (default 8)
-        if (wave_warps < 0) {
+        static const int wave_warps = [] {  // warps per block row at N = 16 / 32: NH_WAVE_WARPS=1|2|4|8 (default 8)
             const char* e = getenv("NH_WAVE_WARPS");
-            wave_warps = (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 8;
-        }
+            return (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 8;
+        }();
         if (size >= 16 && wave_warps > 1) {
             if (grid > sm_count() * 4) grid = sm_count() * 4;
             if (size == 16) {
@@ -713,7 +805,8 @@ static int launch_search_cost(const CoderArgs& a, cudaStream_t st) {
     using C = SearchCfg<N>;
     int rc = ensure_dynamic_smem(search_plane_kernel<N, COST>, C::SMEM_BYTES, "search_plane_kernel");
     if (rc != NH_OK) return rc;
-    SearchArgs s{a.src, a.H, a.W, a.pitch, a.cost_kind, a.n_blocks, a.out.modes, a.out.costs};
+    SearchArgs s{a.src, a.H, a.W, a.pitch, a.cost_kind, a.n_blocks, a.out.modes, a.out.costs, a.blocks_per_frame,
+                 a.frame_stride};
     const int per_sm = COST == NH_COST_SAD ? 6 : 5;  // the kernel's __launch_bounds__; 6 x SMEM_BYTES <= 170 KB for every N
     const int grid = grid_for(a.n_blocks, (int64_t)C::WARPS * C::T, per_sm);
     search_plane_kernel<N, COST><<<grid, C::WARPS * 32, C::SMEM_BYTES, st>>>(s);
@@ -727,7 +820,7 @@ static int launch_search(const CoderArgs& a, cudaStream_t st) {
 
 // 2 (default) = search kernel + winner kernel, 1 = everything in the single coder kernel (A/B
 // profiling); nh_set_search_impl() or NH_SEARCH_IMPL=1|2.
-static int g_search_impl = 0;
+static thread_local int g_search_impl = 0;   // per calling thread: no shared mutable state between callers
 static int split_impl() {
     if (g_search_impl == 0) {
         const char* e = getenv("NH_SEARCH_IMPL");
@@ -746,16 +839,18 @@ static int dispatch_search_then_code(CoderArgs a, int size, cudaStream_t st) {
     }
     if (rc != NH_OK) return rc;
     a.modes_in = a.out.modes;
-    if (size == 8 && (a.pitch % 8) == 0 && aligned16(a.src) && aligned16(a.out.recon_plane)) {
+    if (size == 8 && (a.pitch % 8) == 0 && (a.frame_stride % 8) == 0 && aligned16(a.src) && aligned16(a.out.recon_plane)) {
         // winners on the tensor cores (nh_coder8.cuh); it hands the tiles it cannot take (undecided
         // blocks) back by marking them 0xFF, and the exact coder below only touches marked blocks
-        rc = coder8_plane_mma(a.src, a.H, a.W, a.pitch, a.out.modes, a.out.pred, a.out.coeff, a.out.levels,
-                              a.out.recon_plane, a.qp, a.maxv, st, &a.handed_back);
+        rc = coder8_plane_mma(a.src, a.n_frames, a.frame_stride, a.H, a.W, a.pitch, a.out.modes, a.out.pred, a.out.coeff,
+                              a.out.levels, a.out.recon_plane, a.qp, a.maxv, st, &a.handed_back);
         if (rc != NH_OK) return rc;
         a.only_undecided = 1;
     }
     if (size == 16) return launch_coder<16, 32, SRC_PLANE>(a, grid_for(a.n_blocks, 4, 8), st);
-    return dispatch_coder<SRC_PLANE>(a, size, st);
+    rc = dispatch_coder<SRC_PLANE>(a, size, st);
+    if (a.only_undecided) tile_counter_launched(st);   // last launch that reads the stream's counter slot
+    return rc;
 }
 
 
@@ -835,6 +930,8 @@ NH_API int nh_fused_pipeline_modes(const int16_t* orig, const int16_t* top, cons
     CoderArgs a{};
     a.orig = orig; a.top = top; a.left = left; a.top_left = top_left; a.modes_in = modes; a.mode = mode;
     a.n_blocks = n_blocks;
+    a.n_frames = 1;
+    a.blocks_per_frame = n_blocks;
     a.qp = make_quant_params(qp, l2, is_intra);
     a.fq = make_fast_quant(a.qp);
     a.maxv = (1 << bit_depth) - 1;
@@ -852,74 +949,113 @@ NH_API int nh_set_search_impl(int impl) {
     return NH_OK;
 }
 
+NH_API int64_t nh_encode_frames_scratch_bytes(int n_frames, int height, int width, int size) {
+    if (log2_size(size) < 0 || height < 0 || width < 0 || n_frames < 0) return 0;
+    return 256 + (int64_t)n_frames * (height / size) * width * 2;  // ticket counter + exchange rows of every frame
+}
+
 NH_API int64_t nh_encode_frame_scratch_bytes(int height, int width, int size) {
-    if (log2_size(size) < 0 || height < 0 || width < 0) return 0;
-    return 256 + (int64_t)(height / size) * width * 2;  // ticket counter + exchange rows
+    return nh_encode_frames_scratch_bytes(1, height, width, size);
+}
+
+NH_API int nh_encode_frames(const int16_t* src, int n_frames, int64_t frame_stride, int height, int width, int pitch,
+                            int size, int cost_kind, int qp, int recon_neighbours, int bit_depth, uint8_t* modes,
+                            int32_t* costs, int16_t* pred, int32_t* coeff, int32_t* levels, int16_t* recon_planes,
+                            int64_t* stats, void* scratch, int64_t scratch_bytes, void* stream) {
+    int l2 = log2_size(size);
+    if (l2 < 0) { set_error("Unsupported transform size: %d", size); return NH_E_SIZE; }
+    if (!src || n_frames < 0 || height < 0 || width < 0 || pitch < width ||
+        (n_frames > 1 && frame_stride < (int64_t)height * pitch) ||
+        (cost_kind != NH_COST_SAD && cost_kind != NH_COST_SATD) || bit_depth < 1 || bit_depth > 15) {
+        set_error("nh_encode_frames: bad argument");
+        return NH_E_ARG;
+    }
+    if ((recon_neighbours || stats) && !recon_planes) {
+        set_error("nh_encode_frames: recon_planes is required when recon_neighbours != 0 or stats are requested");
+        return NH_E_ARG;
+    }
+    if (!aligned16(pred) || !aligned16(coeff) || !aligned16(levels)) {
+        set_error("nh_encode_frames: output tensors must be 16-byte aligned");
+        return NH_E_ARG;
+    }
+    if (n_frames == 0) return NH_OK;
+    if (n_frames == 1) frame_stride = (int64_t)height * pitch;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (recon_planes) {  // Plane.zeros semantics (frame.py:41-43): uncovered samples stay 0
+        cudaError_t e = frame_stride == (int64_t)height * pitch
+                            ? cudaMemsetAsync(recon_planes, 0, (size_t)n_frames * height * pitch * sizeof(int16_t), st)
+                            : cudaMemset2DAsync(recon_planes, (size_t)frame_stride * sizeof(int16_t), 0,
+                                                (size_t)height * pitch * sizeof(int16_t), (size_t)n_frames, st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(recon_planes)");
+    }
+    if (stats) {
+        cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)n_frames * 4 * sizeof(int64_t), st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(stats)");
+    }
+    const int bw = width / size, bh = height / size;
+    const bool planes_vec = (pitch % 8) == 0 && (frame_stride % 8) == 0 && aligned16(src) && aligned16(recon_planes);
+    auto launch_stats = [&]() -> int {
+        if (!stats) return NH_OK;
+        const int64_t bpf = (int64_t)bw * bh;
+        dim3 grid((unsigned)(sm_count() * 4 / (n_frames < sm_count() * 4 ? n_frames : sm_count() * 4) + 1), (unsigned)n_frames);
+        frame_stats_kernel<<<grid, 256, 0, st>>>(src, recon_planes, frame_stride, height, width, pitch, planes_vec ? 1 : 0,
+                                                 bpf ? costs : nullptr, bpf ? levels : nullptr, bpf, size * size, stats);
+        NH_CHECK_LAUNCH("frame_stats_kernel");
+        return NH_OK;
+    };
+    if (bw == 0 || bh == 0) return launch_stats();
+    CoderArgs a{};
+    a.src = src; a.H = height; a.W = width; a.pitch = pitch; a.cost_kind = cost_kind;
+    a.n_frames = n_frames;
+    a.frame_stride = frame_stride;
+    a.blocks_per_frame = (int64_t)bw * bh;
+    a.n_blocks = a.blocks_per_frame * n_frames;
+    a.qp = make_quant_params(qp, l2, 1);
+    a.fq = make_fast_quant(a.qp);
+    a.maxv = (1 << bit_depth) - 1;
+    a.use_dst = size == 4;  // docs/frames_and_panes.md:328-329
+    a.out = CoderOut{modes, costs, pred, coeff, levels, nullptr, recon_planes, pitch};
+    a.vec_ok = planes_vec;
+    int rc;
+    if (!recon_neighbours) {
+        // the search kernel reads the plane in 8-byte pieces and needs the modes tensor as its output
+        const bool split_ok = split_impl() && bit_depth <= 8 && modes && (pitch % 4) == 0 && (frame_stride % 4) == 0 &&
+                              (reinterpret_cast<uintptr_t>(src) & 7) == 0;
+        rc = split_ok ? dispatch_search_then_code(a, size, st) : dispatch_coder<SRC_PLANE>(a, size, st);
+        return rc != NH_OK ? rc : launch_stats();
+    }
+    const int64_t need = nh_encode_frames_scratch_bytes(n_frames, height, width, size);
+    if (!scratch || scratch_bytes < need) {
+        set_error("nh_encode_frames: scratch of %lld bytes required, got %lld", (long long)need,
+                  (long long)scratch_bytes);
+        return NH_E_NOMEM;
+    }
+    if ((reinterpret_cast<uintptr_t>(scratch) & 3) != 0) {
+        set_error("nh_encode_frames: scratch must be 4-byte aligned");
+        return NH_E_ARG;
+    }
+    {
+        static const int sleep_ns = [] {  // NH_WAVE_SLEEP_NS overrides the default back-off
+            const char* e = getenv("NH_WAVE_SLEEP_NS");
+            const int v = e ? atoi(e) : 0;  // measured: polling without back-off is as fast or faster (profiles/r1_notes.md)
+            return v < 0 ? 0 : v;
+        }();
+        a.poll_sleep_ns = (unsigned)sleep_ns;
+    }
+    a.ticket = reinterpret_cast<int*>(scratch);
+    a.bottom = reinterpret_cast<int16_t*>(reinterpret_cast<unsigned char*>(scratch) + 256);
+    const int64_t rows = (int64_t)bh * n_frames;
+    init_bottom_kernel<<<grid_for(rows * width, 256, 4), 256, 0, st>>>(a.bottom, rows, width, bw * size, a.ticket);
+    NH_CHECK_LAUNCH("init_bottom_kernel");
+    rc = dispatch_coder<SRC_WAVEFRONT>(a, size, st);
+    return rc != NH_OK ? rc : launch_stats();
 }
 
 NH_API int nh_encode_frame(const int16_t* src, int height, int width, int pitch, int size,
                            int cost_kind, int qp, int recon_neighbours, int bit_depth, uint8_t* modes,
                            int32_t* costs, int16_t* pred, int32_t* coeff, int32_t* levels,
                            int16_t* recon_plane, void* scratch, int64_t scratch_bytes, void* stream) {
-    int l2 = log2_size(size);
-    if (l2 < 0) { set_error("Unsupported transform size: %d", size); return NH_E_SIZE; }
-    if (!src || height < 0 || width < 0 || pitch < width ||
-        (cost_kind != NH_COST_SAD && cost_kind != NH_COST_SATD) || bit_depth < 1 || bit_depth > 15) {
-        set_error("nh_encode_frame: bad argument");
-        return NH_E_ARG;
-    }
-    if (recon_neighbours && !recon_plane) {
-        set_error("nh_encode_frame: recon_plane is required when recon_neighbours != 0");
-        return NH_E_ARG;
-    }
-    if (!aligned16(pred) || !aligned16(coeff) || !aligned16(levels)) {
-        set_error("nh_encode_frame: output tensors must be 16-byte aligned");
-        return NH_E_ARG;
-    }
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (recon_plane) {  // Plane.zeros semantics (frame.py:41-43): uncovered samples stay 0
-        cudaError_t e = cudaMemsetAsync(recon_plane, 0, (size_t)height * pitch * sizeof(int16_t), st);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(recon_plane)");
-    }
-    const int bw = width / size, bh = height / size;
-    if (bw == 0 || bh == 0) return NH_OK;
-    CoderArgs a{};
-    a.src = src; a.H = height; a.W = width; a.pitch = pitch; a.cost_kind = cost_kind;
-    a.n_blocks = (int64_t)bw * bh;
-    a.qp = make_quant_params(qp, l2, 1);
-    a.fq = make_fast_quant(a.qp);
-    a.maxv = (1 << bit_depth) - 1;
-    a.use_dst = size == 4;  // docs/frames_and_panes.md:328-329
-    a.out = CoderOut{modes, costs, pred, coeff, levels, nullptr, recon_plane, pitch};
-    a.vec_ok = (pitch % 8) == 0 && aligned16(src) && aligned16(recon_plane);
-    if (!recon_neighbours) {
-        // the search kernel reads the plane in 8-byte pieces and needs the modes tensor as its output
-        const bool split_ok = split_impl() && bit_depth <= 8 && modes && (pitch % 4) == 0 &&
-                              (reinterpret_cast<uintptr_t>(src) & 7) == 0;
-        return split_ok ? dispatch_search_then_code(a, size, st) : dispatch_coder<SRC_PLANE>(a, size, st);
-    }
-    const int64_t need = nh_encode_frame_scratch_bytes(height, width, size);
-    if (!scratch || scratch_bytes < need) {
-        set_error("nh_encode_frame: scratch of %lld bytes required, got %lld", (long long)need,
-                  (long long)scratch_bytes);
-        return NH_E_NOMEM;
-    }
-    if ((reinterpret_cast<uintptr_t>(scratch) & 3) != 0) {
-        set_error("nh_encode_frame: scratch must be 4-byte aligned");
-        return NH_E_ARG;
-    }
-    {
-        static int sleep_ns = -1;  // NH_WAVE_SLEEP_NS overrides the default back-off
-        if (sleep_ns < 0) {
-            const char* e = getenv("NH_WAVE_SLEEP_NS");
-            sleep_ns = e ? atoi(e) : 0;  // measured: polling without back-off is as fast or faster (profiles/r1_notes.md)
-            if (sleep_ns < 0) sleep_ns = 0;
-        }
-        a.poll_sleep_ns = (unsigned)sleep_ns;
-    }
-    a.ticket = reinterpret_cast<int*>(scratch);
-    a.bottom = reinterpret_cast<int16_t*>(reinterpret_cast<unsigned char*>(scratch) + 256);
-    init_bottom_kernel<<<grid_for((int64_t)bh * width, 256, 4), 256, 0, st>>>(a.bottom, bh, width, bw * size, a.ticket);
-    NH_CHECK_LAUNCH("init_bottom_kernel");
-    return dispatch_coder<SRC_WAVEFRONT>(a, size, st);
+    return nh_encode_frames(src, 1, (int64_t)height * pitch, height, width, pitch, size, cost_kind, qp, recon_neighbours,
+                            bit_depth, modes, costs, pred, coeff, levels, recon_plane, nullptr, scratch, scratch_bytes,
+                            stream);
 }

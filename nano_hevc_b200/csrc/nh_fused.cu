@@ -681,6 +681,7 @@ static int launch_unit4(const FusedArgs& a, cudaStream_t st) {
     }
     fused_unit4_kernel<DST><<<grid, kV2Warps * 32, kSmem, st>>>(a, make_fast_quant(a.qp), counter);
     NH_CHECK_LAUNCH("fused_unit4_kernel");
+    tile_counter_launched(st);
     return NH_OK;
 }
 
@@ -1212,7 +1213,7 @@ static int launch_unit_v3(const FusedArgs& a, cudaStream_t st) {
 // Kernel generation used for N = 4, 8: 4 (default: tensor-core passes at N = 8, the rolled 4x4
 // kernel at N = 4), 2 (cp.async + in-thread butterflies), 1 (first generation) or 3 (TMA tensor-map staging);
 // set by nh_set_fused_impl() or the NH_FUSED_IMPL=v1|v2|v3|v4 environment variable.
-static int g_fused_impl = 0;
+static thread_local int g_fused_impl = 0;   // per calling thread: no shared mutable state between callers
 static int fused_impl() {
     if (g_fused_impl == 0) {
         const char* e = getenv("NH_FUSED_IMPL");
@@ -1250,7 +1251,7 @@ static int launch_rows(const FusedArgs& a, cudaStream_t st) {
 // Kernel behind N = 16, 32: 2 (default) = tensor-core passes (fused_mma_kernel), 1 = CUDA-core
 // butterflies (fused_rows_kernel); nh_set_rows_impl() or NH_ROWS_IMPL=1|2.  The int16-output variant
 // of the host pipeline always uses the CUDA-core kernel.
-static int g_rows_impl = 0;
+static thread_local int g_rows_impl = 0;
 int rows_impl() {
     if (g_rows_impl == 0) {
         const char* e = getenv("NH_ROWS_IMPL");

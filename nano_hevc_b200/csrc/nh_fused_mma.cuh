@@ -478,25 +478,24 @@ static int launch_mma8_occ(const FusedArgs& a, cudaStream_t st) {
     }
     fused_mma8_kernel<OCC><<<grid, kV2Warps * 32, kSmem, st>>>(a, make_fast_quant(a.qp), counter);
     NH_CHECK_LAUNCH("fused_mma8_kernel");
+    tile_counter_launched(st);
     return NH_OK;
 }
 static int launch_mma8(const FusedArgs& a, cudaStream_t st) {
-    static int occ = 0;
-    if (occ == 0) {
+    static const int occ = [] {   // read once (thread-safe static initialisation)
         const char* e = getenv("NH_MMA_OCC");
-        occ = (e && e[0] == '4') ? 4 : 3;  // measured: 0.87 of the HBM peak at 3 CTAs / SM, 0.80 at 4
-    }
+        return (e && e[0] == '4') ? 4 : 3;  // measured: 0.87 of the HBM peak at 3 CTAs / SM, 0.80 at 4
+    }();
     return occ == 3 ? launch_mma8_occ<3>(a, st) : launch_mma8_occ<4>(a, st);
 }
 
 template <int N>
 static int launch_mma(const FusedArgs& a, cudaStream_t st) {
     constexpr int BPW = 32 / N;
-    static int occ = 0;  // resident CTAs per SM the kernel is compiled for: NH_MMA_OCC=3|4 (A/B profiling)
-    if (occ == 0) {
+    static const int occ = [] {  // resident CTAs per SM the kernel is compiled for: NH_MMA_OCC=3|4 (A/B profiling)
         const char* e = getenv("NH_MMA_OCC");
-        occ = (e && e[0] == '3') ? 3 : 4;  // N = 16: 427 vs 414 Gpix/s, N = 32: 445 vs 448
-    }
+        return (e && e[0] == '3') ? 3 : 4;  // N = 16: 427 vs 414 Gpix/s, N = 32: 445 vs 448
+    }();
     int grid = grid_for(a.n_blocks, (int64_t)kMmaWarps * BPW, occ);
     if (occ == 3) fused_mma_kernel<N, 3><<<grid, kMmaWarps * 32, 0, st>>>(a, make_fast_quant(a.qp));
     else fused_mma_kernel<N, 4><<<grid, kMmaWarps * 32, 0, st>>>(a, make_fast_quant(a.qp));

@@ -312,11 +312,10 @@ __global__ void __launch_bounds__(kMmaWarps * 32, OCC)
 
 template <int N, bool INV, bool IN32>
 static int launch_transform_mma(const void* in, int32_t* out, int64_t n_blocks, cudaStream_t st) {
-    static int occ = 0;  // resident CTAs per SM the kernel is compiled for: NH_XF_OCC=3|4|5 (A/B runs)
-    if (occ == 0) {
+    static const int occ = [] {  // resident CTAs per SM the kernel is compiled for: NH_XF_OCC=3|4|5 (A/B runs)
         const char* e = getenv("NH_XF_OCC");
-        occ = (e && e[0] >= '3' && e[0] <= '5') ? e[0] - '0' : 4;  // measured best overall (profiles/r1_notes.md)
-    }
+        return (e && e[0] >= '3' && e[0] <= '5') ? e[0] - '0' : 4;  // measured best overall (profiles/r1_notes.md)
+    }();
     int grid = grid_for(n_blocks, kMmaWarps * (32 / N), occ);
     if (occ == 4) transform_mma_kernel<N, INV, IN32, 4><<<grid, kMmaWarps * 32, 0, st>>>(in, out, n_blocks);
     else if (occ == 5) transform_mma_kernel<N, INV, IN32, 5><<<grid, kMmaWarps * 32, 0, st>>>(in, out, n_blocks);
@@ -533,6 +532,30 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+
+// intra_dc_predict (intra.py:46-62) sums WHATEVER top / left hold (top.sum() + left.sum()), then divides by
+// 2 * size: the (B, n_top) / (B, n_left) form for callers that pass arrays of another length than `size`.
+template <int N>
+__global__ void __launch_bounds__(256)
+    predict_dc_ragged_kernel(const int16_t* __restrict__ top, int n_top, const int16_t* __restrict__ left, int n_left,
+                             int16_t* __restrict__ pred, int64_t n_blocks) {
+    const int64_t total = n_blocks * N;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = t / N;
+        const int r = (int)(t % N);
+        int s = 0;
+        for (int k = 0; k < n_top; ++k) s += (int)__ldg(top + b * n_top + k);
+        for (int k = 0; k < n_left; ++k) s += (int)__ldg(left + b * n_left + k);
+        const int dc = dc_value<N>(s);
+        int p[N];
+#pragma unroll
+        for (int x = 0; x < N; ++x) p[x] = dc;
+        uint32_t w[N / 2];
+        pack_row<N>(p, w);
+        store_row16<N>(pred + b * (N * N) + r * N, w);
+    }
+}
+
 template <int KIND>
 static int launch_predict(const int16_t* top, const int16_t* left, const int16_t* aux0,
                           const int16_t* aux1, const uint8_t* modes, int mode, int allow,
@@ -629,11 +652,15 @@ NH_API int nh_inverse_transform(const int32_t* coeff, int32_t* residual, int64_t
 
 NH_API int nh_quantize(const int32_t* coeff, int32_t* level, int64_t n, int qp, int size, int is_intra,
                        void* stream) {
-    NH_REQUIRE_SIZE(size);
+    // quant.py:72 computes int(np.log2(size)) for whatever size it is given: 1..63 is accepted here (the
+    // 32-bit fast path is exact up to shift 14 + 8 + 5)
+    NH_REQUIRE(size >= 1 && size <= 63, "nh_quantize: size out of range 1..63");
     NH_REQUIRE(coeff && level && n >= 0, "nh_quantize: null pointer or negative count");
     NH_REQUIRE(aligned16(coeff) && aligned16(level), "nh_quantize: tensors must be 16-byte aligned");
     if (n == 0) return NH_OK;
-    QuantF f{make_quant_params(qp, log2_size(size), is_intra), {}};
+    int l2 = 0;
+    while ((2 << l2) <= size) ++l2;   // floor(log2(size))
+    QuantF f{make_quant_params(qp, l2, is_intra), {}};
     f.fq = make_fast_quant(f.p);
     map_i32_kernel<<<grid_elems(n, 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(coeff, level, n, f);
     NH_CHECK_LAUNCH("nh_quantize");
@@ -689,6 +716,25 @@ NH_API int nh_intra_dc_predict(const int16_t* top, const int16_t* left, int16_t*
     NH_REQUIRE(aligned16(pred), "nh_intra_dc_predict: pred must be 16-byte aligned");
     return launch_predict<0>(top, left, nullptr, nullptr, nullptr, 1, 0, pred, n_blocks, size,
                              reinterpret_cast<cudaStream_t>(stream));
+}
+
+NH_API int nh_intra_dc_predict_ragged(const int16_t* top, int n_top, const int16_t* left, int n_left,
+                                      int16_t* pred, int64_t n_blocks, int size, void* stream) {
+    NH_REQUIRE_SIZE(size);
+    NH_REQUIRE(pred && n_blocks >= 0 && n_top >= 0 && n_left >= 0 && (top || n_top == 0) && (left || n_left == 0),
+               "nh_intra_dc_predict_ragged: null pointer or negative count");
+    NH_REQUIRE(aligned16(pred), "nh_intra_dc_predict_ragged: pred must be 16-byte aligned");
+    if (n_blocks == 0) return NH_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = grid_for(n_blocks * size, 256, 8);
+    switch (size) {
+        case 4: predict_dc_ragged_kernel<4><<<grid, 256, 0, st>>>(top, n_top, left, n_left, pred, n_blocks); break;
+        case 8: predict_dc_ragged_kernel<8><<<grid, 256, 0, st>>>(top, n_top, left, n_left, pred, n_blocks); break;
+        case 16: predict_dc_ragged_kernel<16><<<grid, 256, 0, st>>>(top, n_top, left, n_left, pred, n_blocks); break;
+        default: predict_dc_ragged_kernel<32><<<grid, 256, 0, st>>>(top, n_top, left, n_left, pred, n_blocks); break;
+    }
+    NH_CHECK_LAUNCH("predict_dc_ragged_kernel");
+    return NH_OK;
 }
 
 NH_API int nh_intra_planar_predict(const int16_t* top, const int16_t* left, const int16_t* top_right,

@@ -178,6 +178,76 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+
+// Wide-input variants behind the per-block metric wrappers (the reference widens before it reduces:
+// metrics.py:9 float64, :26 / :33 int32, :48 int64), for callers that hand in uint16 samples or the int32
+// output of inverse_transform:
+//   out[0] = sum (a - b)^2 with the difference in int64, accumulated modulo 2^64   (residual_energy, :48)
+//   out[1] = sum |a - b| with the difference and abs() wrapping in int32, summed in int64   (sad, :26)
+//   fsum   = sum of double(a - b)^2, each square rounded like diff ** 2 on float64       (mse, :9-10)
+__global__ void __launch_bounds__(256)
+    metrics_i32_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b, int64_t n, int64_t* out,
+                       double* fsum) {
+    unsigned long long sse = 0;
+    long long sad = 0;
+    double fs = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int32_t x = a[i], y = b ? b[i] : 0;
+        const long long d = (long long)x - (long long)y;
+        sse += (unsigned long long)d * (unsigned long long)d;
+        const uint32_t w = (uint32_t)x - (uint32_t)y;              // int32 wrap-around difference
+        const int32_t wa = (int32_t)((w & 0x80000000u) ? 0u - w : w);   // np.abs on int32 (INT_MIN stays INT_MIN)
+        sad += (long long)wa;
+        const double dd = (double)d;
+        fs += dd * dd;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) fs += __shfl_xor_sync(0xffffffffu, fs, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(fsum, fs);
+    warp_block_atomic_add2((long long)sse, sad, out);
+}
+
+// mse (metrics.py:7-10) for float64 inputs: sum of (a - b)^2 in float64.
+__global__ void __launch_bounds__(256)
+    sse_f64_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n, double* fsum) {
+    double fs = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double d = a[i] - b[i];
+        fs += d * d;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) fs += __shfl_xor_sync(0xffffffffu, fs, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(fsum, fs);
+}
+
+// satd_4x4 (metrics.py:29-43) on int32 inputs with the reference's int32 wrap-around arithmetic; one thread
+// per block pair, out (B,) int64.
+__global__ void __launch_bounds__(128)
+    satd4_i32_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b, int64_t n_blocks, int64_t* out) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_blocks; t += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t d[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) d[e] = (uint32_t)a[t * 16 + e] - (uint32_t)b[t * 16 + e];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t a0 = d[j] + d[4 + j], a1 = d[j] - d[4 + j], a2 = d[8 + j] + d[12 + j], a3 = d[8 + j] - d[12 + j];
+            d[j] = a0 + a2; d[4 + j] = a1 + a3; d[8 + j] = a0 - a2; d[12 + j] = a1 - a3;
+        }
+        long long s = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t a0 = d[4 * i] + d[4 * i + 1], a1 = d[4 * i] - d[4 * i + 1];
+            uint32_t a2 = d[4 * i + 2] + d[4 * i + 3], a3 = d[4 * i + 2] - d[4 * i + 3];
+            const uint32_t r[4] = {a0 + a2, a1 + a3, a0 - a2, a1 - a3};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s += (long long)(int32_t)((r[k] & 0x80000000u) ? 0u - r[k] : r[k]);
+        }
+        out[t] = s;
+    }
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static int launch_sse_sad(const int16_t* a, int64_t pa, const int16_t* b, int64_t pb, int64_t rows,
@@ -208,6 +278,38 @@ NH_API int nh_reduce_sse_sad_2d(const int16_t* a, int pitch_a, const int16_t* b,
         return NH_E_ARG;
     }
     return launch_sse_sad(a, pitch_a, b, pitch_b, height, width, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+NH_API int nh_reduce_metrics_i32(const int32_t* a, const int32_t* b, int64_t n, int64_t* out, double* fsum,
+                                 void* stream) {
+    if (!a || !out || !fsum || n < 0) { set_error("nh_reduce_metrics_i32: null pointer or negative count"); return NH_E_ARG; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(out, 0, 2 * sizeof(int64_t), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(fsum, 0, sizeof(double), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(reduction output)");
+    if (n == 0) return NH_OK;
+    metrics_i32_kernel<<<grid_for(n, 256 * 4, 4), 256, 0, st>>>(a, b, n, out, fsum);
+    NH_CHECK_LAUNCH("metrics_i32_kernel");
+    return NH_OK;
+}
+
+NH_API int nh_reduce_sse_f64(const double* a, const double* b, int64_t n, double* fsum, void* stream) {
+    if (!a || !b || !fsum || n < 0) { set_error("nh_reduce_sse_f64: null pointer or negative count"); return NH_E_ARG; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(fsum, 0, sizeof(double), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(reduction output)");
+    if (n == 0) return NH_OK;
+    sse_f64_kernel<<<grid_for(n, 256 * 4, 4), 256, 0, st>>>(a, b, n, fsum);
+    NH_CHECK_LAUNCH("sse_f64_kernel");
+    return NH_OK;
+}
+
+NH_API int nh_satd_4x4_i32(const int32_t* a, const int32_t* b, int64_t n_blocks, int64_t* out, void* stream) {
+    if (!a || !b || !out || n_blocks < 0) { set_error("nh_satd_4x4_i32: null pointer or negative count"); return NH_E_ARG; }
+    if (n_blocks == 0) return NH_OK;
+    satd4_i32_kernel<<<grid_for(n_blocks, 128, 8), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, b, n_blocks, out);
+    NH_CHECK_LAUNCH("satd4_i32_kernel");
+    return NH_OK;
 }
 
 NH_API int nh_block_costs(const int16_t* a, const int16_t* b, int64_t n_blocks, int size, int32_t* sad,

@@ -70,9 +70,11 @@ struct SearchArgs {
     const int16_t* src;
     int H, W, pitch;
     int cost_kind;
-    int64_t n_blocks;
+    int64_t n_blocks;          // blocks of all frames
     uint8_t* modes;
     int32_t* costs;
+    int64_t blocks_per_frame;  // frames are stacked `frame_stride` samples apart; block b belongs to frame
+    int64_t frame_stride;      // b / blocks_per_frame (a warp tile may straddle two frames)
 };
 
 // SAD (metrics.py:24-26) or the sum of satd_4x4 (metrics.py:29-43) of a strip held as packed bytes.
@@ -167,7 +169,10 @@ __global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, COST == NH_COST_SAD 
         int64_t b = tile * T + bi;
         const bool valid = b < a.n_blocks;
         if (!valid) b = a.n_blocks - 1;
-        const int x = (int)(b % bw) * N, y = (int)(b / bw) * N;
+        const int fr = (int)(b / a.blocks_per_frame);
+        const int64_t bf = b - fr * a.blocks_per_frame;   // block index inside its frame
+        const int x = (int)(bf % bw) * N, y = (int)(bf / bw) * N;
+        const int16_t* srcf = a.src + fr * a.frame_stride;
         int ood = 0;
         __syncwarp();   // the previous tile's arrays are no longer read
 
@@ -180,15 +185,16 @@ __global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, COST == NH_COST_SAD 
             const int e = e0 + lane < RE ? e0 + lane : RE - 1;
             const int i = e / (2 * N + 2), k = e % (2 * N + 2);
             const int xi = __shfl_sync(0xffffffffu, x, (i * SB) & 31), yi = __shfl_sync(0xffffffffu, y, (i * SB) & 31);
+            const int16_t* srci = a.src + __shfl_sync(0xffffffffu, fr, (i * SB) & 31) * a.frame_stride;
             const int kk = k <= 2 * N ? k : 2 * N;   // entry 2N+1: replicate-last padding (only read with weight 0)
             int tv, lv;
             if (interior) {   // no substitution, no truncation: top[k] = plane[y-1][x-1+k], left[k] = plane[y-1+k][x-1]
-                const int16_t* c = a.src + (int64_t)(yi - 1) * a.pitch + xi - 1;
+                const int16_t* c = srci + (int64_t)(yi - 1) * a.pitch + xi - 1;
                 tv = __ldg(c + kk);
                 lv = __ldg(c + (int64_t)kk * a.pitch);
             } else {
-                tv = top_ref<false>(a.src, a.H, a.W, a.pitch, xi, yi, 2 * N, kk);
-                lv = left_ref<false>(a.src, a.H, a.W, a.pitch, xi, yi, 2 * N, kk);
+                tv = top_ref<false>(srci, a.H, a.W, a.pitch, xi, yi, 2 * N, kk);
+                lv = left_ref<false>(srci, a.H, a.W, a.pitch, xi, yi, 2 * N, kk);
             }
             unsigned char* zb = reinterpret_cast<unsigned char*>(wbase + i * C::BLOCK_WORDS);
             zb[k] = (unsigned char)tv;
@@ -202,7 +208,7 @@ __global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, COST == NH_COST_SAD 
         for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int q = 0; q < WPS; ++q) {
-                const uint2 v = __ldg(reinterpret_cast<const uint2*>(a.src + (int64_t)(y + py_ + j) * a.pitch + x + px_ + 4 * q));
+                const uint2 v = __ldg(reinterpret_cast<const uint2*>(srcf + (int64_t)(y + py_ + j) * a.pitch + x + px_ + 4 * q));
                 ood |= (int)((v.x | v.y) & 0xFF00FF00u);
                 ov[j][q] = __byte_perm(v.x, v.y, 0x6420);
             }
@@ -211,7 +217,7 @@ __global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, COST == NH_COST_SAD 
             uint2 r[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                r[i] = __ldg(reinterpret_cast<const uint2*>(a.src + (int64_t)(y + px_ + 4 * q + i) * a.pitch + x + py_));
+                r[i] = __ldg(reinterpret_cast<const uint2*>(srcf + (int64_t)(y + px_ + 4 * q + i) * a.pitch + x + py_));
                 ood |= (int)((r[i].x | r[i].y) & 0xFF00FF00u);
             }
             // 4x4 byte transpose: oh[j][q] byte i = row i, column j

@@ -30,19 +30,6 @@ def _world(group=None):
     return 0, 1
 
 
-_STREAMS: dict = {}
-
-
-def _frame_streams(device, n):
-    """Per-device side streams, created once: the caching allocator keeps one pool per stream, so
-    fresh streams on every call would turn every output allocation into a cudaMalloc."""
-    key = str(torch.device(device))
-    have = _STREAMS.setdefault(key, [])
-    while len(have) < n:
-        have.append(torch.cuda.Stream(device=device))
-    return have[:n]
-
-
 def frame_stats(src: torch.Tensor, result) -> torch.Tensor:
     """(sse, n_samples, sum_sad_cost, nonzero_levels) of one coded frame as an int64 device tensor.
     sse / n_samples follow metrics.py:7-21 over the WHOLE plane (uncovered rows count, as in
@@ -51,58 +38,81 @@ def frame_stats(src: torch.Tensor, result) -> torch.Tensor:
     ss = batched.sse_sad(src, result.recon_plane)
     nnz = batched.count_nonzero_batched(result.levels) if result.levels is not None else ss.new_zeros(())
     cost = result.costs.sum(dtype=torch.int64) if result.costs is not None else ss.new_zeros(())
-    # torch.full, not new_tensor: a host scalar would be copied with a stream synchronisation, which
-    # serialises frames that are meant to overlap on separate streams
     n = torch.full((), src.numel(), dtype=torch.int64, device=ss.device)
     return torch.stack([ss[0], n, cost.to(torch.int64), nnz.to(torch.int64)])
+
+
+def _stack_local_frames(frames, lo, hi, device):
+    """The local frames [lo, hi) as one (F, H, W) int16 tensor on ``device``.  Host frames (numpy arrays or
+    CPU tensors) are uploaded on the CURRENT stream into memory this function owns until the coder that
+    reads it -- enqueued on the same stream -- has been ordered behind the copies: no side streams, no
+    buffer that can be recycled while a kernel still reads it."""
+    local = []
+    for i in range(lo, hi):
+        f = frames[i]
+        if not isinstance(f, torch.Tensor):
+            f = torch.from_numpy(np.ascontiguousarray(f, dtype=np.int16))
+        local.append(f)
+    if not local:
+        return None
+    shapes = {tuple(f.shape) for f in local}
+    if len(shapes) != 1 or len(next(iter(shapes))) != 2:
+        raise ValueError(f"frames of one call must share one (H, W) shape, got {sorted(shapes)}")
+    H, W = local[0].shape
+    out = torch.empty((len(local), H, W), dtype=torch.int16, device=device)
+    for k, f in enumerate(local):
+        out[k].copy_(f.to(torch.int16) if f.dtype != torch.int16 else f, non_blocking=True)
+    return out
 
 
 def encode_frames_sharded(frames: Sequence, size: int, cost: str = "sad", qp: int = 27,
                           recon_neighbours: bool = True, bit_depth: int = 8, group=None,
                           device: torch.device | None = None,
-                          encode_fn: Callable | None = None, stats_fn: Callable | None = None,
-                          max_concurrent_frames: int = 8):
-    """Code ``frames`` (a sequence of (H, W) int16 arrays / tensors, identical on every rank) with
-    frame i on rank ``i mod``-contiguous shard, then all-gather the per-frame statistics.
+                          encode_fn: Callable | None = None, stats_fn: Callable | None = None):
+    """Code ``frames`` (a sequence of (H, W) int16 arrays / tensors, identical on every rank) with the
+    contiguous shard ``shard_range(len(frames), rank, world)`` on this rank, then all-gather the per-frame
+    statistics.
 
-    Returns ``(local_results, stats, psnr)``: the FrameResult objects of this rank's frames, an
-    (n_frames, 4) int64 tensor [sse, n, sum_cost, nnz] identical on every rank, and the per-frame
-    PSNR list (float64, finished on the host from the exact integer SSE).
-    ``encode_fn`` / ``stats_fn`` exist so the host-side logic can be exercised on CPU (gloo)."""
+    The local frames go through ONE ``nh_encode_frames`` call (batched.encode_frames): their block rows
+    share the wavefront scheduler, so several frames per GPU fill it; the per-frame statistics come from
+    the same call.  Returns ``(local_results, stats, psnr)``: the FrameResult objects of this rank's frames
+    (views into the batched outputs), an (n_frames, 4) int64 tensor [sse, n, sum_cost, nnz] identical on
+    every rank, and the per-frame PSNR list (float64, finished on the host from the exact integer SSE).
+    ``encode_fn`` / ``stats_fn`` (per-frame callables) exist so the host-side logic can be exercised on
+    CPU (gloo)."""
     from . import batched
     rank, world = _world(group)
     n = len(frames)
     lo, hi = shard_range(n, rank, world)
-    if encode_fn is None:
-        encode_fn = lambda f: batched.encode_frame(f, size, cost=cost, qp=qp, recon_neighbours=recon_neighbours,
-                                                   bit_depth=bit_depth)
-        stats_fn = frame_stats
     local, local_stats = [], []
-    # A wavefront frame occupies only a few hundred warps (one per block row), so the frames of this
-    # rank run concurrently on separate CUDA streams; the coders are independent (no shared state).
-    use_streams = (device is not None and torch.device(device).type == "cuda" and hi - lo > 1
-                   and max_concurrent_frames > 1)
-    streams = _frame_streams(device, min(hi - lo, max_concurrent_frames)) if use_streams else []
-    main = torch.cuda.current_stream(device) if use_streams else None
-    for n_done, i in enumerate(range(lo, hi)):
-        f = frames[i]
-        if not isinstance(f, torch.Tensor):
-            f = torch.from_numpy(np.ascontiguousarray(f, dtype=np.int16))
-        if device is not None:
-            f = f.to(device, non_blocking=True)
-        if use_streams:
-            st = streams[n_done % len(streams)]
-            st.wait_stream(main)
-            with torch.cuda.stream(st):
-                r = encode_fn(f)
-                local_stats.append(stats_fn(f, r).to(torch.int64))
-            local.append(r)
-        else:
+    if encode_fn is None:
+        dev = torch.device(device) if device is not None else None
+        if dev is None:
+            for i in range(lo, hi):
+                if isinstance(frames[i], torch.Tensor) and frames[i].is_cuda:
+                    dev = frames[i].device
+                    break
+        if hi > lo:
+            if dev is None or dev.type != "cuda":
+                raise RuntimeError("encode_frames_sharded needs a CUDA device (there is no CPU fallback)")
+            with torch.cuda.device(dev):
+                planes = _stack_local_frames(frames, lo, hi, dev)
+                r = batched.encode_frames(planes, size, cost=cost, qp=qp, recon_neighbours=recon_neighbours,
+                                          bit_depth=bit_depth)
+            for k in range(hi - lo):
+                local.append(batched.FrameResult(r.modes[k], r.costs[k], r.pred[k], r.coeff[k], r.levels[k],
+                                                 r.recon_planes[k]))
+                local_stats.append(r.stats[k])
+    else:
+        for i in range(lo, hi):
+            f = frames[i]
+            if not isinstance(f, torch.Tensor):
+                f = torch.from_numpy(np.ascontiguousarray(f, dtype=np.int16))
+            if device is not None:
+                f = f.to(device)
             r = encode_fn(f)
             local.append(r)
-            local_stats.append(stats_fn(f, r).to(torch.int64))
-    for st in streams:
-        main.wait_stream(st)
+            local_stats.append((stats_fn or frame_stats)(f, r).to(torch.int64))
     stat_dev = local_stats[0].device if local_stats else (device or torch.device("cpu"))
     # pad every rank's block to the largest shard so a single all_gather suffices
     per = -(-n // world) if world else n

@@ -60,8 +60,7 @@ for i in range(args.frames):  # encode_frames_sharded only touches [lo, hi)
 # warm-up: one full pass, so that the timed pass reuses the caching allocator's blocks (the
 # outputs of all local frames are kept alive, ~100 MB per 4K frame; fresh cudaMalloc calls would
 # otherwise dominate the timing)
-_w = multi_gpu.encode_frames_sharded(frames, args.size, cost="sad", qp=args.qp, recon_neighbours=True, device=dev,
-                                      max_concurrent_frames=args.concurrent)
+_w = multi_gpu.encode_frames_sharded(frames, args.size, cost="sad", qp=args.qp, recon_neighbours=True, device=dev)
 del _w
 torch.cuda.synchronize()
 if world > 1:
@@ -69,8 +68,7 @@ if world > 1:
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 local_res, stats, psnr = multi_gpu.encode_frames_sharded(frames, args.size, cost="sad", qp=args.qp,
-                                                          recon_neighbours=True, device=dev,
-                                                          max_concurrent_frames=args.concurrent)
+                                                          recon_neighbours=True, device=dev)
 e1.record()
 torch.cuda.synchronize()
 ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
