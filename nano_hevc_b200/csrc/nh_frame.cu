@@ -673,6 +673,10 @@ __global__ void __launch_bounds__(32 * WPB) coder_wave_mw_kernel(const CoderArgs
     }
 }
 
+}  // namespace nh
+#include "nh_wave.cuh"   // latency-oriented wavefront kernels for 8-bit planes (N = 8, N = 4); needs CoderArgs
+namespace nh {
+
 // Exchange rows of the wavefront coder: -1 where a block will publish its bottom row, 0 in the
 // columns no full block covers (the reference reads the zero-initialised plane there).
 __global__ void __launch_bounds__(256) init_bottom_kernel(int16_t* bottom, int64_t rows, int W, int covered, int* ticket) {
@@ -762,6 +766,23 @@ static int dispatch_coder(const CoderArgs& a, int size, cudaStream_t st) {
         const int64_t rows = (int64_t)(a.H / size) * a.n_frames;
         int grid = rows < sm_count() * 16 ? (int)rows : sm_count() * 16;
         if (grid < 1) grid = 1;
+        // 8-bit planes, N = 8: the latency-oriented kernel of nh_wave.cuh (NH_WAVE_IMPL=1 keeps the generic one)
+        static const bool wave_new = [] { const char* e = getenv("NH_WAVE_IMPL"); return !(e && e[0] == '1'); }();
+        const bool wave_ok = wave_new && a.maxv <= 255 && (a.pitch % 4) == 0 && (a.frame_stride % 4) == 0 &&
+                             (reinterpret_cast<uintptr_t>(a.src) & 7) == 0 &&
+                             (reinterpret_cast<uintptr_t>(a.out.recon_plane) & 7) == 0;
+        if (wave_ok && size == 8) {
+            if (a.cost_kind == NH_COST_SAD) wave8_kernel<NH_COST_SAD><<<grid, 96, 0, st>>>(a);
+            else wave8_kernel<NH_COST_SATD><<<grid, 96, 0, st>>>(a);
+            NH_CHECK_LAUNCH("wave8_kernel");
+            return NH_OK;
+        }
+        if (wave_ok && size == 4) {
+            if (a.cost_kind == NH_COST_SAD) wave4_kernel<NH_COST_SAD><<<grid, 32, 0, st>>>(a);
+            else wave4_kernel<NH_COST_SATD><<<grid, 32, 0, st>>>(a);
+            NH_CHECK_LAUNCH("wave4_kernel");
+            return NH_OK;
+        }
         static const int wave_warps = [] {  // warps per block row at N = 16 / 32: NH_WAVE_WARPS=1|2|4|8 (default 8)
             const char* e = getenv("NH_WAVE_WARPS");
             return (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 8;

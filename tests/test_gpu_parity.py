@@ -747,6 +747,34 @@ def test_encode_frames_batch_vs_oracle(Bt, n, rn):
     assert torch.equal(r.recon_planes[0], one.recon_plane)
 
 
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("cost", ("sad", "satd"))
+@pytest.mark.parametrize("W", (264, 268, 262))
+def test_wavefront_out_of_domain_source_and_odd_widths(Bt, n, cost, W):
+    """Wavefront coder (recon neighbours) on an 8-bit plane whose SOURCE holds a few samples outside [0, 255]:
+    those blocks take the exact generic path inside the latency-oriented kernels (N = 4 / 8), the rest the packed
+    8-bit path.  Widths 264 / 268 / 262: 16-byte, 8-byte and unaligned exchange / plane rows (the last one falls
+    back to the generic kernel).  Everything bit-exact against the oracle."""
+    rng = np.random.default_rng(1000 + n + W)
+    H = 5 * n + 3
+    src = _smooth(H, W, n)
+    src[n: 3 * n] = rng.integers(0, 256, (2 * n, W))
+    clean = src.copy()
+    src[1, 2] = 300
+    src[2 * n + 1, 5 * n + 1] = -7
+    src[3 * n, W - 2] = 256
+    src[4 * n + 2, 9 * n] = 1000
+    for plane in (clean, src):
+        r = Bt.encode_frame(dev(plane), n, cost=cost, qp=23, recon_neighbours=True)
+        w = O.encode_frame(plane, n, cost=cost, qp=23, recon_neighbours=True)
+        for name in ("modes", "costs", "pred", "coeff", "levels", "recon_plane"):
+            eq(host(getattr(r, name)), w[name], f"{name} n={n} {cost} W={W}")
+    # optional outputs: only recon + levels
+    r = Bt.encode_frame(dev(src), n, cost=cost, qp=23, recon_neighbours=True, outputs=("levels",))
+    assert r.modes is None and r.pred is None
+    eq(host(r.levels), w["levels"], "levels (subset)"); eq(host(r.recon_plane), w["recon_plane"], "recon (subset)")
+
+
 def test_encode_frames_sharded_host_frames(Bt):
     """multi_gpu.encode_frames_sharded with HOST frames (numpy) and several local frames: the upload and
     the coder are ordered on one stream (the round-1 version uploaded on the main stream and coded on side
