@@ -11,7 +11,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnh_b200.so")
+# NH_B200_LIB points at an alternative build of the same library (instrumented development builds)
+LIB_PATH = os.environ.get("NH_B200_LIB") or os.path.join(_HERE, "libnh_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 NH_OK, NH_E_SIZE, NH_E_ARG, NH_E_CUDA, NH_E_NOMEM = 0, -1, -2, -3, -4

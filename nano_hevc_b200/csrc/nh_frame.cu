@@ -772,8 +772,17 @@ static int dispatch_coder(const CoderArgs& a, int size, cudaStream_t st) {
                              (reinterpret_cast<uintptr_t>(a.src) & 7) == 0 &&
                              (reinterpret_cast<uintptr_t>(a.out.recon_plane) & 7) == 0;
         if (wave_ok && size == 8) {
-            if (a.cost_kind == NH_COST_SAD) wave8_kernel<NH_COST_SAD><<<grid, 96, 0, st>>>(a);
-            else wave8_kernel<NH_COST_SATD><<<grid, 96, 0, st>>>(a);
+            // few rows (one or two frames): the latency build, registers to spare; many rows: the build that keeps
+            // more CTAs resident.  NH_WAVE_OCC=lat|thr forces one of them.
+            static const int force = [] { const char* e = getenv("NH_WAVE_OCC"); return e ? (e[0] == 'l' ? 1 : 2) : 0; }();
+            const bool lat = force ? force == 1 : rows <= (int64_t)sm_count() * 3;
+            if (lat) {
+                if (a.cost_kind == NH_COST_SAD) wave8_kernel<NH_COST_SAD, 3><<<grid, 128, 0, st>>>(a);
+                else wave8_kernel<NH_COST_SATD, 3><<<grid, 128, 0, st>>>(a);
+            } else {
+                if (a.cost_kind == NH_COST_SAD) wave8_kernel<NH_COST_SAD, 4><<<grid, 128, 0, st>>>(a);
+                else wave8_kernel<NH_COST_SATD, 4><<<grid, 128, 0, st>>>(a);
+            }
             NH_CHECK_LAUNCH("wave8_kernel");
             return NH_OK;
         }

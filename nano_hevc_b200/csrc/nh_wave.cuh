@@ -27,6 +27,18 @@
 
 namespace nh {
 
+// Per-phase cycle counters of the first block row (development only: make NVCCFLAGS+=-DNH_WAVE_PROF; the
+// counters land in the scratch header behind the ticket, 8 x int64 at byte 64).
+#ifdef NH_WAVE_PROF
+#define NH_PROF_DECL long long prof_t = clock64(), prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define NH_PROF_MARK(i) { const long long now__ = clock64(); prof_acc[i] += now__ - prof_t; prof_t = now__; }
+#define NH_PROF_DUMP(cond) if (cond) { for (int i__ = 0; i__ < 8; ++i__) atomicAdd(reinterpret_cast<unsigned long long*>(a.ticket) + 8 + i__, (unsigned long long)prof_acc[i__]); }
+#else
+#define NH_PROF_DECL
+#define NH_PROF_MARK(i)
+#define NH_PROF_DUMP(cond)
+#endif
+
 static __constant__ signed char kc_wave_dct8[64] = {
     64, 64, 64, 64, 64, 64, 64, 64, 89, 75, 50, 18, -18, -50, -75, -89, 83, 36, -36, -83, -83, -36, 36, 83,
     75, -18, -89, -50, 50, 89, 18, -75, 64, -64, -64, 64, 64, -64, -64, 64, 50, -89, 18, 75, -75, -18, 89, -50,
@@ -90,6 +102,16 @@ __device__ __noinline__ void wave_block_generic(const CoderArgs& a, const unsign
 }
 
 // ------------------------------------------------------------------------------------------ N = 8
+// Roles inside the CTA of a block row (four warps).  Units: warps 0 / 1 hold modes 2 .. 33, warp 2 mode 34, warp 3 DC
+// and planar (a warp that mixed unit kinds would run them one after the other and hold up the barrier).  Beyond that
+//   warp 0  codes the winner: picks the winner's prediction tile (every unit has written its predicted strip
+//           into a tile of its mode, so nothing is predicted twice and no mode-dependent code sits behind the
+//           argmin), runs the MMA chain, publishes the bottom row, stores prediction / coefficients / levels /
+//           reconstruction straight from its fragments and derives the next block's left references from them;
+//   warp 1  stages the next block's pixels (bytes, transposed bytes, int16 ldmatrix tile);
+//   warp 2  is the service warp: it polls the exchange row for the next block's top references while warp 0
+//           codes the winner, and writes the block's mode / cost.
+// Two barriers per block: references + pixels ready, partial minima ready.
 struct Wave8Smem {
     static constexpr int N = 8;
     using SC = SearchCfg<8>;
@@ -97,37 +119,34 @@ struct Wave8Smem {
     static constexpr int REF_BYTES = SC::BLOCK_WORDS * 4;   // tb | lb | projected extensions (nh_search.cuh layout)
     static constexpr int OB = 0;                            // 2 x { 64 B pixels, 64 B transposed } as bytes
     static constexpr int O16 = OB + 2 * 128;                // 2 x 8 rows of 8 int16 (ldmatrix tiles)
-    static constexpr int P16 = O16 + 2 * 128;               // prediction tile
-    static constexpr int R16 = P16 + 128;                   // reconstruction tile (left references of the next block)
-    static constexpr int TSCR = R16 + 128;                  // 8x8 byte transpose scratch of the winner prediction
-    static constexpr int REFS = TSCR + 64;
+    static constexpr int TILES = O16 + 2 * 128;             // 35 prediction tiles (by candidate position), 8 x 8 int16;
+                                                            // horizontal modes hold the TRANSPOSED prediction
+    static constexpr int R16 = TILES + 35 * 128;            // reconstruction of a generic-path block
+    static constexpr int REFS = R16 + 128;
     static constexpr int GEN = (REFS + REF_BYTES + 15) / 16 * 16;   // generic coder's group (out-of-domain blocks)
     static constexpr int TOTAL = GEN + GC::GROUP_BYTES;
 };
 
-template <int COST>
-__global__ void __launch_bounds__(96, 6) wave8_kernel(const CoderArgs a) {
+template <int COST, int OCC>
+__global__ void __launch_bounds__(128, OCC) wave8_kernel(const CoderArgs a) {
     constexpr int N = 8, NN = 64, SH = 8;
     using SC = SearchCfg<8>;
     using L = Wave8Smem;
     constexpr int PB = SC::PB;
     __shared__ __align__(16) unsigned char smem[L::TOTAL];
-    __shared__ int s_negT0[15];
-    __shared__ int s_keys[3];
+    __shared__ int s_keys[4];
     __shared__ int s_row;
-    __shared__ int s_dc;
+    __shared__ int s_topsum, s_leftsum;
     __shared__ int s_ood[2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned char* refb = smem + L::REFS;          // tb = refb, lb = refb + PB
-    if (tid < 15) s_negT0[tid] = SC::neg_t0(tid);
 
     // ---- this lane's search unit, fixed for the whole kernel
-    const int u = tid;
-    const bool unit = u < 70;
-    const int strip = u & 1;
-    const int mode = u < 66 ? 2 + (u >> 1) : (u < 68 ? 1 : 0);
-    const int pos = u < 66 ? mode : (u < 68 ? 0 : 1);            // candidate order 1, 0, 2 .. 34
-    const bool angular = u < 66;
+    const bool unit = tid < 66 || (tid >= 96 && tid < 100);
+    const int strip = tid & 1;
+    const bool angular = tid < 66;
+    const int mode = angular ? 2 + (tid >> 1) : (tid < 98 ? 1 : 0);
+    const int pos = angular ? mode : (tid < 98 ? 0 : 1);            // candidate order 1, 0, 2 .. 34
     const bool vertical = mode >= 18;
     const int angle = angular ? intra_angle(mode) : 0;
     const bool negmode = angular && angle < 0;
@@ -143,9 +162,10 @@ __global__ void __launch_bounds__(96, 6) wave8_kernel(const CoderArgs a) {
         f8[j] = ((uint32_t)p & 31u) << 3;
     }
     const int obase = L::OB + ((angular && !vertical) ? 64 : 0) + 32 * strip;   // the unit's 4 scan lines of pixels
+    unsigned char* my_tile = smem + L::TILES + (unit ? pos : 0) * 128 + 64 * strip;   // its 4 rows of the mode's tile
     // projected extension (intra.py:180-186, the (k+1) projection of SURVEY Q3): the two strip lanes of a
     // negative-angle mode build the mode's array together, entries tt = strip, strip + 2, ...
-    uint32_t nsrc = 0;
+    int nsrc[4] = {0, 0, 0, 0};
     int nent = 0;
     const int ndst = negoff - 1 - strip;
     if (negmode) {
@@ -156,7 +176,7 @@ __global__ void __launch_bounds__(96, 6) wave8_kernel(const CoderArgs a) {
             const int tt = strip + 2 * i;
             int proj = (-tt * inv + 128) >> 8;
             proj = proj > 2 * N ? 2 * N : proj;
-            nsrc |= (uint32_t)(sec + proj) << (8 * i);
+            nsrc[i] = sec + proj;
             nent += tt < len;
         }
     }
@@ -172,99 +192,111 @@ __global__ void __launch_bounds__(96, 6) wave8_kernel(const CoderArgs a) {
     const uint32_t clip_lo2 = 0x10001000u;
     const uint32_t clip_hi2 = clip_lo2 + (uint32_t)a.maxv * 0x10001u;
     const FastQuant fq = a.fq;
-    const uint32_t row_addr = (uint32_t)(lane & 7) * 16u;   // ldmatrix / stmatrix x1: lanes 0..7 address the 8 rows
+    const uint32_t row_addr = (uint32_t)(lane & 7) * 16u;   // ldmatrix x1: lanes 0..7 address the 8 rows
+    const uint32_t tiles_addr = smem_u32(smem + L::TILES) + row_addr;
+    const uint32_t o16_addr = smem_u32(smem + L::O16) + row_addr;
 
-    const int bw = a.W / N, bh = a.H / N;
-    const bool vec_rows = a.vec_ok != 0;                // 16-byte aligned plane rows (pitch % 8 == 0)
-    const bool vec_exch = (a.W % 8) == 0;               // 16-byte aligned exchange rows
+    // kernel parameters, read once
+    const int bw = a.W / N, bh = a.H / N, W = a.W, pitch = a.pitch, n_frames = a.n_frames;
+    const bool vec_exch = (W % 2) == 0;                 // 4-byte aligned exchange-row pairs
+    uint8_t* const o_modes = a.out.modes;
+    int32_t* const o_costs = a.out.costs;
+    int16_t* const o_pred = a.out.pred;
+    int32_t* const o_coeff = a.out.coeff;
+    int32_t* const o_levels = a.out.levels;
+    const unsigned poll_sleep = a.poll_sleep_ns;
 
     for (;;) {
         __syncthreads();   // everyone is done with the previous row (and has read s_row)
         if (tid == 0) s_row = atomicAdd(a.ticket, 1);
         __syncthreads();
         const int tk = s_row;   // frames interleaved: ticket t = row t / F of frame t % F
-        const int by = tk / a.n_frames, fr = tk - by * a.n_frames;
+        const int by = tk / n_frames, fr = tk - by * n_frames;
         if (by >= bh) break;
-        const int16_t* srcf = a.src + fr * a.frame_stride;
-        int16_t* reconf = a.out.recon_plane + fr * a.frame_stride;
-        int16_t* bottomf = a.bottom + (int64_t)fr * bh * a.W;
-        const int16_t* up = bottomf + (int64_t)(by - 1) * a.W;   // exchange row above (by > 0)
         const int y = by * N;
+        const int16_t* srcf = a.src + fr * a.frame_stride;
+        int16_t* bottomf = a.bottom + (int64_t)fr * bh * W;
+        const int16_t* up = bottomf + (int64_t)(by - 1) * W;   // exchange row above (by > 0)
+        const int64_t blk0 = fr * a.blocks_per_frame + (int64_t)by * bw;
+        // per-row pointers of this lane
+        const int16_t* px_ptr = srcf + (int64_t)(y + (lane >> 1)) * pitch + 4 * (lane & 1);           // warp 1 staging
+        int16_t* recon_ptr = a.out.recon_plane + fr * a.frame_stride + (int64_t)(y + fg) * pitch + 2 * ft;   // warp 0
+        int16_t* bottom_ptr = bottomf + (int64_t)by * W + 2 * ft;
+        int16_t* pred_ptr = o_pred + blk0 * NN + fg * 8 + 2 * ft;
+        int32_t* coeff_ptr = o_coeff + blk0 * NN + (2 * ft) * N + fg;
+        int32_t* levels_ptr = o_levels + blk0 * NN + (2 * ft) * N + fg;
 
-        // the staging lanes (warps 1 / 2, lanes 0..15 of warp 1) hold the next block's pixels in registers
-        uint2 npx = make_uint2(0u, 0u);
-        auto fetch_px = [&](int bx) {   // 4 pixels per lane: row l / 2, columns 4 (l & 1) .. (launcher: pitch % 4 == 0)
-            if (warp == 1 && lane < 16)
-                npx = __ldg(reinterpret_cast<const uint2*>(srcf + (int64_t)(y + (lane >> 1)) * a.pitch + bx * N + 4 * (lane & 1)));
+        // ---- row prologue
+        uint2 npx = make_uint2(0u, 0u);   // warp 1, lanes 0..15: 4 pixels of the block being staged
+        auto fetch_px = [&](int bx) {     // row l / 2, columns 4 (l & 1) .. (launcher: pitch % 4 == 0)
+            if (lane < 16) npx = __ldg(reinterpret_cast<const uint2*>(px_ptr + bx * N));
         };
         auto stage_px = [&](int par) {   // registers -> int16 tile, byte matrix, transposed byte matrix
-            if (warp == 1) {
-                int bad = 0;
-                if (lane < 16) {
-                    const int r = lane >> 1, c4 = 4 * (lane & 1);
-                    *reinterpret_cast<uint2*>(smem + L::O16 + par * 128 + r * 16 + c4 * 2) = npx;
-                    const uint32_t b4 = __byte_perm(npx.x, npx.y, 0x6420);
-                    *reinterpret_cast<uint32_t*>(smem + L::OB + par * 128 + r * 8 + c4) = b4;
-                    unsigned char* t = smem + L::OB + par * 128 + 64 + r;   // transposed: [column][row]
-                    t[(c4 + 0) * 8] = (unsigned char)b4;
-                    t[(c4 + 1) * 8] = (unsigned char)(b4 >> 8);
-                    t[(c4 + 2) * 8] = (unsigned char)(b4 >> 16);
-                    t[(c4 + 3) * 8] = (unsigned char)(b4 >> 24);
-                    bad = (int)((npx.x | npx.y) & 0xFF00FF00u);
-                }
-                bad = __any_sync(0xffffffffu, bad != 0);
-                if (lane == 0) s_ood[par] = bad;
+            int bad = 0;
+            if (lane < 16) {
+                const int r = lane >> 1, c4 = 4 * (lane & 1);
+                *reinterpret_cast<uint2*>(smem + L::O16 + par * 128 + r * 16 + c4 * 2) = npx;
+                const uint32_t b4 = __byte_perm(npx.x, npx.y, 0x6420);
+                *reinterpret_cast<uint32_t*>(smem + L::OB + par * 128 + r * 8 + c4) = b4;
+                unsigned char* t = smem + L::OB + par * 128 + 64 + r;   // transposed: [column][row]
+                t[(c4 + 0) * 8] = (unsigned char)b4;
+                t[(c4 + 1) * 8] = (unsigned char)(b4 >> 8);
+                t[(c4 + 2) * 8] = (unsigned char)(b4 >> 16);
+                t[(c4 + 3) * 8] = (unsigned char)(b4 >> 24);
+                bad = (int)((npx.x | npx.y) & 0xFF00FF00u);
             }
+            bad = __any_sync(0xffffffffu, bad != 0);
+            if (lane == 0) s_ood[par] = bad;
         };
-        // top references of a block, requested early (warp 0, lane k < 18 holds entry k of tb)
-        auto top_load = [&](int bx) -> int {
-            if (by == 0) return 128;
-            const int x = bx * N;
-            if (lane == 0 && x == 0) return 128;
-            int last = x + 2 * N - 1;
-            if (last > a.W - 1) last = a.W - 1;
-            int col = x + (lane > 2 * N ? 2 * N : lane) - 1;
-            if (col > last) col = last;
-            return lane < 18 ? (int)__ldcg(up + col) : 0;
+        // top references of block bx (service warp; lane k < 18 = entry k of tb): poll the exchange row above
+        // until the data is there, then write the bytes, the corner slot of lb and the sum of top[1..N]
+        auto stage_top = [&](int bx) {
+            int v = 128;
+            if (by > 0) {
+                const int x = bx * N;
+                int last = x + 2 * N - 1;
+                if (last > W - 1) last = W - 1;
+                int col = x + (lane > 2 * N ? 2 * N : lane) - 1;
+                if (col > last) col = last;
+                const bool fixed = lane >= 18 || (lane == 0 && x == 0);   // corner of the first column: 128
+                unsigned spins = 0;
+                for (;;) {
+                    v = fixed ? 128 : (int)__ldcg(up + col);
+                    if (__all_sync(0xffffffffu, v >= 0)) break;
+                    if (poll_sleep) __nanosleep(poll_sleep);
+                    if (++spins > (1u << 25)) __trap();   // > 10 s of polling: a protocol error, fail loudly instead of hanging
+                }
+            }
+            if (lane < 18) refb[lane] = (unsigned char)v;
+            if (lane == 0) refb[PB] = (unsigned char)v;
+            const int ts = __reduce_add_sync(0xffffffffu, (lane >= 1 && lane <= N) ? v : 0);
+            if (lane == 0) s_topsum = ts;
         };
-
-        fetch_px(0);
-        int ntop = warp == 0 ? top_load(0) : 0;
+        if (warp == 1) {
+            fetch_px(0);
+            stage_px(0);
+            if (bw > 1) fetch_px(1);
+        } else if (warp == 2) {
+            stage_top(0);
+        } else if (warp == 0) {
+            if (lane >= 1 && lane < 18) refb[PB + lane] = 128;   // left references of the first block (block.py:45-50)
+            if (lane == 0) s_leftsum = N * 128;
+        }
+        NH_PROF_DECL
         for (int bx = 0; bx < bw; ++bx) {
             const int par = bx & 1, x = bx * N;
-            const int64_t b = fr * a.blocks_per_frame + (int64_t)by * bw + bx;
-            if (bx == 0) stage_px(0);
-            // ---- references: warp 0 finishes the poll of the exchange row and takes the left column from
-            // the reconstruction it has just produced
-            if (warp == 0) {
-                unsigned spins = 0;
-                while (!__all_sync(0xffffffffu, ntop >= 0)) {
-                    if (a.poll_sleep_ns) __nanosleep(a.poll_sleep_ns);
-                    if (++spins > (1u << 25)) __trap();   // > 10 s of polling: a protocol error, fail loudly instead of hanging
-                    ntop = top_load(bx);
-                }
-                int lv = 128;
-                if (lane >= 1 && lane < 18 && bx > 0)   // bottom-left is not reconstructed yet: replicate (n_left = N)
-                    lv = (int)reinterpret_cast<const int16_t*>(smem + L::R16)[((lane <= N ? lane : N) - 1) * 8 + 7];
-                if (lane == 0) lv = ntop;               // corner slot
-                if (lane < 18) {
-                    refb[lane] = (unsigned char)ntop;
-                    refb[PB + lane] = (unsigned char)lv;
-                }
-                const int s = (lane >= 1 && lane <= N) ? ntop + lv : 0;
-                const int dc = dc_value<N>(__reduce_add_sync(0xffffffffu, s));   // intra.py:46-62
-                if (lane == 0) s_dc = dc;
-            }
-            __syncthreads();   // #1: references, DC and this block's pixels are in shared memory
-            if (warp == 1 && bx + 1 < bw) fetch_px(bx + 1);
+            NH_PROF_MARK(7)
+            __syncthreads();   // #1: references, sums and this block's pixels are in shared memory
+            NH_PROF_MARK(2)
             const bool ood = s_ood[par] != 0;   // CTA-uniform
-            int best = 0x7fffffff;
             if (!ood) {
                 // ---- search: one unit per lane
                 if (negmode) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (i < nent) refb[ndst - 2 * i] = refb[(nsrc >> (8 * i)) & 0xffu];
+                    for (int i = 0; i < 4; ++i) {
+                        const unsigned char v = refb[nsrc[i]];
+                        if (i < nent) refb[ndst - 2 * i] = v;
+                    }
                     if (strip == 0) {
 #pragma unroll
                         for (int c = 0; c < 3; ++c)
@@ -287,7 +319,7 @@ __global__ void __launch_bounds__(96, 6) wave8_kernel(const CoderArgs a) {
                             predict_line_w<2>(reinterpret_cast<const uint32_t*>(refb + woff[j]), sh[j], 0x3412u + (sh[j] << 5),
                                               f8[j], 256u - f8[j], pr[j]);
                     } else if (mode == 1) {
-                        const uint32_t d4 = (uint32_t)s_dc * 0x01010101u;
+                        const uint32_t d4 = (uint32_t)dc_value<N>(s_topsum + s_leftsum) * 0x01010101u;   // intra.py:46-62
 #pragma unroll
                         for (int j = 0; j < 4; ++j) pr[j][0] = pr[j][1] = d4;
                     } else {   // planar (intra.py:109-111), two samples per multiply-add chain, sample = high byte
@@ -316,6 +348,12 @@ __global__ void __launch_bounds__(96, 6) wave8_kernel(const CoderArgs a) {
                             pr[j][1] = __byte_perm(t[2], t[3], 0x7531);
                         }
                     }
+                    // the unit's predicted strip into the tile of its mode, as int16 (ldmatrix tile rows)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(my_tile + 16 * j) =
+                            make_uint4(__byte_perm(pr[j][0], 0u, 0x4140), __byte_perm(pr[j][0], 0u, 0x4342),
+                                       __byte_perm(pr[j][1], 0u, 0x4140), __byte_perm(pr[j][1], 0u, 0x4342));
                     c = strip_cost_packed<2>(pr, o, COST);
                 }
                 c += __shfl_xor_sync(0xffffffffu, c, 1);
@@ -323,80 +361,40 @@ __global__ void __launch_bounds__(96, 6) wave8_kernel(const CoderArgs a) {
                 const int wmin = (int)__reduce_min_sync(0xffffffffu, (unsigned)key);
                 if (lane == 0) s_keys[warp] = wmin;
             }
-            __syncthreads();   // #2: the three partial minima
-            if (warp == 1 && bx + 1 < bw) stage_px(par ^ 1);   // next block's pixels, while warp 0 codes the winner
-            if (warp == 0) {
-                int16_t* r16 = reinterpret_cast<int16_t*>(smem + L::R16);
-                if (bx + 1 < bw) ntop = top_load(bx + 1);      // requested now, needed after the winner is coded
-                if (!ood) {
-                    best = s_keys[0];
+            NH_PROF_MARK(3)
+            __syncthreads();   // #2: the three partial minima, the prediction tiles
+            NH_PROF_MARK(4)
+            if (warp == 1) {          // next block's pixels, while warp 0 codes the winner
+                if (bx + 1 < bw) stage_px(par ^ 1);
+                if (bx + 2 < bw) fetch_px(bx + 2);
+            } else if (warp == 2) {   // mode / cost of this block, top references of the next one
+                if (!ood && lane == 0) {
+                    int best = s_keys[0];
                     best = s_keys[1] < best ? s_keys[1] : best;
                     best = s_keys[2] < best ? s_keys[2] : best;
-                    const int wmode = mode_of_key(best);
-                    if (lane == 0) {
-                        if (a.out.modes) a.out.modes[b] = (uint8_t)wmode;
-                        if (a.out.costs) a.out.costs[b] = best >> 6;
-                    }
-                    // ---- prediction of the winner into the prediction tile: lane s < 8 = one scan line
-                    unsigned char* p16 = smem + L::P16;
-                    if (lane < 8) {
-                        const unsigned char* tb = refb;
-                        const unsigned char* lb = refb + PB;
-                        uint32_t w4[4];
-                        bool direct = true;
-                        if (wmode == 1) {
-                            const uint32_t dc2 = (uint32_t)s_dc * 0x10001u;
-                            w4[0] = w4[1] = w4[2] = w4[3] = dc2;
-                        } else if (wmode == 0) {   // row `lane`, two pixels per multiply-add chain
-                            const uint32_t tr = tb[N + 1], bl = lb[N + 1], ly = lb[1 + lane];
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint32_t tw = (uint32_t)tb[1 + 2 * k] | ((uint32_t)tb[2 + 2 * k] << 16);
-                                const uint32_t ck1 = (uint32_t)(7 - 2 * k) | ((uint32_t)(6 - 2 * k) << 16);
-                                const uint32_t ck2 = (uint32_t)(2 * k + 1) | ((uint32_t)(2 * k + 2) << 16);
-                                const uint32_t t = tw * (uint32_t)(7 - lane) + (bl * (uint32_t)(lane + 1) + 8u) * 0x10001u +
-                                                   ly * ck1 + tr * ck2;
-                                w4[k] = (t >> 4) & 0x00FF00FFu;
-                            }
-                        } else {
-                            const int wang = intra_angle(wmode);
-                            const bool wvert = wmode >= 18;
-                            const int p = (lane + 1) * wang;
-                            const int k = 1 + (p >> 5);
-                            const uint32_t wf8 = ((uint32_t)p & 31u) << 3;
-                            const int arr = k < 0 ? s_negT0[wmode - 11] : (wvert ? 0 : PB);
-                            uint32_t ln[2];
-                            predict_line_u8<2>(refb, arr + k, wf8, 256u - wf8, ln);
-                            if (wvert) {
-                                w4[0] = __byte_perm(ln[0], 0u, 0x4140);
-                                w4[1] = __byte_perm(ln[0], 0u, 0x4342);
-                                w4[2] = __byte_perm(ln[1], 0u, 0x4140);
-                                w4[3] = __byte_perm(ln[1], 0u, 0x4342);
-                            } else {   // scan line = image column `lane`: through the transpose scratch
-                                unsigned char* t = smem + L::TSCR + lane;
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    t[8 * i] = (unsigned char)(ln[0] >> (8 * i));
-                                    t[8 * (i + 4)] = (unsigned char)(ln[1] >> (8 * i));
-                                }
-                                direct = false;
-                            }
-                        }
-                        if (direct) *reinterpret_cast<uint4*>(p16 + lane * 16) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-                    }
-                    __syncwarp();
-                    if (lane < 8 && wmode >= 2 && wmode < 18) {
-                        const uint2 v = *reinterpret_cast<const uint2*>(smem + L::TSCR + lane * 8);
-                        *reinterpret_cast<uint4*>(p16 + lane * 16) =
-                            make_uint4(__byte_perm(v.x, 0u, 0x4140), __byte_perm(v.x, 0u, 0x4342),
-                                       __byte_perm(v.y, 0u, 0x4140), __byte_perm(v.y, 0u, 0x4342));
-                    }
-                    __syncwarp();
-                    if (a.out.pred && lane < 8)
-                        stg_stream(a.out.pred + b * NN + lane * 8, *reinterpret_cast<const uint4*>(p16 + lane * 16));
+                    best = s_keys[3] < best ? s_keys[3] : best;
+                    if (o_modes) o_modes[blk0 + bx] = (uint8_t)mode_of_key(best);
+                    if (o_costs) o_costs[blk0 + bx] = best >> 6;
+                }
+                // (an out-of-domain block is coded by warp 0 from the CURRENT references: wait for it below)
+                if (!ood && bx + 1 < bw) stage_top(bx + 1);
+            } else if (warp == 0) {
+                uint32_t rr;   // reconstructed pair (row fg, columns 2 ft, 2 ft + 1)
+                if (!ood) {
+                    int best = s_keys[0];
+                    best = s_keys[1] < best ? s_keys[1] : best;
+                    best = s_keys[2] < best ? s_keys[2] : best;
+                    best = s_keys[3] < best ? s_keys[3] : best;
+                    const int wpos = best & 63;
+                    const bool transposed = wpos >= 2 && wpos < 18;   // horizontal modes: the tile holds P^T
+                    const uint32_t tile = tiles_addr + (uint32_t)wpos * 128u;
+                    const uint32_t t_t = ldsm_x1_t(tile), t_n = ldsm_x1(tile);
+                    const uint32_t rp = transposed ? t_n : t_t;   // P as B fragment (k = row, n = column)
+                    const uint32_t pc = transposed ? t_t : t_n;   // P in accumulator layout (row fg, columns 2 ft ..)
+                    const uint32_t ro = ldsm_x1_t(o16_addr + (uint32_t)par * 128u);
+                    if (o_pred) *reinterpret_cast<uint32_t*>(pred_ptr + bx * NN) = pc;
+                    NH_PROF_MARK(5)
                     // ---- the four passes on the tensor cores (see nh_fused_mma.cuh; block b of the pair is empty)
-                    const uint32_t sO = smem_u32(smem + L::O16 + par * 128) + row_addr, sP = smem_u32(p16) + row_addr;
-                    const uint32_t ro = ldsm_x1_t(sO), rp = ldsm_x1_t(sP), pc = ldsm_x1(sP);
                     float acc[4];
                     const uint32_t x0 = h2_bits(__hsub2(bits_h2(ro | 0x64006400u), bits_h2(rp | 0x64006400u)));
                     hmma16816(acc, a_fwd, x0, 0u, rnd, rnd, rnd, rnd);
@@ -405,11 +403,11 @@ __global__ void __launch_bounds__(96, 6) wave8_kernel(const CoderArgs a) {
                     float dqf[2];
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const int c = __float_as_int(floor_shift_magic<SH>(acc[e])) - kMagicI;
-                        const int lvq = quantize_fast(c, fq);
+                        const int cf = __float_as_int(floor_shift_magic<SH>(acc[e])) - kMagicI;
+                        const int lvq = quantize_fast(cf, fq);
                         const int dq = dequantize_fast(lvq, fq);
-                        if (a.out.coeff) __stcs(a.out.coeff + b * NN + (2 * ft + e) * N + fg, c);
-                        if (a.out.levels) __stcs(a.out.levels + b * NN + (2 * ft + e) * N + fg, lvq);
+                        if (o_coeff) __stcs(coeff_ptr + bx * NN + e * N, cf);
+                        if (o_levels) __stcs(levels_ptr + bx * NN + e * N, lvq);
                         dqf[e] = __int_as_float(dq + kMagicI) - kMagicF;
                     }
                     h0 = pack_h2(dqf[0], dqf[1]);
@@ -420,28 +418,42 @@ __global__ void __launch_bounds__(96, 6) wave8_kernel(const CoderArgs a) {
                     const uint32_t m0 = __float_as_uint(__fmaf_rd(acc[0], 1.0f / (float)(1 << SH), kMagicF + 4096.0f));
                     const uint32_t m1 = __float_as_uint(__fmaf_rd(acc[1], 1.0f / (float)(1 << SH), kMagicF + 4096.0f));
                     const uint32_t sum = __byte_perm(m0, m1, 0x5410) + pc;
-                    stsm_x1(smem_u32(r16) + row_addr, __vminu2(__vmaxu2(sum, clip_lo2), clip_hi2) - clip_lo2);
-                    __syncwarp();
+                    rr = __vminu2(__vmaxu2(sum, clip_lo2), clip_hi2) - clip_lo2;
+                    NH_PROF_MARK(6)
                 } else {
-                    // ---- exact generic path: int16 references, int64 quantisation
-                    wave_block_generic<N>(a, refb, PB, srcf, x, y, b, smem + L::GEN, r16);
+                    // ---- exact generic path: int16 references, int64 quantisation; reconstruction through R16
+                    int16_t* r16 = reinterpret_cast<int16_t*>(smem + L::R16);
+                    wave_block_generic<N>(a, refb, PB, srcf, x, y, blk0 + bx, smem + L::GEN, r16);
+                    rr = *reinterpret_cast<const uint32_t*>(r16 + fg * 8 + 2 * ft);
                 }
                 // ---- publish the bottom row first (the row below is polling for it), then the plane
-                if (vec_exch) {
-                    if (lane == 0)
-                        __stcg(reinterpret_cast<uint4*>(bottomf + (int64_t)by * a.W + x), *reinterpret_cast<const uint4*>(r16 + 7 * 8));
-                } else if (lane < 8) {
-                    __stcg(bottomf + (int64_t)by * a.W + x + lane, r16[7 * 8 + lane]);
+                if (fg == 7) {
+                    if (vec_exch) {
+                        __stcg(reinterpret_cast<uint32_t*>(bottom_ptr + x), rr);
+                    } else {
+                        __stcg(bottom_ptr + x, (int16_t)(rr & 0xffffu));
+                        __stcg(bottom_ptr + x + 1, (int16_t)(rr >> 16));
+                    }
                 }
-                if (vec_rows) {
-                    if (lane < 8)
-                        *reinterpret_cast<uint4*>(reconf + (int64_t)(y + lane) * a.pitch + x) = *reinterpret_cast<const uint4*>(r16 + lane * 8);
-                } else {
-                    for (int e = lane; e < NN; e += 32) reconf[(int64_t)(y + e / N) * a.pitch + x + e % N] = r16[e];
+                *reinterpret_cast<uint32_t*>(recon_ptr + x) = rr;
+                // ---- left references of the next block: this block's right-most column, replicated below
+                // (bottom-left is not reconstructed yet: n_left = N), and their sum for the DC predictor
+                const int rc = (int)(rr >> 16);                       // column 2 ft + 1
+                const int r77 = __shfl_sync(0xffffffffu, rc, 31);     // sample (7, 7)
+                if (ft == 3) {
+                    refb[PB + 1 + fg] = (unsigned char)rc;
+                    refb[PB + 9 + fg] = (unsigned char)r77;
+                    if (fg == 7) refb[PB + 17] = (unsigned char)r77;
                 }
-                __syncwarp();
+                const int ls = __reduce_add_sync(0xffffffffu, ft == 3 ? rc : 0);
+                if (lane == 0) s_leftsum = ls;
+            }
+            if (ood) {   // CTA-uniform, rare: the generic coder has finished reading the references
+                __syncthreads();
+                if (warp == 2 && bx + 1 < bw) stage_top(bx + 1);
             }
         }
+        NH_PROF_DUMP(tid == 0 && by == 0 && fr == 0)
     }
 }
 
@@ -542,8 +554,10 @@ __global__ void __launch_bounds__(32, 24) wave4_kernel(const CoderArgs a) {
         int ntop = top_load(0);
         uint2 npx = px_load(0);
         if (lane >= 1 && lane < 10) refb[PB + lane] = 128;   // left references of the first block
+        NH_PROF_DECL
         for (int bx = 0; bx < bw; ++bx) {
             const int x = bx * N;
+            NH_PROF_MARK(7)
             const int64_t b = fr * a.blocks_per_frame + (int64_t)by * bw + bx;
             // ---- references
             unsigned spins = 0;
@@ -552,6 +566,7 @@ __global__ void __launch_bounds__(32, 24) wave4_kernel(const CoderArgs a) {
                 if (++spins > (1u << 25)) __trap();   // > 10 s of polling: a protocol error, fail loudly instead of hanging
                 ntop = top_load(bx);
             }
+            NH_PROF_MARK(0)
             if (lane < 10) refb[lane] = (unsigned char)ntop;
             if (lane == 0) refb[PB] = (unsigned char)ntop;   // corner slot of the left array
             if (lane < 4) obw[lane] = __byte_perm(npx.x, npx.y, 0x6420);
@@ -563,6 +578,7 @@ __global__ void __launch_bounds__(32, 24) wave4_kernel(const CoderArgs a) {
                 const int dc = dc_value<N>(__reduce_add_sync(0xffffffffu, sref));   // intra.py:46-62
                 const uint4 o4 = *reinterpret_cast<const uint4*>(obw);
                 if (bx + 1 < bw) npx = px_load(bx + 1);
+                NH_PROF_MARK(1)
                 // ---- projected extensions of this lane's two modes
                 if (negmode) {
 #pragma unroll
@@ -622,6 +638,7 @@ __global__ void __launch_bounds__(32, 24) wave4_kernel(const CoderArgs a) {
                 }
                 const int best = (int)__reduce_min_sync(0xffffffffu, (unsigned)key);
                 const int wmode = mode_of_key(best);
+                NH_PROF_MARK(3)
                 if (bx + 1 < bw) ntop = top_load(bx + 1);   // requested now, needed after the winner is coded
                 if (lane == 0) {
                     if (a.out.modes) a.out.modes[b] = (uint8_t)wmode;
@@ -647,6 +664,7 @@ __global__ void __launch_bounds__(32, 24) wave4_kernel(const CoderArgs a) {
                 }
                 const int orig = (int)reinterpret_cast<const unsigned char*>(obw)[lane & 15];   // pixel (py, px)
                 const int res = orig - pred;
+                NH_PROF_MARK(5)
                 // ---- forward DST-VII (transform.py:180-194): temp = (T X + 64) >> 7, coeff = (temp T^T + 64) >> 7
                 int acc = 1 << (SHT - 1);
 #pragma unroll
@@ -668,6 +686,7 @@ __global__ void __launch_bounds__(32, 24) wave4_kernel(const CoderArgs a) {
                 for (int k = 0; k < 4; ++k) acc += t_col_x[k] * __shfl_sync(0xffffffffu, temp2, 4 * py + k);
                 const int rres = acc >> SHT;
                 rec = clip_pixel(pred + rres, a.maxv);   // intra.py:70-78
+                NH_PROF_MARK(6)
                 if (lane < 16) {
                     if (a.out.coeff) __stcs(a.out.coeff + b * NN + lane, coef);
                     if (a.out.levels) __stcs(a.out.levels + b * NN + lane, lvq);
@@ -707,6 +726,7 @@ __global__ void __launch_bounds__(32, 24) wave4_kernel(const CoderArgs a) {
                 for (int k = N + 1; k < 10; ++k) refb[PB + k] = (unsigned char)rec;
             }
         }
+        NH_PROF_DUMP(lane == 0 && by == 0 && fr == 0)
     }
 }
 

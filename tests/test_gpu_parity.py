@@ -763,7 +763,7 @@ def test_wavefront_out_of_domain_source_and_odd_widths(Bt, n, cost, W):
     src[1, 2] = 300
     src[2 * n + 1, 5 * n + 1] = -7
     src[3 * n, W - 2] = 256
-    src[4 * n + 2, 9 * n] = 1000
+    src[4 * n + 2, min(9 * n, W - 5)] = 1000
     for plane in (clean, src):
         r = Bt.encode_frame(dev(plane), n, cost=cost, qp=23, recon_neighbours=True)
         w = O.encode_frame(plane, n, cost=cost, qp=23, recon_neighbours=True)

@@ -15,11 +15,13 @@ ap.add_argument("--size", type=int, default=16)
 ap.add_argument("--cost", default="sad")
 ap.add_argument("--wavefront", action="store_true")
 ap.add_argument("--reps", type=int, default=3)
-ap.add_argument("--frames", type=int, default=1, help="frames stacked into one tall plane (config 3 batch)")
+ap.add_argument("--frames", type=int, default=1, help="frames of the batch (one nh_encode_frames call)")
+ap.add_argument("--height", type=int, default=2160)
+ap.add_argument("--width", type=int, default=3840)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
-plane = torch.cat([synth_plane(2160, 3840, i, dev) for i in range(args.frames)], dim=0)
+planes = torch.stack([synth_plane(args.height, args.width, i, dev) for i in range(args.frames)])
 for _ in range(args.reps):
-    r = batched.encode_frame(plane, args.size, cost=args.cost, qp=27, recon_neighbours=args.wavefront)
+    r = batched.encode_frames(planes, args.size, cost=args.cost, qp=27, recon_neighbours=args.wavefront)
 torch.cuda.synchronize()
-print("modes histogram:", torch.bincount(r.modes.to(torch.int64), minlength=35).tolist())
+print("modes histogram:", torch.bincount(r.modes.reshape(-1).to(torch.int64), minlength=35).tolist())
