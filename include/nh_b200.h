@@ -190,8 +190,11 @@ int64_t nh_encode_frame_scratch_bytes(int height, int width, int size);
 /* Selects how recon_neighbours == 0 runs on 8-bit content: 2 (default: a search kernel decides the
  * modes -- every lane of a warp evaluates the same candidate mode on its own strip of pixels --
  * and a second kernel codes the winners; needs the modes tensor, pitch % 4 == 0 and an 8-byte
- * aligned plane, otherwise 1 is used) or 1 (search and winner pipeline in one kernel).  Results
- * are identical. */
+ * aligned plane, otherwise 1 is used) or 1 (search and winner pipeline in one kernel).  At N >= 8
+ * there are two search kernels (strips of 4 scan lines per lane; all lanes on the same scan line,
+ * which needs pitch % 8 == 0 and a 16-byte aligned plane): 2 picks per call by size and cost kind,
+ * 3 / 4 force the second / the first (profiling, tests).  Results are identical.  The setting is
+ * per calling thread. */
 int nh_set_search_impl(int impl);
 int nh_encode_frame(const int16_t* src, int height, int width, int pitch, int size, int cost_kind,
                     int qp, int recon_neighbours, int bit_depth, uint8_t* modes, int32_t* costs,

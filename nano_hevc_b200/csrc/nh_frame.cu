@@ -675,6 +675,7 @@ __global__ void __launch_bounds__(32 * WPB) coder_wave_mw_kernel(const CoderArgs
 
 }  // namespace nh
 #include "nh_wave.cuh"   // latency-oriented wavefront kernels for 8-bit planes (N = 8, N = 4); needs CoderArgs
+#include "nh_search2.cuh"   // line-synchronous search kernel (N = 8 / 16 / 32)
 namespace nh {
 
 // Exchange rows of the wavefront coder: -1 where a block will publish its bottom row, 0 in the
@@ -830,13 +831,46 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 // K7 as two launches (8-bit content): search_plane_kernel decides the modes, coder_kernel codes the
 // winners (one block per warp and the tensor-core winner pipeline at N = 16 / 32).
+// 2 (default) = search kernel + winner kernel, 1 = everything in the single coder kernel (A/B profiling);
+// 3 / 4 = as 2 with the line-synchronous / the strip search kernel forced (2 picks per call, see
+// launch_search_cost); nh_set_search_impl() or NH_SEARCH_IMPL=1|2|3|4.
+static thread_local int g_search_impl = 0;   // per calling thread: no shared mutable state between callers
+static int search_impl() {
+    if (g_search_impl == 0) {
+        const char* e = getenv("NH_SEARCH_IMPL");
+        g_search_impl = (e && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 2;
+    }
+    return g_search_impl;
+}
+static int split_impl() { return search_impl() >= 2; }
+
 template <int N, int COST>
 static int launch_search_cost(const CoderArgs& a, cudaStream_t st) {
+    SearchArgs s{a.src, a.H, a.W, a.pitch, a.cost_kind, a.n_blocks, a.out.modes, a.out.costs, a.blocks_per_frame,
+                 a.frame_stride};
+    if constexpr (N >= 8) {
+        // The line-synchronous kernel (nh_search2.cuh) needs 16-byte pixel loads.  Measured (profiles/r2_search_*):
+        // it wins on SAD once every warp gets a few of its (larger) tiles -- 32 4K frames: N = 8 / 16 / 32
+        // 103 -> 117, 77 -> 84, 98 -> 116 Gpix/s for search + winners -- and on SATD at N = 32; with SATD at
+        // N = 8 / 16 its 128 registers cost more occupancy than the uniform scan lines save.
+        using L = LineCfg<N>;
+        const int per_sm = (N > 8 || COST == NH_COST_SAD) ? L::PER_SM : 4;
+        const bool can = (a.pitch % 8) == 0 && (a.frame_stride % 8) == 0 && (reinterpret_cast<uintptr_t>(a.src) & 15) == 0;
+        const int64_t n_tiles = (a.n_blocks + L::T - 1) / L::T;
+        const bool wins = (COST == NH_COST_SAD || N == 32) && n_tiles >= (int64_t)3 * sm_count() * per_sm * L::WARPS;
+        const int impl = search_impl();
+        if (can && (impl == 3 || (impl != 4 && wins))) {
+            int rc = ensure_dynamic_smem(search_lines_kernel<N, COST>, L::SMEM_BYTES, "search_lines_kernel");
+            if (rc != NH_OK) return rc;
+            const int grid = grid_for(a.n_blocks, (int64_t)L::WARPS * L::T, per_sm);
+            search_lines_kernel<N, COST><<<grid, L::WARPS * 32, L::SMEM_BYTES, st>>>(s);
+            NH_CHECK_LAUNCH("search_lines_kernel");
+            return NH_OK;
+        }
+    }
     using C = SearchCfg<N>;
     int rc = ensure_dynamic_smem(search_plane_kernel<N, COST>, C::SMEM_BYTES, "search_plane_kernel");
     if (rc != NH_OK) return rc;
-    SearchArgs s{a.src, a.H, a.W, a.pitch, a.cost_kind, a.n_blocks, a.out.modes, a.out.costs, a.blocks_per_frame,
-                 a.frame_stride};
     const int per_sm = COST == NH_COST_SAD ? 6 : 5;  // the kernel's __launch_bounds__; 6 x SMEM_BYTES <= 170 KB for every N
     const int grid = grid_for(a.n_blocks, (int64_t)C::WARPS * C::T, per_sm);
     search_plane_kernel<N, COST><<<grid, C::WARPS * 32, C::SMEM_BYTES, st>>>(s);
@@ -846,17 +880,6 @@ static int launch_search_cost(const CoderArgs& a, cudaStream_t st) {
 template <int N>
 static int launch_search(const CoderArgs& a, cudaStream_t st) {
     return a.cost_kind == NH_COST_SAD ? launch_search_cost<N, NH_COST_SAD>(a, st) : launch_search_cost<N, NH_COST_SATD>(a, st);
-}
-
-// 2 (default) = search kernel + winner kernel, 1 = everything in the single coder kernel (A/B
-// profiling); nh_set_search_impl() or NH_SEARCH_IMPL=1|2.
-static thread_local int g_search_impl = 0;   // per calling thread: no shared mutable state between callers
-static int split_impl() {
-    if (g_search_impl == 0) {
-        const char* e = getenv("NH_SEARCH_IMPL");
-        g_search_impl = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 2;
-    }
-    return g_search_impl == 2;
 }
 
 static int dispatch_search_then_code(CoderArgs a, int size, cudaStream_t st) {
@@ -971,8 +994,9 @@ NH_API int nh_fused_pipeline_modes(const int16_t* orig, const int16_t* top, cons
 }
 
 NH_API int nh_set_search_impl(int impl) {
-    if (impl < 1 || impl > 2) {
-        set_error("nh_set_search_impl: impl must be 1 (single coder kernel) or 2 (search + winner kernels), got %d", impl);
+    if (impl < 1 || impl > 4) {
+        set_error("nh_set_search_impl: impl must be 1 (single coder kernel), 2 (search + winner kernels), 3 / 4 (as 2, "
+                  "line-synchronous / strip search kernel forced), got %d", impl);
         return NH_E_ARG;
     }
     g_search_impl = impl;

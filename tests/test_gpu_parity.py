@@ -654,6 +654,16 @@ def test_config3_config5_4k_full_oracle(Bt, n, rn, cost):
     w = O.encode_frame(src, n, cost=cost, qp=27, recon_neighbours=bool(rn), threads=O.n_host_threads())
     for name in ("modes", "costs", "pred", "coeff", "levels", "recon_plane"):
         eq(host(getattr(r, name)), w[name], f"{name} n={n} {cost} rn={rn}")
+    if not rn and n >= 8:   # both search kernels at full size (the library picks one per call)
+        from nano_hevc_b200 import _lib
+        try:
+            for impl in (3, 4):
+                _lib.check(_lib.lib().nh_set_search_impl(impl))
+                r = Bt.encode_frame(d, n, cost=cost, qp=27, outputs=("modes", "costs"))
+                eq(host(r.modes), w["modes"], f"modes n={n} {cost} search impl {impl}")
+                eq(host(r.costs), w["costs"], f"costs n={n} {cost} search impl {impl}")
+        finally:
+            _lib.check(_lib.lib().nh_set_search_impl(2))
     assert np.count_nonzero(w["levels"]) > 0
     sse = int(Bt.sse_sad(d, r.recon_plane)[0].item())
     assert Bt.psnr_from_sse(sse, H * W) == pytest.approx(float(O.psnr(src, w["recon_plane"])), rel=1e-9)
@@ -834,14 +844,17 @@ def test_search_kernel_split_vs_single_kernel_vs_oracle(Bt, n, cost, wmul):
     bad[H - 2, W - 3] = 256   # in the columns / rows no full block covers, or the last block: a reference of nobody
     try:
         for plane in (src, bad):
-            _lib.check(_lib.lib().nh_set_search_impl(2))
-            r2 = Bt.encode_frame(dev(plane), n, cost=cost, qp=26)
             _lib.check(_lib.lib().nh_set_search_impl(1))
             r1 = Bt.encode_frame(dev(plane), n, cost=cost, qp=26)
             w = O.encode_frame(plane, n, cost=cost, qp=26, recon_neighbours=False)
-            for name in ("modes", "costs", "pred", "coeff", "levels", "recon_plane"):
-                eq(host(getattr(r2, name)), host(getattr(r1, name)), f"split vs single {name} n={n} {cost}")
-                eq(host(getattr(r2, name)), w[name], f"split vs oracle {name} n={n} {cost}")
+            # 2 = the kernel the library picks, 3 = line-synchronous search kernel (N >= 8, pitch % 8 == 0: the
+            # wmul = 8 cases), 4 = strip search kernel
+            for impl in (2, 3, 4):
+                _lib.check(_lib.lib().nh_set_search_impl(impl))
+                r2 = Bt.encode_frame(dev(plane), n, cost=cost, qp=26)
+                for name in ("modes", "costs", "pred", "coeff", "levels", "recon_plane"):
+                    eq(host(getattr(r2, name)), host(getattr(r1, name)), f"split({impl}) vs single {name} n={n} {cost}")
+                    eq(host(getattr(r2, name)), w[name], f"split({impl}) vs oracle {name} n={n} {cost}")
             # optional outputs: only what was asked for is written, and it is the same
             _lib.check(_lib.lib().nh_set_search_impl(2))
             r3 = Bt.encode_frame(dev(plane), n, cost=cost, qp=26, outputs=("modes", "levels"))
