@@ -788,9 +788,29 @@ static int dispatch_coder(const CoderArgs& a, int size, cudaStream_t st) {
             return NH_OK;
         }
         if (wave_ok && size == 4) {
-            if (a.cost_kind == NH_COST_SAD) wave4_kernel<NH_COST_SAD><<<grid, 32, 0, st>>>(a);
-            else wave4_kernel<NH_COST_SATD><<<grid, 32, 0, st>>>(a);
-            NH_CHECK_LAUNCH("wave4_kernel");
+            // up to ~4 4K frames in flight: four warps per block row (one 4K frame 4.16 -> 2.57 ms); beyond that the
+            // one-warp kernel, whose 24 resident rows per SM give the higher batch rate (32 frames: 14.7 vs 11.5
+            // Gpix/s, profiles/r2_wave4_probe.jsonl).  NH_WAVE4=1|4 forces the one-warp / four-warp kernel.
+            static const int force_w4 = [] { const char* e = getenv("NH_WAVE4"); return e ? (e[0] == '1' ? 1 : 4) : 0; }();
+            const bool one_warp = force_w4 ? force_w4 == 1 : rows > (int64_t)sm_count() * 16;
+            if (one_warp) {
+                if (a.cost_kind == NH_COST_SAD) wave4_kernel<NH_COST_SAD><<<grid, 32, 0, st>>>(a);
+                else wave4_kernel<NH_COST_SATD><<<grid, 32, 0, st>>>(a);
+                NH_CHECK_LAUNCH("wave4_kernel");
+                return NH_OK;
+            }
+            // few rows: the latency build; many rows: the build that keeps twice the CTAs resident (rows in flight
+            // x 16 pixels per dependent block time is what bounds a batch).  NH_WAVE_OCC=lat|thr forces one of them.
+            static const int force4 = [] { const char* e = getenv("NH_WAVE_OCC"); return e ? (e[0] == 'l' ? 1 : 2) : 0; }();
+            const bool lat4 = force4 ? force4 == 1 : rows <= (int64_t)sm_count() * 4;
+            if (lat4) {
+                if (a.cost_kind == NH_COST_SAD) wave4mw_kernel<NH_COST_SAD, 4><<<grid, 128, 0, st>>>(a);
+                else wave4mw_kernel<NH_COST_SATD, 4><<<grid, 128, 0, st>>>(a);
+            } else {
+                if (a.cost_kind == NH_COST_SAD) wave4mw_kernel<NH_COST_SAD, 8><<<grid, 128, 0, st>>>(a);
+                else wave4mw_kernel<NH_COST_SATD, 8><<<grid, 128, 0, st>>>(a);
+            }
+            NH_CHECK_LAUNCH("wave4mw_kernel");
             return NH_OK;
         }
         static const int wave_warps = [] {  // warps per block row at N = 16 / 32: NH_WAVE_WARPS=1|2|4|8 (default 8)

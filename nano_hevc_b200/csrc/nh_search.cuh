@@ -179,27 +179,34 @@ __global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, COST == NH_COST_SAD 
         // ---- K1: references with the substitution rules of block.py:38-55, as bytes
         // every block of the tile away from the frame edges (warp-uniform): the common case
         const bool interior = __all_sync(0xffffffffu, x > 0 && y > 0 && x + 2 * N <= a.W && y + 2 * N <= a.H);
-        constexpr int RE = T * (2 * N + 2);
+        constexpr int RE = T * (2 * N + 2), RI = (RE + 31) / 32;
+        // all loads first, then all stores: written as one loop the compiler keeps load -> store order and the
+        // tile pays RI global-memory round trips in a row
+        int tv[RI], lv[RI];
 #pragma unroll
-        for (int e0 = 0; e0 < RE; e0 += 32) {   // uniform trip count (the shuffles need every lane), loads in flight together
-            const int e = e0 + lane < RE ? e0 + lane : RE - 1;
+        for (int it = 0; it < RI; ++it) {   // uniform trip count (the shuffles need every lane)
+            const int e = it * 32 + lane < RE ? it * 32 + lane : RE - 1;
             const int i = e / (2 * N + 2), k = e % (2 * N + 2);
             const int xi = __shfl_sync(0xffffffffu, x, (i * SB) & 31), yi = __shfl_sync(0xffffffffu, y, (i * SB) & 31);
             const int16_t* srci = a.src + __shfl_sync(0xffffffffu, fr, (i * SB) & 31) * a.frame_stride;
             const int kk = k <= 2 * N ? k : 2 * N;   // entry 2N+1: replicate-last padding (only read with weight 0)
-            int tv, lv;
             if (interior) {   // no substitution, no truncation: top[k] = plane[y-1][x-1+k], left[k] = plane[y-1+k][x-1]
                 const int16_t* c = srci + (int64_t)(yi - 1) * a.pitch + xi - 1;
-                tv = __ldg(c + kk);
-                lv = __ldg(c + (int64_t)kk * a.pitch);
+                tv[it] = __ldg(c + kk);
+                lv[it] = __ldg(c + (int64_t)kk * a.pitch);
             } else {
-                tv = top_ref<false>(srci, a.H, a.W, a.pitch, xi, yi, 2 * N, kk);
-                lv = left_ref<false>(srci, a.H, a.W, a.pitch, xi, yi, 2 * N, kk);
+                tv[it] = top_ref<false>(srci, a.H, a.W, a.pitch, xi, yi, 2 * N, kk);
+                lv[it] = left_ref<false>(srci, a.H, a.W, a.pitch, xi, yi, 2 * N, kk);
             }
+        }
+#pragma unroll
+        for (int it = 0; it < RI; ++it) {
+            const int e = it * 32 + lane < RE ? it * 32 + lane : RE - 1;
+            const int i = e / (2 * N + 2), k = e % (2 * N + 2);
             unsigned char* zb = reinterpret_cast<unsigned char*>(wbase + i * C::BLOCK_WORDS);
-            zb[k] = (unsigned char)tv;
-            zb[C::PB + k] = (unsigned char)lv;
-            ood |= tv | lv;
+            zb[k] = (unsigned char)tv[it];
+            zb[C::PB + k] = (unsigned char)lv[it];
+            ood |= tv[it] | lv[it];
         }
 
         // ---- the lane's strip, packed bytes: ov = image orientation, oh = transposed (horizontal modes)

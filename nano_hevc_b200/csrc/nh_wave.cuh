@@ -730,4 +730,332 @@ __global__ void __launch_bounds__(32, 24) wave4_kernel(const CoderArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------ N = 4, four warps
+// wave4_kernel above does everything in one warp: about 700 dependent-ish instructions per block, 4230 cycles
+// (profiles/r2d_wave_phase_cycles.jsonl: search 1683, DST chain 760, publish 824).  This kernel splits the block
+// the way wave8_kernel does:
+//   * search: one candidate per lane -- threads 0..32 = angular modes 2..34 (4 scan lines of 4 samples, positions
+//     fixed for the whole kernel), thread 96 = DC, threads 100..103 = one planar row each; every unit leaves its
+//     predicted 4x4 in a 16-byte tile of its candidate position, argmin by REDUX + one barrier;
+//   * warp 0 codes the winner across 16 lanes from the winner's tile (nothing is predicted twice), the DST-VII
+//     passes as shuffles, publishes the bottom row, derives the next block's left references;
+//   * warp 1 stages the next block's pixels, warp 2 polls the exchange row for its top references and writes
+//     mode / cost -- both while warp 0 codes.
+struct Wave4Smem {
+    using SC = SearchCfg<4>;
+    using GC = CoderCfg<4, 32>;
+    static constexpr int REF_BYTES = (SC::BLOCK_WORDS * 4 + 15) / 16 * 16;   // tb | lb | projected extensions
+    static constexpr int OB = 0;                       // 2 x { 16 B pixel rows, 16 B transposed }
+    static constexpr int TILES = OB + 2 * 32;          // 35 predictions of 16 bytes (horizontal modes: transposed)
+    static constexpr int R16 = TILES + 35 * 16;        // reconstruction of a generic-path block (16 int16)
+    static constexpr int REFS = R16 + 32;
+    static constexpr int GEN = REFS + REF_BYTES;       // generic coder's group (out-of-domain blocks)
+    static constexpr int TOTAL = GEN + GC::GROUP_BYTES;
+};
+
+template <int COST, int OCC>
+__global__ void __launch_bounds__(128, OCC) wave4mw_kernel(const CoderArgs a) {
+    constexpr int N = 4, NN = 16, SHT = 7;   // transform shift log2(N) + 5
+    using SC = SearchCfg<4>;
+    using L = Wave4Smem;
+    constexpr int PB = SC::PB;
+    __shared__ __align__(16) unsigned char smem[L::TOTAL];
+    __shared__ int s_keys[4];
+    __shared__ int s_row;
+    __shared__ int s_topsum, s_leftsum;
+    __shared__ int s_ood[2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char* refb = smem + L::REFS;          // tb = refb, lb = refb + PB
+
+    // ---- this lane's search unit, fixed for the whole kernel
+    const bool angular = tid < 33;
+    const bool is_dc = tid == 96, is_planar = tid >= 100 && tid < 104;
+    const bool unit = angular || is_dc || is_planar;
+    const int mode = angular ? 2 + tid : (is_dc ? 1 : 0);
+    const int pos = angular ? mode : (is_dc ? 0 : 1);               // candidate order 1, 0, 2 .. 34
+    const bool vertical = mode >= 18;
+    const int angle = angular ? intra_angle(mode) : 0;
+    const bool negmode = angular && angle < 0;
+    const int negoff = negmode ? SC::neg_t0(mode - 11) : 0;
+    int woff[4];
+    uint32_t sh[4], f8[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int p = (j + 1) * angle;
+        const int k = 1 + (p >> 5);
+        woff[j] = (k < 0 ? negoff : (vertical ? 0 : PB)) + (k & ~3);
+        sh[j] = (uint32_t)(k & 3) * 8u;
+        f8[j] = ((uint32_t)p & 31u) << 3;
+    }
+    const int obase = L::OB + ((angular && !vertical) ? 16 : 0);   // the unit's 4 scan lines of pixels
+    uint32_t nsrc = 0;   // projected indices of entries tt = 0 .. 3 (intra.py:180-186, (k+1) projection)
+    int nlen = 0;
+    if (negmode) {
+        nlen = -((N * angle) >> 5);
+        const int inv = inv_angle_of_mode(mode);
+        const int sec = vertical ? PB : 0;   // vertical: secondary = left
+#pragma unroll
+        for (int tt = 0; tt < 4; ++tt) {
+            int proj = (-tt * inv + 128) >> 8;
+            proj = proj > 2 * N ? 2 * N : proj;
+            nsrc |= (uint32_t)(sec + proj) << (8 * tt);
+        }
+    }
+    const int npri = vertical ? 0 : PB;
+    unsigned char* my_tile = smem + L::TILES + (unit ? pos : 0) * 16;
+
+    // ---- winner constants (warp 0): pixel (py, px) of lanes 0..15, rows / columns of the DST-VII matrix
+    const int py = (lane >> 2) & 3, px = lane & 3;
+    int t_row_y[4], t_row_x[4], t_col_y[4], t_col_x[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        t_row_y[k] = kc_wave_dst4[py * 4 + k];   // T[py][k]
+        t_row_x[k] = kc_wave_dst4[px * 4 + k];   // T[px][k]
+        t_col_y[k] = kc_wave_dst4[k * 4 + py];   // T[k][py]
+        t_col_x[k] = kc_wave_dst4[k * 4 + px];   // T[k][px]
+    }
+    const FastQuant fq = a.fq;
+    const int bw = a.W / N, bh = a.H / N, W = a.W, pitch = a.pitch, n_frames = a.n_frames, maxv = a.maxv;
+    const bool vec_exch = (W % 4) == 0;   // 8-byte aligned exchange rows
+    uint8_t* const o_modes = a.out.modes;
+    int32_t* const o_costs = a.out.costs;
+    int16_t* const o_pred = a.out.pred;
+    int32_t* const o_coeff = a.out.coeff;
+    int32_t* const o_levels = a.out.levels;
+    const unsigned poll_sleep = a.poll_sleep_ns;
+
+    for (;;) {
+        __syncthreads();   // everyone is done with the previous row (and has read s_row)
+        if (tid == 0) s_row = atomicAdd(a.ticket, 1);
+        __syncthreads();
+        const int tk = s_row;   // frames interleaved: ticket t = row t / F of frame t % F
+        const int by = tk / n_frames, fr = tk - by * n_frames;
+        if (by >= bh) break;
+        const int y = by * N;
+        const int16_t* srcf = a.src + fr * a.frame_stride;
+        int16_t* bottomf = a.bottom + (int64_t)fr * bh * W;
+        const int16_t* up = bottomf + (int64_t)(by - 1) * W;   // exchange row above (by > 0)
+        const int64_t blk0 = fr * a.blocks_per_frame + (int64_t)by * bw;
+        const int16_t* px_ptr = srcf + (int64_t)(y + (lane & 3)) * pitch;                                   // warp 1 staging
+        int16_t* recon_ptr = a.out.recon_plane + fr * a.frame_stride + (int64_t)(y + py) * pitch;          // warp 0
+        int16_t* bottom_ptr = bottomf + (int64_t)by * W;
+
+        uint2 npx = make_uint2(0u, 0u);   // warp 1, lanes 0..3: row `lane` of the block being staged
+        auto fetch_px = [&](int bx) {     // (launcher: pitch % 4 == 0, 8-byte aligned plane)
+            if (lane < 4) npx = __ldg(reinterpret_cast<const uint2*>(px_ptr + bx * N));
+        };
+        auto stage_px = [&](int par) {   // registers -> byte rows, transposed bytes
+            int bad = 0;
+            if (lane < 4) {
+                const uint32_t b4 = __byte_perm(npx.x, npx.y, 0x6420);
+                *reinterpret_cast<uint32_t*>(smem + L::OB + par * 32 + 4 * lane) = b4;
+                unsigned char* t = smem + L::OB + par * 32 + 16 + lane;   // transposed: [column][row]
+                t[0] = (unsigned char)b4;
+                t[4] = (unsigned char)(b4 >> 8);
+                t[8] = (unsigned char)(b4 >> 16);
+                t[12] = (unsigned char)(b4 >> 24);
+                bad = (int)((npx.x | npx.y) & 0xFF00FF00u);
+            }
+            bad = __any_sync(0xffffffffu, bad != 0);
+            if (lane == 0) s_ood[par] = bad;
+        };
+        // top references of block bx (service warp; lane k < 10 = entry k of tb): poll the exchange row above
+        auto stage_top = [&](int bx) {
+            int v = 128;
+            if (by > 0) {
+                const int x = bx * N;
+                int last = x + 2 * N - 1;
+                if (last > W - 1) last = W - 1;
+                int col = x + (lane > 2 * N ? 2 * N : lane) - 1;
+                if (col > last) col = last;
+                const bool fixed = lane >= 10 || (lane == 0 && x == 0);   // corner of the first column: 128
+                unsigned spins = 0;
+                for (;;) {
+                    v = fixed ? 128 : (int)__ldcg(up + col);
+                    if (__all_sync(0xffffffffu, v >= 0)) break;
+                    if (poll_sleep) __nanosleep(poll_sleep);
+                    if (++spins > (1u << 25)) __trap();   // > 10 s of polling: a protocol error, fail loudly instead of hanging
+                }
+            }
+            if (lane < 10) refb[lane] = (unsigned char)v;
+            if (lane == 0) refb[PB] = (unsigned char)v;
+            const int ts = __reduce_add_sync(0xffffffffu, (lane >= 1 && lane <= N) ? v : 0);
+            if (lane == 0) s_topsum = ts;
+        };
+        if (warp == 1) {
+            fetch_px(0);
+            stage_px(0);
+            if (bw > 1) fetch_px(1);
+        } else if (warp == 2) {
+            stage_top(0);
+        } else if (warp == 0) {
+            if (lane >= 1 && lane < 10) refb[PB + lane] = 128;   // left references of the first block (block.py:45-50)
+            if (lane == 0) s_leftsum = N * 128;
+        }
+        NH_PROF_DECL
+        for (int bx = 0; bx < bw; ++bx) {
+            const int par = bx & 1, x = bx * N;
+            NH_PROF_MARK(7)
+            __syncthreads();   // #1: references, sums and this block's pixels are in shared memory
+            NH_PROF_MARK(2)
+            const bool ood = s_ood[par] != 0;   // CTA-uniform
+            if (!ood) {
+                // ---- search: one candidate per lane
+                int c = 0;
+                if (unit) {
+                    const uint4 o4 = *reinterpret_cast<const uint4*>(smem + obase + par * 32);
+                    const uint32_t o[4][1] = {{o4.x}, {o4.y}, {o4.z}, {o4.w}};
+                    uint32_t pr[4][1];
+                    if (angular) {
+                        if (negmode) {   // this mode's projected extension + a copy of ref[0 .. 7] behind it
+#pragma unroll
+                            for (int tt = 0; tt < 4; ++tt)
+                                if (tt < nlen) refb[negoff - 1 - tt] = refb[(nsrc >> (8 * tt)) & 0xffu];
+#pragma unroll
+                            for (int cc = 0; cc < 2; ++cc)
+                                reinterpret_cast<uint32_t*>(refb + negoff)[cc] = reinterpret_cast<const uint32_t*>(refb + npri)[cc];
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            predict_line_w<1>(reinterpret_cast<const uint32_t*>(refb + woff[j]), sh[j], 0x3412u + (sh[j] << 5), f8[j],
+                                              256u - f8[j], pr[j]);
+                        c = strip_cost_packed<1>(pr, o, COST);
+                        *reinterpret_cast<uint4*>(my_tile) = make_uint4(pr[0][0], pr[1][0], pr[2][0], pr[3][0]);
+                    } else if (is_dc) {
+                        const uint32_t d4 = (uint32_t)dc_value<N>(s_topsum + s_leftsum) * 0x01010101u;   // intra.py:46-62
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) pr[j][0] = d4;
+                        c = strip_cost_packed<1>(pr, o, COST);
+                        *reinterpret_cast<uint4*>(my_tile) = make_uint4(d4, d4, d4, d4);
+                    } else {   // planar (intra.py:109-111): row yy = lane & 3, two samples per multiply-add chain
+                        constexpr uint32_t SCL = 1u << (7 - 2);
+                        const unsigned char* tb = refb;
+                        const unsigned char* lb = refb + PB;
+                        const uint32_t tr = tb[N + 1], bl = lb[N + 1];
+                        const int yy = lane & 3;
+                        const uint32_t ly = lb[1 + yy];
+                        const uint32_t vy = (uint32_t)(N - 1 - yy) * SCL;
+                        const uint32_t byv = ((uint32_t)(yy + 1) * bl + (uint32_t)N) * SCL * 0x10001u;
+                        uint32_t t[2];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const uint32_t X = (uint32_t)(2 * i);
+                            const uint32_t c1 = (((uint32_t)(N - 1) - X) | (((uint32_t)(N - 2) - X) << 16)) * SCL;
+                            const uint32_t kc = tr * (((X + 1) | ((X + 2) << 16)) * SCL);
+                            const uint32_t zt = (uint32_t)tb[1 + 2 * i] | ((uint32_t)tb[2 + 2 * i] << 16);
+                            t[i] = ly * c1 + kc + vy * zt + byv;
+                        }
+                        const uint32_t prow = __byte_perm(t[0], t[1], 0x7531);
+                        reinterpret_cast<uint32_t*>(my_tile)[yy] = prow;
+                        // cost: SAD adds up over the rows; SATD needs the whole 4x4 in one lane
+                        // (only the four planar lanes, 4..7 of warp 3, are in this branch)
+                        const uint32_t r0 = __shfl_sync(0xF0u, prow, 4), r1 = __shfl_sync(0xF0u, prow, 5);
+                        const uint32_t r2 = __shfl_sync(0xF0u, prow, 6), r3 = __shfl_sync(0xF0u, prow, 7);
+                        pr[0][0] = r0; pr[1][0] = r1; pr[2][0] = r2; pr[3][0] = r3;
+                        c = strip_cost_packed<1>(pr, o, COST);
+                    }
+                }
+                const int key = (unit && !(is_planar && (lane & 3))) ? ((c << 6) | pos) : 0x7fffffff;
+                const int wmin = (int)__reduce_min_sync(0xffffffffu, (unsigned)key);
+                if (lane == 0) s_keys[warp] = wmin;
+            }
+            NH_PROF_MARK(3)
+            __syncthreads();   // #2: the partial minima, the prediction tiles
+            NH_PROF_MARK(4)
+            if (warp == 1) {          // next block's pixels, while warp 0 codes the winner
+                if (bx + 1 < bw) stage_px(par ^ 1);
+                if (bx + 2 < bw) fetch_px(bx + 2);
+            } else if (warp == 2) {   // mode / cost of this block, top references of the next one
+                if (!ood && lane == 0) {
+                    int best = s_keys[0];
+                    best = s_keys[1] < best ? s_keys[1] : best;
+                    best = s_keys[3] < best ? s_keys[3] : best;
+                    if (o_modes) o_modes[blk0 + bx] = (uint8_t)mode_of_key(best);
+                    if (o_costs) o_costs[blk0 + bx] = best >> 6;
+                }
+                if (!ood && bx + 1 < bw) stage_top(bx + 1);
+            } else if (warp == 0) {
+                const int64_t b = blk0 + bx;
+                int rec;   // this lane's reconstructed pixel (lanes 0..15)
+                if (!ood) {
+                    int best = s_keys[0];
+                    best = s_keys[1] < best ? s_keys[1] : best;
+                    best = s_keys[3] < best ? s_keys[3] : best;
+                    const int wpos = best & 63;
+                    const bool transposed = wpos >= 2 && wpos < 18;   // horizontal modes: the tile holds P^T
+                    const int pred = (int)smem[L::TILES + wpos * 16 + (transposed ? px * 4 + py : py * 4 + px)];
+                    const int orig = (int)smem[L::OB + par * 32 + (lane & 15)];   // pixel (py, px)
+                    const int res = orig - pred;
+                    NH_PROF_MARK(5)
+                    // ---- forward DST-VII (transform.py:180-194): temp = (T X + 64) >> 7, coeff = (temp T^T + 64) >> 7
+                    int acc = 1 << (SHT - 1);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc += t_row_y[k] * __shfl_sync(0xffffffffu, res, 4 * k + px);
+                    const int temp = acc >> SHT;
+                    acc = 1 << (SHT - 1);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc += t_row_x[k] * __shfl_sync(0xffffffffu, temp, 4 * py + k);
+                    const int coef = acc >> SHT;   // coeff[py][px]
+                    const int lvq = quantize_fast(coef, fq);
+                    const int dq = dequantize_fast(lvq, fq);
+                    // ---- inverse (transform.py:222-236): temp2 = (T^T C + 64) >> 7, res = (temp2 T + 64) >> 7
+                    acc = 1 << (SHT - 1);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc += t_col_y[k] * __shfl_sync(0xffffffffu, dq, 4 * k + px);
+                    const int temp2 = acc >> SHT;
+                    acc = 1 << (SHT - 1);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc += t_col_x[k] * __shfl_sync(0xffffffffu, temp2, 4 * py + k);
+                    const int rres = acc >> SHT;
+                    rec = clip_pixel(pred + rres, maxv);   // intra.py:70-78
+                    NH_PROF_MARK(6)
+                    if (lane < 16) {
+                        if (o_coeff) __stcs(o_coeff + b * NN + lane, coef);
+                        if (o_levels) __stcs(o_levels + b * NN + lane, lvq);
+                    }
+                    if (o_pred) {
+                        const uint32_t w = (uint32_t)pred | ((uint32_t)__shfl_down_sync(0xffffffffu, pred, 1) << 16);
+                        const uint32_t w2 = __shfl_down_sync(0xffffffffu, w, 2);
+                        if (lane < 16 && px == 0) *reinterpret_cast<uint2*>(o_pred + b * NN + 4 * py) = make_uint2(w, w2);
+                    }
+                } else {
+                    // ---- exact generic path: int16 references, int64 quantisation; reconstruction through R16
+                    int16_t* r16 = reinterpret_cast<int16_t*>(smem + L::R16);
+                    wave_block_generic<N>(a, refb, PB, srcf, x, y, b, smem + L::GEN, r16);
+                    rec = (int)r16[lane & 15];
+                }
+                // ---- publish the bottom row first (the row below is polling for it), then the plane
+                {
+                    const uint32_t w = (uint32_t)rec | ((uint32_t)__shfl_down_sync(0xffffffffu, rec, 1) << 16);
+                    const uint32_t w2 = __shfl_down_sync(0xffffffffu, w, 2);
+                    if (lane == 12) {
+                        if (vec_exch) {
+                            __stcg(reinterpret_cast<uint2*>(bottom_ptr + x), make_uint2(w, w2));
+                        } else {
+                            int16_t* e = bottom_ptr + x;
+                            __stcg(e, (int16_t)(w & 0xffff)); __stcg(e + 1, (int16_t)(w >> 16));
+                            __stcg(e + 2, (int16_t)(w2 & 0xffff)); __stcg(e + 3, (int16_t)(w2 >> 16));
+                        }
+                    }
+                    if (lane < 16 && px == 0) *reinterpret_cast<uint2*>(recon_ptr + x) = make_uint2(w, w2);
+                }
+                // ---- left references of the next block: this block's right-most column; below it is not
+                // reconstructed yet: replicate (n_left = N); and their sum for the DC predictor
+                if (lane < 16 && px == 3) refb[PB + 1 + py] = (unsigned char)rec;
+                if (lane == 15) {
+#pragma unroll
+                    for (int k = N + 1; k < 10; ++k) refb[PB + k] = (unsigned char)rec;
+                }
+                const int ls = __reduce_add_sync(0xffffffffu, (lane < 16 && px == 3) ? rec : 0);
+                if (lane == 0) s_leftsum = ls;
+            }
+            if (ood) {   // CTA-uniform, rare: the generic coder has finished reading the references
+                __syncthreads();
+                if (warp == 2 && bx + 1 < bw) stage_top(bx + 1);
+            }
+        }
+        NH_PROF_DUMP(tid == 0 && by == 0 && fr == 0)
+    }
+}
+
 }  // namespace nh

@@ -14,7 +14,7 @@ from nano_hevc_b200 import batched  # noqa: E402
 dev = torch.device("cuda:0")
 big = synth_plane(4320, 7680, 0, dev)
 names = ["poll", "refs", "barrier1", "search", "barrier2", "winner_predict", "mma_chain", "publish+loop"]
-for n in (8, 4):
+for n in (8, 4):  # NH_WAVE4=1 profiles the one-warp N = 4 kernel
     for name, H, W in (("one_row", n, 7680), ("4k", 2160, 3840)):
         p = big[:H, :W].contiguous().unsqueeze(0)
         res = batched.encode_frames(p, n, qp=27, recon_neighbours=True)
