@@ -318,6 +318,42 @@ def run_secondary(torch, dist, batched, dev, rank, world, peak):
 
     out = {"n_gpus": world, "peak_hbm_gbs": peak,
            "note": "per-GPU work fixed (weak scaling); Gpix_s is the aggregate over all ranks, frac_hbm per GPU"}
+
+    def e2e_frames(host_planes, n, recon_neighbours, outputs, reps=2):
+        """The same coder through nh_host_encode_frames: pinned HOST frames in, pinned HOST results out, copies
+        inside the timed region (wall clock around the blocking call, max over ranks)."""
+        import time
+        L = __import__("nano_hevc_b200")._lib.lib()
+        Fh = host_planes.shape[0]
+        res = batched.host_encode_frames(host_planes, n, cost="sad", qp=27, recon_neighbours=recon_neighbours,
+                                         outputs=outputs, stats=True, frames_per_chunk=2, device=dev)
+        nbytes = int(L.nh_host_encode_frames_scratch_bytes(2, H4, W4, n, int(recon_neighbours)))
+        scratch = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        call = lambda: batched.host_encode_frames(host_planes, n, cost="sad", qp=27, recon_neighbours=recon_neighbours,
+                                                  outputs=outputs, stats=True, frames_per_chunk=2, device=dev,
+                                                  scratch=scratch, out=res)
+        call()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            call()
+        ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / reps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms.item())
+        import ctypes
+        up, down = ctypes.c_int64(0), ctypes.c_int64(0)
+        L.nh_host_encode_frames_last_transfer(ctypes.byref(up), ctypes.byref(down))
+        px = Fh * (H4 // n) * (W4 // n) * n * n
+        return {"Gpix_s": world * px / (ms / 1e3) / 1e9, "ms": ms, "frames_per_gpu": Fh, "outputs": list(outputs),
+                "h2d_bytes_per_call": up.value, "d2h_bytes_per_call": down.value,
+                "GBs_pcie_down_per_gpu": down.value / (ms / 1e3) / 1e9,
+                "api": "nh_host_encode_frames (C ABI, pinned host buffers, chunks of 2 frames over 3 streams)",
+                "bound": "PCIe: results cross the bus in the reference's dtypes"}
+
+    ALL = ("modes", "costs", "pred", "coeff", "levels", "recon_planes")
     # ---- cfg3: 32 4K frames per GPU, one nh_encode_frames call (search + winner pipeline, all outputs)
     F3 = 32
     planes = torch.stack([_synth_plane_dev(torch, H4, W4, 100 * rank + i, dev) for i in range(F3)])
@@ -330,6 +366,9 @@ def run_secondary(torch, dist, batched, dev, rank, world, peak):
             cfg3[f"N{n}_{cost}"] = entry(px, 2 + 12 + 5 / (n * n), ms, frames_per_gpu=F3,
                                          limiter="ALU pipe (search kernel), see profiles/")
         del res
+    host8 = torch.stack([_synth_plane_dev(torch, H4, W4, 100 * rank + i, dev) for i in range(8)]).cpu().pin_memory()
+    cfg3["N8_sad"]["e2e"] = e2e_frames(host8, 8, False, ALL)
+    cfg3["N8_sad"]["e2e_modes_levels_recon"] = e2e_frames(host8, 8, False, ("modes", "levels", "recon_planes"))
     out["cfg3"] = cfg3
     # ---- cfg5: wavefront coder, F 4K frames per GPU in one call + one frame alone (latency); stats by NCCL
     cfg5 = {}
@@ -354,8 +393,9 @@ def run_secondary(torch, dist, batched, dev, rank, world, peak):
                 e["frames_total"] = int(st.shape[0])
             cfg5[f"N{n}_F{F}"] = e
             del res, scratch
+    cfg5["N8_F8"]["e2e"] = e2e_frames(host8, 8, True, ALL)
     out["cfg5"] = cfg5
-    del planes
+    del planes, host8
     # ---- cfg4: 2^20 blocks per size, forward / inverse alone, rotating over buffers > 4x the 126 MB L2
     cfg4 = {}
     Bn = 1 << 20

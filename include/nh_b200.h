@@ -277,6 +277,24 @@ int nh_host_pipeline_dcplanar(const int16_t* orig, const int16_t* top, const int
                               int32_t* coeff, int32_t* levels, int16_t* recon,
                               void* device_scratch, int64_t scratch_bytes, int64_t chunk_blocks);
 
+/* ------------------------------------- host-buffer entry of the frame coders (configs 3 / 5 end to end) */
+/* nh_encode_frames for frames and results in HOST memory (docs/frames_and_panes.md:319-344 with numpy arrays
+ * on both sides): src is n_frames contiguous (height, width) int16 planes; every output is optional (NULL = not
+ * delivered) and has the layout of nh_encode_frames with pitch = width; stats is a HOST (n_frames, 4) int64
+ * array.  The batch is cut into chunks of frames_per_chunk frames that rotate over three internal streams
+ * (upload, kernels and download of neighbouring chunks overlap); the call returns when every result is in
+ * place.  Page-locked caller buffers give asynchronous copies at link speed; pageable ones work.
+ * device_scratch: nh_host_encode_frames_scratch_bytes(frames_per_chunk, height, width, size, recon_neighbours)
+ *   bytes of device memory, 256-byte aligned, idle for the duration of the call.
+ * nh_host_encode_frames_last_transfer: bytes the last call moved over PCIe in each direction. */
+int64_t nh_host_encode_frames_scratch_bytes(int frames_per_chunk, int height, int width, int size,
+                                            int recon_neighbours);
+int nh_host_encode_frames_last_transfer(int64_t* h2d_bytes, int64_t* d2h_bytes);
+int nh_host_encode_frames(const int16_t* src, int n_frames, int height, int width, int size, int cost_kind,
+                          int qp, int recon_neighbours, int bit_depth, uint8_t* modes, int32_t* costs,
+                          int16_t* pred, int32_t* coeff, int32_t* levels, int16_t* recon_planes,
+                          int64_t* stats, int frames_per_chunk, void* device_scratch, int64_t scratch_bytes);
+
 /* ------------------------------------- device-side frame containers */
 /* Sample conversion for planes held on the device (nano_hevc/frame.py): uint8 -> int16 zero-extends
  * (frame.py:45-51, Plane.from_buffer followed by the coder's astype(int16)); int16 -> uint8 keeps the

@@ -66,6 +66,9 @@ PROTOTYPES = {
     "nh_block_costs": (_i, [_p, _p, _i64, _i, _p, _p, _p, _p]),
     "nh_count_nonzero": (_i, [_p, _i64, _p, _p]),
     "nh_level_stats": (_i, [_p, _i64, _p, _p, _p]),
+    "nh_host_encode_frames_scratch_bytes": (_i64, [_i, _i, _i, _i, _i]),
+    "nh_host_encode_frames_last_transfer": (_i, [_p, _p]),
+    "nh_host_encode_frames": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _i64]),
     "nh_host_pipeline_scratch_bytes": (_i64, [_i, _i64]),
     "nh_host_pipeline_last_transfer": (_i, [_p, _p]),
     "nh_convert_u8_to_i16": (_i, [_p, _p, _i64, _p]),

@@ -456,6 +456,48 @@ def encode_frames(planes, size: int, cost: str = "sad", qp: int = 27, recon_neig
     return out
 
 
+def host_encode_frames(planes, size: int, cost: str = "sad", qp: int = 27, recon_neighbours: bool = False,
+                       bit_depth: int = 8, outputs=("modes", "costs", "pred", "coeff", "levels", "recon_planes"),
+                       stats: bool = True, frames_per_chunk: int = 2, device: torch.device | None = None,
+                       scratch: torch.Tensor | None = None, out: FramesResult | None = None):
+    """``encode_frames`` on HOST buffers (numpy array or CPU tensor (F, H, W), pinned memory recommended)
+    through ``nh_host_encode_frames``: chunks of ``frames_per_chunk`` frames rotate over three internal
+    streams (upload, kernels, download overlap) and the results come back as CPU tensors in the
+    reference's dtypes.  Only the ``outputs`` asked for cross PCIe.  This is the call behind the
+    ``e2e`` numbers of BASELINE configs 3 and 5 in bench.py."""
+    import numpy as np
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    _check_size(size)
+    if cost not in ("sad", "satd"):
+        raise ValueError("cost must be 'sad' or 'satd'")
+    p = planes if isinstance(planes, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(planes))
+    if p.is_cuda:
+        raise ValueError("host_encode_frames takes host buffers; use encode_frames for CUDA tensors")
+    if p.dim() != 3:
+        raise ValueError(f"planes must be (F, H, W), got {tuple(p.shape)}")
+    p = p.to(torch.int16).contiguous()
+    F, H, W = p.shape
+    B = (H // size) * (W // size)
+    if out is None:
+        want = set(outputs)
+        mk = lambda name, shape, dt: torch.empty(shape, dtype=dt).pin_memory() if name in want else None
+        out = FramesResult(mk("modes", (F, B), torch.uint8), mk("costs", (F, B), torch.int32),
+                           mk("pred", (F, B, size, size), torch.int16), mk("coeff", (F, B, size, size), torch.int32),
+                           mk("levels", (F, B, size, size), torch.int32), mk("recon_planes", (F, H, W), torch.int16),
+                           torch.empty((F, 4), dtype=torch.int64).pin_memory() if stats else None)
+    L = _lib.lib()
+    fc = max(1, min(int(frames_per_chunk), max(F, 1)))
+    nbytes = int(L.nh_host_encode_frames_scratch_bytes(fc, H, W, size, int(bool(recon_neighbours))))
+    if scratch is None or scratch.numel() < nbytes:
+        scratch = torch.empty((max(nbytes, 256),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.nh_host_encode_frames(_ptr(p), F, H, W, size, int(cost == "satd"), int(qp),
+                                           int(bool(recon_neighbours)), int(bit_depth), _ptr(out.modes), _ptr(out.costs),
+                                           _ptr(out.pred), _ptr(out.coeff), _ptr(out.levels), _ptr(out.recon_planes),
+                                           _ptr(out.stats), fc, _ptr(scratch), scratch.numel()))
+    return out
+
+
 # ------------------------------------------------------------------ reductions
 def sse_sad(a, b):
     """Integer numerators of metrics.py mse / sad: returns a (2,) int64 device tensor [sse, sad]."""

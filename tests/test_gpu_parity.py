@@ -785,6 +785,33 @@ def test_wavefront_out_of_domain_source_and_odd_widths(Bt, n, cost, W):
     eq(host(r.levels), w["levels"], "levels (subset)"); eq(host(r.recon_plane), w["recon_plane"], "recon (subset)")
 
 
+@pytest.mark.parametrize("n,rn,cost", [(8, 0, "sad"), (8, 1, "sad"), (4, 1, "satd"), (16, 0, "satd"), (32, 1, "sad")])
+def test_host_encode_frames_vs_oracle(Bt, n, rn, cost):
+    """nh_host_encode_frames: host frames in, host results out (the e2e path of configs 3 / 5).  Five frames in
+    chunks of two (a ragged last chunk, every slot reused), every output against the C oracle; a second call
+    asks for a subset of the outputs and reuses nothing."""
+    rng = np.random.default_rng(31 + n + rn)
+    H, W = 6 * n + 3, 8 * ((11 * n) // 8) + 8
+    frames = np.stack([_smooth(H, W, 7 * n + 3 * f) for f in range(5)])
+    frames[1, n: 3 * n] = rng.integers(0, 256, (2 * n, W))
+    frames[4, :, : 2 * n] = rng.integers(0, 256, (H, 2 * n))
+    r = Bt.host_encode_frames(frames, n, cost=cost, qp=24, recon_neighbours=bool(rn), frames_per_chunk=2)
+    sub = Bt.host_encode_frames(torch.from_numpy(frames), n, cost=cost, qp=24, recon_neighbours=bool(rn), frames_per_chunk=3,
+                                outputs=("modes", "levels"), stats=False)
+    assert sub.pred is None and sub.coeff is None and sub.costs is None and sub.recon_planes is None and sub.stats is None
+    for f in range(5):
+        w = O.encode_frame(frames[f], n, cost=cost, qp=24, recon_neighbours=bool(rn))
+        for name in ("modes", "costs", "pred", "coeff", "levels"):
+            eq(getattr(r, name)[f].numpy(), w[name], f"{name} frame {f} n={n} rn={rn}")
+        eq(r.recon_planes[f].numpy(), w["recon_plane"], f"recon frame {f}")
+        eq(sub.modes[f].numpy(), w["modes"], "modes (subset)")
+        eq(sub.levels[f].numpy(), w["levels"], "levels (subset)")
+        sse = int(((frames[f].astype(np.int64) - w["recon_plane"].astype(np.int64)) ** 2).sum())
+        assert r.stats[f].tolist() == [sse, H * W, int(w["costs"].astype(np.int64).sum()), int(np.count_nonzero(w["levels"]))]
+    with pytest.raises(ValueError):
+        Bt.host_encode_frames(dev(frames), n)
+
+
 def test_encode_frames_sharded_host_frames(Bt):
     """multi_gpu.encode_frames_sharded with HOST frames (numpy) and several local frames: the upload and
     the coder are ordered on one stream (the round-1 version uploaded on the main stream and coded on side
