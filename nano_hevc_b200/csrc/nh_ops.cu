@@ -71,6 +71,97 @@ __global__ void __launch_bounds__(kXfWarps * 32, 2)
     }
 }
 
+// The same kernel as a software pipeline (default; NH_XF_PIPE=0 keeps the one above): round 1 measured the
+// unpipelined form at 0.65-0.87 of the HBM copy bandwidth (16 warps per SM, load -> transform -> store in
+// sequence per warp, a static tile partition that waits for its slowest SM).  The recipe of the fused kernels
+// applies unchanged: 4 warps per CTA, 3 CTAs per SM, two tile buffers per warp -- the next tile arrives by
+// cp.async while this one is transformed in place and streamed out -- and tiles drawn from a ticket counter.
+constexpr int kXfPipeWarps = 4;
+
+template <int N, bool DST, bool INV, bool IN32>
+__global__ void __launch_bounds__(kXfPipeWarps * 32, 3)
+    transform_unit_pipe_kernel(const void* __restrict__ in, int32_t* __restrict__ out, int64_t n_blocks,
+                               unsigned int* tile_counter) {
+    constexpr int NN = N * N;
+    constexpr int BPU = 64 / NN;
+    using TIn = WarpTile<IN32 ? 256 : 128>;
+    using TOut = WarpTile<256>;
+    constexpr int kInElem = IN32 ? 4 : 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* buf[2] = {smem_raw + (2 * warp) * TOut::kBytes, smem_raw + (2 * warp + 1) * TOut::kBytes};
+
+    const int64_t n_units = (n_blocks + BPU - 1) / BPU;
+    const int64_t n_tiles = (n_units + 31) / 32;
+    auto next_tile = [&]() -> int64_t {
+        unsigned int t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1u);
+        return (int64_t)__shfl_sync(0xffffffffu, t, 0);
+    };
+    auto prefetch = [&](int64_t t, unsigned char* dst) {   // global (linear) -> shared (padded units)
+        const int64_t blk0 = t * 32 * BPU;
+        const int64_t rem = n_blocks - blk0;
+        const int chunks = (int)(rem < 32 * BPU ? rem : 32 * BPU) * (NN * kInElem / 16);
+        const unsigned char* g = reinterpret_cast<const unsigned char*>(in) + blk0 * NN * kInElem;
+#pragma unroll
+        for (int it = 0; it < TIn::kIters; ++it) {
+            const int c = it * 32 + lane;
+            const int u = c / TIn::kChunksPerUnit, k = c % TIn::kChunksPerUnit;
+            if (c < chunks) cp_async16(smem_u32(dst + u * TIn::kPitch + k * 16), g + (size_t)c * 16);
+            else *reinterpret_cast<uint4*>(dst + u * TIn::kPitch + k * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    };
+    int64_t tile = next_tile();
+    int64_t tile_next = tile < n_tiles ? next_tile() : n_tiles;
+    if (tile < n_tiles) prefetch(tile, buf[0]);
+    cp_async_commit();
+    int cur = 0;
+    int64_t tile_after = n_tiles;
+    for (; tile < n_tiles; tile = tile_next, tile_next = tile_after, cur ^= 1) {
+        tile_after = tile_next < n_tiles ? next_tile() : n_tiles;
+        const int64_t blk0 = tile * 32 * BPU;
+        const int64_t rem = n_blocks - blk0;
+        const int blocks_valid = (int)(rem < 32 * BPU ? rem : 32 * BPU);
+        if (tile_next < n_tiles) prefetch(tile_next, buf[cur ^ 1]);   // its last reader finished before the syncwarp below
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        unsigned char* s = buf[cur];
+        int v[BPU][N][N];
+        int* flat = &v[0][0][0];
+        const uint4* ui = TIn::unit(s, lane);
+        if constexpr (IN32) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                uint4 t = ui[e];
+                flat[4 * e] = (int)t.x; flat[4 * e + 1] = (int)t.y;
+                flat[4 * e + 2] = (int)t.z; flat[4 * e + 3] = (int)t.w;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                uint4 t = ui[e];
+                flat[8 * e] = lo16(t.x); flat[8 * e + 1] = hi16(t.x);
+                flat[8 * e + 2] = lo16(t.y); flat[8 * e + 3] = hi16(t.y);
+                flat[8 * e + 4] = lo16(t.z); flat[8 * e + 5] = hi16(t.z);
+                flat[8 * e + 6] = lo16(t.w); flat[8 * e + 7] = hi16(t.w);
+            }
+        }
+        __syncwarp();  // everyone has consumed the input tile before it is overwritten
+#pragma unroll
+        for (int q = 0; q < BPU; ++q) transform2d<N, DST, INV>(v[q]);
+        uint4* uo = TOut::unit(s, lane);
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+            uo[e] = make_uint4(flat[4 * e], flat[4 * e + 1], flat[4 * e + 2], flat[4 * e + 3]);
+        __syncwarp();
+        TOut::store(s, reinterpret_cast<unsigned char*>(out + blk0 * NN), lane, blocks_valid * (NN * 4 / 16));
+        __syncwarp();
+    }
+    cp_async_wait<0>();
+    release_tile_counter(tile_counter, gridDim.x * kXfPipeWarps);
+}
+
 // N = 16, 32: N lanes per block through the shared-memory working matrix.
 constexpr int kRowsWarps = 4;
 
@@ -326,6 +417,27 @@ static int launch_transform_mma(const void* in, int32_t* out, int64_t n_blocks, 
 
 template <int N, bool DST, bool INV, bool IN32>
 static int launch_transform_unit(const void* in, int32_t* out, int64_t n_blocks, cudaStream_t st) {
+    // Measured (tools/sweep_xform.py, profiles/r2_xform_sweep.jsonl): the pipelined kernel wins for the forward
+    // transform once a launch holds enough tiles per warp (2^24 4x4 blocks: 0.88 -> 0.97 of the copy bandwidth,
+    // 2^24 8x8 blocks: 0.92 -> 0.96); small launches are bounded by ramp-up and the launch gap and prefer the
+    // larger grid of the kernel above, and the inverse (int32 in AND out: twice the staging per tile) is no
+    // faster pipelined.  NH_XF_PIPE=0|1 forces one of them.
+    static const int force = [] { const char* e = getenv("NH_XF_PIPE"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+    const bool pipe = force >= 0 ? force == 1 : (!INV && (n_blocks * N * N) / 64 >= (int64_t(1) << 21));
+    if (pipe) {
+        constexpr int kSmemP = kXfPipeWarps * 2 * WarpTile<256>::kBytes;
+        int rc = ensure_dynamic_smem(transform_unit_pipe_kernel<N, DST, INV, IN32>, kSmemP, "cudaFuncSetAttribute(transform_unit_pipe_kernel)");
+        if (rc != NH_OK) return rc;
+        constexpr int BPUP = 64 / (N * N);
+        const int gridp = grid_for((n_blocks + BPUP - 1) / BPUP, kXfPipeWarps * 32, 3);
+        unsigned int* counter = nullptr;
+        rc = acquire_tile_counter(st, &counter);
+        if (rc != NH_OK) return rc;
+        transform_unit_pipe_kernel<N, DST, INV, IN32><<<gridp, kXfPipeWarps * 32, kSmemP, st>>>(in, out, n_blocks, counter);
+        NH_CHECK_LAUNCH("transform_unit_pipe_kernel");
+        tile_counter_launched(st);
+        return NH_OK;
+    }
     constexpr int kSmem = kXfWarps * WarpTile<256>::kBytes;
     {
         const int rc = ensure_dynamic_smem(transform_unit_kernel<N, DST, INV, IN32>, kSmem, "cudaFuncSetAttribute(transform_unit_kernel)");
