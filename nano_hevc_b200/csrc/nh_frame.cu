@@ -897,6 +897,25 @@ static int launch_search_cost(const CoderArgs& a, cudaStream_t st) {
     NH_CHECK_LAUNCH("search_plane_kernel");
     return NH_OK;
 }
+// N = 4 with the winner stage fused into the search kernel (nh_search.cuh, CODE = true).  *handed_back = the
+// stream's counter of tiles left to the exact coder kernel.
+template <int COST>
+static int launch_search_code4(const CoderArgs& a, cudaStream_t st, unsigned int** handed_back) {
+    using C = SearchCfg<4>;
+    int rc = ensure_dynamic_smem(search_plane_kernel<4, COST, true>, C::SMEM_BYTES, "search_plane_kernel<code>");
+    if (rc != NH_OK) return rc;
+    unsigned int* counter = nullptr;
+    rc = acquire_tile_counter(st, &counter);
+    if (rc != NH_OK) return rc;
+    *handed_back = counter + 2;
+    SearchArgs s{a.src, a.H, a.W, a.pitch, a.cost_kind, a.n_blocks, a.out.modes, a.out.costs, a.blocks_per_frame,
+                 a.frame_stride, a.fq, a.maxv, a.out.pred, a.out.coeff, a.out.levels, a.out.recon_plane, counter + 2};
+    const int grid = grid_for(a.n_blocks, (int64_t)C::WARPS * C::T, 4);
+    search_plane_kernel<4, COST, true><<<grid, C::WARPS * 32, C::SMEM_BYTES, st>>>(s);
+    NH_CHECK_LAUNCH("search_plane_kernel<code>");
+    return NH_OK;
+}
+
 template <int N>
 static int launch_search(const CoderArgs& a, cudaStream_t st) {
     return a.cost_kind == NH_COST_SAD ? launch_search_cost<N, NH_COST_SAD>(a, st) : launch_search_cost<N, NH_COST_SATD>(a, st);
@@ -904,6 +923,18 @@ static int launch_search(const CoderArgs& a, cudaStream_t st) {
 
 static int dispatch_search_then_code(CoderArgs a, int size, cudaStream_t st) {
     int rc;
+    // N = 4: the lane that searched a block codes it (NH_SEARCH4_FUSED=0 keeps the two-kernel form)
+    static const bool fused4 = [] { const char* e = getenv("NH_SEARCH4_FUSED"); return !(e && e[0] == '0'); }();
+    if (size == 4 && fused4 && a.use_dst && a.out.recon_plane && (reinterpret_cast<uintptr_t>(a.out.recon_plane) & 7) == 0) {
+        rc = a.cost_kind == NH_COST_SAD ? launch_search_code4<NH_COST_SAD>(a, st, &a.handed_back)
+                                        : launch_search_code4<NH_COST_SATD>(a, st, &a.handed_back);
+        if (rc != NH_OK) return rc;
+        a.modes_in = a.out.modes;
+        a.only_undecided = 1;   // the exact coder only touches the tiles marked 0xFF (samples outside [0, 255])
+        rc = dispatch_coder<SRC_PLANE>(a, size, st);
+        tile_counter_launched(st);
+        return rc;
+    }
     switch (size) {
         case 4: rc = launch_search<4>(a, st); break;
         case 8: rc = launch_search<8>(a, st); break;
