@@ -524,16 +524,18 @@ def run_ours(args, rank, world, local_rank):
         scratch = torch.empty((sbytes,), dtype=torch.uint8, device=dev)
         import ctypes
 
-        def e2e_leg(frames_np, ksteps, what):
+        def e2e_leg(frames_np, ksteps, what, int16_results=False):
             Fe = frames_np.shape[0]
             Be = Fe * BLOCKS_PER_FRAME
             h_in_p = [pin(a) for a in frame_to_cfg2_inputs(frames_np)]
-            h_out = [torch.empty((Be, N, N), dtype=dt).pin_memory() for dt in (torch.int16, torch.int32, torch.int32, torch.int16)]
+            wide = torch.int16 if int16_results else torch.int32
+            h_out = [torch.empty((Be, N, N), dtype=dt).pin_memory() for dt in (torch.int16, wide, wide, torch.int16)]
+            entry = L.nh_host_pipeline_dcplanar_i16 if int16_results else L.nh_host_pipeline_dcplanar
 
             def e2e_step():
                 for mode in MODES:
                     for qp in QPS:
-                        _lib.check(L.nh_host_pipeline_dcplanar(
+                        _lib.check(entry(
                             *[t.data_ptr() for t in h_in_p], None, mode, Be, N, qp, 1, 0, 8,
                             *[t.data_ptr() for t in h_out], scratch.data_ptr(), sbytes, chunk))
 
@@ -560,8 +562,8 @@ def run_ours(args, rank, world, local_rank):
             # spot-check the e2e outputs against the device-resident path (first 8 frames)
             nb = min(Be, 8 * BLOCKS_PER_FRAME)
             chk = batched.fused_block_pipeline(*[t[:nb].to(dev) for t in h_in_p], MODES[-1], QPS[-1])
-            assert torch.equal(chk.levels.cpu(), h_out[2][:nb]) and torch.equal(chk.recon.cpu(), h_out[3][:nb]), "e2e mismatch"
-            assert torch.equal(chk.coeff.cpu(), h_out[1][:nb]) and torch.equal(chk.pred.cpu(), h_out[0][:nb]), "e2e mismatch"
+            assert torch.equal(chk.levels.cpu(), h_out[2][:nb].to(torch.int32)) and torch.equal(chk.recon.cpu(), h_out[3][:nb]), "e2e mismatch"
+            assert torch.equal(chk.coeff.cpu(), h_out[1][:nb].to(torch.int32)) and torch.equal(chk.pred.cpu(), h_out[0][:nb]), "e2e mismatch"
             return res
 
         Fe = min(F, args.e2e_frames)
@@ -575,6 +577,13 @@ def run_ours(args, rank, world, local_rank):
                         "traffic (tools/ubench_pcie.py: 46 GB/s per direction under duplex load)")
         Fn = min(Fe, 32)
         e2e_noise = e2e_leg(noise_frames(Fn, 1000 * rank), 1, "noise (SURVEY 8d i): every level segment non-zero, int16 wire format")
+        # the same workload with coefficients / levels delivered as int16 (an option of the API, not the reference's
+        # dtypes): DMA straight into the caller's arrays, no host pass -- what is left is PCIe
+        e2e_i16 = e2e_leg(frames_e, max(1, min(args.steps, 3)), "smooth, int16 delivery of coefficients and levels", int16_results=True)
+        e2e_i16["api"] = ("nh_host_pipeline_dcplanar_i16 (C ABI, pinned host buffers, 3-stream chunked overlap; pred / coeff / levels / "
+                          "recon by DMA into the caller's int16 arrays: 8 B/px down, no host threads)")
+        e2e_i16["bound"] = "PCIe (2.56 B/px up, 8 B/px down)"
+        e2e["int16_delivery"] = e2e_i16
         del scratch
 
     secondary = None

@@ -277,6 +277,17 @@ int nh_host_pipeline_dcplanar(const int16_t* orig, const int16_t* top, const int
                               int32_t* coeff, int32_t* levels, int16_t* recon,
                               void* device_scratch, int64_t scratch_bytes, int64_t chunk_blocks);
 
+/* nh_host_pipeline_dcplanar with coefficients and levels delivered as int16 (an option next to the reference's
+ * int32 dtypes; same arguments otherwise, same device scratch): results go by DMA straight into the caller's
+ * arrays, no host thread touches them.  Valid while every block stays in the pixel domain (samples in [0, 4095]:
+ * |coeff| <= 32394, |level| <= 13600); otherwise the call fails with NH_E_ARG after its transfers have drained. */
+int nh_host_pipeline_dcplanar_i16(const int16_t* orig, const int16_t* top, const int16_t* left,
+                                  const int16_t* top_right, const int16_t* bottom_left,
+                                  const uint8_t* modes, int mode, int64_t n_blocks, int size, int qp,
+                                  int is_intra, int use_dst, int bit_depth, int16_t* pred,
+                                  int16_t* coeff16, int16_t* levels16, int16_t* recon,
+                                  void* device_scratch, int64_t scratch_bytes, int64_t chunk_blocks);
+
 /* ------------------------------------- host-buffer entry of the frame coders (configs 3 / 5 end to end) */
 /* nh_encode_frames for frames and results in HOST memory (docs/frames_and_panes.md:319-344 with numpy arrays
  * on both sides): src is n_frames contiguous (height, width) int16 planes; every output is optional (NULL = not

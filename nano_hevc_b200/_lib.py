@@ -75,6 +75,8 @@ PROTOTYPES = {
     "nh_convert_i16_to_u8": (_i, [_p, _p, _i64, _p]),
     "nh_host_pipeline_dcplanar": (_i, [_p, _p, _p, _p, _p, _p, _i, _i64, _i, _i, _i, _i, _i,
                                        _p, _p, _p, _p, _p, _i64, _i64]),
+    "nh_host_pipeline_dcplanar_i16": (_i, [_p, _p, _p, _p, _p, _p, _i, _i64, _i, _i, _i, _i, _i,
+                                           _p, _p, _p, _p, _p, _i64, _i64]),
 }
 
 

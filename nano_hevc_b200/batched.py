@@ -288,10 +288,12 @@ def host_block_pipeline(orig, top, left, top_right, bottom_left, mode, qp: int, 
                         use_dst: bool = False, bit_depth: int = 8,
                         outputs=("pred", "coeff", "levels", "recon"), chunk_blocks: int | None = None,
                         device: torch.device | None = None, scratch: torch.Tensor | None = None,
-                        out: PipelineResult | None = None):
+                        out: PipelineResult | None = None, int16_results: bool = False):
     """K6 on HOST buffers (numpy arrays or CPU tensors, pinned memory recommended) through
     ``nh_host_pipeline_dcplanar``: the library overlaps H2D, the kernel and D2H on internal streams
-    and returns CPU tensors.  This is the call behind the ``e2e`` number of bench.py."""
+    and returns CPU tensors.  This is the call behind the ``e2e`` number of bench.py.
+    ``int16_results``: coefficients and levels come back as int16 (``nh_host_pipeline_dcplanar_i16``:
+    DMA straight into the result tensors, no host pass; raises when a block leaves the pixel domain)."""
     import numpy as np
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     as_cpu = lambda a, dt: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(dt).contiguous()
@@ -316,15 +318,19 @@ def host_block_pipeline(orig, top, left, top_right, bottom_left, mode, qp: int, 
     if out is None:
         want = set(outputs)
         mk = lambda name, dt: torch.empty((B, N, N), dtype=dt).pin_memory() if name in want else None
-        out = PipelineResult(mk("pred", torch.int16), mk("coeff", torch.int32), mk("levels", torch.int32),
-                             mk("recon", torch.int16))
+        wide = torch.int16 if int16_results else torch.int32
+        out = PipelineResult(mk("pred", torch.int16), mk("coeff", wide), mk("levels", wide), mk("recon", torch.int16))
+    for res_t in (out.coeff, out.levels):
+        if res_t is not None and res_t.dtype != (torch.int16 if int16_results else torch.int32):
+            raise ValueError("coeff / levels of `out` must be int16 with int16_results, int32 otherwise")
     chunk = int(chunk_blocks) if chunk_blocks else max(1024, (1 << 23) // (N * N))
     L = _lib.lib()
     nbytes = int(L.nh_host_pipeline_scratch_bytes(N, chunk))
     if scratch is None or scratch.numel() < nbytes:
         scratch = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(L.nh_host_pipeline_dcplanar(
+        entry = L.nh_host_pipeline_dcplanar_i16 if int16_results else L.nh_host_pipeline_dcplanar
+        _lib.check(entry(
             _ptr(o), _ptr(t), _ptr(l), _ptr(tr), _ptr(bl), _ptr(m), ms, B, N, int(qp), int(bool(is_intra)),
             int(bool(use_dst)), int(bit_depth), _ptr(out.pred), _ptr(out.coeff), _ptr(out.levels),
             _ptr(out.recon), _ptr(scratch), scratch.numel(), chunk))

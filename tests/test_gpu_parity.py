@@ -448,6 +448,27 @@ def test_host_pipeline_vs_oracle(Bt, n, B, chunk):
     eq(got.levels.numpy(), O.pipeline_dcplanar_batch(orig, top, left, tr, bl, 0, 31, threads=O.n_host_threads())[2], "levels only")
 
 
+@pytest.mark.parametrize("n,B,chunk", [(4, 70001, 8192), (8, 20011, 4096), (16, 3001, 1024), (32, 1000, 300)])
+def test_host_pipeline_int16_delivery(Bt, n, B, chunk):
+    """nh_host_pipeline_dcplanar_i16: coefficients and levels delivered as int16 by DMA (no host pass).  Equal to
+    the oracle's int32 results in the pixel domain (10-bit samples here); a batch with a block outside it is
+    refused loudly instead of being truncated."""
+    rng = np.random.default_rng(n * 17 + 3)
+    orig, top, left, tr, bl = _dcplanar_inputs(rng, B, n, 1024)
+    modes = rng.integers(0, 2, B).astype(np.uint8)
+    want = O.pipeline_dcplanar_batch(orig, top, left, tr, bl, modes, 22, use_dst=(n == 4), bit_depth=10,
+                                     threads=O.n_host_threads())
+    got = Bt.host_block_pipeline(orig, top, left, tr, bl, modes, 22, use_dst=(n == 4), bit_depth=10, chunk_blocks=chunk,
+                                 int16_results=True)
+    assert got.coeff.dtype == torch.int16 and got.levels.dtype == torch.int16
+    for name, w in zip(("pred", "coeff", "levels", "recon"), want):
+        eq(getattr(got, name).numpy().astype(w.dtype), w, f"{name} n={n}")
+    orig[chunk + 5] = 20000   # far outside the pixel domain
+    with pytest.raises(ValueError, match="pixel domain"):
+        Bt.host_block_pipeline(orig, top, left, tr, bl, modes, 22, use_dst=(n == 4), bit_depth=10, chunk_blocks=chunk,
+                               int16_results=True)
+
+
 @pytest.mark.parametrize("n,B,chunk", [(4, 70003, 8192), (8, 20011, 4096), (16, 3001, 1024), (32, 701, 300)])
 def test_host_pipeline_compact_wire(Bt, n, B, chunk):
     """Compact wire format of the host pipeline (csrc/nh_host.cu): int8 coefficients with int16
