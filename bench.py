@@ -584,6 +584,42 @@ def run_ours(args, rank, world, local_rank):
                           "recon by DMA into the caller's int16 arrays: 8 B/px down, no host threads)")
         e2e_i16["bound"] = "PCIe (2.56 B/px up, 8 B/px down)"
         e2e["int16_delivery"] = e2e_i16
+
+        # ---- the box's DMA ceiling: every rank copies pinned host <-> device in both directions AT THE SAME TIME, in
+        # the up : down ratio of the int16-delivery path (1 : 3), nothing else running.  What the ranks reach together
+        # is what the host's memory / IO fabric gives the e2e legs; per-rank share x bytes per pixel = their ceiling.
+        def dma_probe():
+            n_up, n_down = 256 << 20, 768 << 20
+            h_up = torch.empty(n_up, dtype=torch.uint8).pin_memory()
+            h_down = torch.empty(n_down, dtype=torch.uint8).pin_memory()
+            d_up = torch.empty(n_up, dtype=torch.uint8, device=dev)
+            d_down = torch.empty(n_down, dtype=torch.uint8, device=dev)
+            s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+            def both():
+                with torch.cuda.stream(s1):
+                    d_up.copy_(h_up, non_blocking=True)
+                with torch.cuda.stream(s2):
+                    h_down.copy_(d_down, non_blocking=True)
+
+            both()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                both()
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            per_rank = 3 * (n_up + n_down) / float(dt.item()) / 1e9
+            return {"per_rank_GBs": per_rank, "all_ranks_GBs": per_rank * world, "ranks": world,
+                    "pattern": "pinned H2D 256 MB + D2H 768 MB concurrently on every rank, 3 rounds",
+                    "int16_delivery_ceiling_Mpix_s": world * per_rank * 1e9 / 10.56 / 1e6,
+                    "note": "int16 delivery moves 2.56 + 8 = 10.56 B/px over PCIe; its ceiling is this aggregate DMA rate / 10.56"}
+
+        e2e["dma_ceiling"] = dma_probe()
         del scratch
 
     secondary = None
