@@ -358,7 +358,7 @@ def run_secondary(torch, dist, batched, dev, rank, world, peak):
     F3 = 32
     planes = torch.stack([_synth_plane_dev(torch, H4, W4, 100 * rank + i, dev) for i in range(F3)])
     cfg3 = {}
-    for n in (8, 32):
+    for n in (4, 8, 16, 32):
         px = F3 * (H4 // n) * (W4 // n) * n * n
         res = batched.encode_frames(planes, n, cost="sad", qp=27, stats=False)
         for cost in ("sad", "satd"):

@@ -51,7 +51,9 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) coder8_plane_mma_kernel(cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fg = lane >> 2, ft = lane & 3;
     unsigned char* wbase = smem_raw + warp * kWarpBytes;
-    unsigned char* s16[2] = {wbase, wbase + T16::kBytes};
+    // (a function of the buffer index, not an array of pointers: indexing a pointer array with a run-time value makes
+    // the compiler forget the address space -- generic LD / ST instead of LDS / STS, tracked on the long scoreboard)
+    auto s16 = [&](int i) -> unsigned char* { return wbase + i * T16::kBytes; };
     unsigned char* sP = wbase + 2 * T16::kBytes;
     unsigned char* rb = wbase + 3 * T16::kBytes + lane * kC8RefBytes;   // odd word stride: conflict-free
     const uint32_t lane_off = (uint32_t)((lane >> 3) * T16::kPitch + (lane & 7) * 16);
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) coder8_plane_mma_kernel(cons
         n_mode = bx0 + lane < bw ? (int)a.modes[(int64_t)byg * bw + bx0 + lane] : 1;
     };
     if (tile < n_tiles) {
-        prefetch(tile, s16[0]);
+        prefetch(tile, s16(0));
         load_mode(tile);
     }
     cp_async_commit();
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) coder8_plane_mma_kernel(cons
             }
         }
         // the other pixel tile is free: start fetching the next tile into it, then wait for this one
-        if (tile_next < n_tiles) prefetch(tile_next, s16[cur ^ 1]);
+        if (tile_next < n_tiles) prefetch(tile_next, s16(cur ^ 1));
         cp_async_commit();
         cp_async_wait<1>();
         __syncwarp();
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) coder8_plane_mma_kernel(cons
             continue;
         }
         if (a.pred) T16::store(sP, reinterpret_cast<unsigned char*>(a.pred + blk0 * NN), lane, chunks16);
-        const uint32_t sO = smem_u32(s16[cur]) + lane_off, sPa = smem_u32(sP) + lane_off;
+        const uint32_t sO = smem_u32(s16(cur)) + lane_off, sPa = smem_u32(sP) + lane_off;
         // unrolled 2x, not 8x as in fused_mma8_kernel: with the 35-mode prediction code in front of it the
         // kernel waited on instruction fetch (ncu: no-instruction 1.08 warps per issue -> 0.08)
 #pragma unroll 2
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) coder8_plane_mma_kernel(cons
             int16_t* gp = a.recon_plane + fr * a.frame_stride + (int64_t)by * N * a.pitch + (bx0 + lane) * N;
             uint4 v[8];
 #pragma unroll
-            for (int it = 0; it < 8; ++it) v[it] = *reinterpret_cast<const uint4*>(s16[cur] + lane * T16::kPitch + it * 16);
+            for (int it = 0; it < 8; ++it) v[it] = *reinterpret_cast<const uint4*>(s16(cur) + lane * T16::kPitch + it * 16);
 #pragma unroll
             for (int it = 0; it < 8; ++it) stg_stream(gp + (int64_t)it * a.pitch, v[it]);
         }

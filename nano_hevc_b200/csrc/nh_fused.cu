@@ -277,7 +277,9 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit_kernel_v2(const F
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* wbase = smem_raw + warp * kWarpBytes;
-    unsigned char* s16[2] = {wbase, wbase + T16::kBytes};
+    // (a function of the buffer index, not an array of pointers: indexing a pointer array with a run-time value makes
+    // the compiler forget the address space -- generic LD / ST instead of LDS / STS, tracked on the long scoreboard)
+    auto s16 = [&](int i) -> unsigned char* { return wbase + i * T16::kBytes; };
     unsigned char* s32 = wbase + 2 * T16::kBytes;
 
     const int64_t n_units = (a.n_blocks + BPU - 1) / BPU;
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit_kernel_v2(const F
 
     Refs nxt;
     if (tile < n_tiles) {
-        prefetch(tile, s16[0]);
+        prefetch(tile, s16(0));
         load_refs(tile, nxt);
     }
     cp_async_commit();
@@ -350,13 +352,13 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit_kernel_v2(const F
         if (tile + warp_stride < n_tiles) load_refs(tile + warp_stride, nxt);
         // the other pixel tile is free (its reconstruction left at the end of the previous
         // iteration): start fetching the next tile into it, then wait for the current one
-        if (tile + warp_stride < n_tiles) prefetch(tile + warp_stride, s16[cur ^ 1]);
+        if (tile + warp_stride < n_tiles) prefetch(tile + warp_stride, s16(cur ^ 1));
         cp_async_commit();
         cp_async_wait<1>();
         __syncwarp();
 
         int res[BPU][N][N];
-        uint4* u16 = T16::unit(s16[cur], lane);
+        uint4* u16 = T16::unit(s16(cur), lane);
         uint32_t ood = 0;  // out-of-domain bits: any sample outside [0, 4095]
 #pragma unroll
         for (int q = 0; q < BPU; ++q) {
@@ -409,7 +411,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit_kernel_v2(const F
         }
         const bool fast = ood == 0;  // in the pixel domain: 32-bit arithmetic is exact
         __syncwarp();
-        if (a.pred) T16::store(s16[cur], reinterpret_cast<unsigned char*>(a.pred + blk0 * NN), lane, chunks16);
+        if (a.pred) T16::store(s16(cur), reinterpret_cast<unsigned char*>(a.pred + blk0 * NN), lane, chunks16);
         __syncwarp();  // the tile keeps the prediction until the reconstruction rewrites it
 
         // -- forward transform (in-thread, both passes)
@@ -474,7 +476,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit_kernel_v2(const F
                 u16[c] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             }
             __syncwarp();
-            T16::store(s16[cur], reinterpret_cast<unsigned char*>(a.recon + blk0 * NN), lane, chunks16);
+            T16::store(s16(cur), reinterpret_cast<unsigned char*>(a.recon + blk0 * NN), lane, chunks16);
         }
         __syncwarp();
         // -- a lane whose inputs left the pixel domain recodes its unit exactly (cold path); the
@@ -506,7 +508,9 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit4_kernel(const Fus
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* wbase = smem_raw + warp * kWarpBytes;
-    unsigned char* s16[2] = {wbase, wbase + T16::kBytes};
+    // (a function of the buffer index, not an array of pointers: indexing a pointer array with a run-time value makes
+    // the compiler forget the address space -- generic LD / ST instead of LDS / STS, tracked on the long scoreboard)
+    auto s16 = [&](int i) -> unsigned char* { return wbase + i * T16::kBytes; };
     unsigned char* s32 = wbase + 2 * T16::kBytes;
     // block j of the tile lives in unit j >> 2 (padded pitch), slot j & 3
     auto px_of = [&](unsigned char* tile, int j) { return reinterpret_cast<uint4*>(tile + (j >> 2) * T16::kPitch + (j & 3) * 32); };
@@ -550,10 +554,16 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit4_kernel(const Fus
             rf.mode = 1;
         }
     };
-    Refs rfA, rfB;  // references of the coming even / odd round
-    load_refs(tile, 0, rfA);
-    load_refs(tile, 1, rfB);
-    if (tile < n_tiles) prefetch(tile, s16[0]);
+    // references of the four rounds of the coming tile, one register set per round, each refilled for the NEXT
+    // tile right after its round has used it: a full tile of lead.  (Round 1 kept two sets refilled two rounds
+    // ahead -- only one round1() of lead for rounds 2 / 3: ncu put 45 % of the stall samples on the first use of
+    // those loads, long-scoreboard 2.7 warps per issue.)
+    Refs rf0, rf1, rf2, rf3;
+    load_refs(tile, 0, rf0);
+    load_refs(tile, 1, rf1);
+    load_refs(tile, 2, rf2);
+    load_refs(tile, 3, rf3);
+    if (tile < n_tiles) prefetch(tile, s16(0));
     cp_async_commit();
     int cur = 0;
     int64_t tile_after = n_tiles;
@@ -563,15 +573,13 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit4_kernel(const Fus
         const int64_t trem = a.n_blocks - blk0;
         const int blocks_valid = (int)(trem < 128 ? trem : 128);
         const int chunks16 = blocks_valid * 2, chunks32 = blocks_valid * 4;
-        if (tile_next < n_tiles) prefetch(tile_next, s16[cur ^ 1]);
+        if (tile_next < n_tiles) prefetch(tile_next, s16(cur ^ 1));
         cp_async_commit();
         cp_async_wait<1>();
         __syncwarp();
-        unsigned char* px = s16[cur];
+        unsigned char* px = s16(cur);
         uint32_t ood_mask = 0;  // bit q: this lane's block of round q left the pixel domain [0, 4095]
         // ---- loop 1: predict, residual, forward transform; prediction and coefficients into the tiles.
-        // References travel two rounds ahead in two register sets (even / odd rounds); the sets for
-        // rounds 0 / 1 of the NEXT tile are fetched during rounds 2 / 3 of this one.
         auto round1 = [&](int q, const Refs& rf) {
             const int j = q * 32 + lane;
             uint4* p16 = px_of(px, j);
@@ -605,13 +613,14 @@ __global__ void __launch_bounds__(kV2Warps * 32, 3) fused_unit4_kernel(const Fus
             for (int i = 0; i < 4; ++i) c32[i] = make_uint4(res[i][0], res[i][1], res[i][2], res[i][3]);
             ood_mask |= (ood != 0 ? 1u : 0u) << q;
         };
-#pragma unroll 1
-        for (int i = 0; i < 2; ++i) {
-            round1(2 * i, rfA);
-            load_refs(i == 0 ? tile : tile_next, i == 0 ? 2 : 0, rfA);
-            round1(2 * i + 1, rfB);
-            load_refs(i == 0 ? tile : tile_next, i == 0 ? 3 : 1, rfB);
-        }
+        round1(0, rf0);
+        load_refs(tile_next, 0, rf0);
+        round1(1, rf1);
+        load_refs(tile_next, 1, rf1);
+        round1(2, rf2);
+        load_refs(tile_next, 2, rf2);
+        round1(3, rf3);
+        load_refs(tile_next, 3, rf3);
         __syncwarp();
         if (a.pred) T16::store(px, reinterpret_cast<unsigned char*>(a.pred + blk0 * NN), lane, chunks16);
         if (a.coeff) T32::store(s32, reinterpret_cast<unsigned char*>(a.coeff + blk0 * NN), lane, chunks32);

@@ -272,7 +272,9 @@ __global__ void __launch_bounds__(kV2Warps * 32, OCC) fused_mma8_kernel(const Fu
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fg = lane >> 2, ft = lane & 3;
     unsigned char* wbase = smem_raw + warp * kWarpBytes;
-    unsigned char* s16[2] = {wbase, wbase + T16::kBytes};
+    // (a function of the buffer index, not an array of pointers: indexing a pointer array with a run-time value makes
+    // the compiler forget the address space -- generic LD / ST instead of LDS / STS, tracked on the long scoreboard)
+    auto s16 = [&](int i) -> unsigned char* { return wbase + i * T16::kBytes; };
     unsigned char* sP = wbase + 2 * T16::kBytes;
     // ldmatrix / stmatrix x4: 8x8 tile j = lane >> 3 is block 4q + j, row lane & 7
     const uint32_t lane_off = (uint32_t)((lane >> 3) * T16::kPitch + (lane & 7) * 16);
@@ -337,7 +339,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, OCC) fused_mma8_kernel(const Fu
         }
     };
     if (tile < n_tiles) {
-        prefetch(tile, s16[0]);
+        prefetch(tile, s16(0));
         load_refs(tile);
     }
     cp_async_commit();
@@ -387,12 +389,12 @@ __global__ void __launch_bounds__(kV2Warps * 32, OCC) fused_mma8_kernel(const Fu
             }
         }
         // the other pixel tile is free: start fetching the next tile into it, then wait for this one
-        if (tile_next < n_tiles) prefetch(tile_next, s16[cur ^ 1]);
+        if (tile_next < n_tiles) prefetch(tile_next, s16(cur ^ 1));
         cp_async_commit();
         cp_async_wait<1>();
         __syncwarp();
         if (a.pred) T16::store(sP, reinterpret_cast<unsigned char*>(a.pred + blk0 * NN), lane, chunks16);
-        const uint32_t sO = smem_u32(s16[cur]) + lane_off, sPa = smem_u32(sP) + lane_off;
+        const uint32_t sO = smem_u32(s16(cur)) + lane_off, sPa = smem_u32(sP) + lane_off;
         uint32_t oodw = 0;
 #pragma unroll kMma8Unroll
         for (int q = 0; q < 8; ++q) {
@@ -449,7 +451,7 @@ __global__ void __launch_bounds__(kV2Warps * 32, OCC) fused_mma8_kernel(const Fu
         }
         ood |= oodw & 0xFF00FF00u;
         __syncwarp();
-        if (a.recon) T16::store(s16[cur], reinterpret_cast<unsigned char*>(a.recon + blk0 * NN), lane, chunks16);
+        if (a.recon) T16::store(s16(cur), reinterpret_cast<unsigned char*>(a.recon + blk0 * NN), lane, chunks16);
         __syncwarp();
         // any sample of the tile outside [0, 255]: recode it exactly, one block per lane (cold path;
         // the __syncwarp above orders the cooperative stores before these)

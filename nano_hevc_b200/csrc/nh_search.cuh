@@ -38,6 +38,41 @@ __host__ __device__ constexpr int neg_angle_at(int mi) {
     return d == 0 ? -2 : d == 1 ? -5 : d == 2 ? -9 : d == 3 ? -13 : d == 4 ? -17 : d == 5 ? -21 : d == 6 ? -26 : -32;
 }
 
+// Position of scan line yy of the mirror pair (mode, 36 - mode), mode = 2 .. 18 (intra.py:191-207), ready to use:
+//   k4 = byte offset of the word that holds ref[k]  (k = 1 + ((yy+1) * angle >> 5), k4 = k & ~3, may be negative)
+//   x  = 8 k     (funnel-shift amount: the hardware takes it modulo 32 = 8 (k & 3))
+//   y  = selector of the last sample's byte         (0x3412 + ((k & 3) << 8))
+//   z  = 8 f     (f = (yy+1) * angle & 31; weights scaled by 8: the sample is the high byte of its 16-bit lane)
+//   w  = 8 (32 - f)
+// The compiler keeps per-mode values in vector registers and recomputed all of this on the ALU pipe for every
+// line (13 instructions per mirror-pair line); constant loads replace them.  k4 has a table of its own: it only
+// enters addresses, and a value that is not a vector operand can stay in a uniform register.
+struct LineTab { int4 e[17][32]; int k4[17][32]; };
+constexpr LineTab make_line_tab() {
+    constexpr int ang[17] = {32, 26, 21, 17, 13, 9, 5, 2, 0, -2, -5, -9, -13, -17, -21, -26, -32};
+    LineTab t{};
+    for (int m = 0; m < 17; ++m)
+        for (int yy = 0; yy < 32; ++yy) {
+            const int p = (yy + 1) * ang[m];
+            const int k = 1 + (p >> 5);
+            t.k4[m][yy] = k & ~3;
+            t.e[m][yy].x = 8 * k;
+            t.e[m][yy].y = 0x3412 + ((k & 3) << 8);
+            t.e[m][yy].z = (p & 31) << 3;
+            t.e[m][yy].w = 256 - ((p & 31) << 3);
+        }
+    return t;
+}
+static __constant__ LineTab kc_line_tab = make_line_tab();
+
+// PRMT with a run-time selector handed over as it is (__byte_perm masks it with 0x7777 first: one more ALU-pipe
+// instruction per use)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
 template <int N>
 struct SearchCfg {
     static constexpr int SW = N >= 8 ? 8 : 4;          // strip width (a lane owns 4 scan lines x SW samples)
@@ -63,7 +98,8 @@ struct SearchCfg {
     static constexpr int GP = T >= 16 ? 1 : (T == 4 ? 4 : 8);   // build: groups of modes per orientation and block
     static constexpr int MPG = 8 / GP;                 // modes per group
     static constexpr int WARPS = 4;
-    static constexpr int SMEM_BYTES = (WARPS * WARP_WORDS + 16) * 4;
+    static constexpr int TAB_WORDS = N == 4 ? 17 * 4 * 5 : 0;   // N = 4: the CTA's copy of the scan-line table (int4 + int per entry)
+    static constexpr int SMEM_BYTES = (WARPS * WARP_WORDS + 16 + TAB_WORDS) * 4;
 };
 
 struct SearchArgs {
@@ -113,7 +149,7 @@ __device__ __forceinline__ int strip_cost_packed(const uint32_t (&pr)[4][WPS], c
 //   ((32-f) ref[k+i] + f ref[k+i+1] + 16) >> 5  for i = 0 .. SW-1   (intra.py:191-207; f8 = 8 f, g8 = 8 (32 - f)).
 // wp = word that holds ref[k], sh = 8 (k & 3), sel_last = 0x3412 + ((k & 3) << 8): the three depend on k
 // only, so the two halves of a mirror pair share them.
-template <int WPS>
+template <int WPS, bool RAW_SEL = false>
 __device__ __forceinline__ void predict_line_w(const uint32_t* wp, uint32_t sh, uint32_t sel_last, uint32_t f8,
                                                uint32_t g8, uint32_t (&out)[WPS]) {
     uint32_t w[WPS + 1], v[WPS];
@@ -126,7 +162,7 @@ __device__ __forceinline__ void predict_line_w(const uint32_t* wp, uint32_t sh, 
         const uint32_t e0 = __byte_perm(v[q], 0u, 0x4240);        // (b0, b2)
         const uint32_t o0 = __byte_perm(v[q], 0u, 0x4341);        // (b1, b3)
         const uint32_t e1 = q + 1 < WPS ? __byte_perm(e0, v[q + 1], 0x3412)      // (b2, b4)
-                                        : __byte_perm(e0, w[WPS], sel_last);     // b4 = byte k & 3 of the last word
+                                        : (RAW_SEL ? prmt(e0, w[WPS], sel_last) : __byte_perm(e0, w[WPS], sel_last));   // b4 = byte k & 3 of the last word
         const uint32_t t02 = g8 * e0 + 0x00800080u + f8 * o0;     // samples 0, 2 in the high bytes
         const uint32_t t13 = g8 * o0 + 0x00800080u + f8 * e1;     // samples 1, 3
         out[q] = __byte_perm(t02, t13, 0x7351);
@@ -164,6 +200,16 @@ __global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, CODE ? 4 : (COST == 
     int* negT0 = reinterpret_cast<int*>(smem_w + C::WARPS * C::WARP_WORDS);   // byte t = 0 of mode 11+mi, from the block base
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < 15) negT0[threadIdx.x] = C::neg_t0((int)threadIdx.x);
+    // N = 4 (lane = block: every lane is on the same scan line): the scan-line positions come from the table
+    // instead of 13 ALU-pipe instructions per mirror-pair line; see nh_search2.cuh for the measurements
+    const int4* s_tab = reinterpret_cast<const int4*>(smem_w + C::WARPS * C::WARP_WORDS + 16);
+    const int* s_k4 = reinterpret_cast<const int*>(smem_w + C::WARPS * C::WARP_WORDS + 16 + 17 * 4 * 4);
+    if constexpr (N == 4) {
+        for (int i = threadIdx.x; i < 17 * 4; i += blockDim.x) {
+            const_cast<int4*>(s_tab)[i] = kc_line_tab.e[i / 4][i % 4];
+            const_cast<int*>(s_k4)[i] = kc_line_tab.k4[i / 4][i % 4];
+        }
+    }
     __syncthreads();
 
     uint32_t* wbase = smem_w + warp * C::WARP_WORDS;
@@ -349,7 +395,33 @@ __global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, CODE ? 4 : (COST == 
             const int negh = negT0[mi_c];          // only used when k < 0 (modes 11..25)
             const int negv = negT0[14 - mi_c];
             int p = (py_ + 1) * angle;
-            if ((angle & 31) == 0) {   // modes 2 / 34, 10 / 26, 18: every fraction is 0
+            if constexpr (N == 4) {
+                // a negative-angle mode reads its own array on every line (k <= 0 there, and the array holds a copy
+                // of ref[0 .. 7] behind the projection): one base per mode and orientation
+                const unsigned char* bv = blk + (angle < 0 ? negv : 0);
+                const unsigned char* bh = blk + (angle < 0 ? negh : C::PB);
+                const int4* tab = s_tab + (mode - 2) * 4;
+                const int* tk4 = s_k4 + (mode - 2) * 4;
+                if ((angle & 31) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k4 = tk4[j];
+                        const uint32_t sh = (uint32_t)tab[j].x;
+                        copy_line_w<WPS>(reinterpret_cast<const uint32_t*>(bv + k4), sh, pr[j]);
+                        copy_line_w<WPS>(reinterpret_cast<const uint32_t*>(bh + k4), sh, prh[j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k4 = tk4[j];
+                        const int4 e = tab[j];
+                        predict_line_w<WPS, true>(reinterpret_cast<const uint32_t*>(bv + k4), (uint32_t)e.x, (uint32_t)e.y, (uint32_t)e.z,
+                                                  (uint32_t)e.w, pr[j]);
+                        predict_line_w<WPS, true>(reinterpret_cast<const uint32_t*>(bh + k4), (uint32_t)e.x, (uint32_t)e.y, (uint32_t)e.z,
+                                                  (uint32_t)e.w, prh[j]);
+                    }
+                }
+            } else if ((angle & 31) == 0) {   // modes 2 / 34, 10 / 26, 18: every fraction is 0
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int k = px_ + 1 + (p >> 5);

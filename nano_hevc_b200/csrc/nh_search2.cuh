@@ -60,40 +60,7 @@ struct LineCfg {
                          LineCfg<N>::neg_t0(12), LineCfg<N>::neg_t0(13), LineCfg<N>::neg_t0(14), 0}
 static __constant__ int kc_line_negt0[3][16] = {NH_NEGT0_ROW(8), NH_NEGT0_ROW(16), NH_NEGT0_ROW(32)};
 
-// Position of scan line yy of the mirror pair (mode, 36 - mode), mode = 2 .. 18 (intra.py:191-207), ready to use:
-//   k4 = byte offset of the word that holds ref[k]  (k = 1 + ((yy+1) * angle >> 5), k4 = k & ~3, may be negative)
-//   x  = 8 k     (funnel-shift amount: the hardware takes it modulo 32 = 8 (k & 3))
-//   y  = selector of the last sample's byte         (0x3412 + ((k & 3) << 8))
-//   z  = 8 f     (f = (yy+1) * angle & 31; weights scaled by 8: the sample is the high byte of its 16-bit lane)
-//   w  = 8 (32 - f)
-// The compiler keeps per-mode values in vector registers and recomputed all of this on the ALU pipe for every
-// line (13 instructions per mirror-pair line); constant loads replace them.  k4 has a table of its own: it only
-// enters addresses, and a value that is not a vector operand can stay in a uniform register.
-struct LineTab { int4 e[17][32]; int k4[17][32]; };
-constexpr LineTab make_line_tab() {
-    constexpr int ang[17] = {32, 26, 21, 17, 13, 9, 5, 2, 0, -2, -5, -9, -13, -17, -21, -26, -32};
-    LineTab t{};
-    for (int m = 0; m < 17; ++m)
-        for (int yy = 0; yy < 32; ++yy) {
-            const int p = (yy + 1) * ang[m];
-            const int k = 1 + (p >> 5);
-            t.k4[m][yy] = k & ~3;
-            t.e[m][yy].x = 8 * k;
-            t.e[m][yy].y = 0x3412 + ((k & 3) << 8);
-            t.e[m][yy].z = (p & 31) << 3;
-            t.e[m][yy].w = 256 - ((p & 31) << 3);
-        }
-    return t;
-}
-static __constant__ LineTab kc_line_tab = make_line_tab();
-
-// predict_line_w() / copy_line_w() of nh_search.cuh with the selector handed to PRMT as it is (__byte_perm masks a
-// run-time selector with 0x7777 first: one more ALU-pipe instruction per line)
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
-    uint32_t r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-    return r;
-}
+// (the scan-line table kc_line_tab and prmt() live in nh_search.cuh: the strip kernel uses them at N = 4)
 __device__ __forceinline__ void predict_line8(const uint32_t* wp, uint32_t sh, uint32_t sel_last, uint32_t f8, uint32_t g8,
                                               uint32_t (&out)[2]) {
     const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
