@@ -675,7 +675,8 @@ __global__ void __launch_bounds__(32 * WPB) coder_wave_mw_kernel(const CoderArgs
 
 }  // namespace nh
 #include "nh_wave.cuh"   // latency-oriented wavefront kernels for 8-bit planes (N = 8, N = 4); needs CoderArgs
-#include "nh_search2.cuh"   // line-synchronous search kernel (N = 8 / 16 / 32)
+#include "nh_search2.cuh"
+#include "nh_search3.cuh"   // line-synchronous search kernel (N = 8 / 16 / 32)
 namespace nh {
 
 // Exchange rows of the wavefront coder: -1 where a block will publish its bottom row, 0 in the
@@ -853,21 +854,42 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // winners (one block per warp and the tensor-core winner pipeline at N = 16 / 32).
 // 2 (default) = search kernel + winner kernel, 1 = everything in the single coder kernel (A/B profiling);
 // 3 / 4 = as 2 with the line-synchronous / the strip search kernel forced (2 picks per call, see
-// launch_search_cost); nh_set_search_impl() or NH_SEARCH_IMPL=1|2|3|4.
+// launch_search_cost), 5 = as 2 with the fraction-major search kernel forced at N = 16 / 32 (nh_search3.cuh);
+// nh_set_search_impl() or NH_SEARCH_IMPL=1|2|3|4|5.
 static thread_local int g_search_impl = 0;   // per calling thread: no shared mutable state between callers
 static int search_impl() {
     if (g_search_impl == 0) {
         const char* e = getenv("NH_SEARCH_IMPL");
-        g_search_impl = (e && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 2;
+        g_search_impl = (e && e[0] >= '1' && e[0] <= '5') ? e[0] - '0' : 2;
     }
     return g_search_impl;
 }
 static int split_impl() { return search_impl() >= 2; }
+static bool frac_default() {
+    static const bool on = [] { const char* e = getenv("NH_SEARCH_FRAC"); return !(e && e[0] == '0'); }();
+    return on;
+}
 
 template <int N, int COST>
 static int launch_search_cost(const CoderArgs& a, cudaStream_t st) {
     SearchArgs s{a.src, a.H, a.W, a.pitch, a.cost_kind, a.n_blocks, a.out.modes, a.out.costs, a.blocks_per_frame,
                  a.frame_stride};
+    if constexpr (N >= 16) {
+        // The fraction-major kernel (nh_search3.cuh): every scan line is a window of a reference array filtered once
+        // per fraction.  Measured against the line-synchronous kernel (32 4K frames, search + winners): N = 32 SAD
+        // +6 %, SATD +17 %, one frame +11 %; at N = 16 it loses on SAD (four blocks per warp: 17 KB of arrays per warp,
+        // 12 warps per SM), so it is the default at N = 32 only (NH_SEARCH_FRAC=0 turns that off).
+        using F = FracCfg<N>;
+        const int impl = search_impl();
+        if (impl == 5 || (impl == 2 && N == 32 && frac_default())) {
+            int rc = ensure_dynamic_smem(search_frac_kernel<N, COST>, F::SMEM_BYTES, "search_frac_kernel");
+            if (rc != NH_OK) return rc;
+            const int grid = grid_for(a.n_blocks, (int64_t)F::WARPS * F::T, F::PER_SM);
+            search_frac_kernel<N, COST><<<grid, F::WARPS * 32, F::SMEM_BYTES, st>>>(s);
+            NH_CHECK_LAUNCH("search_frac_kernel");
+            return NH_OK;
+        }
+    }
     if constexpr (N >= 8) {
         // The line-synchronous kernel (nh_search2.cuh) needs 16-byte pixel loads.  Measured (profiles/r2_search_*):
         // it wins on SAD once every warp gets a few of its (larger) tiles -- 32 4K frames: N = 8 / 16 / 32
@@ -1045,9 +1067,9 @@ NH_API int nh_fused_pipeline_modes(const int16_t* orig, const int16_t* top, cons
 }
 
 NH_API int nh_set_search_impl(int impl) {
-    if (impl < 1 || impl > 4) {
-        set_error("nh_set_search_impl: impl must be 1 (single coder kernel), 2 (search + winner kernels), 3 / 4 (as 2, "
-                  "line-synchronous / strip search kernel forced), got %d", impl);
+    if (impl < 1 || impl > 5) {
+        set_error("nh_set_search_impl: impl must be 1 (single coder kernel), 2 (search + winner kernels), 3 / 4 / 5 (as 2, "
+                  "line-synchronous / strip / fraction-major search kernel forced), got %d", impl);
         return NH_E_ARG;
     }
     g_search_impl = impl;
