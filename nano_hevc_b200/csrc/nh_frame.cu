@@ -142,8 +142,17 @@ struct CoderArgs {
     CoderOut out;
 };
 
+// Resident CTAs per SM the kernel is compiled for.  The 16x16 tensor-core winner instance (one block per warp, from
+// a plane) takes 246 registers when left alone: 2 CTAs per SM, issue slots 38 % busy, the stalls are fixed-latency
+// waits.  Capped at 168 registers (3 CTAs, 32 bytes of spills) with a grid of 3 CTAs per SM: 407 -> 373 us for 8 4K
+// frames.  (4 CTAs: 340 bytes of spills, slower; the 32x32 instance gains nothing from the same cap.)
+#ifndef NH_WINNER_OCC
+#define NH_WINNER_OCC 3
+#endif
 template <int N, int G, int SRC>
-__global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128) coder_kernel(const CoderArgs a) {
+constexpr int coder_occ() { return (N == 16 && G == 32 && SRC == 1) ? NH_WINNER_OCC : 1; }
+template <int N, int G, int SRC>
+__global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128, coder_occ<N, G, SRC>()) coder_kernel(const CoderArgs a) {
     using Cfg = CoderCfg<N, G>;
     constexpr int GPW = 32 / G;  // groups (blocks) per warp
     constexpr int WARPS = SRC == SRC_WAVEFRONT ? 1 : 4;
@@ -973,7 +982,7 @@ static int dispatch_search_then_code(CoderArgs a, int size, cudaStream_t st) {
         if (rc != NH_OK) return rc;
         a.only_undecided = 1;
     }
-    if (size == 16) return launch_coder<16, 32, SRC_PLANE>(a, grid_for(a.n_blocks, 4, 8), st);
+    if (size == 16) return launch_coder<16, 32, SRC_PLANE>(a, grid_for(a.n_blocks, 4, NH_WINNER_OCC), st);
     rc = dispatch_coder<SRC_PLANE>(a, size, st);
     if (a.only_undecided) tile_counter_launched(st);   // last launch that reads the stream's counter slot
     return rc;
