@@ -144,13 +144,20 @@ def intra_planar_predict_batched(top, left, top_right, bottom_left, size: int) -
     return out
 
 
-def _mode_args(mode, B, dev, lo):
-    """(modes_tensor_or_None, scalar_mode) with the reference's range errors."""
+def _mode_args(mode, B, dev, lo, hi=34):
+    """(modes_tensor_or_None, scalar_mode) with the reference's range errors.  A per-block mode tensor is checked
+    on the device (one min/max reduction and a host read) so that an out-of-range entry raises like the scalar
+    path and the reference do, instead of being clamped by the kernel."""
     if isinstance(mode, torch.Tensor):
-        m = _c(mode.to(dev), torch.uint8).reshape(-1)
-        if m.numel() != B:
-            raise ValueError(f"modes must have {B} entries, got {m.numel()}")
-        return m, 0
+        if mode.numel() != B:
+            raise ValueError(f"modes must have {B} entries, got {mode.numel()}")
+        if B:
+            mn, mx = (int(v) for v in torch.aminmax(mode.to(dev)))
+            if mx > 34:
+                raise IndexError("list index out of range")  # intra.py:142 indexes INTRA_PRED_ANGLE[mode - 2]
+            if mn < lo or mx > hi:
+                raise ValueError(f"modes tensor holds values outside {lo}..{hi} (min {mn}, max {mx})")
+        return _c(mode.to(dev), torch.uint8).reshape(-1), 0
     mode = int(mode)
     if mode > 34:
         raise IndexError("list index out of range")  # intra.py:142 indexes INTRA_PRED_ANGLE[mode - 2]
@@ -250,7 +257,7 @@ def fused_block_pipeline(orig, top, left, top_right, bottom_left, mode, qp: int,
     tr, bl = _c(top_right, torch.int16).reshape(-1), _c(bottom_left, torch.int16).reshape(-1)
     if t.shape != (B, N) or l.shape != (B, N) or tr.numel() != B or bl.numel() != B:
         raise ValueError("refs must be top/left (B, N) and top_right/bottom_left (B,)")
-    m, ms = _mode_args(mode, B, dev, 0)
+    m, ms = _mode_args(mode, B, dev, 0, 1)
     if m is None and ms > 1:
         raise ValueError("fused_block_pipeline handles modes 0 (planar) and 1 (DC); use "
                          "fused_block_pipeline_modes for angular modes")

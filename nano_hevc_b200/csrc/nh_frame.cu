@@ -548,6 +548,10 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128, coder_occ<N, 
     }
 }
 
+}  // namespace nh
+#include "nh_winner16.cuh"
+namespace nh {
+
 // K8, N = 16 / 32: WPB warps per block row.  With one warp per row the critical path of the wavefront
 // is bw + 2 bh block times, and a 32x32 block is ~17 us of dependent work for a single warp, most of
 // it the 35-mode search.  Here a CTA owns the row: every warp searches a share of the candidate
@@ -982,7 +986,27 @@ static int dispatch_search_then_code(CoderArgs a, int size, cudaStream_t st) {
         if (rc != NH_OK) return rc;
         a.only_undecided = 1;
     }
-    if (size == 16) return launch_coder<16, 32, SRC_PLANE>(a, grid_for(a.n_blocks, 4, NH_WINNER_OCC), st);
+    if (size == 16) {
+        // two blocks per warp on the tensor cores (nh_winner16.cuh); undecided blocks (0xFF) go to the exact coder
+        static const bool pair = [] { const char* e = getenv("NH_WINNER16_PAIR"); return !(e && e[0] == '0'); }();
+        if (pair && (a.pitch % 8) == 0 && (a.frame_stride % 8) == 0 && aligned16(a.src) && aligned16(a.out.recon_plane) &&
+            a.maxv <= 1023) {
+            rc = ensure_dynamic_smem(winner16_pair_kernel, Winner16Cfg::SMEM_BYTES, "winner16_pair_kernel");
+            if (rc != NH_OK) return rc;
+            unsigned int* counter = nullptr;
+            rc = acquire_tile_counter(st, &counter);
+            if (rc != NH_OK) return rc;
+            a.handed_back = counter + 2;
+            winner16_pair_kernel<<<grid_for((a.n_blocks + 1) / 2, Winner16Cfg::WARPS, 4), Winner16Cfg::WARPS * 32,
+                                   Winner16Cfg::SMEM_BYTES, st>>>(a);
+            NH_CHECK_LAUNCH("winner16_pair_kernel");
+            a.only_undecided = 1;
+            rc = launch_coder<16, 32, SRC_PLANE>(a, grid_for(a.n_blocks, 4, NH_WINNER_OCC), st);
+            tile_counter_launched(st);
+            return rc;
+        }
+        return launch_coder<16, 32, SRC_PLANE>(a, grid_for(a.n_blocks, 4, NH_WINNER_OCC), st);
+    }
     rc = dispatch_coder<SRC_PLANE>(a, size, st);
     if (a.only_undecided) tile_counter_launched(st);   // last launch that reads the stream's counter slot
     return rc;

@@ -149,6 +149,32 @@ def test_predict_modes_vs_oracle(Bt, n):
         eq(got[b], O.predict_mode(top[b], left[b], corner[b], int(modes[b]), n), f"block {b} mode {modes[b]}")
 
 
+def test_mode_tensor_range_errors(Bt):
+    """A per-block mode tensor with an entry out of range raises like the scalar path and the reference
+    (intra.py:142 IndexError above 34; DC / planar refused by the angular predictor) instead of being clamped."""
+    n, B = 8, 6
+    rng = np.random.default_rng(5)
+    top = dev(rng.integers(0, 256, (B, 2 * n + 1)).astype(np.int16))
+    left = dev(rng.integers(0, 256, (B, 2 * n + 1)).astype(np.int16))
+    corner = dev(rng.integers(0, 256, B).astype(np.int16))
+    ok = np.array([2, 10, 18, 26, 34, 7], dtype=np.uint8)
+    Bt.intra_angular_predict_batched(top, left, corner, dev(ok), n)
+    bad = ok.copy(); bad[3] = 35
+    with pytest.raises(IndexError):
+        Bt.intra_predict_modes_batched(top, left, corner, dev(bad), n)
+    with pytest.raises(IndexError):
+        Bt.intra_predict_modes_batched(top, left, corner, dev(np.array([2, 3, 4, 5, 6, 300], dtype=np.int64)), n)
+    low = ok.copy(); low[0] = 1
+    with pytest.raises(ValueError):
+        Bt.intra_angular_predict_batched(top, left, corner, dev(low), n)
+    Bt.intra_predict_modes_batched(top, left, corner, dev(low), n)   # DC allowed here
+    orig = dev(rng.integers(0, 256, (B, n, n)).astype(np.int16))
+    with pytest.raises(ValueError):
+        Bt.fused_block_pipeline(orig, top[:, 1:n + 1], left[:, 1:n + 1], top[:, n + 1], left[:, n + 1], dev(ok), 27)
+    with pytest.raises(ValueError):
+        Bt.intra_predict_modes_batched(top, left, corner, dev(ok[:4]), n)
+
+
 # --------------------------------------------------------------- transforms
 @pytest.mark.parametrize("tag", ["4", "4dst", "8", "16", "32"])
 def test_transforms_golden(P, Bt, tag):
