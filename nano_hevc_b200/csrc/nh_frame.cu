@@ -891,10 +891,10 @@ static int launch_search_cost(const CoderArgs& a, cudaStream_t st) {
         // The fraction-major kernel (nh_search3.cuh): every scan line is a window of a reference array filtered once
         // per fraction.  Measured against the line-synchronous kernel (32 4K frames, search + winners): N = 32 SAD
         // +6 %, SATD +17 %, one frame +11 %; at N = 16 it loses on SAD (four blocks per warp: 17 KB of arrays per warp,
-        // 12 warps per SM), so it is the default at N = 32 only (NH_SEARCH_FRAC=0 turns that off).
+        // 12 warps per SM) and wins 7 % on SATD, so it is the default at N = 32 and for SATD at N = 16 (NH_SEARCH_FRAC=0 turns that off).
         using F = FracCfg<N>;
         const int impl = search_impl();
-        if (impl == 5 || (impl == 2 && N == 32 && frac_default())) {
+        if (impl == 5 || (impl == 2 && (N == 32 || COST == NH_COST_SATD) && frac_default())) {
             int rc = ensure_dynamic_smem(search_frac_kernel<N, COST>, F::SMEM_BYTES, "search_frac_kernel");
             if (rc != NH_OK) return rc;
             const int grid = grid_for(a.n_blocks, (int64_t)F::WARPS * F::T, F::PER_SM);
