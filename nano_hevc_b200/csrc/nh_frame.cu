@@ -690,6 +690,7 @@ __global__ void __launch_bounds__(32 * WPB) coder_wave_mw_kernel(const CoderArgs
 #include "nh_wave.cuh"   // latency-oriented wavefront kernels for 8-bit planes (N = 8, N = 4); needs CoderArgs
 #include "nh_search2.cuh"
 #include "nh_search3.cuh"   // line-synchronous search kernel (N = 8 / 16 / 32)
+#include "nh_search4.cuh"   // SATD search with the Hadamard transforms on the tensor cores
 namespace nh {
 
 // Exchange rows of the wavefront coder: -1 where a block will publish its bottom row, 0 in the
@@ -867,13 +868,14 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // winners (one block per warp and the tensor-core winner pipeline at N = 16 / 32).
 // 2 (default) = search kernel + winner kernel, 1 = everything in the single coder kernel (A/B profiling);
 // 3 / 4 = as 2 with the line-synchronous / the strip search kernel forced (2 picks per call, see
-// launch_search_cost), 5 = as 2 with the fraction-major search kernel forced at N = 16 / 32 (nh_search3.cuh);
-// nh_set_search_impl() or NH_SEARCH_IMPL=1|2|3|4|5.
+// launch_search_cost), 5 = as 2 with the fraction-major search kernel forced at N = 16 / 32 (nh_search3.cuh),
+// 6 = as 2 with the tensor-core SATD search kernel forced (nh_search4.cuh; SATD, N >= 8);
+// nh_set_search_impl() or NH_SEARCH_IMPL=1|2|3|4|5|6.
 static thread_local int g_search_impl = 0;   // per calling thread: no shared mutable state between callers
 static int search_impl() {
     if (g_search_impl == 0) {
         const char* e = getenv("NH_SEARCH_IMPL");
-        g_search_impl = (e && e[0] >= '1' && e[0] <= '5') ? e[0] - '0' : 2;
+        g_search_impl = (e && e[0] >= '1' && e[0] <= '6') ? e[0] - '0' : 2;
     }
     return g_search_impl;
 }
@@ -883,10 +885,38 @@ static bool frac_default() {
     return on;
 }
 
+static bool quad_default() {
+    static const bool on = [] { const char* e = getenv("NH_SEARCH_QUAD"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 template <int N, int COST>
 static int launch_search_cost(const CoderArgs& a, cudaStream_t st) {
     SearchArgs s{a.src, a.H, a.W, a.pitch, a.cost_kind, a.n_blocks, a.out.modes, a.out.costs, a.blocks_per_frame,
                  a.frame_stride};
+    if constexpr (N >= 8 && COST == NH_COST_SATD) {
+        // SATD with the 4x4 Hadamard transforms on the tensor cores (nh_search4.cuh); needs 16-byte pixel loads
+        using Q = QuadCfg<N>;
+        const bool can = (a.pitch % 8) == 0 && (a.frame_stride % 8) == 0 && (reinterpret_cast<uintptr_t>(a.src) & 15) == 0;
+        const int impl = search_impl();
+        if (can && (impl == 6 || (impl == 2 && quad_default()))) {
+            static const int occ_env = [] { const char* e = getenv("NH_QUAD_OCC"); return e ? atoi(e) : 0; }();
+            if (occ_env == 4) {   // development: A/B of the occupancy
+                int rc = ensure_dynamic_smem(search_quad_kernel<N, 4>, Q::SMEM_BYTES, "search_quad_kernel");
+                if (rc != NH_OK) return rc;
+                const int grid = grid_for(a.n_blocks, (int64_t)Q::WARPS * Q::T, 4);
+                search_quad_kernel<N, 4><<<grid, Q::WARPS * 32, Q::SMEM_BYTES, st>>>(s);
+                NH_CHECK_LAUNCH("search_quad_kernel");
+                return NH_OK;
+            }
+            int rc = ensure_dynamic_smem(search_quad_kernel<N>, Q::SMEM_BYTES, "search_quad_kernel");
+            if (rc != NH_OK) return rc;
+            const int grid = grid_for(a.n_blocks, (int64_t)Q::WARPS * Q::T, Q::PER_SM);
+            search_quad_kernel<N><<<grid, Q::WARPS * 32, Q::SMEM_BYTES, st>>>(s);
+            NH_CHECK_LAUNCH("search_quad_kernel");
+            return NH_OK;
+        }
+    }
     if constexpr (N >= 16) {
         // The fraction-major kernel (nh_search3.cuh): every scan line is a window of a reference array filtered once
         // per fraction.  Measured against the line-synchronous kernel (32 4K frames, search + winners): N = 32 SAD
@@ -1100,9 +1130,9 @@ NH_API int nh_fused_pipeline_modes(const int16_t* orig, const int16_t* top, cons
 }
 
 NH_API int nh_set_search_impl(int impl) {
-    if (impl < 1 || impl > 5) {
-        set_error("nh_set_search_impl: impl must be 1 (single coder kernel), 2 (search + winner kernels), 3 / 4 / 5 (as 2, "
-                  "line-synchronous / strip / fraction-major search kernel forced), got %d", impl);
+    if (impl < 1 || impl > 6) {
+        set_error("nh_set_search_impl: impl must be 1 (single coder kernel), 2 (search + winner kernels), 3 / 4 / 5 / 6 (as 2, "
+                  "line-synchronous / strip / fraction-major / tensor-core SATD search kernel forced), got %d", impl);
         return NH_E_ARG;
     }
     g_search_impl = impl;

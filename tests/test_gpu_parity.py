@@ -704,7 +704,7 @@ def test_config3_config5_4k_full_oracle(Bt, n, rn, cost):
     if not rn and n >= 8:   # both search kernels at full size (the library picks one per call)
         from nano_hevc_b200 import _lib
         try:
-            for impl in (3, 4, 5):   # 5 = fraction-major kernel (N = 16 / 32; the strip kernel elsewhere)
+            for impl in (3, 4, 5, 6):   # 5 = fraction-major kernel (N = 16 / 32; the strip kernel elsewhere), 6 = tensor-core SATD kernel
                 _lib.check(_lib.lib().nh_set_search_impl(impl))
                 r = Bt.encode_frame(d, n, cost=cost, qp=27, outputs=("modes", "costs"))
                 eq(host(r.modes), w["modes"], f"modes n={n} {cost} search impl {impl}")
@@ -922,8 +922,9 @@ def test_search_kernel_split_vs_single_kernel_vs_oracle(Bt, n, cost, wmul):
             r1 = Bt.encode_frame(dev(plane), n, cost=cost, qp=26)
             w = O.encode_frame(plane, n, cost=cost, qp=26, recon_neighbours=False)
             # 2 = the kernel the library picks, 3 = line-synchronous search kernel (N >= 8, pitch % 8 == 0: the
-            # wmul = 8 cases), 4 = strip search kernel, 5 = fraction-major search kernel (N = 16 / 32)
-            for impl in (2, 3, 4, 5):
+            # wmul = 8 cases), 4 = strip search kernel, 5 = fraction-major search kernel (N = 16 / 32), 6 = SATD
+            # search with the Hadamard transforms on the tensor cores (SATD, N >= 8, pitch % 8 == 0)
+            for impl in (2, 3, 4, 5, 6):
                 _lib.check(_lib.lib().nh_set_search_impl(impl))
                 r2 = Bt.encode_frame(dev(plane), n, cost=cost, qp=26)
                 for name in ("modes", "costs", "pred", "coeff", "levels", "recon_plane"):
