@@ -900,15 +900,6 @@ static int launch_search_cost(const CoderArgs& a, cudaStream_t st) {
         const bool can = (a.pitch % 8) == 0 && (a.frame_stride % 8) == 0 && (reinterpret_cast<uintptr_t>(a.src) & 15) == 0;
         const int impl = search_impl();
         if (can && (impl == 6 || (impl == 2 && quad_default()))) {
-            static const int occ_env = [] { const char* e = getenv("NH_QUAD_OCC"); return e ? atoi(e) : 0; }();
-            if (occ_env == 4) {   // development: A/B of the occupancy
-                int rc = ensure_dynamic_smem(search_quad_kernel<N, 4>, Q::SMEM_BYTES, "search_quad_kernel");
-                if (rc != NH_OK) return rc;
-                const int grid = grid_for(a.n_blocks, (int64_t)Q::WARPS * Q::T, 4);
-                search_quad_kernel<N, 4><<<grid, Q::WARPS * 32, Q::SMEM_BYTES, st>>>(s);
-                NH_CHECK_LAUNCH("search_quad_kernel");
-                return NH_OK;
-            }
             int rc = ensure_dynamic_smem(search_quad_kernel<N>, Q::SMEM_BYTES, "search_quad_kernel");
             if (rc != NH_OK) return rc;
             const int grid = grid_for(a.n_blocks, (int64_t)Q::WARPS * Q::T, Q::PER_SM);

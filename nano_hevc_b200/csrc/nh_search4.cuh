@@ -5,15 +5,23 @@
 // instructions per pixel against 162 for SAD, ALU pipe 81 % -- the Hadamard butterflies of 33 candidates on biased
 // 16-bit pairs cost more than predicting the candidates.  But sum |H d H^T| of a 4x4 sub-block is sum |(H (x) H) d|
 // over its 16 samples: a 16 x 16 matrix of +-1 applied to a 16-vector, i.e. one row of an m16n8k16 MMA.
-//   * A row of the A operand = the 16 predicted samples of one sub-block of one candidate, as the f16 numbers
-//     1024 + p (bit pattern 0x6400 | p: ONE PRMT turns two interpolated samples into an operand register -- it
-//     replaces the PRMT that packed them as bytes for VABSDIFF4); B = H (x) H as +-1.0 (two n8 halves: 2 HMMA per 16
-//     sub-blocks).  Products and sums are small integers: exact in f16 x f16 -> f32.
-//   * The transform is linear: (H (x) H)(p - o) = (H (x) H) p - (H (x) H) o.  The second term does not depend on the
-//     candidate, so it is computed once per block (the same MMAs on the original samples, negated B) and kept as
-//     the START VALUE of the accumulator; the bias 16 * 1024 of the first coefficient cancels the same way.  The
-//     cost of a candidate's sub-blocks is then sum |d| over the accumulators: 8 FADD |.| per lane and MMA pair, on
-//     the FMA pipe -- no subtraction, no butterflies, nothing on the ALU pipe that bounds the search.
+//   * A row of the A operand = the 16 predicted samples of one sub-block of one candidate.  A sample s becomes the
+//     f16 SUBNORMAL s * 2^-24, whose bit pattern is 0x00ss: ONE PRMT turns two interpolated samples into an operand
+//     register (it replaces the PRMT that packed them as bytes for VABSDIFF4), there is no bias to remove, and
+//     mma.sync keeps subnormal operands and results.
+//   * The transform is linear: T(p - o) = T p - T o.  T o does not depend on the candidate: it is computed once per
+//     block (the same MMAs on the original samples, negated B) and kept as the START VALUE of the accumulators.
+//   * First stage, ONE BUTTERFLY SHORT, f16 accumulators: with a[0..7] the transform of rows 0, 1 of the sub-block
+//     (vertical sum / difference x four horizontal coefficients) and c[0..7] that of rows 2, 3, the 16 coefficients
+//     are a[n] +- c[n] and |a + c| + |a - c| = 2 max(|a|, |c|).  a and c are sums of 8 sample differences, |.| <=
+//     2040: exact in f16 (the full coefficients, <= 4080, are not), so the accumulators are 2 registers per MMA and
+//     max(|a|, |c|) is one HMNMX2 with |.| operand modifiers per two values.
+//   * Second stage: a SELECTOR MMA (f32 accumulators) adds up the 8 maxima of a sub-block -- which sit in the four
+//     lanes of a quad -- over both sub-blocks of a unit, over the steps and into the accumulator column of the
+//     candidate: B = 2.0 in the candidate's column.  After four mirror pairs lane t of the quad reads the finished
+//     costs of pair t from its own accumulator registers.  No shuffle, no FADD chain, no per-candidate reduction
+//     (the first version -- f32 accumulators, 8 FADD |.| per MMA pair, shuffle reductions per candidate -- ran at
+//     232 thread instructions per pixel, this one at 170; profiles/r4_search_quad8_*).
 //   * An MMA row spreads its 16 k-slots over the four lanes of a quad, so the four lanes of a quad work on four
 //     CONSECUTIVE SCAN LINES of the same 8-sample segment (lane = (segment unit g, line t)); a lane's 8 samples are
 //     the row of the left sub-block (MMA row g) and of the right one (MMA row g + 8).  The k-slot <-> sample map is
@@ -47,14 +55,15 @@ struct QuadCfg {
     static constexpr int WARPS = 4;
     static constexpr int TAB_WORDS = 17 * N * 5;
     static constexpr int SMEM_BYTES = (WARPS * WARP_WORDS + TAB_WORDS) * 4;
-    static constexpr int PER_SM = N == 32 ? 3 : 5;
+    static constexpr int PER_SM = 5;                   // 96 registers; 6 CTAs (80 registers) measured +1 % / 0 / 0
 };
 
-// two interpolated samples (high bytes of the 16-bit lanes of t) as the f16 pair (1024 + s0, 1024 + s1)
-__device__ __forceinline__ uint32_t hi_bytes_f16(uint32_t t) { return __byte_perm(t, 0x64646464u, 0x4341); }
+// two interpolated samples (high bytes of the 16-bit lanes of t) as an f16 pair.  The bit pattern 0x00ss is the
+// f16 SUBNORMAL s * 2^-24: no bias, every sum below stays a multiple of 2^-24 and the MMA units keep subnormals.
+__device__ __forceinline__ uint32_t hi_bytes_f16(uint32_t t) { return __byte_perm(t, 0u, 0x4341); }
 // bytes (0, 2) / (1, 3) of a packed word as f16 pairs
-__device__ __forceinline__ uint32_t even_bytes_f16(uint32_t w) { return __byte_perm(w, 0x64646464u, 0x4240); }
-__device__ __forceinline__ uint32_t odd_bytes_f16(uint32_t w) { return __byte_perm(w, 0x64646464u, 0x4341); }
+__device__ __forceinline__ uint32_t even_bytes_f16(uint32_t w) { return __byte_perm(w, 0u, 0x4240); }
+__device__ __forceinline__ uint32_t odd_bytes_f16(uint32_t w) { return __byte_perm(w, 0u, 0x4341); }
 
 // One scan line of 8 predicted samples as the A-operand registers of the lane:
 // {(s0, s2), (s4, s6), (s1, s3), (s5, s7)} = rows g / g+8 slots 2t.., rows g / g+8 slots 2t+8..
@@ -69,6 +78,7 @@ __device__ __forceinline__ uint4 predict_line8_f16(const uint32_t* wp, uint32_t 
     const uint32_t t46 = g8 * e2 + 0x00800080u + f8 * o2, t57 = g8 * o2 + 0x00800080u + f8 * e3;
     return make_uint4(hi_bytes_f16(t02), hi_bytes_f16(t46), hi_bytes_f16(t13), hi_bytes_f16(t57));
 }
+// fraction 0: the samples are the bytes themselves, and (b0, b2) (b1, b3) are what the interpolation spreads anyway
 __device__ __forceinline__ uint4 copy_line8_f16(const uint32_t* wp, uint32_t sh) {
     const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
     const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh);
@@ -78,13 +88,29 @@ __device__ __forceinline__ uint4 packed_line8_f16(uint32_t w0, uint32_t w1) {
     return make_uint4(even_bytes_f16(w0), even_bytes_f16(w1), odd_bytes_f16(w0), odd_bytes_f16(w1));
 }
 
-// sum |(H (x) H) a + c| over the lane's share of the 16 x 16 outputs
-__device__ __forceinline__ float satd_mma(const uint4& av, const uint32_t (&hb)[2][2], const float (&c)[8]) {
-    float d0[4], d1[4];
-    hmma16816(d0, av, hb[0][0], hb[0][1], c[0], c[1], c[2], c[3]);
-    hmma16816(d1, av, hb[1][0], hb[1][1], c[4], c[5], c[6], c[7]);
-    return ((fabsf(d0[0]) + fabsf(d0[1])) + (fabsf(d0[2]) + fabsf(d0[3]))) +
-           ((fabsf(d1[0]) + fabsf(d1[1])) + (fabsf(d1[2]) + fabsf(d1[3])));
+// D = A(16x16, row) * B(16x8, col) + C with f16 accumulators (exact here: every partial result is an integer of at
+// most 11 bits times 2^-24)
+__device__ __forceinline__ void hmma16816_h(uint32_t (&d)[2], const uint4& a, uint32_t b0, uint32_t b1, uint32_t c0, uint32_t c1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f16.f16.f16.f16 {%0,%1}, {%2,%3,%4,%5}, {%6,%7}, {%8,%9};"
+        : "=r"(d[0]), "=r"(d[1])
+        : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1), "r"(c0), "r"(c1));
+}
+// The transform one butterfly stage short.  With rows 0, 1 of a sub-block transformed into a[0..7] and rows 2, 3 into
+// c[0..7] (vertical sum / difference of the two rows x the four horizontal coefficients), the 16 coefficients of
+// H d H^T are a[n] + c[n] and a[n] - c[n], and |a + c| + |a - c| = 2 max(|a|, |c|).  Both halves are sums of 8 sample
+// differences, |.| <= 2040: exact in f16, which the full coefficients (<= 4080) are not.  hb[0] produces a, hb[1] c;
+// c4 = the start values -(transform of the original samples).  Returns max(|a|, |c|) for the lane's 2 x 2 outputs.
+__device__ __forceinline__ void satd_halves(uint32_t (&m)[2], const uint4& av, const uint32_t (&hb)[2][2], const uint32_t (&c4)[4]) {
+    uint32_t da[2], dc[2];
+    hmma16816_h(da, av, hb[0][0], hb[0][1], c4[0], c4[1]);
+    hmma16816_h(dc, av, hb[1][0], hb[1][1], c4[2], c4[3]);
+    m[0] = h2_bits(__hmax2(__habs2(bits_h2(da[0])), __habs2(bits_h2(dc[0]))));
+    m[1] = h2_bits(__hmax2(__habs2(bits_h2(da[1])), __habs2(bits_h2(dc[1]))));
+}
+// acc[row][n] += 2 * (sum over the slots k < 8 of mx[row][k] if n == column of x) + (the same for my, k >= 8): the sum
+// over a sub-block's outputs AND over the four lanes of the quad in one MMA, one accumulator column per candidate
+__device__ __forceinline__ void satd_sum(float (&acc)[4], const uint32_t (&mx)[2], const uint32_t (&my)[2], uint32_t sx, uint32_t sy) {
+    hmma16816(acc, make_uint4(mx[0], mx[1], my[0], my[1]), sx, sy, acc[0], acc[1], acc[2], acc[3]);
 }
 
 template <int N, int OCC = QuadCfg<N>::PER_SM>
@@ -102,7 +128,6 @@ __global__ void __launch_bounds__(QuadCfg<N>::WARPS * 32, OCC) search_quad_kerne
     __syncthreads();
     uint32_t* const wbase = smem_w0 + C::TAB_WORDS + warp * C::WARP_WORDS;
     const int t = lane & 3, g = lane >> 2;
-    const bool odd = lane & 1;
     const int bi = g / C::GL, gl = g % C::GL;          // block of the tile, quad of the block
     const int sg = gl % C::SEG, ql = gl / C::SEG;      // segment of the scan line, group of 4 lines within a step
     const int px_ = 8 * sg;
@@ -115,24 +140,25 @@ __global__ void __launch_bounds__(QuadCfg<N>::WARPS * 32, OCC) search_quad_kerne
     const int bw = a.W / N;
     const int64_t n_tiles = (a.n_blocks + T - 1) / T;
 
-    // B operand: column n = coefficient (u, v) = (n >> 2, n & 3) of H d H^T, row k = sample (row, x) of the sub-block
-    // with row = (k & 7) >> 1, x = 2 (k & 1) + (k >> 3); H = rows ++++, ++--, +--+, +-+- (metrics.py:35-40).
-    // hb = +(H (x) H) for the candidates, hn = -(H (x) H) for the original samples.
-    uint32_t hb[2][2], hn[2][2];
+    // B operands of the first stage.  Slot k holds sample (row, x) of the sub-block, row = (k & 7) >> 1 = the lane's t,
+    // x = 2 (k & 1) + (k >> 3).  Column n = (vs, v) = (n >> 2, n & 3): vertical sum (vs = 0) or difference (vs = 1) of
+    // the two rows of a half, horizontal coefficient v of H = rows ++++, ++--, +--+, +-+- (metrics.py:35-40).
+    // hb[0] takes rows 0, 1 (zero in lanes t >= 2), hb[1] rows 2, 3.
+    uint32_t hb[2][2];
     {
         auto hneg = [](int i, int j) { return i == 1 ? j >= 2 : (i == 2 ? (j == 1 || j == 2) : (i == 3 ? (j & 1) : 0)); };
-        auto entry = [&](int n, int k) -> uint32_t {
-            const int row = (k & 7) >> 1, x = 2 * (k & 1) + (k >> 3);
-            return (hneg(n >> 2, row) ^ hneg(n & 3, x)) ? 0xBC00u : 0x3C00u;
-        };
+        const int vs = g >> 2, v = g & 3;
+        const bool vneg = vs && (t & 1);
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                hb[m][h] = entry(g + 8 * m, 2 * t + 8 * h) | (entry(g + 8 * m, 2 * t + 1 + 8 * h) << 16);
-                hn[m][h] = hb[m][h] ^ 0x80008000u;
-            }
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t lo = (vneg ^ (bool)hneg(v, h)) ? 0xBC00u : 0x3C00u;          // x = h
+            const uint32_t hi = (vneg ^ (bool)hneg(v, 2 + h)) ? 0xBC00u : 0x3C00u;      // x = 2 + h
+            const uint32_t w = lo | (hi << 16);
+            hb[0][h] = t < 2 ? w : 0u;
+            hb[1][h] = t < 2 ? 0u : w;
+        }
     }
+    const uint32_t kSel = 0x40004000u;   // (2.0, 2.0): the factor of 2 max(|a|, |c|)
 
     for (int64_t tile = (int64_t)blockIdx.x * C::WARPS + warp; tile < n_tiles; tile += (int64_t)gridDim.x * C::WARPS) {
         int64_t b = tile * T + bi;
@@ -188,31 +214,26 @@ __global__ void __launch_bounds__(QuadCfg<N>::WARPS * 32, OCC) search_quad_kerne
             ood |= tv[it] | lv[it];
         }
 
-        // ---- start values of the accumulators: -(H (x) H) applied to the original samples (f16: 1024 + o)
-        float cin[STEPS][2][8];
-        {
-            const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        // ---- start values of the first-stage accumulators: minus the half transforms of the original samples
+        uint32_t cin[STEPS][2][4];
 #pragma unroll
-            for (int s = 0; s < STEPS; ++s) {
-                ood |= (int)((ovr[s].x | ovr[s].y | ovr[s].z | ovr[s].w) & 0xFF00FF00u) ? 0x100 : 0;
-                const uint4 av = packed_line8_f16(__byte_perm(ovr[s].x, ovr[s].y, 0x6420), __byte_perm(ovr[s].z, ovr[s].w, 0x6420));
-                uint32_t h0 = 0, h1 = 0;
+        for (int s = 0; s < STEPS; ++s) {
+            ood |= (int)((ovr[s].x | ovr[s].y | ovr[s].z | ovr[s].w) & 0xFF00FF00u) ? 0x100 : 0;
+            const uint4 av = packed_line8_f16(__byte_perm(ovr[s].x, ovr[s].y, 0x6420), __byte_perm(ovr[s].z, ovr[s].w, 0x6420));
+            uint32_t h0 = 0, h1 = 0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    ood |= ohr[s][j] | ohr[s][4 + j];
-                    h0 |= (uint32_t)(ohr[s][j] & 0xff) << (8 * j);
-                    h1 |= (uint32_t)(ohr[s][4 + j] & 0xff) << (8 * j);
-                }
-                const uint4 ah = packed_line8_f16(h0, h1);
-                float d0[4], d1[4];
-                hmma16816(d0, av, hn[0][0], hn[0][1], z[0], z[1], z[2], z[3]);
-                hmma16816(d1, av, hn[1][0], hn[1][1], z[0], z[1], z[2], z[3]);
+            for (int j = 0; j < 4; ++j) {
+                ood |= ohr[s][j] | ohr[s][4 + j];
+                h0 |= (uint32_t)(ohr[s][j] & 0xff) << (8 * j);
+                h1 |= (uint32_t)(ohr[s][4 + j] & 0xff) << (8 * j);
+            }
+            const uint4 ah = packed_line8_f16(h0, h1);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { cin[s][0][i] = d0[i]; cin[s][0][4 + i] = d1[i]; }
-                hmma16816(d0, ah, hn[0][0], hn[0][1], z[0], z[1], z[2], z[3]);
-                hmma16816(d1, ah, hn[1][0], hn[1][1], z[0], z[1], z[2], z[3]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { cin[s][1][i] = d0[i]; cin[s][1][4 + i] = d1[i]; }
+            for (int o = 0; o < 2; ++o) {
+                uint32_t da[2], dc[2];
+                hmma16816_h(da, o ? ah : av, hb[0][0] ^ 0x80008000u, hb[0][1] ^ 0x80008000u, 0u, 0u);
+                hmma16816_h(dc, o ? ah : av, hb[1][0] ^ 0x80008000u, hb[1][1] ^ 0x80008000u, 0u, 0u);
+                cin[s][o][0] = da[0]; cin[s][o][1] = da[1]; cin[s][o][2] = dc[0]; cin[s][o][3] = dc[1];
             }
         }
         if (__any_sync(0xffffffffu, (ood & ~0xff) != 0)) {   // leave the tile to the coder kernel's exact search
@@ -266,95 +287,102 @@ __global__ void __launch_bounds__(QuadCfg<N>::WARPS * 32, OCC) search_quad_kerne
         __syncwarp();
 
         int best = 0x7fffffff;
-        // Two candidates at a time: the lanes of a quad first swap one of the two values with their neighbour (even lanes
-        // collect the first candidate, odd lanes the second), then every lane sums ITS candidate over the block's
-        // lanes and keeps its key -- half the shuffles of two full reductions; the keys meet once per tile.
-        // The call for one mirror pair is issued with the work of the next one, so that its shuffle chain
-        // (ncu: 30 % of the stall samples, short scoreboard) overlaps independent instructions.
-        auto settle2 = [&](float v0, float v1, int pos) {
-            const float give = odd ? v0 : v1, keep = odd ? v1 : v0;
-            float c = keep + __shfl_xor_sync(0xffffffffu, give, 1);
+        // Accumulator columns 2j, 2j+1 collect the vertical / horizontal candidate of the j-th mirror pair of a group of
+        // four; lane t of a quad ends up with columns 2t, 2t+1 of the unit's left (row g) and right (row g+8) sub-block
+        // column: the cost of ONE pair, already summed over the quad and the steps.  The costs are scaled by 2^-24.
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        auto take = [&](int pos_v, int pos_h, bool has_v, bool has_h) {
+            float cv = acc[0] + acc[2], ch = acc[1] + acc[3];
 #pragma unroll
-            for (int off = 2; off < LPB; off <<= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
-            const int key = (__float2int_rn(c) << 6) | pos;
-            best = key < best ? key : best;
+            for (int off = 4; off < LPB; off <<= 1) {
+                cv += __shfl_xor_sync(0xffffffffu, cv, off);
+                ch += __shfl_xor_sync(0xffffffffu, ch, off);
+            }
+            const int kv = (__float2int_rn(cv * 16777216.f) << 6) | pos_v;
+            const int kh = (__float2int_rn(ch * 16777216.f) << 6) | pos_h;
+            if (has_v) best = kv < best ? kv : best;
+            if (has_h) best = kh < best ? kh : best;
+            acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
         };
-        constexpr float kNoCand = 16777216.f / LPB;   // summed over the block's lanes: 2^24, above every cost (<= 4.2e6 at N = 32), key still positive
-        float p0, p1;   // the pair waiting to be settled
-        int ppos;
-        {   // position 0: DC
-            const uint32_t d2 = (0x6400u | (uint32_t)dc) * 0x10001u;
-            const uint4 av = make_uint4(d2, d2, d2, d2);
-            float c = 0.f;
+        // ---- positions 2..34: horizontal mode r + 2 together with its mirror, vertical mode 34 - r (same angle: same
+        // table row).  FRAC = false: every fraction of the pair is 0 (modes 2 / 34, 10 / 26, 18).
+        auto eval_pair = [&](int r, const unsigned char* bv, const unsigned char* bh, auto frac_tag) {
+            constexpr bool FRAC = decltype(frac_tag)::value;
+            const int4* tab = s_tab + r * N + y0;
+            const int* tk4 = s_k4 + r * N + y0;
+            const uint32_t sx = g == 2 * (r & 3) ? kSel : 0u, sy = g == 2 * (r & 3) + 1 ? kSel : 0u;
 #pragma unroll
-            for (int s = 0; s < STEPS; ++s) c += satd_mma(av, hb, cin[s][0]);
-            p0 = c;
-        }
-        {   // position 1: planar (intra.py:109-111); weights scaled so that the sample is the high byte of its 16-bit lane
+            for (int s = 0; s < STEPS; ++s) {
+                const int k4 = tk4[4 * C::QS * s];
+                const int4 e = tab[4 * C::QS * s];
+                uint32_t mv[2], mh[2];
+                if (FRAC) {
+                    satd_halves(mv, predict_line8_f16(reinterpret_cast<const uint32_t*>(bv + k4), (uint32_t)e.x, (uint32_t)e.y,
+                                                      (uint32_t)e.z, (uint32_t)e.w), hb, cin[s][0]);
+                    satd_halves(mh, predict_line8_f16(reinterpret_cast<const uint32_t*>(bh + k4), (uint32_t)e.x, (uint32_t)e.y,
+                                                      (uint32_t)e.z, (uint32_t)e.w), hb, cin[s][1]);
+                } else {
+                    satd_halves(mv, copy_line8_f16(reinterpret_cast<const uint32_t*>(bv + k4), (uint32_t)e.x), hb, cin[s][0]);
+                    satd_halves(mh, copy_line8_f16(reinterpret_cast<const uint32_t*>(bh + k4), (uint32_t)e.x), hb, cin[s][1]);
+                }
+                satd_sum(acc, mv, mh, sx, sy);
+            }
+        };
+        const std::true_type frac_t{};
+        const std::false_type copy_t{};
+        eval_pair(0, lane_v, lane_v + PB, copy_t);
+#pragma unroll 1
+        for (int r = 1; r < 4; ++r) eval_pair(r, lane_v, lane_v + PB, frac_t);
+        take(34 - t, 2 + t, true, true);
+#pragma unroll 1
+        for (int r = 4; r < 8; ++r) eval_pair(r, lane_v, lane_v + PB, frac_t);
+        take(30 - t, 6 + t, true, true);
+        eval_pair(8, lane_v, lane_v + PB, copy_t);
+#pragma unroll 1
+        for (int r = 9; r < 12; ++r) eval_pair(r, lane_v + negt0[23 - r], lane_v + negt0[r - 9], frac_t);
+        take(26 - t, 10 + t, true, true);
+#pragma unroll 1
+        for (int r = 12; r < 16; ++r) eval_pair(r, lane_v + negt0[23 - r], lane_v + negt0[r - 9], frac_t);
+        take(22 - t, 14 + t, true, true);
+        {   // last group: column 0 = mode 18 (vertical only), columns 2 / 3 = DC / planar (positions 0 / 1)
+            const uint32_t s0 = g == 0 ? kSel : 0u, s2 = g == 2 ? kSel : 0u, s3 = g == 3 ? kSel : 0u;
             constexpr uint32_t SCL = 1u << (7 - S);
             const uint32_t tr = (uint32_t)tb[N + 1], bl = (uint32_t)lb[N + 1];
             uint32_t kc[4], c1[4], zt[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {   // sample pairs (0, 2) (4, 6) (1, 3) (5, 7): the A-operand order
+            for (int i = 0; i < 4; ++i) {   // planar (intra.py:109-111), sample pairs (0, 2) (4, 6) (1, 3) (5, 7): the A-operand order
                 const uint32_t X = (uint32_t)(px_ + (i & 1) * 4 + (i >> 1));
                 c1[i] = (((uint32_t)(N - 1) - X) | (((uint32_t)(N - 3) - X) << 16)) * SCL;
                 kc[i] = tr * (((X + 1) | ((X + 3) << 16)) * SCL);
                 zt[i] = (uint32_t)tb[1 + X] | ((uint32_t)tb[3 + X] << 16);
             }
-            float c = 0.f;
+            const uint32_t d2 = (uint32_t)dc * 0x10001u;
+            const int4* tab = s_tab + 16 * N + y0;
+            const int* tk4 = s_k4 + 16 * N + y0;
+            const unsigned char* b18 = lane_v + negt0[7];
 #pragma unroll
             for (int s = 0; s < STEPS; ++s) {
                 const int yy = y0 + 4 * C::QS * s;
+                uint32_t m18[2], mdc[2], mpl[2];
+                satd_halves(m18, copy_line8_f16(reinterpret_cast<const uint32_t*>(b18 + tk4[4 * C::QS * s]), (uint32_t)tab[4 * C::QS * s].x),
+                            hb, cin[s][0]);
+                satd_halves(mdc, make_uint4(d2, d2, d2, d2), hb, cin[s][0]);
                 const uint32_t ly = (uint32_t)lb[1 + yy];
                 const uint32_t vy = (uint32_t)(N - 1 - yy) * SCL;
                 const uint32_t by = ((uint32_t)(yy + 1) * bl + (uint32_t)N) * SCL * 0x10001u;
                 uint32_t tt[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) tt[i] = ly * c1[i] + kc[i] + vy * zt[i] + by;
-                c += satd_mma(make_uint4(hi_bytes_f16(tt[0]), hi_bytes_f16(tt[1]), hi_bytes_f16(tt[2]), hi_bytes_f16(tt[3])), hb, cin[s][0]);
+                satd_halves(mpl, make_uint4(hi_bytes_f16(tt[0]), hi_bytes_f16(tt[1]), hi_bytes_f16(tt[2]), hi_bytes_f16(tt[3])), hb, cin[s][0]);
+                const uint32_t zero[2] = {0u, 0u};
+                satd_sum(acc, m18, zero, s0, 0u);
+                satd_sum(acc, mdc, mpl, s2, s3);
             }
-            p1 = c;
-            ppos = odd;   // even lanes: position 0, odd lanes: position 1
+            take(t == 0 ? 18 : 0, 1, t < 2, t == 1);
         }
-        // ---- positions 2..34: horizontal mode r + 2 together with its mirror, vertical mode 34 - r (same angle: same
-        // table row).  Even lanes end up with the vertical candidate, odd lanes with the horizontal one.
-        // FRAC = false: every fraction of the pair is 0 (modes 2 / 34, 10 / 26, 18).
-        auto eval_pair = [&](int r, const unsigned char* bv, const unsigned char* bh, auto frac_tag, bool has_h) {
-            constexpr bool FRAC = decltype(frac_tag)::value;
-            settle2(p0, p1, ppos);
-            const int4* tab = s_tab + r * N + y0;
-            const int* tk4 = s_k4 + r * N + y0;
-            float cv = 0.f, ch = 0.f;
 #pragma unroll
-            for (int s = 0; s < STEPS; ++s) {
-                const int k4 = tk4[4 * C::QS * s];
-                const int4 e = tab[4 * C::QS * s];
-                if (FRAC) {
-                    cv += satd_mma(predict_line8_f16(reinterpret_cast<const uint32_t*>(bv + k4), (uint32_t)e.x, (uint32_t)e.y,
-                                                     (uint32_t)e.z, (uint32_t)e.w), hb, cin[s][0]);
-                    ch += satd_mma(predict_line8_f16(reinterpret_cast<const uint32_t*>(bh + k4), (uint32_t)e.x, (uint32_t)e.y,
-                                                     (uint32_t)e.z, (uint32_t)e.w), hb, cin[s][1]);
-                } else {
-                    cv += satd_mma(copy_line8_f16(reinterpret_cast<const uint32_t*>(bv + k4), (uint32_t)e.x), hb, cin[s][0]);
-                    ch += satd_mma(copy_line8_f16(reinterpret_cast<const uint32_t*>(bh + k4), (uint32_t)e.x), hb, cin[s][1]);
-                }
-            }
-            p0 = cv;
-            p1 = has_h ? ch : kNoCand;
-            ppos = odd ? r + 2 : 34 - r;
-        };
-        const std::true_type frac_t{};
-        const std::false_type copy_t{};
-        eval_pair(0, lane_v, lane_v + PB, copy_t, true);
-#pragma unroll 1
-        for (int r = 1; r < 8; ++r) eval_pair(r, lane_v, lane_v + PB, frac_t, true);
-        eval_pair(8, lane_v, lane_v + PB, copy_t, true);
-#pragma unroll 1
-        for (int r = 9; r < 16; ++r) eval_pair(r, lane_v + negt0[23 - r], lane_v + negt0[r - 9], frac_t, true);
-        eval_pair(16, lane_v + negt0[7], lane_v + negt0[7], copy_t, false);   // mode 18: vertical only
-        settle2(p0, p1, ppos);
-        {   // even and odd lanes hold different candidates
-            const int other = __shfl_xor_sync(0xffffffffu, best, 1);
+        for (int off = 1; off < 4; off <<= 1) {   // the lanes of a quad hold different candidates
+            const int other = __shfl_xor_sync(0xffffffffu, best, off);
             best = other < best ? other : best;
         }
         if (valid && lane % LPB == 0) {
