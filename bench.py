@@ -516,7 +516,10 @@ def run_ours(args, rank, world, local_rank):
             avail = os.cpu_count() or 8
         # host threads of the widening pass: this rank's share of the cores the job may use
         share = numa.get("cpus_before", avail) // max(world, 1) if world > 1 else avail - 1
-        os.environ.setdefault("NH_HOST_THREADS", str(max(2, min(16, share))))
+        # ... capped at 6: measured on the 16-vCPU box (profiles/r4_host_threads.txt), e2e 8.3 / 7.7 / 7.2 / 6.0 / 3.9 Gpix/s
+        # with 4 / 6 / 8 / 10 / 15 threads -- the pass is bound by host memory, and threads beyond what saturates it
+        # only delay the DMA engines' traffic (the time spent waiting for a chunk's copies grows 2.5x from 8 to 15)
+        os.environ.setdefault("NH_HOST_THREADS", str(max(2, min(6, share))))
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         chunk = int(os.environ.get("NH_E2E_CHUNK", 128 * 1024))  # measured best of 4K..128K (profiles/r1_notes.md)
         L = _lib.lib()

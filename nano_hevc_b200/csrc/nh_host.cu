@@ -424,6 +424,14 @@ NH_API int nh_host_pipeline_dcplanar(const int16_t* orig, const int16_t* top, co
     if (rc != NH_OK) return rc;
     Pool& workers = pool();
     const bool compact = compact_wire_enabled();
+    // Which format a chunk's coefficients / levels travel in is decided when the chunk is ENQUEUED, from the list
+    // counters of the chunks that have already come back: content whose segments overflow the exception lists
+    // (noise: every level segment non-zero) would otherwise pay the compact transfer, a host round trip and a
+    // second, unoverlapped int16 transfer per chunk.  A wrong guess costs time, never correctness (compact + overflow
+    // still falls back below; int16 is always complete).  Per call, starting from the compact format: no state is
+    // kept between calls.
+    bool s_coeff8 = true, s_levelz = true;
+    bool fmt_coeff8[kSlots] = {false, false, false}, fmt_levelz[kSlots] = {false, false, false};
     unsigned char* base = reinterpret_cast<unsigned char*>(device_scratch);
     const int64_t n_chunks = (n_blocks + chunk_blocks - 1) / chunk_blocks;
     // On any error path copies may still be in flight on the internal streams, targeting the caller's buffers, the
@@ -479,7 +487,10 @@ NH_API int nh_host_pipeline_dcplanar(const int16_t* orig, const int16_t* top, co
         if (r != NH_OK) return r;
         const int64_t elems = n * nn, segs = (elems + kSeg - 1) / kSeg;
         const int64_t cap = L.cap < segs ? L.cap : segs;  // list entries that travel
-        if (compact && (coeff || levels)) {
+        const bool c8 = compact && coeff && s_coeff8, lz = compact && levels && s_levelz;
+        fmt_coeff8[slot] = c8;
+        fmt_levelz[slot] = lz;
+        if (compact && (coeff || levels)) {   // always run: its counters steer the format of the chunks behind this one
             const int64_t pairs = (segs + 1) / 2;
             pack_wire_kernel<<<grid_for(pairs, 8, 8), 256, 0, s>>>(
                 coeff ? reinterpret_cast<int16_t*>(d + L.coeff16) : nullptr,
@@ -492,7 +503,7 @@ NH_API int nh_host_pipeline_dcplanar(const int16_t* orig, const int16_t* top, co
         NH_CP(ctx->cnt + slot, dcnt, sizeof(WireCounters), cudaMemcpyDeviceToHost, s);
         if (pred) NH_CP(pred + first * nn, d + L.pred, n * nn * 2, cudaMemcpyDeviceToHost, s);
         if (coeff) {
-            if (compact) {
+            if (c8) {
                 NH_CP(st.coeff8, d + L.coeff8, elems, cudaMemcpyDeviceToHost, s);
                 NH_CP(st.wide_idx, d + L.wide_idx, cap * 4, cudaMemcpyDeviceToHost, s);
                 NH_CP(st.wide_val, d + L.wide_val, cap * kSeg * 2, cudaMemcpyDeviceToHost, s);
@@ -501,7 +512,7 @@ NH_API int nh_host_pipeline_dcplanar(const int16_t* orig, const int16_t* top, co
             }
         }
         if (levels) {
-            if (compact) {
+            if (lz) {
                 NH_CP(st.nz_idx, d + L.nz_idx, cap * 4, cudaMemcpyDeviceToHost, s);
                 NH_CP(st.nz_val, d + L.nz_val, cap * kSeg * 2, cudaMemcpyDeviceToHost, s);
             } else {
@@ -551,7 +562,12 @@ NH_API int nh_host_pipeline_dcplanar(const int16_t* orig, const int16_t* top, co
         int32_t* dl = levels ? levels + first * nn : nullptr;
         if (!dc && !dl) return NH_OK;
         // a list overflowed: that tensor comes over as int16 after all (still resident on the device)
-        bool use8 = compact && dc, usez = compact && dl;
+        bool use8 = fmt_coeff8[slot] && dc, usez = fmt_levelz[slot] && dl;
+        if (compact) {   // steer the chunks that are enqueued from now on (hysteresis: back to compact below 3/4 of the capacity)
+            const int64_t segs_i = ((int64_t)elems + kSeg - 1) / kSeg, cap_i = L.cap < segs_i ? L.cap : segs_i;
+            if (dc) s_coeff8 = s_coeff8 ? c.n_wide <= cap_i : 4 * (int64_t)c.n_wide <= 3 * cap_i;
+            if (dl) s_levelz = s_levelz ? c.n_nz <= cap_i : 4 * (int64_t)c.n_nz <= 3 * cap_i;
+        }
         if (use8 && c.n_wide > L.cap) {
             NH_CP(st.coeff16, d + L.coeff16, elems * 2, cudaMemcpyDeviceToHost, s);
             use8 = false;
@@ -560,7 +576,7 @@ NH_API int nh_host_pipeline_dcplanar(const int16_t* orig, const int16_t* top, co
             NH_CP(st.levels16, d + L.levels16, elems * 2, cudaMemcpyDeviceToHost, s);
             usez = false;
         }
-        if (compact && ((dc && !use8) || (dl && !usez))) {
+        if ((dc && fmt_coeff8[slot] && !use8) || (dl && fmt_levelz[slot] && !usez)) {   // a guess was wrong: wait for the second transfer
             e = cudaStreamSynchronize(s);
             if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
         }
