@@ -363,8 +363,10 @@ def run_secondary(torch, dist, batched, dev, rank, world, peak):
         res = batched.encode_frames(planes, n, cost="sad", qp=27, stats=False)
         for cost in ("sad", "satd"):
             ms = timed(lambda: batched.encode_frames(planes, n, cost=cost, qp=27, stats=False, out=res), 2)
-            cfg3[f"N{n}_{cost}"] = entry(px, 2 + 12 + 5 / (n * n), ms, frames_per_gpu=F3,
-                                         limiter="ALU pipe (search kernel), see profiles/")
+            lim = ("instruction issue (search kernel: ALU pipe 55 %, tensor pipe 33 %, issue 62 %; SATD on the tensor cores, "
+                   "profiles/r4_search_quad8_v3_ncu_summary.json)" if cost == "satd" and n >= 8
+                   else "ALU pipe (search kernel), see profiles/")
+            cfg3[f"N{n}_{cost}"] = entry(px, 2 + 12 + 5 / (n * n), ms, frames_per_gpu=F3, limiter=lim)
         del res
     host8 = torch.stack([_synth_plane_dev(torch, H4, W4, 100 * rank + i, dev) for i in range(8)]).cpu().pin_memory()
     cfg3["N8_sad"]["e2e"] = e2e_frames(host8, 8, False, ALL)

@@ -309,7 +309,7 @@ static Pool& pool() {
         if (const char* e = getenv("NH_HOST_THREADS")) n = atoi(e);
         if (n <= 0) {
             n = (int)std::thread::hardware_concurrency();
-            if (n > 8) n = 8;
+            if (n > 6) n = 6;   // more threads than saturate host memory only delay the DMA traffic (profiles/r4_host_threads.txt)
         }
         g_pool = new Pool(n);
     }
