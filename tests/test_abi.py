@@ -76,9 +76,9 @@ def test_kernel_selection_and_accounting_entry_points():
     for bad in (0, 3, -1):
         assert L.nh_set_rows_impl(bad) != 0 and b"nh_set_rows_impl" in L.nh_last_error()
     L.nh_set_rows_impl(2)
-    for good in (1, 2, 3, 4, 5):
+    for good in (1, 2, 3, 4, 5, 6):
         assert L.nh_set_search_impl(good) == 0
-    assert L.nh_set_search_impl(6) != 0 and b"nh_set_search_impl" in L.nh_last_error()
+    assert L.nh_set_search_impl(7) != 0 and b"nh_set_search_impl" in L.nh_last_error()
     L.nh_set_search_impl(2)
     for good in (1, 2, 3, 4):
         assert L.nh_set_fused_impl(good) == 0
