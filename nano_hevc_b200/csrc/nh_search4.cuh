@@ -55,7 +55,7 @@ struct QuadCfg {
     static constexpr int WARPS = 4;
     static constexpr int TAB_WORDS = 17 * N * 5;
     static constexpr int SMEM_BYTES = (WARPS * WARP_WORDS + TAB_WORDS) * 4;
-    static constexpr int PER_SM = 5;                   // 96 registers; 6 CTAs (80 registers) measured +1 % / 0 / 0
+    static constexpr int PER_SM = 5;                   // 96 registers; 6 CTAs (80 registers) measured +1 % / 0 / 0, the r loops unrolled 2x -0.3 / -1 / -6 % (N = 8 / 16 / 32)
 };
 
 // two interpolated samples (high bytes of the 16-bit lanes of t) as an f16 pair.  The bit pattern 0x00ss is the
