@@ -578,8 +578,9 @@ def run_ours(args, rank, world, local_rank):
         e2e["api"] = ("nh_host_pipeline_dcplanar (C ABI, pinned host buffers, 3-stream chunked overlap; compact wire format: "
                       "int8 coefficients + int16 exception segments, all-zero level segments elided, widened / zero-filled "
                       "on host threads into the reference's int32 arrays; d2h bytes are those of the last pass)")
-        e2e["bound"] = ("host DRAM + PCIe: 12 B/px of int32 / int16 results are written to host memory per pass on top of the DMA "
-                        "traffic (tools/ubench_pcie.py: 46 GB/s per direction under duplex load)")
+        e2e["bound"] = ("host memory + PCIe: per pixel 7.8 B cross PCIe (2.56 up, 5.26 down) and the host threads write 8 B of int32 "
+                        "coefficients / levels; the DMA probe below gives the box's ceiling, profiles/r4_host_threads.txt the "
+                        "thread sweep (more than ~6 widening threads only delay the DMA traffic)")
         Fn = min(Fe, 32)
         e2e_noise = e2e_leg(noise_frames(Fn, 1000 * rank), 1, "noise (SURVEY 8d i): every level segment non-zero, int16 wire format")
         # the same workload with coefficients / levels delivered as int16 (an option of the API, not the reference's
