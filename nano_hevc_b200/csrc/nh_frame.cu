@@ -966,6 +966,18 @@ static int launch_search_code4(const CoderArgs& a, cudaStream_t st, unsigned int
     *handed_back = counter + 2;
     SearchArgs s{a.src, a.H, a.W, a.pitch, a.cost_kind, a.n_blocks, a.out.modes, a.out.costs, a.blocks_per_frame,
                  a.frame_stride, a.fq, a.maxv, a.out.pred, a.out.coeff, a.out.levels, a.out.recon_plane, counter + 2};
+    if constexpr (COST == NH_COST_SATD) {
+        // SATD with the Hadamard transforms on the tensor cores (nh_search4.cuh, search_quad4_kernel)
+        const int impl = search_impl();
+        if (impl == 6 || (impl == 2 && quad_default())) {
+            rc = ensure_dynamic_smem(search_quad4_kernel<true>, Quad4Cfg::SMEM_BYTES, "search_quad4_kernel");
+            if (rc != NH_OK) return rc;
+            const int gridq = grid_for(a.n_blocks, (int64_t)C::WARPS * C::T, Quad4Cfg::PER_SM);
+            search_quad4_kernel<true><<<gridq, C::WARPS * 32, Quad4Cfg::SMEM_BYTES, st>>>(s);
+            NH_CHECK_LAUNCH("search_quad4_kernel");
+            return NH_OK;
+        }
+    }
     const int grid = grid_for(a.n_blocks, (int64_t)C::WARPS * C::T, 4);
     search_plane_kernel<4, COST, true><<<grid, C::WARPS * 32, C::SMEM_BYTES, st>>>(s);
     NH_CHECK_LAUNCH("search_plane_kernel<code>");

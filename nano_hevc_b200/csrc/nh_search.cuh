@@ -185,6 +185,105 @@ __device__ __forceinline__ void copy_line_w(const uint32_t* wp, uint32_t sh, uin
     for (int i = 0; i < WPS; ++i) out[i] = __funnelshift_r(w[i], w[i + 1], sh);
 }
 
+// Winner stage of the 4x4 search kernels, lane = block: prediction of the decided mode as four packed rows, then
+// residual, forward DST-VII, quantise, dequantise, inverse, reconstruct in this lane's registers (8-bit samples: the
+// 32-bit quantiser forms are exact).  blk = the block's reference arrays (top | left | per-mode
+// negative-angle arrays), negT0 = byte t = 0 of mode 11 + mi from blk, ov = the block's pixels as packed rows.
+__device__ __forceinline__ void code_winner4(const SearchArgs& a, int wmode, int dc, const unsigned char* blk, const int* negT0,
+                                             const uint32_t (&ov)[4][1], bool valid, int64_t b, int fr, int x, int y) {
+    constexpr int N = 4;
+    constexpr int PB4 = ((2 * N + 9) + 3) / 4 * 4;
+    const unsigned char* tb = blk;
+    const unsigned char* lb = blk + PB4;
+    uint32_t pw[4];
+    if (wmode == 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pw[j] = (uint32_t)dc * 0x01010101u;
+    } else if (wmode == 0) {   // intra.py:109-111
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                w |= (uint32_t)planar_px<N>(i, j, lb[1 + j], tb[1 + i], tb[N + 1], lb[N + 1]) << (8 * i);
+            pw[j] = w;
+        }
+    } else {   // intra.py:116-207 with this lane's own angle
+        const int wangle = intra_angle(wmode);
+        const bool vert = wmode >= 18;
+        const int pri = vert ? 0 : PB4;
+        const int ngo = wangle < 0 ? negT0[wmode - 11] : pri;
+        uint32_t ln[4][1];
+        int p = wangle;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t f8 = ((uint32_t)p & 31u) << 3;
+            const int k = 1 + (p >> 5);
+            predict_line_u8<1>(blk, (k < 0 ? ngo : pri) + k, f8, 256u - f8, ln[j]);
+            p += wangle;
+        }
+        if (vert) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pw[j] = ln[j][0];
+        } else {   // scan line = image column: 4x4 byte transpose
+            const uint32_t u0 = __byte_perm(ln[0][0], ln[1][0], 0x5140), v0 = __byte_perm(ln[2][0], ln[3][0], 0x5140);
+            const uint32_t u1 = __byte_perm(ln[0][0], ln[1][0], 0x7362), v1 = __byte_perm(ln[2][0], ln[3][0], 0x7362);
+            pw[0] = __byte_perm(u0, v0, 0x5410);
+            pw[1] = __byte_perm(u0, v0, 0x7632);
+            pw[2] = __byte_perm(u1, v1, 0x5410);
+            pw[3] = __byte_perm(u1, v1, 0x7632);
+        }
+    }
+    // ---- residual, forward DST-VII, quantise, dequantise, inverse, reconstruct: all in this lane's registers
+    // (8-bit samples: the 32-bit quantiser forms are exact)
+    int r[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            r[j][i] = (int)((ov[j][0] >> (8 * i)) & 0xffu) - (int)((pw[j] >> (8 * i)) & 0xffu);
+    transform2d<4, true, false>(r);
+    int lv[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) lv[j][i] = quantize_fast(r[j][i], a.fq);
+    if (valid) {
+        if (a.pred) {
+            uint4* pp = reinterpret_cast<uint4*>(a.pred + b * 16);
+            __stcs(pp, make_uint4(__byte_perm(pw[0], 0u, 0x4140), __byte_perm(pw[0], 0u, 0x4342),
+                                  __byte_perm(pw[1], 0u, 0x4140), __byte_perm(pw[1], 0u, 0x4342)));
+            __stcs(pp + 1, make_uint4(__byte_perm(pw[2], 0u, 0x4140), __byte_perm(pw[2], 0u, 0x4342),
+                                      __byte_perm(pw[3], 0u, 0x4140), __byte_perm(pw[3], 0u, 0x4342)));
+        }
+        if (a.coeff) {
+            uint4* cp = reinterpret_cast<uint4*>(a.coeff + b * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) __stcs(cp + j, make_uint4(r[j][0], r[j][1], r[j][2], r[j][3]));
+        }
+        if (a.levels) {
+            uint4* lp = reinterpret_cast<uint4*>(a.levels + b * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) __stcs(lp + j, make_uint4(lv[j][0], lv[j][1], lv[j][2], lv[j][3]));
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r[j][i] = dequantize_fast(lv[j][i], a.fq);
+    transform2d<4, true, true>(r);
+    if (valid && a.recon_plane) {
+        int16_t* rp = a.recon_plane + fr * a.frame_stride + (int64_t)y * a.pitch + x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int q[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[i] = recon_px((int)((pw[j] >> (8 * i)) & 0xffu), r[j][i], a.maxv);
+            *reinterpret_cast<uint2*>(rp + (int64_t)j * a.pitch) = make_uint2(pack16(q[0], q[1]), pack16(q[2], q[3]));
+        }
+    }
+}
+
 // COST is a template parameter so that the SAD instance is not compiled around the registers of the SATD code
 // (6 resident CTAs per SM without spills; the SATD instance runs at 5).
 // CODE (N = 4 only; lane = block there): after the search the lane codes its block's winner -- it already holds the
@@ -463,97 +562,7 @@ __global__ void __launch_bounds__(SearchCfg<N>::WARPS * 32, CODE ? 4 : (COST == 
             a.modes[b] = (uint8_t)mode_of_key(best);
             if (a.costs) a.costs[b] = best >> 6;
         }
-        if constexpr (CODE) {
-            // ---- winner stage, lane = block: prediction of the decided mode as four packed rows
-            const int wmode = mode_of_key(best);
-            uint32_t pw[4];
-            if (wmode == 1) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) pw[j] = (uint32_t)dc * 0x01010101u;
-            } else if (wmode == 0) {   // intra.py:109-111
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t w = 0;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        w |= (uint32_t)planar_px<N>(i, j, lb[1 + j], tb[1 + i], tb[N + 1], lb[N + 1]) << (8 * i);
-                    pw[j] = w;
-                }
-            } else {   // intra.py:116-207 with this lane's own angle
-                const int wangle = intra_angle(wmode);
-                const bool vert = wmode >= 18;
-                const int pri = vert ? 0 : C::PB;
-                const int ngo = wangle < 0 ? negT0[wmode - 11] : pri;
-                uint32_t ln[4][1];
-                int p = wangle;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t f8 = ((uint32_t)p & 31u) << 3;
-                    const int k = 1 + (p >> 5);
-                    predict_line_u8<1>(blk, (k < 0 ? ngo : pri) + k, f8, 256u - f8, ln[j]);
-                    p += wangle;
-                }
-                if (vert) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) pw[j] = ln[j][0];
-                } else {   // scan line = image column: 4x4 byte transpose
-                    const uint32_t u0 = __byte_perm(ln[0][0], ln[1][0], 0x5140), v0 = __byte_perm(ln[2][0], ln[3][0], 0x5140);
-                    const uint32_t u1 = __byte_perm(ln[0][0], ln[1][0], 0x7362), v1 = __byte_perm(ln[2][0], ln[3][0], 0x7362);
-                    pw[0] = __byte_perm(u0, v0, 0x5410);
-                    pw[1] = __byte_perm(u0, v0, 0x7632);
-                    pw[2] = __byte_perm(u1, v1, 0x5410);
-                    pw[3] = __byte_perm(u1, v1, 0x7632);
-                }
-            }
-            // ---- residual, forward DST-VII, quantise, dequantise, inverse, reconstruct: all in this lane's registers
-            // (8-bit samples: the 32-bit quantiser forms are exact)
-            int r[4][4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    r[j][i] = (int)((ov[j][0] >> (8 * i)) & 0xffu) - (int)((pw[j] >> (8 * i)) & 0xffu);
-            transform2d<4, true, false>(r);
-            int lv[4][4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) lv[j][i] = quantize_fast(r[j][i], a.fq);
-            if (valid) {
-                if (a.pred) {
-                    uint4* pp = reinterpret_cast<uint4*>(a.pred + b * 16);
-                    __stcs(pp, make_uint4(__byte_perm(pw[0], 0u, 0x4140), __byte_perm(pw[0], 0u, 0x4342),
-                                          __byte_perm(pw[1], 0u, 0x4140), __byte_perm(pw[1], 0u, 0x4342)));
-                    __stcs(pp + 1, make_uint4(__byte_perm(pw[2], 0u, 0x4140), __byte_perm(pw[2], 0u, 0x4342),
-                                              __byte_perm(pw[3], 0u, 0x4140), __byte_perm(pw[3], 0u, 0x4342)));
-                }
-                if (a.coeff) {
-                    uint4* cp = reinterpret_cast<uint4*>(a.coeff + b * 16);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) __stcs(cp + j, make_uint4(r[j][0], r[j][1], r[j][2], r[j][3]));
-                }
-                if (a.levels) {
-                    uint4* lp = reinterpret_cast<uint4*>(a.levels + b * 16);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) __stcs(lp + j, make_uint4(lv[j][0], lv[j][1], lv[j][2], lv[j][3]));
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) r[j][i] = dequantize_fast(lv[j][i], a.fq);
-            transform2d<4, true, true>(r);
-            if (valid && a.recon_plane) {
-                int16_t* rp = a.recon_plane + fr * a.frame_stride + (int64_t)y * a.pitch + x;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    int q[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) q[i] = recon_px((int)((pw[j] >> (8 * i)) & 0xffu), r[j][i], a.maxv);
-                    *reinterpret_cast<uint2*>(rp + (int64_t)j * a.pitch) = make_uint2(pack16(q[0], q[1]), pack16(q[2], q[3]));
-                }
-            }
-        }
+        if constexpr (CODE) code_winner4(a, mode_of_key(best), dc, blk, negT0, ov, valid, b, fr, x, y);
     }
 }
 

@@ -392,4 +392,304 @@ __global__ void __launch_bounds__(QuadCfg<N>::WARPS * 32, OCC) search_quad_kerne
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// N = 4 (one 4x4 sub-block per block): the same two MMA stages, with the winner stage of search_plane_kernel<4, ., true>
+// behind them.  That kernel gives a lane a whole block; an MMA row wants the block's four lines in the four lanes of a
+// quad.  So for the SATD search -- and only there -- lane t of a quad predicts LINE t of each of the quad's four blocks
+// (the same four predict calls per lane and mode, each against another block's arrays; the scan-line position is now
+// the same for all four, one table entry per lane and mode instead of four), which is the operand layout as it
+// stands: blocks 0 / 2 of the quad are rows g / g + 8 of one MMA, blocks 1 / 3 of a second one.  The finished costs of
+// mirror pair t of a group come out in lane t for all four blocks; every lane keeps four running minima and the quad
+// merges them once per tile.  Gather, projected extensions, DC and the winner stage are those of search_plane_kernel.
+__device__ __forceinline__ void predict_line4_f16(const uint32_t* wp, uint32_t sh, uint32_t sel_last, uint32_t f8, uint32_t g8,
+                                                  uint32_t& p02, uint32_t& p13) {
+    const uint32_t w0 = wp[0], w1 = wp[1];
+    const uint32_t v0 = __funnelshift_r(w0, w1, sh);
+    const uint32_t e0 = __byte_perm(v0, 0u, 0x4240), o0 = __byte_perm(v0, 0u, 0x4341);
+    const uint32_t e1 = prmt(e0, w1, sel_last);
+    p02 = hi_bytes_f16(g8 * e0 + 0x00800080u + f8 * o0);
+    p13 = hi_bytes_f16(g8 * o0 + 0x00800080u + f8 * e1);
+}
+__device__ __forceinline__ void copy_line4_f16(const uint32_t* wp, uint32_t sh, uint32_t& p02, uint32_t& p13) {
+    const uint32_t v0 = __funnelshift_r(wp[0], wp[1], sh);
+    p02 = even_bytes_f16(v0);
+    p13 = odd_bytes_f16(v0);
+}
+
+struct Quad4Cfg {
+    using C = SearchCfg<4>;
+    static constexpr int SCR_WORDS = 32 * 8;   // per warp: the tile's pixels as rows (4 words) and columns (4 words) per block
+    static constexpr int SMEM_BYTES = C::SMEM_BYTES + C::WARPS * SCR_WORDS * 4;
+    static constexpr int PER_SM = 4;
+};
+
+template <bool CODE>
+__global__ void __launch_bounds__(SearchCfg<4>::WARPS * 32, Quad4Cfg::PER_SM) search_quad4_kernel(const SearchArgs a) {
+    constexpr int N = 4, S = 2, T = 32;
+    using C = SearchCfg<4>;
+    constexpr int PB = C::PB;
+    extern __shared__ __align__(16) uint32_t smem_w[];
+    int* negT0 = reinterpret_cast<int*>(smem_w + C::WARPS * C::WARP_WORDS);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 15) negT0[threadIdx.x] = C::neg_t0((int)threadIdx.x);
+    int4* s_tab = reinterpret_cast<int4*>(smem_w + C::WARPS * C::WARP_WORDS + 16);
+    int* s_k4 = reinterpret_cast<int*>(smem_w + C::WARPS * C::WARP_WORDS + 16 + 17 * 4 * 4);
+    for (int i = threadIdx.x; i < 17 * 4; i += blockDim.x) {
+        s_tab[i] = kc_line_tab.e[i / 4][i % 4];
+        s_k4[i] = kc_line_tab.k4[i / 4][i % 4];
+    }
+    __syncthreads();
+    uint32_t* wbase = smem_w + warp * C::WARP_WORDS;
+    uint32_t* scr = smem_w + C::WARPS * C::WARP_WORDS + 16 + C::TAB_WORDS + warp * Quad4Cfg::SCR_WORDS;
+    const int t = lane & 3, g = lane >> 2, q0 = lane & ~3;
+    unsigned char* blk = reinterpret_cast<unsigned char*>(wbase + lane * C::BLOCK_WORDS);   // lane = block for K1 / DC / winner
+    const unsigned char* tb = blk;
+    const unsigned char* lb = blk + PB;
+    const unsigned char* qblk = reinterpret_cast<const unsigned char*>(wbase + q0 * C::BLOCK_WORDS);   // block j of the quad: + j * BLOCK_WORDS * 4
+    const int bw = a.W / N;
+    const int64_t n_tiles = (a.n_blocks + T - 1) / T;
+
+    uint32_t hb[2][2];   // first-stage B operands, as in search_quad_kernel
+    {
+        auto hneg = [](int i, int j) { return i == 1 ? j >= 2 : (i == 2 ? (j == 1 || j == 2) : (i == 3 ? (j & 1) : 0)); };
+        const int vs = g >> 2, v = g & 3;
+        const bool vneg = vs && (t & 1);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t lo = (vneg ^ (bool)hneg(v, h)) ? 0xBC00u : 0x3C00u;
+            const uint32_t hi = (vneg ^ (bool)hneg(v, 2 + h)) ? 0xBC00u : 0x3C00u;
+            const uint32_t w = lo | (hi << 16);
+            hb[0][h] = t < 2 ? w : 0u;
+            hb[1][h] = t < 2 ? 0u : w;
+        }
+    }
+    const uint32_t kSel = 0x40004000u;
+
+    for (int64_t tile = (int64_t)blockIdx.x * C::WARPS + warp; tile < n_tiles; tile += (int64_t)gridDim.x * C::WARPS) {
+        int64_t b = tile * T + lane;
+        const bool valid = b < a.n_blocks;
+        if (!valid) b = a.n_blocks - 1;
+        const int fr = (int)(b / a.blocks_per_frame);
+        const int64_t bf = b - fr * a.blocks_per_frame;
+        const int x = (int)(bf % bw) * N, y = (int)(bf / bw) * N;
+        const int16_t* srcf = a.src + fr * a.frame_stride;
+        int ood = 0;
+        __syncwarp();   // the previous tile's arrays and scratch are no longer read
+
+        // ---- K1: references with the substitution rules of block.py:38-55, as bytes (loads, then stores)
+        const bool interior = __all_sync(0xffffffffu, x > 0 && y > 0 && x + 2 * N <= a.W && y + 2 * N <= a.H);
+        constexpr int RE = T * (2 * N + 2), RI = (RE + 31) / 32;
+        int tv[RI], lv[RI];
+#pragma unroll
+        for (int it = 0; it < RI; ++it) {
+            const int e = it * 32 + lane;
+            const int i = e / (2 * N + 2), k = e % (2 * N + 2);
+            const int xi = __shfl_sync(0xffffffffu, x, i), yi = __shfl_sync(0xffffffffu, y, i);
+            const int16_t* srci = a.src + __shfl_sync(0xffffffffu, fr, i) * a.frame_stride;
+            const int kk = k <= 2 * N ? k : 2 * N;
+            if (interior) {
+                const int16_t* c = srci + (int64_t)(yi - 1) * a.pitch + xi - 1;
+                tv[it] = __ldg(c + kk);
+                lv[it] = __ldg(c + (int64_t)kk * a.pitch);
+            } else {
+                tv[it] = top_ref<false>(srci, a.H, a.W, a.pitch, xi, yi, 2 * N, kk);
+                lv[it] = left_ref<false>(srci, a.H, a.W, a.pitch, xi, yi, 2 * N, kk);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < RI; ++it) {
+            const int e = it * 32 + lane;
+            const int i = e / (2 * N + 2), k = e % (2 * N + 2);
+            unsigned char* zb = reinterpret_cast<unsigned char*>(wbase + i * C::BLOCK_WORDS);
+            zb[k] = (unsigned char)tv[it];
+            zb[PB + k] = (unsigned char)lv[it];
+            ood |= tv[it] | lv[it];
+        }
+
+        // ---- the lane's block as packed rows (ov: the winner stage needs them) and packed columns (oh)
+        uint32_t ov[4][1], oh[4][1];
+        {
+            uint2 r[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                r[j] = __ldg(reinterpret_cast<const uint2*>(srcf + (int64_t)(y + j) * a.pitch + x));
+                ood |= (int)((r[j].x | r[j].y) & 0xFF00FF00u);
+                ov[j][0] = __byte_perm(r[j].x, r[j].y, 0x6420);
+            }
+            transpose4x4_u8_s(ov[0][0], ov[1][0], ov[2][0], ov[3][0], oh[0][0], oh[1][0], oh[2][0], oh[3][0]);
+        }
+        const bool fast8 = !__any_sync(0xffffffffu, (ood & ~0xff) != 0);
+        if (!fast8) {   // leave the tile to the coder kernel's exact search
+            if (valid) a.modes[b] = 0xFF;
+            if (CODE && lane == 0) atomicAdd(a.handed_back, 1u);
+            continue;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            scr[lane * 8 + j] = ov[j][0];
+            scr[lane * 8 + 4 + j] = oh[j][0];
+        }
+        __syncwarp();
+
+        // ---- projected extensions of the negative-angle modes (as search_plane_kernel: unit = (block, orientation))
+        for (int u0 = 0; u0 < 2 * T * C::GP; u0 += 32) {
+            const int u = u0 + lane;
+            const int i = u / (2 * C::GP), r = u % (2 * C::GP), o = r / C::GP, gq = r % C::GP;
+            unsigned char* zb = reinterpret_cast<unsigned char*>(wbase + i * C::BLOCK_WORDS);
+            const unsigned char* sec = zb + (o ? PB : 0);
+            uint32_t pw[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) pw[c] = reinterpret_cast<const uint32_t*>(zb + (o ? 0 : PB))[c];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int len = C::neg_len(14 - q);
+                const int inv = inv_angle(neg_angle_at(14 - q));
+                if (q / C::MPG == gq && (q < 7 || o)) {
+                    unsigned char* dst = zb + (o ? C::neg_t0(14 - q) : C::neg_t0(q < 7 ? q : 6));
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) reinterpret_cast<uint32_t*>(dst)[c] = pw[c];
+#pragma unroll
+                    for (int tt = 0; tt < len; ++tt) {
+                        const int proj = (-tt * inv + 128) >> 8;
+                        dst[-1 - tt] = sec[proj > 2 * N ? 2 * N : proj];
+                    }
+                }
+            }
+        }
+
+        // ---- DC of the lane's block (intra.py:46-62)
+        int rs = 0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) rs += (int)tb[1 + k] + (int)lb[1 + k];
+        const int dc = dc_value<N>(rs);
+        __syncwarp();
+
+        // ---- start values: minus the half transforms of line t of the quad's four blocks (rows, and columns for the
+        // horizontal modes); cin[o][p] belongs to the MMA of blocks p / p + 2
+        uint32_t cin[2][2][4];
+#pragma unroll
+        for (int o = 0; o < 2; ++o)
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const uint32_t wa = scr[(q0 + p) * 8 + 4 * o + t], wb = scr[(q0 + p + 2) * 8 + 4 * o + t];
+                const uint4 av = make_uint4(even_bytes_f16(wa), even_bytes_f16(wb), odd_bytes_f16(wa), odd_bytes_f16(wb));
+                uint32_t da[2], dcc[2];
+                hmma16816_h(da, av, hb[0][0] ^ 0x80008000u, hb[0][1] ^ 0x80008000u, 0u, 0u);
+                hmma16816_h(dcc, av, hb[1][0] ^ 0x80008000u, hb[1][1] ^ 0x80008000u, 0u, 0u);
+                cin[o][p][0] = da[0]; cin[o][p][1] = da[1]; cin[o][p][2] = dcc[0]; cin[o][p][3] = dcc[1];
+            }
+
+        int best[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};   // blocks 0 .. 3 of the quad, this lane's candidates
+        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        // columns 2t / 2t+1 of blocks p (row g) and p + 2 (row g + 8): the vertical / horizontal candidate of mirror pair t
+        auto take = [&](int pos_v, int pos_h, bool has_v, bool has_h) {
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const int kva = (__float2int_rn(acc[p][0] * 16777216.f) << 6) | pos_v, kha = (__float2int_rn(acc[p][1] * 16777216.f) << 6) | pos_h;
+                const int kvb = (__float2int_rn(acc[p][2] * 16777216.f) << 6) | pos_v, khb = (__float2int_rn(acc[p][3] * 16777216.f) << 6) | pos_h;
+                if (has_v) { best[p] = kva < best[p] ? kva : best[p]; best[p + 2] = kvb < best[p + 2] ? kvb : best[p + 2]; }
+                if (has_h) { best[p] = kha < best[p] ? kha : best[p]; best[p + 2] = khb < best[p + 2] ? khb : best[p + 2]; }
+                acc[p][0] = acc[p][1] = acc[p][2] = acc[p][3] = 0.f;
+            }
+        };
+        // one mirror pair: line t of the four blocks, vertical (arrays at voff) and horizontal (arrays at hoff)
+        auto eval_pair = [&](int r, int voff, int hoff, auto frac_tag) {
+            constexpr bool FRAC = decltype(frac_tag)::value;
+            const int4 e = s_tab[r * 4 + t];
+            const int k4 = s_k4[r * 4 + t];
+            const uint32_t sx = g == 2 * (r & 3) ? kSel : 0u, sy = g == 2 * (r & 3) + 1 ? kSel : 0u;
+            uint32_t ve[4], vo[4], he[4], ho[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned char* bj = qblk + j * (C::BLOCK_WORDS * 4) + k4;
+                if (FRAC) {
+                    predict_line4_f16(reinterpret_cast<const uint32_t*>(bj + voff), (uint32_t)e.x, (uint32_t)e.y, (uint32_t)e.z, (uint32_t)e.w, ve[j], vo[j]);
+                    predict_line4_f16(reinterpret_cast<const uint32_t*>(bj + hoff), (uint32_t)e.x, (uint32_t)e.y, (uint32_t)e.z, (uint32_t)e.w, he[j], ho[j]);
+                } else {
+                    copy_line4_f16(reinterpret_cast<const uint32_t*>(bj + voff), (uint32_t)e.x, ve[j], vo[j]);
+                    copy_line4_f16(reinterpret_cast<const uint32_t*>(bj + hoff), (uint32_t)e.x, he[j], ho[j]);
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                uint32_t mv[2], mh[2];
+                satd_halves(mv, make_uint4(ve[p], ve[p + 2], vo[p], vo[p + 2]), hb, cin[0][p]);
+                satd_halves(mh, make_uint4(he[p], he[p + 2], ho[p], ho[p + 2]), hb, cin[1][p]);
+                satd_sum(acc[p], mv, mh, sx, sy);
+            }
+        };
+        const std::true_type frac_t{};
+        const std::false_type copy_t{};
+        eval_pair(0, 0, PB, copy_t);
+#pragma unroll 1
+        for (int r = 1; r < 4; ++r) eval_pair(r, 0, PB, frac_t);
+        take(34 - t, 2 + t, true, true);
+#pragma unroll 1
+        for (int r = 4; r < 8; ++r) eval_pair(r, 0, PB, frac_t);
+        take(30 - t, 6 + t, true, true);
+        eval_pair(8, 0, PB, copy_t);
+#pragma unroll 1
+        for (int r = 9; r < 12; ++r) eval_pair(r, negT0[23 - r], negT0[r - 9], frac_t);
+        take(26 - t, 10 + t, true, true);
+#pragma unroll 1
+        for (int r = 12; r < 16; ++r) eval_pair(r, negT0[23 - r], negT0[r - 9], frac_t);
+        take(22 - t, 14 + t, true, true);
+        {   // last group: column 0 = mode 18 (vertical only), columns 2 / 3 = DC / planar (positions 0 / 1)
+            const uint32_t s0 = g == 0 ? kSel : 0u, s2 = g == 2 ? kSel : 0u, s3 = g == 3 ? kSel : 0u;
+            constexpr uint32_t SCL = 1u << (7 - S);
+            const int4 e = s_tab[16 * 4 + t];
+            const int k4 = s_k4[16 * 4 + t];
+            const int off18 = negT0[7];
+            uint32_t e18[4], o18[4], pl0[4], pl1[4], dq[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned char* bj = qblk + j * (C::BLOCK_WORDS * 4);
+                copy_line4_f16(reinterpret_cast<const uint32_t*>(bj + off18 + k4), (uint32_t)e.x, e18[j], o18[j]);
+                dq[j] = (uint32_t)__shfl_sync(0xffffffffu, dc, q0 + j) * 0x10001u;
+                // planar (intra.py:109-111), line t of block j, sample pairs (0, 2) and (1, 3)
+                const unsigned char* tj = bj;
+                const unsigned char* lj = bj + PB;
+                const uint32_t tr = (uint32_t)tj[N + 1], bl = (uint32_t)lj[N + 1];
+                const uint32_t ly = (uint32_t)lj[1 + t];
+                const uint32_t vy = (uint32_t)(N - 1 - t) * SCL;
+                const uint32_t by = ((uint32_t)(t + 1) * bl + (uint32_t)N) * SCL * 0x10001u;
+                const uint32_t c10 = (3u | (1u << 16)) * SCL, c11 = (2u | (0u << 16)) * SCL;      // (N-1-X, N-3-X), X = 0 / 1
+                const uint32_t kc0 = tr * ((1u | (3u << 16)) * SCL), kc1 = tr * ((2u | (4u << 16)) * SCL);
+                const uint32_t zt0 = (uint32_t)tj[1] | ((uint32_t)tj[3] << 16), zt1 = (uint32_t)tj[2] | ((uint32_t)tj[4] << 16);
+                pl0[j] = hi_bytes_f16(ly * c10 + kc0 + vy * zt0 + by);
+                pl1[j] = hi_bytes_f16(ly * c11 + kc1 + vy * zt1 + by);
+            }
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                uint32_t m18[2], mdc[2], mpl[2];
+                const uint32_t zero[2] = {0u, 0u};
+                satd_halves(m18, make_uint4(e18[p], e18[p + 2], o18[p], o18[p + 2]), hb, cin[0][p]);
+                satd_halves(mdc, make_uint4(dq[p], dq[p + 2], dq[p], dq[p + 2]), hb, cin[0][p]);
+                satd_halves(mpl, make_uint4(pl0[p], pl0[p + 2], pl1[p], pl1[p + 2]), hb, cin[0][p]);
+                satd_sum(acc[p], m18, zero, s0, 0u);
+                satd_sum(acc[p], mdc, mpl, s2, s3);
+            }
+            take(t == 0 ? 18 : 0, 1, t < 2, t == 1);
+        }
+        // ---- the quad's lanes hold different candidates: merge, then lane t keeps the key of ITS block
+        int mine = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int k = best[j];
+#pragma unroll
+            for (int off = 1; off < 4; off <<= 1) {
+                const int other = __shfl_xor_sync(0xffffffffu, k, off);
+                k = other < k ? other : k;
+            }
+            mine = t == j ? k : mine;
+        }
+        if (valid) {
+            a.modes[b] = (uint8_t)mode_of_key(mine);
+            if (a.costs) a.costs[b] = mine >> 6;
+        }
+        if constexpr (CODE) code_winner4(a, mode_of_key(mine), dc, blk, negT0, ov, valid, b, fr, x, y);
+    }
+}
+
 }  // namespace nh
