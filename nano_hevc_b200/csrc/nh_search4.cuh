@@ -619,22 +619,15 @@ __global__ void __launch_bounds__(SearchCfg<4>::WARPS * 32, Quad4Cfg::PER_SM) se
                 satd_sum(acc[p], mv, mh, sx, sy);
             }
         };
+        // ONE instance of the pair code for all 16 mirror pairs (the fraction-0 pairs r = 0 and 8 go through the
+        // interpolation with weight 0): with an instance per loop as in search_quad_kernel this kernel -- which also
+        // carries the winner stage -- waited on instruction fetch (ncu: no-instruction 1.3 warps per issue, issue 56 %)
         const std::true_type frac_t{};
-        const std::false_type copy_t{};
-        eval_pair(0, 0, PB, copy_t);
 #pragma unroll 1
-        for (int r = 1; r < 4; ++r) eval_pair(r, 0, PB, frac_t);
-        take(34 - t, 2 + t, true, true);
-#pragma unroll 1
-        for (int r = 4; r < 8; ++r) eval_pair(r, 0, PB, frac_t);
-        take(30 - t, 6 + t, true, true);
-        eval_pair(8, 0, PB, copy_t);
-#pragma unroll 1
-        for (int r = 9; r < 12; ++r) eval_pair(r, negT0[23 - r], negT0[r - 9], frac_t);
-        take(26 - t, 10 + t, true, true);
-#pragma unroll 1
-        for (int r = 12; r < 16; ++r) eval_pair(r, negT0[23 - r], negT0[r - 9], frac_t);
-        take(22 - t, 14 + t, true, true);
+        for (int r = 0; r < 16; ++r) {
+            eval_pair(r, r > 8 ? negT0[23 - r] : 0, r > 8 ? negT0[r - 9] : PB, frac_t);
+            if ((r & 3) == 3) take(37 - r - t, r - 1 + t, true, true);
+        }
         {   // last group: column 0 = mode 18 (vertical only), columns 2 / 3 = DC / planar (positions 0 / 1)
             const uint32_t s0 = g == 0 ? kSel : 0u, s2 = g == 2 ? kSel : 0u, s3 = g == 3 ? kSel : 0u;
             constexpr uint32_t SCL = 1u << (7 - S);
