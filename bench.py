@@ -364,7 +364,7 @@ def run_secondary(torch, dist, batched, dev, rank, world, peak):
         for cost in ("sad", "satd"):
             ms = timed(lambda: batched.encode_frames(planes, n, cost=cost, qp=27, stats=False, out=res), 2)
             lim = ("instruction issue (search kernel: ALU pipe 55 %, tensor pipe 33 %, issue 62 %; SATD on the tensor cores, "
-                   "profiles/r4_search_quad8_v3_ncu_summary.json)" if cost == "satd" and n >= 8
+                   "profiles/r4_search_quad8_v3_ncu_summary.json, r4_search_quad4_v2_ncu_summary.json)" if cost == "satd"
                    else "ALU pipe (search kernel), see profiles/")
             cfg3[f"N{n}_{cost}"] = entry(px, 2 + 12 + 5 / (n * n), ms, frames_per_gpu=F3, limiter=lim)
         del res

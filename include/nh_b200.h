@@ -194,8 +194,8 @@ int64_t nh_encode_frame_scratch_bytes(int height, int width, int size);
  * there are two search kernels (strips of 4 scan lines per lane; all lanes on the same scan line,
  * which needs pitch % 8 == 0 and a 16-byte aligned plane): 2 picks per call by size and cost kind,
  * 3 / 4 force the second / the first, 5 the fraction-major kernel (N = 16 / 32), 6 the SATD kernel
- * with the 4x4 Hadamard transforms on the tensor cores (SATD, N >= 8, pitch % 8 == 0, 16-byte aligned
- * plane; what 2 picks for SATD) -- profiling, tests.  Results are identical.  The setting is per
+ * with the 4x4 Hadamard transforms on the tensor cores (SATD; N >= 8 needs pitch % 8 == 0 and a 16-byte
+ * aligned plane; what 2 picks for SATD) -- profiling, tests.  Results are identical.  The setting is per
  * calling thread. */
 int nh_set_search_impl(int impl);
 int nh_encode_frame(const int16_t* src, int height, int width, int pitch, int size, int cost_kind,
