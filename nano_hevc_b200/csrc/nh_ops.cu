@@ -26,6 +26,12 @@ __global__ void __launch_bounds__(kXfWarps * 32, 2)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* s = smem_raw + warp * TOut::kBytes;  // one buffer, reused for input and output
 
+    // Programmatic dependent launch (launch_transform_unit): the next launch on the stream may be scheduled while this
+    // grid drains, and this grid touches global memory only after the grid in front of it has completed and flushed.
+    // Both instructions are no-ops in a launch without the attribute.
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
     const int64_t n_units = (n_blocks + BPU - 1) / BPU;
     const int64_t n_tiles = (n_units + 31) / 32;
     for (int64_t tile = (int64_t)blockIdx.x * kXfWarps + warp; tile < n_tiles;
@@ -445,6 +451,24 @@ static int launch_transform_unit(const void* in, int32_t* out, int64_t n_blocks,
     }
     constexpr int BPU = 64 / (N * N);
     int grid = grid_for((n_blocks + BPU - 1) / BPU, kXfWarps * 32, 2);
+    // A 2^20-block launch of 4x4 blocks runs for 20 us: the launch gap and the ramp of the next grid are a tenth of it.
+    // With programmatic stream serialization the next grid's CTAs are placed while this one drains (NH_XF_PDL=0: plain launch).
+    static const bool pdl = [] { const char* e = getenv("NH_XF_PDL"); return !(e && e[0] == '0'); }();
+    if (pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(kXfWarps * 32);
+        cfg.dynamicSmemBytes = kSmem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, transform_unit_kernel<N, DST, INV, IN32>, in, out, n_blocks);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(transform_unit_kernel)");
+        return NH_OK;
+    }
     transform_unit_kernel<N, DST, INV, IN32><<<grid, kXfWarps * 32, kSmem, st>>>(in, out, n_blocks);
     NH_CHECK_LAUNCH("transform_unit_kernel");
     return NH_OK;
