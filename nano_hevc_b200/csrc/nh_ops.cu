@@ -34,8 +34,9 @@ __global__ void __launch_bounds__(kXfWarps * 32, 2)
 
     const int64_t n_units = (n_blocks + BPU - 1) / BPU;
     const int64_t n_tiles = (n_units + 31) / 32;
-    for (int64_t tile = (int64_t)blockIdx.x * kXfWarps + warp; tile < n_tiles;
-         tile += (int64_t)gridDim.x * kXfWarps) {
+    const int cta_warps = (int)(blockDim.x >> 5);   // 5 .. kXfWarps: picked per launch (launch_transform_unit)
+    for (int64_t tile = (int64_t)blockIdx.x * cta_warps + warp; tile < n_tiles;
+         tile += (int64_t)gridDim.x * cta_warps) {
         const int64_t blk0 = tile * 32 * BPU;
         int64_t rem = n_blocks - blk0;
         const int blocks_valid = (int)(rem < 32 * BPU ? rem : 32 * BPU);
@@ -450,14 +451,29 @@ static int launch_transform_unit(const void* in, int32_t* out, int64_t n_blocks,
         if (rc != NH_OK) return rc;
     }
     constexpr int BPU = 64 / (N * N);
-    int grid = grid_for((n_blocks + BPU - 1) / BPU, kXfWarps * 32, 2);
+    // Warps per CTA: a small launch hands every warp only a few tiles (2^20 4x4 blocks: 55.4 tiles per SM, 3.46 per warp
+    // with 16 warps -- a quarter of the warps runs a fourth round while the rest idles).  Pick the CTA size whose rounds
+    // waste the least: 14 warps per SM make that 3.95 -> 4 rounds.
+    int cta_warps = kXfWarps;
+    {
+        const int64_t tiles = ((n_blocks + BPU - 1) / BPU + 31) / 32;
+        const double per_sm = (double)tiles / sm_count();
+        double best_cost = 1e30;
+        for (int w = kXfWarps; w >= 5; --w) {
+            const double rounds = per_sm / (2 * w);
+            const double cost = (double)(int64_t)(rounds + 0.999999) * (2 * w);   // warp-rounds the SM spends
+            if (cost < best_cost * 0.97) { best_cost = cost; cta_warps = w; }      // fewer warps only for a clear gain
+        }
+        if (per_sm > 400) cta_warps = kXfWarps;   // many rounds: the remainder does not matter
+    }
+    int grid = grid_for((n_blocks + BPU - 1) / BPU, cta_warps * 32, 2);
     // A 2^20-block launch of 4x4 blocks runs for 20 us: the launch gap and the ramp of the next grid are a tenth of it.
     // With programmatic stream serialization the next grid's CTAs are placed while this one drains (NH_XF_PDL=0: plain launch).
     static const bool pdl = [] { const char* e = getenv("NH_XF_PDL"); return !(e && e[0] == '0'); }();
     if (pdl) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid);
-        cfg.blockDim = dim3(kXfWarps * 32);
+        cfg.blockDim = dim3(cta_warps * 32);
         cfg.dynamicSmemBytes = kSmem;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
@@ -469,7 +485,7 @@ static int launch_transform_unit(const void* in, int32_t* out, int64_t n_blocks,
         if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(transform_unit_kernel)");
         return NH_OK;
     }
-    transform_unit_kernel<N, DST, INV, IN32><<<grid, kXfWarps * 32, kSmem, st>>>(in, out, n_blocks);
+    transform_unit_kernel<N, DST, INV, IN32><<<grid, cta_warps * 32, kSmem, st>>>(in, out, n_blocks);
     NH_CHECK_LAUNCH("transform_unit_kernel");
     return NH_OK;
 }
