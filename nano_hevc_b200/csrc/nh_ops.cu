@@ -412,7 +412,10 @@ template <int N, bool INV, bool IN32>
 static int launch_transform_mma(const void* in, int32_t* out, int64_t n_blocks, cudaStream_t st) {
     static const int occ = [] {  // resident CTAs per SM the kernel is compiled for: NH_XF_OCC=3|4|5 (A/B runs)
         const char* e = getenv("NH_XF_OCC");
-        return (e && e[0] >= '3' && e[0] <= '5') ? e[0] - '0' : 4;  // measured best overall (profiles/r1_notes.md)
+        // measured per direction (tools/time_xform_mma.py, 2^20 16x16 / 2^18 32x32 blocks): the forward transform (int16 in,
+        // int32 out) runs at 0.82 / 0.89 / 0.97 of the copy bandwidth with 3 / 4 / 5 CTAs per SM at N = 16 (0.93 / 0.95 / 0.96 at
+        // N = 32), the inverse (int32 in and out) at 0.90 / 1.00 / 0.91 (1.00 / 0.99 / 0.95)
+        return (e && e[0] >= '3' && e[0] <= '5') ? e[0] - '0' : (INV ? 4 : 5);
     }();
     int grid = grid_for(n_blocks, kMmaWarps * (32 / N), occ);
     if (occ == 4) transform_mma_kernel<N, INV, IN32, 4><<<grid, kMmaWarps * 32, 0, st>>>(in, out, n_blocks);
