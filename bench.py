@@ -374,9 +374,11 @@ def run_secondary(torch, dist, batched, dev, rank, world, peak):
     out["cfg3"] = cfg3
     # ---- cfg5: wavefront coder, F 4K frames per GPU in one call + one frame alone (latency); stats by NCCL
     cfg5 = {}
-    for n in (8, 32):
+    for n in (4, 8, 16, 32):
         px1 = (H4 // n) * (W4 // n) * n * n
-        for F in (1, 8):
+        # N = 8 / 32: one frame (latency), 8 frames (the config), 32 frames (rows in flight fill the GPU);
+        # N = 4 / 16: the one-frame latency only
+        for F in ((1, 8, 32) if n in (8, 32) else (1,)):
             sub = planes[:F]
             res = batched.encode_frames(sub, n, cost="sad", qp=27, recon_neighbours=True)
             scratch = torch.empty((int(1 << 26),), dtype=torch.uint8, device=dev)
