@@ -198,6 +198,13 @@ int64_t nh_encode_frame_scratch_bytes(int height, int width, int size);
  * aligned plane; what 2 picks for SATD) -- profiling, tests.  Results are identical.  The setting is per
  * calling thread. */
 int nh_set_search_impl(int impl);
+/* Selects how recon_neighbours == 1 (the anti-diagonal wavefront over block rows) is laid out, for the calling
+ * thread.  warps: 0 (default) = pick per call from the block rows in flight (rows of a frame x frames of the call),
+ * 1 / 2 / 4 / 8 = warps per block row at N = 16 / 32 (more warps: shorter dependent block time, fewer rows resident),
+ * 1 / 4 = the one-warp / four-warp kernel at N = 4; ignored at N = 8 (always four warps per row on 8-bit planes).
+ * build: 0 (default) = pick per call, 1 = latency build (one or two frames), 2 = throughput build (more CTAs per SM),
+ * 3 = throughput build at the highest occupancy (N = 8; elsewhere as 2); N = 4 / 8 only.  Results are identical. */
+int nh_set_wave_impl(int warps, int build);
 int nh_encode_frame(const int16_t* src, int height, int width, int pitch, int size, int cost_kind,
                     int qp, int recon_neighbours, int bit_depth, uint8_t* modes, int32_t* costs,
                     int16_t* pred, int32_t* coeff, int32_t* levels, int16_t* recon_plane,

@@ -47,6 +47,7 @@ PROTOTYPES = {
     "nh_set_fused_impl": (_i, [_i]),
     "nh_set_rows_impl": (_i, [_i]),
     "nh_set_search_impl": (_i, [_i]),
+    "nh_set_wave_impl": (_i, [_i, _i]),
     "nh_fused_pipeline_modes": (_i, [_p, _p, _p, _p, _p, _i, _i64, _i, _i, _i, _i, _i,
                                      _p, _p, _p, _p, _p]),
     "nh_gather_refs": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),

@@ -776,10 +776,42 @@ static int launch_coder(const CoderArgs& a, int grid, cudaStream_t st) {
     return NH_OK;
 }
 
+// How the wavefront coder (recon_neighbours = 1) is laid out on the GPU.  Every kernel below gives the same results;
+// which one is fastest depends on the block rows in flight (rows of a frame x frames of the call), so the default
+// picks per call.  nh_set_wave_impl(warps, build) forces a choice for the calling thread (tests, profiling), the
+// environment gives a thread's initial setting: NH_WAVE_WARPS=1|2|4|8 (N = 16 / 32), NH_WAVE4=1|4 (N = 4),
+// NH_WAVE_OCC=lat|thr|hi (N = 4 / 8 builds).
+struct WaveImpl { int warps, build; bool init; };
+static thread_local WaveImpl g_wave_impl = {0, 0, false};
+static const WaveImpl& wave_impl() {
+    if (!g_wave_impl.init) {
+        const char* w = getenv("NH_WAVE_WARPS");
+        const char* w4 = getenv("NH_WAVE4");
+        const char* o = getenv("NH_WAVE_OCC");
+        if (w && (w[0] == '1' || w[0] == '2' || w[0] == '4' || w[0] == '8')) g_wave_impl.warps = w[0] - '0';
+        else if (w4 && (w4[0] == '1' || w4[0] == '4')) g_wave_impl.warps = w4[0] - '0';
+        if (o) g_wave_impl.build = o[0] == 'l' ? 1 : o[0] == 'h' ? 3 : 2;
+        g_wave_impl.init = true;
+    }
+    return g_wave_impl;
+}
+// Warps per block row at N = 16 / 32, from the rows in flight R (measured on one B200, 1 ... 32 4K frames per call,
+// profiles/r5_wave_warps.txt): a row's warps share the candidate modes, so more warps shorten the dependent block
+// time, but the resident rows per SM drop (8 warps: 1 CTA per SM, 4: 2-3, 2: 4-6, 1: 8+), and once a call has more
+// rows in flight than fit, the rows that wait cost more than the slower block.  N = 16: 8 warps for one frame, 4 up
+// to ~5 frames, 2 up to ~14, then 1 (32 frames: 10.6 -> 30.2 Gpix/s); N = 32: 8 warps up to ~7 frames, 4 up to ~28,
+// then 1 (32 frames: 23.9 -> 41.3 Gpix/s).
+static int wave_warps_for(int size, int64_t rows) {
+    const int64_t sm = sm_count();
+    if (size == 16) return rows * 10 <= sm * 11 ? 8 : rows * 10 <= sm * 47 ? 4 : rows <= sm * 13 ? 2 : 1;
+    return rows * 10 <= sm * 32 ? 8 : rows <= sm * 13 ? 4 : 1;
+}
+
 template <int SRC>
 static int dispatch_coder(const CoderArgs& a, int size, cudaStream_t st) {
     if (SRC == SRC_WAVEFRONT) {
         const int64_t rows = (int64_t)(a.H / size) * a.n_frames;
+        const WaveImpl& wi = wave_impl();
         int grid = rows < sm_count() * 16 ? (int)rows : sm_count() * 16;
         if (grid < 1) grid = 1;
         // 8-bit planes, N = 8: the latency-oriented kernel of nh_wave.cuh (NH_WAVE_IMPL=1 keeps the generic one)
@@ -788,13 +820,19 @@ static int dispatch_coder(const CoderArgs& a, int size, cudaStream_t st) {
                              (reinterpret_cast<uintptr_t>(a.src) & 7) == 0 &&
                              (reinterpret_cast<uintptr_t>(a.out.recon_plane) & 7) == 0;
         if (wave_ok && size == 8) {
-            // few rows (one or two frames): the latency build, registers to spare; many rows: the build that keeps
-            // more CTAs resident.  NH_WAVE_OCC=lat|thr forces one of them.
-            static const int force = [] { const char* e = getenv("NH_WAVE_OCC"); return e ? (e[0] == 'l' ? 1 : 2) : 0; }();
-            const bool lat = force ? force == 1 : rows <= (int64_t)sm_count() * 3;
-            if (lat) {
+            // few rows (one or two frames): the latency build, registers to spare (3 CTAs per SM); many rows: the build
+            // that keeps 4 CTAs resident; SAD with more than ~5 4K frames in flight: 5 CTAs per SM (96 registers, 28
+            // bytes of spills; 8 / 16 / 32 frames 20.6 / 23.3 / 24.6 -> 22.1 / 24.7 / 26.1 Gpix/s, fewer frames and SATD
+            // lose or stay; 6 CTAs at 80 registers: slower everywhere; profiles/r5_wave8_occ.txt).
+            const int build = wi.build ? wi.build
+                              : rows <= (int64_t)sm_count() * 3 ? 1
+                              : (a.cost_kind == NH_COST_SAD && rows > (int64_t)sm_count() * 8) ? 3 : 2;
+            if (build == 1) {
                 if (a.cost_kind == NH_COST_SAD) wave8_kernel<NH_COST_SAD, 3><<<grid, 128, 0, st>>>(a);
                 else wave8_kernel<NH_COST_SATD, 3><<<grid, 128, 0, st>>>(a);
+            } else if (build == 3) {
+                if (a.cost_kind == NH_COST_SAD) wave8_kernel<NH_COST_SAD, 5><<<grid, 128, 0, st>>>(a);
+                else wave8_kernel<NH_COST_SATD, 5><<<grid, 128, 0, st>>>(a);
             } else {
                 if (a.cost_kind == NH_COST_SAD) wave8_kernel<NH_COST_SAD, 4><<<grid, 128, 0, st>>>(a);
                 else wave8_kernel<NH_COST_SATD, 4><<<grid, 128, 0, st>>>(a);
@@ -805,9 +843,8 @@ static int dispatch_coder(const CoderArgs& a, int size, cudaStream_t st) {
         if (wave_ok && size == 4) {
             // up to ~4 4K frames in flight: four warps per block row (one 4K frame 4.16 -> 2.57 ms); beyond that the
             // one-warp kernel, whose 24 resident rows per SM give the higher batch rate (32 frames: 14.7 vs 11.5
-            // Gpix/s, profiles/r2_wave4_probe.jsonl).  NH_WAVE4=1|4 forces the one-warp / four-warp kernel.
-            static const int force_w4 = [] { const char* e = getenv("NH_WAVE4"); return e ? (e[0] == '1' ? 1 : 4) : 0; }();
-            const bool one_warp = force_w4 ? force_w4 == 1 : rows > (int64_t)sm_count() * 16;
+            // Gpix/s, profiles/r2_wave4_probe.jsonl).  nh_set_wave_impl(1 | 4, ...) / NH_WAVE4=1|4 forces the one-warp / four-warp kernel.
+            const bool one_warp = wi.warps ? wi.warps == 1 : rows > (int64_t)sm_count() * 16;
             if (one_warp) {
                 if (a.cost_kind == NH_COST_SAD) wave4_kernel<NH_COST_SAD><<<grid, 32, 0, st>>>(a);
                 else wave4_kernel<NH_COST_SATD><<<grid, 32, 0, st>>>(a);
@@ -815,9 +852,8 @@ static int dispatch_coder(const CoderArgs& a, int size, cudaStream_t st) {
                 return NH_OK;
             }
             // few rows: the latency build; many rows: the build that keeps twice the CTAs resident (rows in flight
-            // x 16 pixels per dependent block time is what bounds a batch).  NH_WAVE_OCC=lat|thr forces one of them.
-            static const int force4 = [] { const char* e = getenv("NH_WAVE_OCC"); return e ? (e[0] == 'l' ? 1 : 2) : 0; }();
-            const bool lat4 = force4 ? force4 == 1 : rows <= (int64_t)sm_count() * 4;
+            // x 16 pixels per dependent block time is what bounds a batch).  nh_set_wave_impl(..., 1 | 2) / NH_WAVE_OCC=lat|thr forces one of them.
+            const bool lat4 = wi.build ? wi.build == 1 : rows <= (int64_t)sm_count() * 4;
             if (lat4) {
                 if (a.cost_kind == NH_COST_SAD) wave4mw_kernel<NH_COST_SAD, 4><<<grid, 128, 0, st>>>(a);
                 else wave4mw_kernel<NH_COST_SATD, 4><<<grid, 128, 0, st>>>(a);
@@ -828,10 +864,7 @@ static int dispatch_coder(const CoderArgs& a, int size, cudaStream_t st) {
             NH_CHECK_LAUNCH("wave4mw_kernel");
             return NH_OK;
         }
-        static const int wave_warps = [] {  // warps per block row at N = 16 / 32: NH_WAVE_WARPS=1|2|4|8 (default 8)
-            const char* e = getenv("NH_WAVE_WARPS");
-            return (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 8;
-        }();
+        const int wave_warps = size >= 16 ? (wi.warps ? wi.warps : wave_warps_for(size, rows)) : 1;
         if (size >= 16 && wave_warps > 1) {
             if (grid > sm_count() * 4) grid = sm_count() * 4;
             if (size == 16) {
@@ -1139,6 +1172,18 @@ NH_API int nh_set_search_impl(int impl) {
         return NH_E_ARG;
     }
     g_search_impl = impl;
+    return NH_OK;
+}
+
+NH_API int nh_set_wave_impl(int warps, int build) {
+    if (!(warps == 0 || warps == 1 || warps == 2 || warps == 4 || warps == 8) || build < 0 || build > 3) {
+        set_error("nh_set_wave_impl: warps must be 0 (pick per call), 1, 2, 4 or 8 and build 0 (pick per call), 1 (latency), "
+                  "2 (throughput) or 3 (throughput, highest occupancy), got %d, %d", warps, build);
+        return NH_E_ARG;
+    }
+    g_wave_impl.warps = warps;
+    g_wave_impl.build = build;
+    g_wave_impl.init = true;
     return NH_OK;
 }
 

@@ -804,6 +804,37 @@ def test_encode_frames_batch_vs_oracle(Bt, n, rn):
     assert torch.equal(r.recon_planes[0], one.recon_plane)
 
 
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("cost", ("sad", "satd"))
+def test_wavefront_every_layout_vs_oracle(Bt, n, cost):
+    """The wavefront coder picks its layout (warps per block row, latency / throughput build) from the block rows in
+    flight, so the small frames of the other tests only ever see the few-rows choice.  Here every layout is forced in
+    turn through nh_set_wave_impl on a batch of frames (noise regions, ragged sizes, one frame of pure noise) and
+    every output of every frame is compared with the oracle coding that frame alone."""
+    from nano_hevc_b200 import _lib
+    F = 4
+    H, W = 9 * n + 2, 8 * ((17 * n + 8) // 8) + 8
+    rng = np.random.default_rng(77 * n + len(cost))
+    frames = np.stack([_smooth(H, W, 11 * n + f) for f in range(F)])
+    frames[2] = rng.integers(0, 256, (H, W))
+    frames[1, H // 3:] = rng.integers(0, 256, (H - H // 3, W))
+    thr = O.n_host_threads()
+    want = [O.encode_frame(frames[f], n, cost=cost, qp=29, recon_neighbours=True, threads=thr) for f in range(F)]
+    layouts = {4: [(1, 0), (4, 1), (4, 2)], 8: [(0, 1), (0, 2), (0, 3)],
+               16: [(1, 0), (2, 0), (4, 0), (8, 0)], 32: [(1, 0), (2, 0), (4, 0), (8, 0)]}[n]
+    try:
+        for warps, build in layouts:
+            _lib.check(_lib.lib().nh_set_wave_impl(warps, build))
+            r = Bt.encode_frames(dev(frames), n, cost=cost, qp=29, recon_neighbours=True)
+            for f in range(F):
+                for name in ("modes", "costs", "pred", "coeff", "levels"):
+                    eq(host(getattr(r, name)[f]), want[f][name], f"{name} frame {f} n={n} {cost} layout={warps},{build}")
+                eq(host(r.recon_planes[f]), want[f]["recon_plane"], f"recon_plane frame {f} n={n} {cost} layout={warps},{build}")
+    finally:
+        _lib.check(_lib.lib().nh_set_wave_impl(0, 0))
+
+
 @pytest.mark.parametrize("n", SIZES)
 @pytest.mark.parametrize("cost", ("sad", "satd"))
 @pytest.mark.parametrize("W", (264, 268, 262))
