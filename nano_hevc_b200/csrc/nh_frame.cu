@@ -853,7 +853,7 @@ static int dispatch_coder(const CoderArgs& a, int size, cudaStream_t st) {
             }
             // few rows: the latency build; many rows: the build that keeps twice the CTAs resident (rows in flight
             // x 16 pixels per dependent block time is what bounds a batch).  nh_set_wave_impl(..., 1 | 2) / NH_WAVE_OCC=lat|thr forces one of them.
-            const bool lat4 = wi.build ? wi.build == 1 : rows <= (int64_t)sm_count() * 4;
+            const bool lat4 = wi.build ? wi.build == 1 : rows <= (int64_t)sm_count() * 8;   // two 4K frames: 3.35 -> 2.93 ms, four: 4.70 / 3.99 ms
             if (lat4) {
                 if (a.cost_kind == NH_COST_SAD) wave4mw_kernel<NH_COST_SAD, 4><<<grid, 128, 0, st>>>(a);
                 else wave4mw_kernel<NH_COST_SATD, 4><<<grid, 128, 0, st>>>(a);
@@ -866,6 +866,9 @@ static int dispatch_coder(const CoderArgs& a, int size, cudaStream_t st) {
         }
         const int wave_warps = size >= 16 ? (wi.warps ? wi.warps : wave_warps_for(size, rows)) : 1;
         if (size >= 16 && wave_warps > 1) {
+            // (measured and not kept, profiles/r5_wave_more.txt: register caps for more resident rows -- 168 / 128 registers,
+            // up to 8 CTAs per SM -- gain nothing over the choice of warps per row, and the grid size beyond the resident
+            // CTAs makes no difference)
             if (grid > sm_count() * 4) grid = sm_count() * 4;
             if (size == 16) {
                 if (wave_warps == 2) coder_wave_mw_kernel<16, 2><<<grid, 64, 0, st>>>(a);
