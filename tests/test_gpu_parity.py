@@ -711,6 +711,18 @@ def test_config3_config5_4k_full_oracle(Bt, n, rn, cost):
                 eq(host(r.costs), w["costs"], f"costs n={n} {cost} search impl {impl}")
         finally:
             _lib.check(_lib.lib().nh_set_search_impl(2))
+    if rn:   # every layout of the wavefront at full size (the library picks one per call from the rows in flight)
+        from nano_hevc_b200 import _lib
+        layouts = {4: [(1, 0), (4, 1), (4, 2)], 8: [(0, 1), (0, 2), (0, 3)],
+                   16: [(1, 0), (2, 0), (4, 0), (8, 0)], 32: [(1, 0), (2, 0), (4, 0), (8, 0)]}[n]
+        try:
+            for warps, build in layouts:
+                _lib.check(_lib.lib().nh_set_wave_impl(warps, build))
+                r = Bt.encode_frame(d, n, cost=cost, qp=27, recon_neighbours=True)
+                for name in ("modes", "costs", "pred", "coeff", "levels", "recon_plane"):
+                    eq(host(getattr(r, name)), w[name], f"{name} n={n} {cost} wavefront layout {warps},{build}")
+        finally:
+            _lib.check(_lib.lib().nh_set_wave_impl(0, 0))
     assert np.count_nonzero(w["levels"]) > 0
     sse = int(Bt.sse_sad(d, r.recon_plane)[0].item())
     assert Bt.psnr_from_sse(sse, H * W) == pytest.approx(float(O.psnr(src, w["recon_plane"])), rel=1e-9)
@@ -831,6 +843,14 @@ def test_wavefront_every_layout_vs_oracle(Bt, n, cost):
                 for name in ("modes", "costs", "pred", "coeff", "levels"):
                     eq(host(getattr(r, name)[f]), want[f][name], f"{name} frame {f} n={n} {cost} layout={warps},{build}")
                 eq(host(r.recon_planes[f]), want[f]["recon_plane"], f"recon_plane frame {f} n={n} {cost} layout={warps},{build}")
+            if n >= 16 and cost == "sad":   # the same kernels serve deeper planes: 10-bit samples through every layout
+                f10 = (frames[:2].astype(np.int32) * 4 + 1).astype(np.int16)
+                r = Bt.encode_frames(dev(f10), n, cost=cost, qp=29, recon_neighbours=True, bit_depth=10)
+                for f in range(2):
+                    w = O.encode_frame(f10[f], n, cost=cost, qp=29, recon_neighbours=True, bit_depth=10, threads=thr)
+                    for name in ("modes", "costs", "pred", "coeff", "levels"):
+                        eq(host(getattr(r, name)[f]), w[name], f"10-bit {name} frame {f} n={n} layout={warps},{build}")
+                    eq(host(r.recon_planes[f]), w["recon_plane"], f"10-bit recon_plane frame {f} n={n} layout={warps},{build}")
     finally:
         _lib.check(_lib.lib().nh_set_wave_impl(0, 0))
 
