@@ -559,8 +559,11 @@ namespace nh {
 // the exchange row above and runs the winner pipeline, all threads move pixels.  Same exchange-row
 // protocol and ticket order as the one-warp kernel, so a waiting CTA only ever waits on a row that a
 // resident CTA owns.
+// resident CTAs per SM the 32x32 instances are held to (168 registers: what they took before the look-ahead poll)
 template <int N, int WPB>
-__global__ void __launch_bounds__(32 * WPB) coder_wave_mw_kernel(const CoderArgs a) {
+constexpr int mw_occ() { return N == 32 ? (WPB == 4 ? 3 : WPB == 2 ? 6 : 1) : 1; }
+template <int N, int WPB>
+__global__ void __launch_bounds__(32 * WPB, mw_occ<N, WPB>()) coder_wave_mw_kernel(const CoderArgs a) {
     using Cfg = CoderCfg<N, 32>;
     constexpr int T = 32 * WPB;
     using MC = MmaConsts<N>;
@@ -569,12 +572,14 @@ __global__ void __launch_bounds__(32 * WPB) coder_wave_mw_kernel(const CoderArgs
     __shared__ __align__(16) uint4 ctab[MC::V_END][32];        // per-lane MMA constants
     __shared__ int s_keys[WPB];
     __shared__ int s_row;
+    __shared__ __align__(16) int16_t s_top2[(Cfg::REF_W + 7) / 8 * 8];   // top references of the NEXT block (polled ahead)
+    static_assert(WPB >= 2, "warp 1 polls ahead while warp 0 codes the winner");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     stage_mma_consts<N, T>(&ctab[0][0]);  // made visible by the first barrier of the row loop
     const MmaWinnerCtx mctx = make_mma_winner_ctx<N>(&ctab[0][0], lane, a.fq, a.maxv);
     const bool mma_ok = a.maxv <= 1023;
-    int16_t* top = reinterpret_cast<int16_t*>(smem);
-    int16_t* left = top + Cfg::REF_W;
+    int16_t* const top = reinterpret_cast<int16_t*>(smem);
+    int16_t* const left = top + Cfg::REF_W;
     int16_t* neg = reinterpret_cast<int16_t*>(smem + Cfg::REFS_PAD);
     int16_t* O = reinterpret_cast<int16_t*>(smem + Cfg::REFS_PAD + Cfg::NEG_BYTES);
     int* M = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(O) + Cfg::O_BYTES);
@@ -590,16 +595,53 @@ __global__ void __launch_bounds__(32 * WPB) coder_wave_mw_kernel(const CoderArgs
         const int16_t* srcf = a.src + fr * a.frame_stride;
         int16_t* reconf = a.out.recon_plane + fr * a.frame_stride;
         int16_t* bottomf = a.bottom + (int64_t)fr * bh * a.W;
-        for (int bx = 0; bx < bw; ++bx) {
-            const int x = bx * N, y = by * N;
-            const int64_t b = fr * a.blocks_per_frame + (int64_t)by * bw + bx;
-            // original pixels do not depend on any neighbour: fetch them before the wait
-            int ov[OPL];
+        // original pixels do not depend on any neighbour: they are fetched one block ahead (the loads of block bx + 1
+        // are issued as soon as those of block bx have been stored into O, and complete under its search)
+        int ov[OPL];
+        auto fetch_px = [&](int bxn) {
 #pragma unroll
             for (int i = 0; i < OPL; ++i) {
                 const int e = tid + i * T;
-                ov[i] = e < N * N ? (int)__ldg(srcf + (int64_t)(y + e / N) * a.pitch + x + e % N) : 0;
+                ov[i] = e < N * N ? (int)__ldg(srcf + (int64_t)(by * N + e / N) * a.pitch + bxn * N + e % N) : 0;
             }
+        };
+        fetch_px(0);
+        // one warp fetches the top references of block bxn into dst; returns the OR of the samples (domain check)
+        auto poll_top = [&](int bxn, int16_t* dst) -> int {
+            int o = 0;
+            if (by == 0) {
+                for (int k = lane; k < Cfg::REF_W; k += 32) dst[k] = 128;
+                return 128;
+            }
+            const int xn = bxn * N;
+            const int16_t* up = bottomf + (int64_t)(by - 1) * a.W;
+            int last = xn + 2 * N - 1;
+            if (last > a.W - 1) last = a.W - 1;
+            bool ready;
+            do {
+                ready = true;
+                for (int k = lane; k < Cfg::REF_W; k += 32) {
+                    int v;
+                    if (k == 0 && xn == 0) {
+                        v = 128;
+                    } else {
+                        int col = xn + k - 1;
+                        if (col > last) col = last;
+                        v = (int)__ldcg(up + col);
+                    }
+                    if (v < 0) ready = false;
+                    else dst[k] = (int16_t)v;
+                }
+                ready = __all_sync(0xffffffffu, ready);
+                if (!ready && a.poll_sleep_ns) __nanosleep(a.poll_sleep_ns);
+            } while (!ready);
+            for (int k = lane; k < Cfg::REF_W; k += 32) o |= (int)dst[k];
+            return o;
+        };
+        int ood_top_next = 0;   // warp 1: domain check of the references polled ahead
+        for (int bx = 0; bx < bw; ++bx) {
+            const int x = bx * N, y = by * N;
+            const int64_t b = fr * a.blocks_per_frame + (int64_t)by * bw + bx;
             int ood = 0;
             // left references = right-most column of the block this CTA has just reconstructed (still
             // in O); bottom-left is not reconstructed yet -> replicate (n_left = N)
@@ -609,35 +651,15 @@ __global__ void __launch_bounds__(32 * WPB) coder_wave_mw_kernel(const CoderArgs
                 left[k] = (int16_t)lv;
                 ood |= lv;
             }
-            // top references from the exchange row above (data-as-flag, -1 = not written yet): warp 0
-            // polls, the other warps wait at the barrier below without taking issue slots
-            if (warp == 0) {
-                if (by == 0) {
-                    for (int k = lane; k < Cfg::REF_W; k += 32) top[k] = 128;
-                } else {
-                    const int16_t* up = bottomf + (int64_t)(by - 1) * a.W;
-                    int last = x + 2 * N - 1;
-                    if (last > a.W - 1) last = a.W - 1;
-                    bool ready;
-                    do {
-                        ready = true;
-                        for (int k = lane; k < Cfg::REF_W; k += 32) {
-                            int v;
-                            if (k == 0 && x == 0) {
-                                v = 128;
-                            } else {
-                                int col = x + k - 1;
-                                if (col > last) col = last;
-                                v = (int)__ldcg(up + col);
-                            }
-                            if (v < 0) ready = false;
-                            else top[k] = (int16_t)v;
-                        }
-                        ready = __all_sync(0xffffffffu, ready);
-                        if (!ready && a.poll_sleep_ns) __nanosleep(a.poll_sleep_ns);
-                    } while (!ready);
-                    for (int k = lane; k < Cfg::REF_W; k += 32) ood |= (int)top[k];
-                }
+            // top references from the exchange row above (data-as-flag, -1 = not written yet).  Block 0 of a row:
+            // warp 0 polls here; every later block: warp 1 has polled them into s_top2 while warp 0 coded the previous
+            // winner (the L2 round trip of the poll is then off the row's critical path whenever the row above is
+            // ahead), and they are copied over here.  The other warps wait at the barrier below.
+            if (bx == 0) {
+                if (warp == 0) ood |= poll_top(0, top);
+            } else if (warp == 1) {
+                for (int k = lane; k < Cfg::REF_W; k += 32) top[k] = s_top2[k];
+                ood |= ood_top_next;
             }
             __syncthreads();  // O (previous reconstruction) has been consumed, top / left are in place
             if (tid == 0) left[0] = top[0];
@@ -647,6 +669,7 @@ __global__ void __launch_bounds__(32 * WPB) coder_wave_mw_kernel(const CoderArgs
                 if (e < N * N) O[(e / N) * Cfg::O_PITCH + (e % N)] = (int16_t)ov[i];
                 ood |= ov[i];
             }
+            if (bx + 1 < bw) fetch_px(bx + 1);
             const bool fast8 = __syncthreads_or((ood & ~0xff) != 0) == 0;
             const int corner = (int)top[0];
             const int dc = dc_from_refs<N>(top, left);
@@ -676,8 +699,10 @@ __global__ void __launch_bounds__(32 * WPB) coder_wave_mw_kernel(const CoderArgs
                 // publish the bottom row first: the row below is polling for it
                 for (int e = lane; e < N; e += 32)
                     __stcg(bottomf + (int64_t)by * a.W + x + e, O[(N - 1) * Cfg::O_PITCH + e]);
+            } else if (warp == 1 && bx + 1 < bw) {
+                ood_top_next = poll_top(bx + 1, s_top2);
             }
-            __syncthreads();  // the reconstruction is in O
+            __syncthreads();  // the reconstruction is in O (and the next block's top references in s_top2)
             for (int e = tid; e < N * N; e += T)
                 reconf[(int64_t)(y + e / N) * a.pitch + x + e % N] = O[(e / N) * Cfg::O_PITCH + (e % N)];
             // no barrier needed here: the next block only reads O (left references) before the
