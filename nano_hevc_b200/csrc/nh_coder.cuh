@@ -550,4 +550,14 @@ __device__ __forceinline__ int dc_from_refs(const int16_t* top, const int16_t* l
     return dc_value<N>(s);
 }
 
+// The same sum by a whole (converged) warp: two loads per lane and one REDUX instead of 2N dependent shared-memory loads
+// per thread (the multi-warp wavefront kernels compute the DC value on a block's critical path).
+template <int N>
+__device__ __forceinline__ int dc_from_refs_warp(int lane, const int16_t* top, const int16_t* left) {
+    int s = 0;
+#pragma unroll
+    for (int k = lane; k < N; k += 32) s += (int)top[1 + k] + (int)left[1 + k];
+    return dc_value<N>(__reduce_add_sync(0xffffffffu, s));
+}
+
 }  // namespace nh

@@ -146,6 +146,9 @@ struct CoderArgs {
 // a plane) takes 246 registers when left alone: 2 CTAs per SM, issue slots 38 % busy, the stalls are fixed-latency
 // waits.  Capped at 168 registers (3 CTAs, 32 bytes of spills) with a grid of 3 CTAs per SM: 407 -> 373 us for 8 4K
 // frames.  (4 CTAs: 340 bytes of spills, slower; the 32x32 instance gains nothing from the same cap.)
+#ifndef NH_WAVE1_PREFETCH
+#define NH_WAVE1_PREFETCH 1
+#endif
 #ifndef NH_WINNER_OCC
 #define NH_WINNER_OCC 3
 #endif
@@ -211,17 +214,22 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128, coder_occ<N, 
             const int16_t* srcf = a.src + fr * a.frame_stride;
             int16_t* reconf = a.out.recon_plane + fr * a.frame_stride;
             int16_t* bottomf = a.bottom + (int64_t)fr * bh * a.W;
-            for (int bx = 0; bx < bw; ++bx) {
-                const int x = bx * N, y = by * N;
-                const int64_t b = fr * a.blocks_per_frame + (int64_t)by * bw + bx;
-                // original pixels do not depend on any neighbour: fetch them before the wait
-                constexpr int OPL = (N * N + G - 1) / G;  // orig samples per lane
-                int ov[OPL];
+            // original pixels do not depend on any neighbour: they are fetched one block ahead (the loads of block
+            // bx + 1 are issued as soon as those of block bx sit in O and complete under its search)
+            constexpr int OPL = (N * N + G - 1) / G;  // orig samples per lane
+            int ov[OPL];
+            auto fetch_px = [&](int bxn) {
 #pragma unroll
                 for (int i = 0; i < OPL; ++i) {
                     const int e = gl + i * G;
-                    ov[i] = e < N * N ? (int)__ldg(srcf + (int64_t)(y + e / N) * a.pitch + x + e % N) : 0;
+                    ov[i] = e < N * N ? (int)__ldg(srcf + (int64_t)(by * N + e / N) * a.pitch + bxn * N + e % N) : 0;
                 }
+            };
+            fetch_px(0);
+            for (int bx = 0; bx < bw; ++bx) {
+                const int x = bx * N, y = by * N;
+                const int64_t b = fr * a.blocks_per_frame + (int64_t)by * bw + bx;
+                if (!NH_WAVE1_PREFETCH && bx > 0) fetch_px(bx);
                 int ood = 0;  // any sample outside [0, 255] disables the packed 8-bit search
                 // left references = right-most column of the block this warp has just reconstructed
                 // (still in O); bottom-left is not reconstructed yet -> replicate (n_left = N)
@@ -272,10 +280,11 @@ __global__ void __launch_bounds__(SRC == SRC_WAVEFRONT ? 32 : 128, coder_occ<N, 
                     if (e < N * N) O[(e / N) * Cfg::O_PITCH + (e % N)] = (int16_t)ov[i];
                     ood |= ov[i];
                 }
+                if (NH_WAVE1_PREFETCH && bx + 1 < bw) fetch_px(bx + 1);
                 const bool fast8 = !__any_sync(0xffffffffu, (ood & ~0xff) != 0);
                 __syncwarp();
                 const int corner = (int)top[0];
-                const int dc = dc_from_refs<N>(top, left);
+                const int dc = dc_from_refs_warp<N>(lane, top, left);   // G == 32: the whole warp codes one block
                 int key;
                 if (fast8) {
                     build_neg_arrays<N, G>(gl, top, left, neg);
@@ -672,7 +681,7 @@ __global__ void __launch_bounds__(32 * WPB, mw_occ<N, WPB>()) coder_wave_mw_kern
             if (bx + 1 < bw) fetch_px(bx + 1);
             const bool fast8 = __syncthreads_or((ood & ~0xff) != 0) == 0;
             const int corner = (int)top[0];
-            const int dc = dc_from_refs<N>(top, left);
+            const int dc = dc_from_refs_warp<N>(lane, top, left);
             if (fast8) {
                 build_neg_arrays<N, T>(tid, top, left, neg);
                 __syncthreads();
