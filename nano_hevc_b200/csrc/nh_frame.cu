@@ -665,13 +665,19 @@ __global__ void __launch_bounds__(32 * WPB, mw_occ<N, WPB>()) coder_wave_mw_kern
             // winner (the L2 round trip of the poll is then off the row's critical path whenever the row above is
             // ahead), and they are copied over here.  The other warps wait at the barrier below.
             if (bx == 0) {
-                if (warp == 0) ood |= poll_top(0, top);
+                if (warp == 0) {
+                    ood |= poll_top(0, top);
+                    if (lane == 0) left[0] = top[0];   // lane 0 wrote top[0] itself
+                }
             } else if (warp == 1) {
                 for (int k = lane; k < Cfg::REF_W; k += 32) top[k] = s_top2[k];
+                if (lane == 0) left[0] = s_top2[0];
                 ood |= ood_top_next;
             }
             __syncthreads();  // O (previous reconstruction) has been consumed, top / left are in place
-            if (tid == 0) left[0] = top[0];
+            // the per-mode arrays of the negative angles only need the references: built beside the pixel stores, the
+            // barrier of the domain vote below publishes both (unused when the block leaves the 8-bit domain)
+            build_neg_arrays<N, T>(tid, top, left, neg);
 #pragma unroll
             for (int i = 0; i < OPL; ++i) {
                 const int e = tid + i * T;
@@ -682,10 +688,6 @@ __global__ void __launch_bounds__(32 * WPB, mw_occ<N, WPB>()) coder_wave_mw_kern
             const bool fast8 = __syncthreads_or((ood & ~0xff) != 0) == 0;
             const int corner = (int)top[0];
             const int dc = dc_from_refs_warp<N>(lane, top, left);
-            if (fast8) {
-                build_neg_arrays<N, T>(tid, top, left, neg);
-                __syncthreads();
-            }
             int key = fast8 ? search_modes_u8<N, 32>(lane, O, top, left, neg, dc, a.cost_kind, warp, WPB)
                             : search_modes<N, 32>(lane, O, top, left, corner, dc, a.cost_kind, warp, WPB);
             if (lane == 0) s_keys[warp] = key;
