@@ -409,6 +409,59 @@ __device__ __forceinline__ int search_modes_u8(int gl, const int16_t* O, const i
     return best;
 }
 
+// search_modes_u8() with the block's pixels given as packed bytes: Ob = N rows of N bytes, ObT = the transposed block.
+// The int16 form costs every lane 2 x 16 WPS dependent 16-bit loads plus the packing per block (the multi-warp wavefront
+// kernels ran that preamble in every warp: ~2500 of a 16x16 block's 5400 cycles); here a strip is 8 WPS word loads.
+template <int N, int G>
+__device__ __forceinline__ int search_modes_u8_pk(int gl, const unsigned char* Ob, const unsigned char* ObT, const int16_t* top,
+                                               const int16_t* left, const int16_t* neg, int dc,
+                                               int cost_kind, int it0 = 0, int it_step = 1) {
+    using Cfg = CoderCfg<N, G>;
+    using SC = StripCfg<N, G>;
+    constexpr int SW = SC::SW, WPS = SC::WPS;
+    // ov: the lane's strip for vertical / DC / planar modes (SW wide, 4 tall at (px, py));
+    // oh: its strip for horizontal modes, stored transposed (4 wide, SW tall at (py, px) mirrored:
+    //     scan line j = image column qx + j, base i = image row qy + i)
+    uint32_t ov[SC::SPL][4][WPS], oh[SC::SPL][4][WPS];
+    int px[SC::SPL], py[SC::SPL];
+#pragma unroll
+    for (int s = 0; s < SC::SPL; ++s) {
+        const int st = (SC::MS == 1) ? gl + s * G : gl % SC::SB;
+        px[s] = (st % SC::SPR) * SW;   // base offset of the strip (x for vertical, y for horizontal)
+        py[s] = (st / SC::SPR) * 4;    // scan offset of the strip (y for vertical, x for horizontal)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < WPS; ++q) {
+                const int w = (py[s] + j) * N + px[s] + 4 * q;   // bytes (sc, b .. b+3); px is a multiple of 4
+                ov[s][j][q] = *reinterpret_cast<const uint32_t*>(Ob + w);    // (y = sc, x = b + i)
+                oh[s][j][q] = *reinterpret_cast<const uint32_t*>(ObT + w);   // (y = b + i, x = sc)
+            }
+    }
+    const int ms = (SC::MS == 1) ? 0 : gl / SC::SB;
+    int best = 0x7fffffff;
+    constexpr int ITERS = (35 + SC::MS - 1) / SC::MS;
+    for (int it = it0; it < ITERS; it += it_step) {
+        const int pos = it * SC::MS + ms;
+        const bool active = pos < 35;
+        const int mode = !active ? 1 : (pos == 0 ? 1 : (pos == 1 ? 0 : pos));
+        int c = 0;
+#pragma unroll
+        for (int s = 0; s < SC::SPL; ++s)
+            c += strip_cost_u8<N, G>(mode, px[s], py[s], ov[s], oh[s], top, left, neg, dc, cost_kind);
+#pragma unroll
+        for (int off = SC::SBL / 2; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+        const int key = active ? ((c << 6) | pos) : 0x7fffffff;
+        best = key < best ? key : best;
+    }
+#pragma unroll
+    for (int off = G / 2; off >= SC::SBL; off >>= 1) {
+        int other = __shfl_xor_sync(0xffffffffu, best, off);
+        best = other < best ? other : best;
+    }
+    return best;
+}
+
 __device__ __forceinline__ int mode_of_key(int key) {
     const int pos = key & 63;
     return pos == 0 ? 1 : (pos == 1 ? 0 : pos);

@@ -568,6 +568,16 @@ namespace nh {
 // the exchange row above and runs the winner pipeline, all threads move pixels.  Same exchange-row
 // protocol and ticket order as the one-warp kernel, so a waiting CTA only ever waits on a row that a
 // resident CTA owns.
+// Per-phase cycle counters of the first block row (development only, `make prof`; see nh_wave.cuh)
+#ifdef NH_WAVE_PROF
+#define NH_MWPROF_DECL long long mwp_t = clock64(), mwp_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define NH_MWPROF_MARK(i) { const long long now__ = clock64(); mwp_acc[i] += now__ - mwp_t; mwp_t = now__; }
+#define NH_MWPROF_DUMP(cond) if (cond) { for (int i__ = 0; i__ < 8; ++i__) atomicAdd(reinterpret_cast<unsigned long long*>(a.ticket) + 8 + i__, (unsigned long long)mwp_acc[i__]); }
+#else
+#define NH_MWPROF_DECL
+#define NH_MWPROF_MARK(i)
+#define NH_MWPROF_DUMP(cond)
+#endif
 // resident CTAs per SM the 32x32 instances are held to (168 registers: what they took before the look-ahead poll)
 template <int N, int WPB>
 constexpr int mw_occ() { return N == 32 ? (WPB == 4 ? 3 : WPB == 2 ? 6 : 1) : 1; }
@@ -582,6 +592,7 @@ __global__ void __launch_bounds__(32 * WPB, mw_occ<N, WPB>()) coder_wave_mw_kern
     __shared__ int s_keys[WPB];
     __shared__ int s_row;
     __shared__ __align__(16) int16_t s_top2[(Cfg::REF_W + 7) / 8 * 8];   // top references of the NEXT block (polled ahead)
+    __shared__ __align__(16) unsigned char s_ob[2 * N * N];              // the block's pixels as bytes, and transposed
     static_assert(WPB >= 2, "warp 1 polls ahead while warp 0 codes the winner");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     stage_mma_consts<N, T>(&ctab[0][0]);  // made visible by the first barrier of the row loop
@@ -648,7 +659,9 @@ __global__ void __launch_bounds__(32 * WPB, mw_occ<N, WPB>()) coder_wave_mw_kern
             return o;
         };
         int ood_top_next = 0;   // warp 1: domain check of the references polled ahead
+        NH_MWPROF_DECL
         for (int bx = 0; bx < bw; ++bx) {
+            NH_MWPROF_MARK(7)
             const int x = bx * N, y = by * N;
             const int64_t b = fr * a.blocks_per_frame + (int64_t)by * bw + bx;
             int ood = 0;
@@ -675,23 +688,31 @@ __global__ void __launch_bounds__(32 * WPB, mw_occ<N, WPB>()) coder_wave_mw_kern
                 ood |= ood_top_next;
             }
             __syncthreads();  // O (previous reconstruction) has been consumed, top / left are in place
+            NH_MWPROF_MARK(0)
             // the per-mode arrays of the negative angles only need the references: built beside the pixel stores, the
             // barrier of the domain vote below publishes both (unused when the block leaves the 8-bit domain)
             build_neg_arrays<N, T>(tid, top, left, neg);
 #pragma unroll
             for (int i = 0; i < OPL; ++i) {
                 const int e = tid + i * T;
-                if (e < N * N) O[(e / N) * Cfg::O_PITCH + (e % N)] = (int16_t)ov[i];
+                if (e < N * N) {
+                    O[(e / N) * Cfg::O_PITCH + (e % N)] = (int16_t)ov[i];
+                    s_ob[e] = (unsigned char)ov[i];                               // only read on the 8-bit path
+                    s_ob[N * N + (e % N) * N + e / N] = (unsigned char)ov[i];
+                }
                 ood |= ov[i];
             }
             if (bx + 1 < bw) fetch_px(bx + 1);
             const bool fast8 = __syncthreads_or((ood & ~0xff) != 0) == 0;
+            NH_MWPROF_MARK(1)
             const int corner = (int)top[0];
             const int dc = dc_from_refs_warp<N>(lane, top, left);
-            int key = fast8 ? search_modes_u8<N, 32>(lane, O, top, left, neg, dc, a.cost_kind, warp, WPB)
+            int key = fast8 ? search_modes_u8_pk<N, 32>(lane, s_ob, s_ob + N * N, top, left, neg, dc, a.cost_kind, warp, WPB)
                             : search_modes<N, 32>(lane, O, top, left, corner, dc, a.cost_kind, warp, WPB);
+            NH_MWPROF_MARK(2)
             if (lane == 0) s_keys[warp] = key;
             __syncthreads();
+            NH_MWPROF_MARK(3)
 #pragma unroll
             for (int w = 0; w < WPB; ++w) key = s_keys[w] < key ? s_keys[w] : key;
             const int mode = mode_of_key(key);
@@ -713,12 +734,16 @@ __global__ void __launch_bounds__(32 * WPB, mw_occ<N, WPB>()) coder_wave_mw_kern
             } else if (warp == 1 && bx + 1 < bw) {
                 ood_top_next = poll_top(bx + 1, s_top2);
             }
+            NH_MWPROF_MARK(4)
             __syncthreads();  // the reconstruction is in O (and the next block's top references in s_top2)
+            NH_MWPROF_MARK(5)
             for (int e = tid; e < N * N; e += T)
                 reconf[(int64_t)(y + e / N) * a.pitch + x + e % N] = O[(e / N) * Cfg::O_PITCH + (e % N)];
             // no barrier needed here: the next block only reads O (left references) before the
             // barrier that precedes its overwrite
+            NH_MWPROF_MARK(6)
         }
+        NH_MWPROF_DUMP(by == 0 && fr == 0 && tid == 0)
     }
 }
 
