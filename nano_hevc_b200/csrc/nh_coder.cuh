@@ -324,19 +324,34 @@ __device__ __forceinline__ int strip_cost_u8(int mode, int b0, int s0,
 #pragma unroll
             for (int q = 0; q < WPS; ++q) pr[j][q] = d4;
     } else {
-        // planar, image orientation: b0 = x, s0 = y
+        // planar (intra.py:109-111), image orientation: b0 = x, s0 = y.  Two samples per multiply-add chain: every term
+        // is non-negative for 8-bit references and the weights carry a factor 2^(7 - log2 N), so that the sample
+        // ((N-1-x) l[y] + (x+1) tr + (N-1-y) t[x] + (y+1) bl + N) >> (log2 N + 1) is the high byte of its 16-bit lane
+        // (largest lane value 65408).  (One planar_px per sample made the DC / planar / angular iteration of a warp --
+        // three diverged branches -- the longest phase of a block in the multi-warp wavefront kernels.)
+        constexpr uint32_t SCL = 1u << (7 - Log2<N>::v);
+        const uint32_t tr = (uint32_t)(uint16_t)top[N + 1], bl = (uint32_t)(uint16_t)left[N + 1];
+        uint32_t c1[2 * WPS], kc[2 * WPS], zt[2 * WPS];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int i = 0; i < 2 * WPS; ++i) {
+            const uint32_t X = (uint32_t)(b0 + 2 * i);
+            c1[i] = (((uint32_t)(N - 1) - X) | (((uint32_t)(N - 2) - X) << 16)) * SCL;
+            kc[i] = tr * (((X + 1) | ((X + 2) << 16)) * SCL);
+            zt[i] = (uint32_t)(uint16_t)top[1 + b0 + 2 * i] | ((uint32_t)(uint16_t)top[2 + b0 + 2 * i] << 16);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int y = s0 + j;
+            const uint32_t ly = (uint32_t)(uint16_t)left[1 + y];
+            const uint32_t vy = (uint32_t)(N - 1 - y) * SCL;
+            const uint32_t by = ((uint32_t)(y + 1) * bl + (uint32_t)N) * SCL * 0x10001u;
 #pragma unroll
             for (int q = 0; q < WPS; ++q) {
-                uint32_t word = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int x = b0 + 4 * q + i, y = s0 + j;
-                    word |= (uint32_t)planar_px<N>(x, y, left[1 + y], top[1 + x], top[N + 1], left[N + 1]) << (8 * i);
-                }
-                pr[j][q] = word;
+                const uint32_t t0 = ly * c1[2 * q] + kc[2 * q] + vy * zt[2 * q] + by;
+                const uint32_t t1 = ly * c1[2 * q + 1] + kc[2 * q + 1] + vy * zt[2 * q + 1] + by;
+                pr[j][q] = __byte_perm(t0, t1, 0x7531);
             }
+        }
     }
     int c = 0;
     if (cost_kind == NH_COST_SAD) {
