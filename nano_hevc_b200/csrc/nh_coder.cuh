@@ -457,7 +457,13 @@ __device__ __forceinline__ int search_modes_u8_pk(int gl, const unsigned char* O
     int best = 0x7fffffff;
     constexpr int ITERS = (35 + SC::MS - 1) / SC::MS;
     for (int it = it0; it < ITERS; it += it_step) {
-        const int pos = it * SC::MS + ms;
+        // Candidate positions rotated by one iteration: iteration 1 holds positions 0 .. MS-1 -- DC, planar and the first
+        // angular modes, three diverged branches -- and iteration 0 the last ones.  With W warps sharing the iterations
+        // (it0 = warp, it_step = W) the warp that runs one iteration more than the others is warp 0, which then gets
+        // uniform angular iterations only; the key carries the true position, so the winner does not depend on the order.
+        // (MS == 1, N = 32: every iteration is uniform already and the plain order happens to be the better balanced.)
+        int pos = it * SC::MS + ms - (SC::MS > 1 ? SC::MS : 0);
+        if (pos < 0) pos += ITERS * SC::MS;
         const bool active = pos < 35;
         const int mode = !active ? 1 : (pos == 0 ? 1 : (pos == 1 ? 0 : pos));
         int c = 0;
