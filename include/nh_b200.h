@@ -200,7 +200,8 @@ int64_t nh_encode_frame_scratch_bytes(int height, int width, int size);
 int nh_set_search_impl(int impl);
 /* Selects how recon_neighbours == 1 (the anti-diagonal wavefront over block rows) is laid out, for the calling
  * thread.  warps: 0 (default) = pick per call from the block rows in flight (rows of a frame x frames of the call),
- * 1 / 2 / 4 / 8 = warps per block row at N = 16 / 32 (more warps: shorter dependent block time, fewer rows resident),
+ * 1 / 2 / 4 / 8 / 12 = warps per block row at N = 16 / 32 (more warps: shorter dependent block time, fewer rows
+ * resident; 12 exists at N = 32 only and means 8 at N = 16),
  * 1 / 4 = the one-warp / four-warp kernel at N = 4; ignored at N = 8 (always four warps per row on 8-bit planes).
  * build: 0 (default) = pick per call, 1 = latency build (one or two frames), 2 = throughput build (more CTAs per SM),
  * 3 = throughput build at the highest occupancy (N = 8; elsewhere as 2); N = 4 / 8 only.  Results are identical. */

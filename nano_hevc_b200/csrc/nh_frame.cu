@@ -849,7 +849,8 @@ static const WaveImpl& wave_impl() {
         const char* w = getenv("NH_WAVE_WARPS");
         const char* w4 = getenv("NH_WAVE4");
         const char* o = getenv("NH_WAVE_OCC");
-        if (w && (w[0] == '1' || w[0] == '2' || w[0] == '4' || w[0] == '8')) g_wave_impl.warps = w[0] - '0';
+        if (w && atoi(w) == 12) g_wave_impl.warps = 12;
+        else if (w && (w[0] == '1' || w[0] == '2' || w[0] == '4' || w[0] == '8')) g_wave_impl.warps = w[0] - '0';
         else if (w4 && (w4[0] == '1' || w4[0] == '4')) g_wave_impl.warps = w4[0] - '0';
         if (o) g_wave_impl.build = o[0] == 'l' ? 1 : o[0] == 'h' ? 3 : 2;
         g_wave_impl.init = true;
@@ -860,12 +861,14 @@ static const WaveImpl& wave_impl() {
 // profiles/r5_wave_warps.txt): a row's warps share the candidate modes, so more warps shorten the dependent block
 // time, but the resident rows per SM drop (8 warps: 1 CTA per SM, 4: 2-3, 2: 4-6, 1: 8+), and once a call has more
 // rows in flight than fit, the rows that wait cost more than the slower block.  N = 16: 8 warps for one frame, 4 up
-// to ~5 frames, 2 up to ~14, then 1 (32 frames: 10.6 -> 30.2 Gpix/s); N = 32: 8 warps up to ~7 frames, 4 up to ~28,
+// to ~5 frames, 2 up to ~14, then 1 (32 frames: 10.6 -> 30.2 Gpix/s); N = 32: 12 warps up to ~8 frames, 4 up to ~28,
 // then 1 (32 frames: 23.9 -> 41.3 Gpix/s).
 static int wave_warps_for(int size, int64_t rows) {
     const int64_t sm = sm_count();
     if (size == 16) return rows * 10 <= sm * 11 ? 8 : rows * 10 <= sm * 47 ? 4 : rows <= sm * 13 ? 2 : 1;
-    return rows * 10 <= sm * 32 ? 8 : rows <= sm * 13 ? 4 : 1;
+    // N = 32: one candidate per warp iteration, 35 iterations: 12 warps run 3 each where 8 run 5 (one 4K frame 1.244 ->
+    // 1.202 ms, 8 frames 27.5 (4 warps) -> 28.0 Gpix/s; 9 / 10 / 16 / 18 warps are slower than 8)
+    return rows <= sm * 4 ? 12 : rows <= sm * 13 ? 4 : 1;
 }
 
 template <int SRC>
@@ -925,7 +928,8 @@ static int dispatch_coder(const CoderArgs& a, int size, cudaStream_t st) {
             NH_CHECK_LAUNCH("wave4mw_kernel");
             return NH_OK;
         }
-        const int wave_warps = size >= 16 ? (wi.warps ? wi.warps : wave_warps_for(size, rows)) : 1;
+        int wave_warps = size >= 16 ? (wi.warps ? wi.warps : wave_warps_for(size, rows)) : 1;
+        if (size == 16 && wave_warps == 12) wave_warps = 8;   // 12 warps per row exist at N = 32 only
         if (size >= 16 && wave_warps > 1) {
             // (measured and not kept, profiles/r5_wave_more.txt: register caps for more resident rows -- 168 / 128 registers,
             // up to 8 CTAs per SM -- gain nothing over the choice of warps per row, and the grid size beyond the resident
@@ -937,6 +941,7 @@ static int dispatch_coder(const CoderArgs& a, int size, cudaStream_t st) {
                 else coder_wave_mw_kernel<16, 4><<<grid, 128, 0, st>>>(a);
             } else {
                 if (wave_warps == 2) coder_wave_mw_kernel<32, 2><<<grid, 64, 0, st>>>(a);
+                else if (wave_warps == 12) coder_wave_mw_kernel<32, 12><<<grid, 384, 0, st>>>(a);
                 else if (wave_warps == 8) coder_wave_mw_kernel<32, 8><<<grid, 256, 0, st>>>(a);
                 else coder_wave_mw_kernel<32, 4><<<grid, 128, 0, st>>>(a);
             }
@@ -1240,8 +1245,8 @@ NH_API int nh_set_search_impl(int impl) {
 }
 
 NH_API int nh_set_wave_impl(int warps, int build) {
-    if (!(warps == 0 || warps == 1 || warps == 2 || warps == 4 || warps == 8) || build < 0 || build > 3) {
-        set_error("nh_set_wave_impl: warps must be 0 (pick per call), 1, 2, 4 or 8 and build 0 (pick per call), 1 (latency), "
+    if (!(warps == 0 || warps == 1 || warps == 2 || warps == 4 || warps == 8 || warps == 12) || build < 0 || build > 3) {
+        set_error("nh_set_wave_impl: warps must be 0 (pick per call), 1, 2, 4, 8 or 12 and build 0 (pick per call), 1 (latency), "
                   "2 (throughput) or 3 (throughput, highest occupancy), got %d, %d", warps, build);
         return NH_E_ARG;
     }

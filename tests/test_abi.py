@@ -80,7 +80,7 @@ def test_kernel_selection_and_accounting_entry_points():
         assert L.nh_set_search_impl(good) == 0
     assert L.nh_set_search_impl(7) != 0 and b"nh_set_search_impl" in L.nh_last_error()
     L.nh_set_search_impl(2)
-    for w, b in ((0, 0), (1, 2), (2, 0), (4, 1), (8, 3)):
+    for w, b in ((0, 0), (1, 2), (2, 0), (4, 1), (8, 3), (12, 0)):
         assert L.nh_set_wave_impl(w, b) == 0
     for w, b in ((3, 0), (16, 0), (-1, 0), (0, 4), (0, -1)):
         assert L.nh_set_wave_impl(w, b) != 0 and b"nh_set_wave_impl" in L.nh_last_error()

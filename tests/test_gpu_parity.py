@@ -714,7 +714,7 @@ def test_config3_config5_4k_full_oracle(Bt, n, rn, cost):
     if rn:   # every layout of the wavefront at full size (the library picks one per call from the rows in flight)
         from nano_hevc_b200 import _lib
         layouts = {4: [(1, 0), (4, 1), (4, 2)], 8: [(0, 1), (0, 2), (0, 3)],
-                   16: [(1, 0), (2, 0), (4, 0), (8, 0)], 32: [(1, 0), (2, 0), (4, 0), (8, 0)]}[n]
+                   16: [(1, 0), (2, 0), (4, 0), (8, 0)], 32: [(1, 0), (2, 0), (4, 0), (8, 0), (12, 0)]}[n]
         try:
             for warps, build in layouts:
                 _lib.check(_lib.lib().nh_set_wave_impl(warps, build))
@@ -834,7 +834,7 @@ def test_wavefront_every_layout_vs_oracle(Bt, n, cost):
     thr = O.n_host_threads()
     want = [O.encode_frame(frames[f], n, cost=cost, qp=29, recon_neighbours=True, threads=thr) for f in range(F)]
     layouts = {4: [(1, 0), (4, 1), (4, 2)], 8: [(0, 1), (0, 2), (0, 3)],
-               16: [(1, 0), (2, 0), (4, 0), (8, 0)], 32: [(1, 0), (2, 0), (4, 0), (8, 0)]}[n]
+               16: [(1, 0), (2, 0), (4, 0), (8, 0)], 32: [(1, 0), (2, 0), (4, 0), (8, 0), (12, 0)]}[n]
     try:
         for warps, build in layouts:
             _lib.check(_lib.lib().nh_set_wave_impl(warps, build))
