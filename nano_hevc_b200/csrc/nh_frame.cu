@@ -860,15 +860,16 @@ static const WaveImpl& wave_impl() {
 // Warps per block row at N = 16 / 32, from the rows in flight R (measured on one B200, 1 ... 32 4K frames per call,
 // profiles/r5_wave_warps.txt): a row's warps share the candidate modes, so more warps shorten the dependent block
 // time, but the resident rows per SM drop (8 warps: 1 CTA per SM, 4: 2-3, 2: 4-6, 1: 8+), and once a call has more
-// rows in flight than fit, the rows that wait cost more than the slower block.  N = 16: 8 warps for one frame, 4 up
-// to ~5 frames, 2 up to ~14, then 1 (32 frames: 10.6 -> 30.2 Gpix/s); N = 32: 12 warps up to ~8 frames, 4 up to ~28,
-// then 1 (32 frames: 23.9 -> 41.3 Gpix/s).
+// rows in flight than fit, the rows that wait cost more than the slower block.  Thresholds re-measured with the
+// look-ahead / packed-search kernels (profiles/r5_wave_more.txt, last sweep): N = 16: 8 warps up to two 4K frames, 4 up
+// to ~5, then 2 (the one-warp kernel no longer wins anywhere up to 48 frames; 32 frames: 10.6 -> 30.9 Gpix/s);
+// N = 32: 12 warps up to ~8 frames, 4 up to ~44, then 1 (32 frames: 23.9 -> 43.4 Gpix/s).
 static int wave_warps_for(int size, int64_t rows) {
     const int64_t sm = sm_count();
-    if (size == 16) return rows * 10 <= sm * 11 ? 8 : rows * 10 <= sm * 47 ? 4 : rows <= sm * 13 ? 2 : 1;
+    if (size == 16) return rows * 10 <= sm * 25 ? 8 : rows * 10 <= sm * 47 ? 4 : 2;
     // N = 32: one candidate per warp iteration, 35 iterations: 12 warps run 3 each where 8 run 5 (one 4K frame 1.244 ->
     // 1.202 ms, 8 frames 27.5 (4 warps) -> 28.0 Gpix/s; 9 / 10 / 16 / 18 warps are slower than 8)
-    return rows <= sm * 4 ? 12 : rows <= sm * 13 ? 4 : 1;
+    return rows <= sm * 4 ? 12 : rows <= sm * 20 ? 4 : 1;
 }
 
 template <int SRC>
