@@ -544,6 +544,49 @@ __device__ __forceinline__ void predict_row_u8(int mode, int r, const int16_t* t
     }
 }
 
+// Samples x0 .. x0 + 7 of row r: the formulas of predict_row_u8() on a segment, so that two lanes can share a row of a
+// 16x16 block (its winner stage would otherwise run the prediction on half a warp).
+template <int N, int G>
+__device__ __forceinline__ void predict_seg8_u8(int mode, int r, int x0, const int16_t* top, const int16_t* left,
+                                                const int16_t* neg, int dc, int (&p)[8]) {
+    using Cfg = CoderCfg<N, G>;
+    if (mode == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p[i] = dc;
+        return;
+    }
+    if (mode == 0) {
+        const int ly = (int)left[1 + r], tr = (int)top[N + 1], bl = (int)left[N + 1];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p[i] = planar_px<N>(x0 + i, r, ly, (int)top[1 + x0 + i], tr, bl);
+        return;
+    }
+    const int angle = intra_angle(mode);
+    const bool vertical = mode >= 18;
+    const int16_t* pos = vertical ? top : left;
+    const int16_t* ng = neg + (mode - 11) * Cfg::NEG_W + N;  // only dereferenced when k < 0
+    auto ref = [&](int k) -> int { return (int)(k < 0 ? ng : pos)[k]; };
+    if (vertical) {
+        const int pr = (r + 1) * angle;
+        const int ip = pr >> 5, f = pr & 31;
+        int v[9];
+#pragma unroll
+        for (int i = 0; i <= 8; ++i) v[i] = (i < 8 || f != 0) ? ref(x0 + i + 1 + ip) : 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p[i] = ((32 - f) * v[i] + f * v[i + 1] + 16) >> 5;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int pr = (x0 + i + 1) * angle;
+            const int ip = pr >> 5, f = pr & 31;
+            const int k = r + 1 + ip;
+            const int a = ref(k);
+            const int b2 = f != 0 ? ref(k + 1) : 0;
+            p[i] = ((32 - f) * a + f * b2 + 16) >> 5;
+        }
+    }
+}
+
 // Winner pipeline for one block: row owner r (< N) predicts row r, then the K6 chain through
 // the shared working matrix.  All lanes of the warp must call this (it contains __syncwarp).
 // The reconstruction is left in O (pitch O_PITCH) for the caller to copy out.

@@ -82,7 +82,14 @@ __device__ __forceinline__ void winner_mma(int lane, int64_t b, int mode, int16_
                                            const CoderOut& out) {
     constexpr int PITCH = N * 2 + 16;
     static_assert(PITCH == CoderCfg<N, 32>::O_PITCH * 2, "O tile must have the ldmatrix pitch");
-    if (lane < N) {
+    if constexpr (N == 16) {   // two lanes per row: lane = (row, half)
+        const int r = lane >> 1, x0 = (lane & 1) * 8;
+        int p[8];
+        predict_seg8_u8<N, 32>(mode, r, x0, top, left, neg, dc, p);
+        const uint4 w = make_uint4(pack16(p[0], p[1]), pack16(p[2], p[3]), pack16(p[4], p[5]), pack16(p[6], p[7]));
+        if (out.pred) stg_stream(out.pred + b * N * N + r * N + x0, w);
+        *reinterpret_cast<uint4*>(ptile + r * PITCH + 2 * x0) = w;
+    } else if (lane < N) {
         int p[N];
         uint32_t pw[N / 2];
         predict_row_u8<N, 32>(mode, lane, top, left, neg, dc, p);
